@@ -1,0 +1,244 @@
+"""TEST INFRASTRUCTURE ONLY — writes tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference):   python -m oracle.gen_golden
+Every file stores the seeded inputs, the reference outputs and provenance (torch version).  The
+reference has no tests or fixtures of its own, so these files are the pin for
+`oracle/ref_port.py` and, through it, for the CUDA path.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+from oracle import ref_harness as rh
+from objectdetectionpl_b200 import synth
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+META = dict(torch=torch.__version__, reference="Leyan529/ObjectDetectionPL @ /root/reference")
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _save(name, **arrays):
+    os.makedirs(OUT, exist_ok=True)
+    arrays["_meta"] = np.array(repr(META))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrays)
+    print("wrote", name, {k: getattr(v, "shape", None) for k, v in arrays.items() if k != "_meta"})
+
+
+def _pack_list(prefix, lst, d):
+    d[prefix + "_n"] = np.array(len(lst))
+    for i, t in enumerate(lst):
+        d[f"{prefix}_{i}"] = np.zeros((0,), np.float32) if t is None else _np(t)
+        d[f"{prefix}_{i}_none"] = np.array(t is None)
+
+
+def yolo_cases():
+    cases = [
+        # name, version, A, C, grids, img, seed, conf_lo
+        ("yolo_v5_tiny", 5, 3, 4, [8, 4, 2], 64, 11, 0.0),
+        ("yolo_v5_mid", 5, 3, 20, [20, 10, 5], 160, 12, 0.0),
+        ("yolo_v3_mid", 3, 3, 7, [5, 10, 20], 160, 13, 0.0),
+        ("yolo_v2_g13", 2, 5, 20, [13], 416, 14, 0.0),
+        ("yolo_v4_filter", 4, 3, 3, [6, 12], 96, 15, -0.1),   # some conf < -0.0151 -> filtered rows
+    ]
+    for name, ver, A, C, grids, img, seed, conf_lo in cases:
+        B = 2
+        lv = synth.yolo_planar(B, A, C, grids, img, seed, v5_view=(ver == 5), tie_free=False)
+        if conf_lo < 0:
+            g = torch.Generator().manual_seed(seed + 1000)
+            for t in lv:
+                p = t.view(B, A, 5 + C, t.shape[2], t.shape[3])
+                p[:, :, 4] = conf_lo + torch.rand(p[:, :, 4].shape, generator=g) * (1.0 - conf_lo)
+        synth.make_tie_free(lv, A)
+        fn = rh.yolo_nms(ver)
+        arg = [t.clone() for t in lv]
+        if ver != 5 and len(arg) == 1:
+            arg = arg[0]  # exercises the "single tensor" branch (YOLOV3.py:281-282)
+        out = fn(None, arg)
+        d = {f"level_{i}": _np(t) for i, t in enumerate(lv)}
+        d["n_levels"] = np.array(len(lv))
+        d["A"], d["C"], d["version"] = np.array(A), np.array(C), np.array(ver)
+        _pack_list("out", out, d)
+        _save(name, **d)
+
+
+def ssd_cases():
+    acc_priors = rh.ref_import("LightningFunc.utils.SSDUtils").get_dboxes()
+    ret_priors = rh.ref_import("LightningFunc.utils.RetinaUtils").get_anchor_boxes(torch.Tensor([128, 128]))
+    for name, which, priors, C, seed, mean in [("ssd300_c5", "SSD", acc_priors, 5, 21, -3.0),
+                                               ("retina128_c6", "RetinaNet", ret_priors, 6, 22, -2.0),
+                                               ("ssd300_sparse", "SSD", acc_priors, 3, 23, -6.5)]:
+        loc, cls = synth.prior_heads(2, priors.shape[0], C, seed, cls_mean=mean)
+        fn = rh.ssd_nms(which)
+        out = fn(types.SimpleNamespace(iou_boxes=priors), (loc.clone(), cls.clone()))
+        d = dict(loc=_np(loc), cls=_np(cls), priors=_np(priors))
+        _pack_list("out", out, d)
+        # 'min' mode and other thresholds on the same inputs
+        out2 = fn(types.SimpleNamespace(iou_boxes=priors), (loc.clone(), cls.clone()), topk=50, nms_thresh=0.3,
+                  class_thresh=0.3, mode="min")
+        _pack_list("out_min", out2, d)
+        _save(name, **d)
+    _save("priors", ssd=_np(acc_priors),
+          retina600=_np(rh.ref_import("LightningFunc.utils.RetinaUtils").get_anchor_boxes(torch.Tensor([600, 600]))),
+          retina800_head=_np(rh.ref_import("LightningFunc.utils.RetinaUtils").get_anchor_boxes(torch.Tensor([800, 800]))[:4096]),
+          retina800_count=np.array(rh.ref_import("LightningFunc.utils.RetinaUtils").get_anchor_boxes(torch.Tensor([800, 800])).shape[0]))
+
+
+def iou_cases():
+    acc = rh.accuracy()
+    g = torch.Generator().manual_seed(31)
+    n = 257
+    xy = torch.rand(n, 2, generator=g) * 100
+    wh = torch.rand(n, 2, generator=g) * 40 + 0.5
+    b1 = torch.cat([xy, wh], 1)
+    b2 = torch.cat([xy + torch.randn(n, 2, generator=g) * 10, wh * (0.5 + torch.rand(n, 2, generator=g))], 1)
+    d = dict(b1=_np(b1), b2=_np(b2))
+    d["plus1_xywh"] = _np(acc.bbox_iou(b1, b2, x1y1x2y2=False))
+    c1, c2 = acc.xywh2xyxy(b1), acc.xywh2xyxy(b2)
+    d["c1"], d["c2"] = _np(c1), _np(c2)
+    d["plus1_xyxy"] = _np(acc.bbox_iou(c1, c2, x1y1x2y2=True))
+    d["plus1_one_vs_all"] = _np(acc.bbox_iou(c1[:1], c2, x1y1x2y2=True))
+    for kind in ("IoU", "GIoU", "DIoU", "CIoU"):
+        for corner in (False, True):
+            a = (c1 if corner else b1).t().clone().requires_grad_(True)
+            bb = (c2 if corner else b2).t().clone()
+            kw = {} if kind == "IoU" else {kind: True}
+            v = acc.bbox_iou_v5(a, bb, x1y1x2y2=corner, **kw)
+            gw = torch.linspace(0.5, 1.5, n)
+            (v * gw).sum().backward()
+            tag = f"v5_{kind}_{'xyxy' if corner else 'xywh'}"
+            d[tag], d[tag + "_grad"] = _np(v), _np(a.grad)
+    d["pair_iou"] = _np(acc.iou(c1.clamp(0, 100), c2.clamp(0, 100)))
+    _save("iou", **d)
+
+
+def build_targets_cases():
+    acc = rh.accuracy()
+    for name, B, A, G, C, seed, maxn in [("bt_g13", 4, 3, 13, 5, 41, 12), ("bt_g26_dups", 2, 3, 26, 3, 42, 60)]:
+        g = torch.Generator().manual_seed(seed)
+        tg = synth.labels(B, C, seed, max_per_image=maxn)
+        if "dups" in name:  # force duplicate cells: repeat a block of rows with other classes / sizes
+            extra = tg[:10].clone()
+            extra[:, 1] = (extra[:, 1] + 1) % C
+            extra[:, 4:6] *= 1.1
+            tg = torch.cat([tg, extra], 0)
+        pred_boxes = torch.rand(B, A, G, G, 4, generator=g) * G
+        pred_cls = torch.rand(B, A, G, G, C, generator=g)
+        anchors = torch.tensor([[1.25, 1.625], [2.0, 3.75], [4.125, 2.875]])
+        out = acc.build_targets(pred_boxes, pred_cls, tg, anchors, 0.5)
+        names = ["iou_scores", "class_mask", "obj_mask", "noobj_mask", "tx", "ty", "tw", "th", "tcls", "tconf"]
+        d = dict(pred_boxes=_np(pred_boxes), pred_cls=_np(pred_cls), target=_np(tg), anchors=_np(anchors))
+        for k, v in zip(names, out):
+            d[k] = _np(v)
+        _save(name, **d)
+
+
+def build_targets_v5_cases():
+    acc, losses = rh.accuracy(), rh.losses()
+    for name, B, C, img, seed, maxn in [("btv5_small", 4, 5, 160, 51, 12), ("btv5_mid", 8, 80, 640, 52, 40)]:
+        tg = synth.labels(B, C, seed, max_per_image=maxn)
+        stride = torch.tensor([8., 16., 32.])
+        anchors = torch.tensor(synth.YOLOV5_ANCHORS).float().view(3, -1, 2) / stride.view(-1, 1, 1)
+        g = torch.Generator().manual_seed(seed + 1)
+        p = [torch.randn(B, 3, img // s, img // s, 5 + C, generator=g) for s in (8, 16, 32)]
+        tcls, tbox, indices, anch = acc.build_targets_v5(p, tg, anchors, 3, 3)
+        d = dict(target=_np(tg), anchors=_np(anchors), B=np.array(B), C=np.array(C), img=np.array(img))
+        for i in range(3):
+            d[f"p_{i}"] = _np(p[i]) if name == "btv5_small" else np.array(p[i].shape)
+            d[f"tcls_{i}"], d[f"tbox_{i}"], d[f"anch_{i}"] = _np(tcls[i]), _np(tbox[i]), _np(anch[i])
+            for k, nm in enumerate("b a gj gi".split()):
+                d[f"{nm}_{i}"] = _np(indices[i][k])
+        if name == "btv5_small":
+            # reference criterion forward: pins the matched-row decode + GIoU (losses.py:105-123)
+            crit = losses.MultiScaleRegionLoss_v5(synth.YOLOV5_ANCHORS, None, None, None, None, C, img)
+            pr = [t.clone().requires_grad_(True) for t in p]
+            m = crit(pr, tg)
+            d["lbox"], d["lobj"], d["lcls"] = _np(m["Localization"]), _np(m["Conf_obj"]), _np(m["Classification"])
+            m["Localization"].sum().backward()
+            for i in range(3):
+                d[f"lbox_grad_{i}"] = _np(pr[i].grad)
+        _save(name, **d)
+
+
+def decode_cases():
+    acc = rh.accuracy()
+    B, A, C, G, img = 2, 3, 4, 13, 416
+    head = synth.raw_logits(B, A, C, G, 61)
+    anchors = [(116 / 32, 90 / 32), (156 / 32, 198 / 32), (373 / 32, 326 / 32)]  # YOLOV3.py:55-56 (pre-divided)
+    tg = synth.labels(B, C, 62, max_per_image=6)
+    selfobj = types.SimpleNamespace(anch_masks=None, anchors=[anchors, anchors, anchors], num_classes=C,
+                                    img_size=img, ignore_thres=0.5)
+    bm = acc.get_yolo_statistics(selfobj, [head.clone()], tg)
+    d = dict(head=_np(head), anchors=np.array(anchors, np.float32), img=np.array(img), target=_np(tg))
+    d["d1_output"] = _np(bm[G][6])
+    d["d1_scaled_anchors"] = _np(selfobj.scaled_anchors)
+    d["d1_metrics"] = np.array([float(x) for x in bm[G][:6]], np.float64)
+    v4 = rh.ref_import("LightningFunc.utils.YoloV4Utils")
+    flat = [v for a in anchors for v in a]
+    boxes, confs = v4.yolo_forward_dynamic(head.clone(), 0.5, C, flat, A, scale_x_y=1.05)
+    d["d3_boxes"], d["d3_confs"] = _np(boxes), _np(confs)
+    _save("decode", **d)
+
+
+def match_cases():
+    losses = rh.losses()
+    g = torch.Generator().manual_seed(71)
+    priors = rh.ref_import("LightningFunc.utils.SSDUtils").get_dboxes()
+    gt = torch.cat([0.1 + torch.rand(7, 2, generator=g) * 0.8, 0.05 + torch.rand(7, 2, generator=g) * 0.4], 1)
+    S = losses.SSDLoss
+    ns = types.SimpleNamespace()
+    ns.center_to_points = lambda t: S.center_to_points(ns, t)
+    ns.expand_defaults_and_annotations = lambda a, b: S.expand_defaults_and_annotations(ns, a, b)
+    idx, matched = S.match(ns, priors, gt, 0.5)
+    d = dict(priors=_np(priors), gt=_np(gt), ssd_idx=_np(idx), ssd_matched=_np(matched))
+
+    # RetinaNet: capture the targets the criterion builds (losses.py:423-445) via stub criteria.
+    anchors = rh.ref_import("LightningFunc.utils.RetinaUtils").get_anchor_boxes(torch.Tensor([160, 160]))
+    B, C = 3, 4
+    tg = synth.labels(B, C, 72, max_per_image=5)
+    tg[:, 4:6] = tg[:, 4:6] * 1.5 + 0.1
+    cap = {}
+
+    def cls_crit(num_classes, reduction="sum"):
+        def f(pred, tgt):
+            cap["cls_t"] = tgt.clone()
+            return pred.sum() * 0
+        return f
+
+    def coord_crit(reduction="sum"):
+        def f(pred, tgt):
+            cap["loc_t"] = tgt.clone()
+            return pred.sum() * 0
+        return f
+
+    crit = losses.RetinaNetLoss(anchors, cls_crit, coord_crit, C, 160)
+    A = anchors.shape[0]
+    crit((torch.zeros(B, A, 4), torch.zeros(B, A, C)), tg)
+    d.update(r_anchors=_np(anchors), r_target=_np(tg), r_B=np.array(B), r_img=np.array(160),
+             r_loc_pos=_np(cap["loc_t"]), r_cls_nonignored=_np(cap["cls_t"]))
+    d["r_iou"] = _np(crit.box_iou(anchors, tg[tg[:, 0] == 0][:, 2:] * 160, order="xywh"))
+    _save("match", **d)
+
+
+def main():
+    if not rh.available():
+        sys.exit("reference tree not present; golden vectors can only be generated in the build container")
+    torch.manual_seed(0)
+    yolo_cases()
+    ssd_cases()
+    iou_cases()
+    build_targets_cases()
+    build_targets_v5_cases()
+    decode_cases()
+    match_cases()
+
+
+if __name__ == "__main__":
+    main()
