@@ -1,0 +1,223 @@
+/*
+ * b200det — C ABI of the B200-native detection post-processing / target-assignment library.
+ *
+ * This is the drop-in boundary for the hot path of Leyan529/ObjectDetectionPL.  The reference has no
+ * FFI layer (it is pure Python); its seams are Python functions monkey-patched onto the Lightning
+ * modules (model/YOLOV5.py:134-150) and module globals of LightningFunc/losses.py:5-6.  The Python
+ * package `objectdetectionpl_b200` re-creates those functions with the reference signatures and calls
+ * ONLY the entry points below (ctypes).  Each entry point names the reference
+ * code it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - the caller owns all memory (inputs, outputs, workspace); the library never allocates, frees or
+ *     keeps pointers.  Workspace sizes come from the *_workspace_bytes() queries;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it, no
+ *     device-wide synchronisation happens inside the library;
+ *   - return value: 0 on success, a negative B200DET_E* code or a positive cudaError_t otherwise;
+ *     b200det_last_error() returns a thread-local message;
+ *   - fp32 everywhere; indices int32 on the ABI (the Python layer widens to int64 where the reference
+ *     returns int64);
+ *   - there is no CPU fallback.
+ */
+#ifndef B200DET_H_
+#define B200DET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200DET_VERSION 100
+
+#define B200DET_OK 0
+#define B200DET_EINVAL (-1)      /* bad argument (shape, range, alignment, null pointer)   */
+#define B200DET_ELIMIT (-2)      /* size beyond a compiled limit (see the limits below)     */
+#define B200DET_EWORKSPACE (-3)  /* workspace too small                                     */
+
+/* compiled limits */
+#define B200DET_MAX_LEVELS 8     /* detection levels per call                               */
+#define B200DET_MAX_ANCHORS 16   /* anchors per level                                       */
+#define B200DET_MAX_CLASSES 4095 /* class id is packed in 12 bits of the sort payload       */
+#define B200DET_MAX_CANDIDATES (1 << 20) /* candidates per image (20-bit slot)              */
+#define B200DET_TILE 512         /* candidate tile: per-image regions are padded to this    */
+
+/* decode modes of the YOLO head kernel */
+#define B200DET_DECODE_NONE 0      /* values used as-is: what every reference NMS does (model/YOLOV3.py:289-305) */
+#define B200DET_DECODE_YOLO_EXP 1  /* D1: sigmoid xy + grid, exp wh * anchor, * stride (accuracy.py:412-435,461) */
+#define B200DET_DECODE_YOLOV5 2    /* D2: (2s-0.5+grid)*stride, (2s)^2*anchor (utils/YoloV5Utils.py:244-248)    */
+
+int b200det_version(void);
+const char* b200det_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * N1 — YOLOv2..v5 test-time post-processing: planar head -> filter -> score sort -> class-aware
+ * merge-NMS.  Replaces `non_max_suppression(self, predictions, conf_thres, nms_thres)` of
+ * model/YOLOV5.py:157-218, YOLOV3.py:273-335, YOLOV4.py:221-283, YOLOV2.py:159-222 together with the
+ * helpers it calls (xywh2xyxy accuracy.py:289, bbox_iou accuracy.py:39).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct b200det_yolo_desc {
+    int32_t batch;                                   /* B                                              */
+    int32_t num_anchors;                             /* A (3; YOLOv2: 5)                               */
+    int32_t num_classes;                             /* C; every level holds A*(5+C) planes            */
+    int32_t num_levels;                              /* <= B200DET_MAX_LEVELS                          */
+    const float* head[B200DET_MAX_LEVELS];           /* level storage read as planar [B,A,5+C,G,G]     */
+    int32_t grid[B200DET_MAX_LEVELS];                /* G per level, in the caller's list order        */
+    int32_t decode_mode;                             /* B200DET_DECODE_*                               */
+    float stride[B200DET_MAX_LEVELS];                /* decode modes only                              */
+    float anchors[B200DET_MAX_LEVELS][B200DET_MAX_ANCHORS][2]; /* decode modes only: D1 scaled anchors
+                                                        (grid units), D2 pixel anchors                 */
+    float conf_thres;                                /* keep rows with conf >= conf_thres              */
+    float nms_thres;                                 /* suppress when IoU_+1 > nms_thres               */
+} b200det_yolo_desc;
+
+/* candidates per image N = sum_l A*G_l^2; per-image regions are padded to n_pad = roundup(N, TILE) */
+int b200det_yolo_num_candidates(const b200det_yolo_desc* d, int32_t* n, int32_t* n_pad);
+size_t b200det_yolo_workspace_bytes(const b200det_yolo_desc* d);
+
+/*
+ * Full pipeline (decode+filter, per-image sort, merge-NMS, ordered emit), enqueued on `stream`.
+ *   out_rows  [B, n_pad, 7] fp32: x1,y1,x2,y2 (cluster-merged), obj conf, class conf, class id;
+ *                                 image b holds out_count[b] rows in descending score order
+ *   out_index [B, n_pad] int32 (may be NULL): original candidate index of every kept row
+ *   out_count [B] int32
+ */
+int b200det_yolo_nms(const b200det_yolo_desc* d, void* workspace, size_t workspace_bytes,
+                     float* out_rows, int32_t* out_index, int32_t* out_count, void* stream);
+
+/* Stage entry points (the pipeline above is exactly these four calls in order); used by the tests
+ * and by profiling.  All operate on the workspace laid out by b200det_yolo_workspace_bytes(). */
+int b200det_yolo_stage_decode(const b200det_yolo_desc* d, void* workspace, size_t workspace_bytes, void* stream);
+int b200det_yolo_stage_sort(const b200det_yolo_desc* d, void* workspace, size_t workspace_bytes, void* stream);
+int b200det_yolo_stage_nms(const b200det_yolo_desc* d, void* workspace, size_t workspace_bytes, void* stream);
+int b200det_yolo_stage_emit(const b200det_yolo_desc* d, void* workspace, size_t workspace_bytes,
+                            float* out_rows, int32_t* out_index, int32_t* out_count, void* stream);
+
+/* Workspace introspection for tests: byte offset and element count of a named internal array
+ * ("box4","cc2","orig","key","pay","rank","count","tile_count","cls_hist","seg_off","sorted_pay",
+ *  "sorted_rank","kpay","mbox").  Returns B200DET_EINVAL for an unknown name. */
+int b200det_yolo_workspace_field(const b200det_yolo_desc* d, const char* name, size_t* offset, size_t* bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * decode_box — full decoded map [B, A*G*G, 5+C] of one level (north-star API; restates D1/D2).
+ * Replaces the inline decode of accuracy.py:402-435,459-466 / losses.py:679-703 (mode YOLO_EXP) and
+ * utils/YoloV5Utils.py:241-248 (mode YOLOV5).  mode NONE is the planar->rows permute of
+ * model/YOLOV3.py:294-300 with xywh left untouched.
+ * ---------------------------------------------------------------------------------------------- */
+int b200det_decode_box(const float* head, int32_t batch, int32_t num_anchors, int32_t num_classes,
+                       int32_t grid, int32_t decode_mode, const float* anchors /*[A,2] device; NULL for DECODE_NONE*/, float stride,
+                       float* out /*[B, A*G*G, 5+C]*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * D4 + N2 — SSD / RetinaNet prior decode, sigmoid-argmax, score filter, top-k, class-agnostic greedy
+ * NMS.  Replaces `non_max_suppression(self, predictions, topk, nms_thresh, class_thresh, mode)` of
+ * model/SSD.py:249-310 == model/RetinaNet.py:117-178.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct b200det_prior_desc {
+    int32_t batch;            /* B */
+    int32_t num_priors;       /* P */
+    int32_t num_classes;      /* C */
+    const float* loc;         /* [B,P,4] */
+    const float* cls;         /* [B,P,C] logits */
+    const float* priors;      /* [P,4] cx,cy,w,h */
+    int32_t topk;             /* 100 */
+    float nms_thresh;         /* 0.5: a box survives a keeper when ovr <= nms_thresh */
+    float class_thresh;       /* 0.45: candidate when sigmoid(max logit) > class_thresh */
+    int32_t mode_min;         /* 0: 'union', 1: 'min' (SSD.py:291-296) */
+    int32_t compat;           /* 1: reproduce quirks (i) drop-last and (ii) filtered-index gather */
+} b200det_prior_desc;
+
+size_t b200det_prior_workspace_bytes(const b200det_prior_desc* d);
+/*   out_rows  [B, topk, 7]: x1,y1,x2,y2, 0, score, label ; out_index [B, topk] (may be NULL): index
+ *   of the prior whose box/label the row carries ; out_count [B] ; cand_count [B] (may be NULL):
+ *   number of candidates that passed class_thresh (the Python layer raises IndexError on 1, SSD.py:266) */
+int b200det_prior_nms(const b200det_prior_desc* d, void* workspace, size_t workspace_bytes,
+                      float* out_rows, int32_t* out_index, int32_t* out_count, int32_t* cand_count, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * N3 / N4 / T3 / T5 — elementwise box maths.
+ * ---------------------------------------------------------------------------------------------- */
+/* xywh2xyxy, accuracy.py:289-295.  x,y: [n,4] */
+int b200det_xywh2xyxy(const float* x, float* y, int64_t n, void* stream);
+/* bbox_iou (IoU_+1, +1e-16), accuracy.py:39-69.  box1 [n1,4] with n1 in {1,n}, box2 [n,4] -> out[n] */
+int b200det_bbox_iou_plus1(const float* box1, int64_t n1, const float* box2, int64_t n, int32_t x1y1x2y2,
+                           float* out, void* stream);
+/* iou, accuracy.py:6-37 (corner boxes, no +1, no eps).  a,b: [n,4] -> out[n] */
+int b200det_pair_iou(const float* a, const float* b, int64_t n, float* out, void* stream);
+
+#define B200DET_IOU 0
+#define B200DET_GIOU 1
+#define B200DET_DIOU 2
+#define B200DET_CIOU 3
+/* bbox_iou_v5, accuracy.py:71-114.  box1, box2 are the reference's TRANSPOSED [4,n] tensors
+ * (row stride `ld1` / `ld2` elements, so .t() views need no copy: element (k,i) at p[k*ld + i*inc]).
+ * backward: grad wrt box1 only (box2 is the target; CIoU's alpha is a constant, accuracy.py:110). */
+int b200det_bbox_iou_v5_fwd(const float* box1, int64_t ld1, int64_t inc1, const float* box2, int64_t ld2,
+                            int64_t inc2, int64_t n, int32_t x1y1x2y2, int32_t kind, float* out, void* stream);
+int b200det_bbox_iou_v5_bwd(const float* box1, int64_t ld1, int64_t inc1, const float* box2, int64_t ld2,
+                            int64_t inc2, int64_t n, int32_t x1y1x2y2, int32_t kind, const float* grad_out,
+                            float* grad_box1 /*[4,n] contiguous*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * T2 / T4 — YOLOv5 target assignment.  Replaces build_targets_v5 (accuracy.py:472-521) and the
+ * matched-row gather + decode + GIoU + objectness scatter of losses.py:105-123.
+ * ---------------------------------------------------------------------------------------------- */
+/* One level.  targets [nt,6] (img,cls,cx,cy,w,h normalised); anchors_host [na,2] (grid units).
+ * Outputs have capacity 5*na*nt rows, written in the reference's row order:
+ *   out_b,out_a,out_gj,out_gi,out_cls int32 [cap]; out_tbox [cap,4]; out_anch [cap,2]; out_count[1] */
+int b200det_build_targets_v5_level(const float* targets, int32_t num_targets, const float* anchors_host,
+                                   int32_t num_anchors, int32_t nx, int32_t ny, int32_t* out_b, int32_t* out_a,
+                                   int32_t* out_gj, int32_t* out_gi, int32_t* out_cls, float* out_tbox,
+                                   float* out_anch, int32_t* out_count, void* stream);
+/* Matched-row forward: pi [B,na,ny,nx,5+C] channels-last (losses.py:112), rows from the call above.
+ *   giou[m]; tobj[B,na,ny,nx] must be zero-filled by the caller, receives clamp(giou,0) with
+ *   "last row wins" on duplicate cells (losses.py:123). */
+int b200det_v5_match_fwd(const float* pi, int32_t batch, int32_t num_anchors, int32_t ny, int32_t nx,
+                         int32_t fields, const int32_t* b, const int32_t* a, const int32_t* gj,
+                         const int32_t* gi, const float* tbox, const float* anch, int32_t m, float* giou,
+                         float* tobj, void* stream);
+/* Backward of giou wrt pi (only the 4 box fields of the matched rows receive gradient; accumulated
+ * with atomics into grad_pi, which the caller zero-fills). */
+int b200det_v5_match_bwd(const float* pi, int32_t batch, int32_t num_anchors, int32_t ny, int32_t nx,
+                         int32_t fields, const int32_t* b, const int32_t* a, const int32_t* gj,
+                         const int32_t* gi, const float* tbox, const float* anch, int32_t m,
+                         const float* grad_giou, float* grad_pi, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * T1 — build_targets (YOLOv2..v4 grid scatter builder), accuracy.py:305-380.
+ * pred_boxes [B,A,G,G,4] (grid units), pred_cls [B,A,G,G,C], target [nt,6], anchors [A,2] device.
+ * Outputs (caller-allocated, any content): iou_scores, class_mask, tx,ty,tw,th fp32 [B,A,G,G];
+ * obj_mask, noobj_mask uint8 [B,A,G,G]; tcls fp32 [B,A,G,G,C].  Duplicate cells: highest target row
+ * wins (the reference's CPU index_put_ order); tcls is multi-hot.  status[0] (int32, device) is set
+ * to a bit mask: bit0 = index guard of accuracy.py:340-344 tripped, bit1 = label guard of :361-367. */
+size_t b200det_build_targets_workspace_bytes(int32_t batch, int32_t num_anchors, int32_t grid, int32_t num_targets);
+int b200det_build_targets(const float* pred_boxes, const float* pred_cls, const float* target,
+                          const float* anchors, int32_t batch, int32_t num_anchors, int32_t grid,
+                          int32_t num_classes, int32_t num_targets, float ignore_thres, void* workspace,
+                          size_t workspace_bytes, float* iou_scores, float* class_mask, uint8_t* obj_mask,
+                          uint8_t* noobj_mask, float* tx, float* ty, float* tw, float* th, float* tcls,
+                          int32_t* status, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * T5 — SSD prior matching (SSDLoss.match, losses.py:199-218) and
+ * T6 — RetinaNet anchor assignment + target encoding (losses.py:375-403, 423-443).
+ * ---------------------------------------------------------------------------------------------- */
+size_t b200det_ssd_match_workspace_bytes(int32_t num_priors, int32_t num_gt);
+/* priors [P,4], gt [M,4] (cx,cy,w,h in [0,1]) -> box_with_annotation int32 [P], matched uint8 [P] */
+int b200det_ssd_match(const float* priors, int32_t num_priors, const float* gt, int32_t num_gt,
+                      float match_thresh, void* workspace, size_t workspace_bytes,
+                      int32_t* box_with_annotation, uint8_t* matched, void* stream);
+/* anchors [A,4] pixel cxcywh; targets [nt,6] sorted or not; per image b the rows with targets[:,0]==b
+ * in their original order.  loc_targets [B,A,4], cls_targets int32 [B,A] (1+label, 0 background,
+ * -1 ignore).  An image without targets gets all-zero rows (the reference raises there). */
+size_t b200det_retina_assign_workspace_bytes(int32_t batch, int32_t num_targets);
+int b200det_retina_assign(const float* anchors, int32_t num_anchors, const float* targets,
+                          int32_t num_targets, int32_t batch, float img_size, void* workspace,
+                          size_t workspace_bytes, float* loc_targets, int32_t* cls_targets, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DET_H_ */

@@ -1,0 +1,253 @@
+// C ABI of libb200det.so (include/b200det.h): argument checks + dispatch to the stage launchers.
+#include "yolo_ws.cuh"
+
+namespace b200det {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return (int)e;
+}
+
+// launchers defined in the stage files
+int yolo_stage_decode(const b200det_yolo_desc*, void*, size_t, cudaStream_t);
+int yolo_stage_sort(const b200det_yolo_desc*, void*, size_t, cudaStream_t);
+int yolo_stage_nms(const b200det_yolo_desc*, void*, size_t, cudaStream_t);
+int yolo_stage_emit(const b200det_yolo_desc*, void*, size_t, float*, int32_t*, int32_t*, cudaStream_t);
+int decode_box_launch(const float*, int, int, int, int, int, const float*, float, float*, cudaStream_t);
+size_t prior_workspace_bytes(const b200det_prior_desc*);
+int prior_nms_pipeline(const b200det_prior_desc*, void*, size_t, float*, int32_t*, int32_t*, int32_t*, cudaStream_t);
+int xywh2xyxy_launch(const float*, float*, long long, cudaStream_t);
+int bbox_iou_plus1_launch(const float*, long long, const float*, long long, int, float*, cudaStream_t);
+int pair_iou_launch(const float*, const float*, long long, float*, cudaStream_t);
+int bbox_iou_v5_fwd_launch(const float*, long long, long long, const float*, long long, long long, long long, int, int,
+                           float*, cudaStream_t);
+int bbox_iou_v5_bwd_launch(const float*, long long, long long, const float*, long long, long long, long long, int, int,
+                           const float*, float*, cudaStream_t);
+int build_targets_v5_launch(const float*, int, const float*, int, int, int, int32_t*, int32_t*, int32_t*, int32_t*,
+                            int32_t*, float*, float*, int32_t*, cudaStream_t);
+int v5_match_fwd_launch(const float*, int, int, int, int, int, const int32_t*, const int32_t*, const int32_t*,
+                        const int32_t*, const float*, const float*, int, float*, float*, cudaStream_t);
+int v5_match_bwd_launch(const float*, int, int, int, int, int, const int32_t*, const int32_t*, const int32_t*,
+                        const int32_t*, const float*, const float*, int, const float*, float*, cudaStream_t);
+size_t build_targets_ws_bytes(int, int, int, int);
+int build_targets_launch(const float*, const float*, const float*, const float*, int, int, int, int, int, float, void*,
+                         float*, float*, uint8_t*, uint8_t*, float*, float*, float*, float*, float*, int32_t*, cudaStream_t);
+size_t ssd_match_ws_bytes(int, int);
+int ssd_match_launch(const float*, int, const float*, int, float, void*, int32_t*, uint8_t*, cudaStream_t);
+size_t retina_assign_ws_bytes(int, int);
+int retina_assign_launch(const float*, int, const float*, int, int, float, void*, float*, int32_t*, cudaStream_t);
+
+}  // namespace b200det
+
+using namespace b200det;
+
+extern "C" {
+
+int b200det_version(void) { return B200DET_VERSION; }
+const char* b200det_last_error(void) { return g_err; }
+
+int b200det_yolo_num_candidates(const b200det_yolo_desc* d, int32_t* n, int32_t* n_pad) {
+    B2_CHECK_ARG(d && n && n_pad, "null argument");
+    int a = 0, b = 0;
+    B2_CHECK_LIMIT(yolo_counts(d, &a, &b) == 0, "candidates per image out of (0, %d]", B200DET_MAX_CANDIDATES);
+    *n = a; *n_pad = b;
+    return 0;
+}
+
+size_t b200det_yolo_workspace_bytes(const b200det_yolo_desc* d) {
+    if (!d) return 0;
+    int a = 0, b = 0;
+    if (yolo_counts(d, &a, &b) != 0 || d->batch <= 0 || d->num_classes <= 0) return 0;
+    YoloWs w;
+    yolo_ws_layout(d, nullptr, &w);
+    return w.total_bytes;
+}
+
+int b200det_yolo_stage_decode(const b200det_yolo_desc* d, void* ws, size_t n, void* st) {
+    return yolo_stage_decode(d, ws, n, (cudaStream_t)st);
+}
+int b200det_yolo_stage_sort(const b200det_yolo_desc* d, void* ws, size_t n, void* st) {
+    return yolo_stage_sort(d, ws, n, (cudaStream_t)st);
+}
+int b200det_yolo_stage_nms(const b200det_yolo_desc* d, void* ws, size_t n, void* st) {
+    return yolo_stage_nms(d, ws, n, (cudaStream_t)st);
+}
+int b200det_yolo_stage_emit(const b200det_yolo_desc* d, void* ws, size_t n, float* out_rows, int32_t* out_index,
+                            int32_t* out_count, void* st) {
+    return yolo_stage_emit(d, ws, n, out_rows, out_index, out_count, (cudaStream_t)st);
+}
+
+int b200det_yolo_nms(const b200det_yolo_desc* d, void* ws, size_t n, float* out_rows, int32_t* out_index,
+                     int32_t* out_count, void* st) {
+    int rc = yolo_stage_decode(d, ws, n, (cudaStream_t)st);
+    if (rc) return rc;
+    rc = yolo_stage_sort(d, ws, n, (cudaStream_t)st);
+    if (rc) return rc;
+    rc = yolo_stage_nms(d, ws, n, (cudaStream_t)st);
+    if (rc) return rc;
+    return yolo_stage_emit(d, ws, n, out_rows, out_index, out_count, (cudaStream_t)st);
+}
+
+int b200det_yolo_workspace_field(const b200det_yolo_desc* d, const char* name, size_t* offset, size_t* bytes) {
+    B2_CHECK_ARG(d && name && offset && bytes, "null argument");
+    int a = 0, b = 0;
+    B2_CHECK_LIMIT(yolo_counts(d, &a, &b) == 0, "bad descriptor");
+    YoloWs w;
+    yolo_ws_layout(d, nullptr, &w);
+    const size_t B = (size_t)w.B, P = (size_t)w.n_pad, C = (size_t)w.C;
+    struct F { const char* n; const void* p; size_t bytes; };
+    const F fields[] = {
+        {"count", w.count, B * 4}, {"cls_hist", w.cls_hist, B * C * 4}, {"seg_off", w.seg_off, B * (C + 1) * 4},
+        {"tile_count", w.tile_count, B * (size_t)w.n_tiles * 4}, {"box4", w.box4, B * P * 16}, {"cc2", w.cc2, B * P * 8},
+        {"orig", w.orig, B * P * 4}, {"key", w.key[0], B * P * 4}, {"pay", w.pay[0], B * P * 4},
+        {"sorted_pay", yolo_sorted_pay(w), B * P * 4}, {"sorted_rank", yolo_sorted_rank(w), B * P * 4},
+        {"kpay", w.kpay, B * P * 4}, {"mbox", w.mbox, B * P * 16},
+    };
+    for (const F& f : fields) {
+        if (strcmp(f.n, name) == 0) {
+            *offset = (size_t)(uintptr_t)f.p;
+            *bytes = f.bytes;
+            return 0;
+        }
+    }
+    set_error("unknown workspace field '%s'", name);
+    return B200DET_EINVAL;
+}
+
+int b200det_decode_box(const float* head, int32_t B, int32_t A, int32_t C, int32_t G, int32_t mode,
+                       const float* anchors_dev, float stride, float* out, void* st) {
+    B2_CHECK_ARG(head && out, "head / out is null");
+    B2_CHECK_ARG(B > 0 && A > 0 && C > 0 && G > 0, "B, A, C, G must be > 0");
+    B2_CHECK_ARG(mode >= B200DET_DECODE_NONE && mode <= B200DET_DECODE_YOLOV5, "bad decode mode %d", mode);
+    B2_CHECK_ARG(mode == B200DET_DECODE_NONE || anchors_dev, "anchors required for decode modes");
+    B2_CHECK_LIMIT((long long)B * A <= 65535, "B*A %lld > 65535", (long long)B * A);
+    return decode_box_launch(head, B, A, C, G, mode, anchors_dev, stride, out, (cudaStream_t)st);
+}
+
+size_t b200det_prior_workspace_bytes(const b200det_prior_desc* d) {
+    if (!d || d->batch <= 0 || d->num_priors <= 0) return 0;
+    return prior_workspace_bytes(d);
+}
+int b200det_prior_nms(const b200det_prior_desc* d, void* ws, size_t n, float* out_rows, int32_t* out_index,
+                      int32_t* out_count, int32_t* cand_count, void* st) {
+    return prior_nms_pipeline(d, ws, n, out_rows, out_index, out_count, cand_count, (cudaStream_t)st);
+}
+
+int b200det_xywh2xyxy(const float* x, float* y, int64_t n, void* st) {
+    B2_CHECK_ARG(n >= 0 && (n == 0 || (x && y)), "null argument");
+    B2_CHECK_ARG((((uintptr_t)x | (uintptr_t)y) & 15) == 0, "x and y must be 16-byte aligned");
+    return xywh2xyxy_launch(x, y, n, (cudaStream_t)st);
+}
+int b200det_bbox_iou_plus1(const float* box1, int64_t n1, const float* box2, int64_t n, int32_t corner, float* out, void* st) {
+    B2_CHECK_ARG(n >= 0 && (n == 0 || (box1 && box2 && out)), "null argument");
+    B2_CHECK_ARG(n1 == 1 || n1 == n, "box1 must hold 1 or n rows (got %lld vs %lld)", (long long)n1, (long long)n);
+    B2_CHECK_ARG((((uintptr_t)box1 | (uintptr_t)box2) & 15) == 0, "boxes must be 16-byte aligned");
+    return bbox_iou_plus1_launch(box1, n1, box2, n, corner, out, (cudaStream_t)st);
+}
+int b200det_pair_iou(const float* a, const float* b, int64_t n, float* out, void* st) {
+    B2_CHECK_ARG(n >= 0 && (n == 0 || (a && b && out)), "null argument");
+    B2_CHECK_ARG((((uintptr_t)a | (uintptr_t)b) & 15) == 0, "boxes must be 16-byte aligned");
+    return pair_iou_launch(a, b, n, out, (cudaStream_t)st);
+}
+int b200det_bbox_iou_v5_fwd(const float* box1, int64_t ld1, int64_t inc1, const float* box2, int64_t ld2, int64_t inc2,
+                            int64_t n, int32_t corner, int32_t kind, float* out, void* st) {
+    B2_CHECK_ARG(n >= 0 && (n == 0 || (box1 && box2 && out)), "null argument");
+    B2_CHECK_ARG(kind >= B200DET_IOU && kind <= B200DET_CIOU, "bad IoU kind %d", kind);
+    return bbox_iou_v5_fwd_launch(box1, ld1, inc1, box2, ld2, inc2, n, corner, kind, out, (cudaStream_t)st);
+}
+int b200det_bbox_iou_v5_bwd(const float* box1, int64_t ld1, int64_t inc1, const float* box2, int64_t ld2, int64_t inc2,
+                            int64_t n, int32_t corner, int32_t kind, const float* grad_out, float* grad_box1, void* st) {
+    B2_CHECK_ARG(n >= 0 && (n == 0 || (box1 && box2 && grad_out && grad_box1)), "null argument");
+    B2_CHECK_ARG(kind >= B200DET_IOU && kind <= B200DET_CIOU, "bad IoU kind %d", kind);
+    return bbox_iou_v5_bwd_launch(box1, ld1, inc1, box2, ld2, inc2, n, corner, kind, grad_out, grad_box1, (cudaStream_t)st);
+}
+
+int b200det_build_targets_v5_level(const float* targets, int32_t nt, const float* anchors_host, int32_t na, int32_t nx,
+                                   int32_t ny, int32_t* ob, int32_t* oa, int32_t* ogj, int32_t* ogi, int32_t* ocls,
+                                   float* otbox, float* oanch, int32_t* ocount, void* st) {
+    B2_CHECK_ARG(nt >= 0 && na > 0 && nx > 0 && ny > 0, "bad sizes");
+    B2_CHECK_LIMIT(na <= B200DET_MAX_ANCHORS, "num_anchors %d > %d", na, B200DET_MAX_ANCHORS);
+    B2_CHECK_ARG(anchors_host && ocount, "null argument");
+    B2_CHECK_ARG(nt == 0 || (targets && ob && oa && ogj && ogi && ocls && otbox && oanch), "null argument");
+    B2_CHECK_LIMIT((long long)nt * na < (1ll << 30), "too many targets");
+    return build_targets_v5_launch(targets, nt, anchors_host, na, nx, ny, ob, oa, ogj, ogi, ocls, otbox, oanch, ocount,
+                                   (cudaStream_t)st);
+}
+int b200det_v5_match_fwd(const float* pi, int32_t B, int32_t na, int32_t ny, int32_t nx, int32_t F, const int32_t* b,
+                         const int32_t* a, const int32_t* gj, const int32_t* gi, const float* tbox, const float* anch,
+                         int32_t m, float* giou, float* tobj, void* st) {
+    B2_CHECK_ARG(m >= 0 && F >= 5, "bad sizes");
+    B2_CHECK_ARG(m == 0 || (pi && b && a && gj && gi && tbox && anch && giou && tobj), "null argument");
+    B2_CHECK_ARG(((uintptr_t)tbox & 15) == 0, "tbox must be 16-byte aligned");
+    return v5_match_fwd_launch(pi, B, na, ny, nx, F, b, a, gj, gi, tbox, anch, m, giou, tobj, (cudaStream_t)st);
+}
+int b200det_v5_match_bwd(const float* pi, int32_t B, int32_t na, int32_t ny, int32_t nx, int32_t F, const int32_t* b,
+                         const int32_t* a, const int32_t* gj, const int32_t* gi, const float* tbox, const float* anch,
+                         int32_t m, const float* ggiou, float* gpi, void* st) {
+    B2_CHECK_ARG(m >= 0 && F >= 5, "bad sizes");
+    B2_CHECK_ARG(m == 0 || (pi && b && a && gj && gi && tbox && anch && ggiou && gpi), "null argument");
+    B2_CHECK_ARG(((uintptr_t)tbox & 15) == 0, "tbox must be 16-byte aligned");
+    return v5_match_bwd_launch(pi, B, na, ny, nx, F, b, a, gj, gi, tbox, anch, m, ggiou, gpi, (cudaStream_t)st);
+}
+
+size_t b200det_build_targets_workspace_bytes(int32_t B, int32_t A, int32_t G, int32_t nt) {
+    if (B <= 0 || A <= 0 || G <= 0 || nt < 0) return 0;
+    return build_targets_ws_bytes(B, A, G, nt);
+}
+int b200det_build_targets(const float* pred_boxes, const float* pred_cls, const float* target, const float* anchors,
+                          int32_t B, int32_t A, int32_t G, int32_t C, int32_t nt, float ignore_thres, void* ws,
+                          size_t ws_bytes, float* iou_scores, float* class_mask, uint8_t* obj_mask, uint8_t* noobj_mask,
+                          float* tx, float* ty, float* tw, float* th, float* tcls, int32_t* status, void* st) {
+    B2_CHECK_ARG(B > 0 && A > 0 && G > 0 && C > 0 && nt >= 0, "bad sizes");
+    B2_CHECK_ARG(pred_boxes && pred_cls && anchors && ws && iou_scores && class_mask && obj_mask && noobj_mask && tx &&
+                     ty && tw && th && tcls && status && (nt == 0 || target), "null argument");
+    B2_CHECK_ARG(((uintptr_t)pred_boxes & 15) == 0, "pred_boxes must be 16-byte aligned");
+    if (ws_bytes < build_targets_ws_bytes(B, A, G, nt)) {
+        set_error("workspace too small");
+        return B200DET_EWORKSPACE;
+    }
+    return build_targets_launch(pred_boxes, pred_cls, target, anchors, B, A, G, C, nt, ignore_thres, ws, iou_scores,
+                                class_mask, obj_mask, noobj_mask, tx, ty, tw, th, tcls, status, (cudaStream_t)st);
+}
+
+size_t b200det_ssd_match_workspace_bytes(int32_t P, int32_t M) {
+    if (P <= 0 || M < 0) return 0;
+    return ssd_match_ws_bytes(P, M);
+}
+int b200det_ssd_match(const float* priors, int32_t P, const float* gt, int32_t M, float thresh, void* ws, size_t ws_bytes,
+                      int32_t* idx, uint8_t* matched, void* st) {
+    B2_CHECK_ARG(P > 0 && M >= 0 && priors && ws && idx && matched && (M == 0 || gt), "bad argument");
+    B2_CHECK_ARG((((uintptr_t)priors | (uintptr_t)gt) & 15) == 0, "priors / gt must be 16-byte aligned");
+    if (ws_bytes < ssd_match_ws_bytes(P, M)) {
+        set_error("workspace too small");
+        return B200DET_EWORKSPACE;
+    }
+    return ssd_match_launch(priors, P, gt, M, thresh, ws, idx, matched, (cudaStream_t)st);
+}
+
+size_t b200det_retina_assign_workspace_bytes(int32_t B, int32_t nt) {
+    if (B <= 0 || nt < 0) return 0;
+    return retina_assign_ws_bytes(B, nt);
+}
+int b200det_retina_assign(const float* anchors, int32_t A, const float* targets, int32_t nt, int32_t B, float img_size,
+                          void* ws, size_t ws_bytes, float* loc, int32_t* cls, void* st) {
+    B2_CHECK_ARG(A > 0 && B > 0 && nt >= 0 && anchors && ws && loc && cls && (nt == 0 || targets), "bad argument");
+    B2_CHECK_LIMIT(B <= 65535, "batch %d > 65535", B);
+    B2_CHECK_ARG((((uintptr_t)anchors | (uintptr_t)loc) & 15) == 0, "anchors / loc_targets must be 16-byte aligned");
+    if (ws_bytes < retina_assign_ws_bytes(B, nt)) {
+        set_error("workspace too small");
+        return B200DET_EWORKSPACE;
+    }
+    return retina_assign_launch(anchors, A, targets, nt, B, img_size, ws, loc, cls, (cudaStream_t)st);
+}
+
+}  // extern "C"

@@ -1,0 +1,271 @@
+// K1' — SSD / RetinaNet prior decode + sigmoid-argmax + score filter, and the prior NMS pipeline.
+//
+// Replaces model/SSD.py:249-310 == model/RetinaNet.py:117-178:
+//   xy = loc_xy * p_wh + p_xy ; wh = exp(loc_wh) * p_wh ; box = [xy - wh/2, xy + wh/2]     (SSD.py:253-258)
+//   score, label = sigmoid(cls).max(1) ; candidates = score > class_thresh                   (SSD.py:260-262)
+//   sort by score, keep top-k, class-agnostic greedy NMS                                     (SSD.py:270-302)
+//
+// Class logits are row-major [P, C]: a CTA streams a contiguous block of 128 rows through shared
+// memory with fully coalesced 128-bit loads, then each thread scans its own row with a per-row
+// rotation so that the 32 lanes of a warp hit 32 different banks (row stride C would otherwise put
+// C%32==0 heads on 1-2 banks).  sigmoid is monotone, so the argmax is taken on the logits and only
+// the winner is squashed (first maximal index on ties, like torch.max).
+#include "yolo_ws.cuh"
+
+namespace b200det {
+
+constexpr int kPriRows = 128;      // rows (priors) per staging round == threads per CTA
+constexpr int kPriMaxCC = 128;     // classes staged per round
+
+struct PriorWs {
+    uint32_t* count;        // [B]   (zeroed)
+    uint32_t* digit_hist;   // [B][kMaxPasses][256] (zeroed)
+    size_t zero_bytes;
+    uint32_t* tile_count;   // [B][n_tiles]
+    uint32_t* tile_prefix;  // [B][n_tiles]
+    float4* box4;           // [B][n_pad]
+    float2* cc2;            // [B][n_pad]  (0, score)
+    uint32_t* orig;         // [B][n_pad]
+    uint32_t* key[2];
+    uint32_t* pay[2];
+    float4* kbox;           // [B][n_pad]
+    uint32_t* kpos;         // [B][n_pad]
+    float4* dense_box;      // [B][P]
+    int32_t* dense_label;   // [B][P]
+    size_t total_bytes;
+    int n_pad, n_tiles;
+};
+
+static void prior_ws_layout(const b200det_prior_desc* d, void* base, PriorWs* w) {
+    const size_t B = (size_t)d->batch;
+    w->n_pad = (int)align_up((size_t)d->num_priors, kTile);
+    w->n_tiles = w->n_pad / kTile;
+    const size_t P = (size_t)w->n_pad;
+    char* p = (char*)base;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* r = p + off; off = align_up(off + bytes, 256); return r; };
+    w->count = (uint32_t*)take(B * 4);
+    w->digit_hist = (uint32_t*)take(B * kMaxPasses * 256 * 4);
+    w->zero_bytes = off;
+    w->tile_count = (uint32_t*)take(B * (size_t)w->n_tiles * 4);
+    w->tile_prefix = (uint32_t*)take(B * (size_t)w->n_tiles * 4);
+    w->box4 = (float4*)take(B * P * 16);
+    w->cc2 = (float2*)take(B * P * 8);
+    w->orig = (uint32_t*)take(B * P * 4);
+    for (int i = 0; i < 2; ++i) w->key[i] = (uint32_t*)take(B * P * 4);
+    for (int i = 0; i < 2; ++i) w->pay[i] = (uint32_t*)take(B * P * 4);
+    w->kbox = (float4*)take(B * P * 16);
+    w->kpos = (uint32_t*)take(B * P * 4);
+    w->dense_box = (float4*)take(B * (size_t)d->num_priors * 16);
+    w->dense_label = (int32_t*)take(B * (size_t)d->num_priors * 4);
+    w->total_bytes = off;
+}
+
+struct K1pParams {
+    const float* loc;
+    const float* cls;
+    const float* priors;
+    int P, C, n_pad, n_tiles;
+    float class_thresh;
+    int write_dense;
+    float4* box4;
+    float2* cc2;
+    uint32_t* orig;
+    uint32_t* key;
+    uint32_t* pay;
+    uint32_t* tile_count;
+    uint32_t* count;
+    float4* dense_box;
+    int32_t* dense_label;
+};
+
+// argmax step for a rotated scan order: first maximal index wins, first NaN wins over everything
+__device__ __forceinline__ void argmax_rot(float v, int c, float& best, int& besti) {
+    const bool vn = v != v, bn = best != best;
+    bool take;
+    if (vn) take = !bn || c < besti;
+    else if (bn) take = false;
+    else take = v > best || (v == best && c < besti);
+    if (take) { best = v; besti = c; }
+}
+
+template <bool VEC4>
+__global__ void __launch_bounds__(kPriRows) prior_decode_filter_kernel(const K1pParams p) {
+    extern __shared__ float s_cls[];           // [kPriRows][cc]
+    __shared__ int s_scan[33];
+    const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+    const int C = p.C;
+    int run = 0;                                // survivors written so far in this tile
+    const size_t img = (size_t)b * p.n_pad;
+
+    for (int round = 0; round < kTile / kPriRows; ++round) {
+        const int p0 = tile * kTile + round * kPriRows;
+        const int nrows = min(kPriRows, p.P - p0);           // may be <= 0 (uniform)
+        float best = 0.f;
+        int besti = 0;
+        bool first = true;
+        for (int c0 = 0; c0 < C; c0 += kPriMaxCC) {
+            const int cc = min(kPriMaxCC, C - c0);
+            __syncthreads();                                  // staging buffer free
+            if (nrows > 0) {
+                const float* src = p.cls + ((size_t)b * p.P + p0) * C;
+                if (VEC4 && cc == C) {
+                    // one contiguous block of nrows*C floats
+                    const int nvec = nrows * C / 4;
+                    for (int i = tid; i < nvec; i += kPriRows) {
+                        const float4 v = ldg_stream4(src + (size_t)i * 4);
+                        reinterpret_cast<float4*>(s_cls)[i] = v;
+                    }
+                } else {
+                    const int tot = nrows * cc;
+                    for (int i = tid; i < tot; i += kPriRows) {
+                        const int r = i / cc, c = i - r * cc;
+                        s_cls[i] = ldg_stream1(src + (size_t)r * C + c0 + c);
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid < nrows) {
+                const float* row = s_cls + (size_t)tid * cc;
+                int k = (cc & 1) ? 0 : (tid % cc);           // rotation only needed for even strides
+                for (int it = 0; it < cc; ++it) {
+                    const float v = row[k];
+                    if (first) { best = v; besti = c0 + k; first = false; }
+                    else argmax_rot(v, c0 + k, best, besti);
+                    if (++k == cc) k = 0;
+                }
+            }
+        }
+
+        bool keep = false;
+        float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+        float score = 0.f;
+        const int pi = p0 + tid;
+        if (tid < nrows) {
+            const float4 l = *reinterpret_cast<const float4*>(p.loc + ((size_t)b * p.P + pi) * 4);
+            const float4 pr = *reinterpret_cast<const float4*>(p.priors + (size_t)pi * 4);
+            const float cx = __fadd_rn(__fmul_rn(l.x, pr.z), pr.x);          // SSD.py:256
+            const float cy = __fadd_rn(__fmul_rn(l.y, pr.w), pr.y);
+            const float w = __fmul_rn(expf(l.z), pr.z);                      // SSD.py:257
+            const float h = __fmul_rn(expf(l.w), pr.w);
+            const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
+            bx = make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+            score = sigmoidf_acc(best);                                       // SSD.py:260
+            keep = score > p.class_thresh;                                    // SSD.py:261
+            if (p.write_dense) {
+                p.dense_box[(size_t)b * p.P + pi] = bx;
+                p.dense_label[(size_t)b * p.P + pi] = besti;
+            }
+        }
+        int total;
+        const int ex = block_exclusive_scan(keep ? 1 : 0, s_scan, &total);
+        if (keep) {
+            const uint32_t slot = (uint32_t)(tile * kTile + run + ex);
+            const size_t i = img + slot;
+            p.box4[i] = bx;
+            p.cc2[i] = make_float2(0.0f, score);
+            p.orig[i] = (uint32_t)pi;
+            p.key[i] = score_sort_key(score);
+            p.pay[i] = ((uint32_t)besti << kSlotBits) | slot;
+        }
+        run += total;
+    }
+    if (tid == 0) {
+        p.tile_count[(size_t)b * p.n_tiles + tile] = (uint32_t)run;
+        if (run) atomicAdd(&p.count[b], (uint32_t)run);
+    }
+}
+
+// exclusive scan of tile_count per image -> filtered-space index of the first slot of every tile
+__global__ void __launch_bounds__(256) tile_prefix_kernel(const uint32_t* __restrict__ tile_count,
+                                                          uint32_t* __restrict__ tile_prefix, int n_tiles) {
+    __shared__ int s_scan[33];
+    const int b = blockIdx.x;
+    int carry = 0;
+    for (int t0 = 0; t0 < n_tiles; t0 += 256) {
+        const int t = t0 + threadIdx.x;
+        int v = t < n_tiles ? (int)tile_count[(size_t)b * n_tiles + t] : 0;
+        int total;
+        const int ex = block_exclusive_scan(v, s_scan, &total);
+        if (t < n_tiles) tile_prefix[(size_t)b * n_tiles + t] = (uint32_t)(carry + ex);
+        carry += total;
+    }
+}
+
+// from segsort.cu / nms.cu
+int score_sort_launch(const uint32_t* tile_count, const uint32_t* count, uint32_t* digit_hist, uint32_t* key[2],
+                      uint32_t* pay[2], int n_pad, int n_tiles, int batch, cudaStream_t st);
+struct NmsParams;
+int prior_nms_launch_raw(const uint32_t* count, const uint32_t* spay, const float4* box4, const float2* cc2,
+                         float4* kbox, uint32_t* kpos, int n_pad, float thr, int topk, int compat,
+                         const uint32_t* tile_prefix, int n_tiles, const uint32_t* orig, const float4* dense_box,
+                         const int32_t* dense_label, int P, float* out_rows, int32_t* out_index, int32_t* out_count,
+                         int batch, int mode_min, cudaStream_t st);
+
+static int prior_validate(const b200det_prior_desc* d) {
+    B2_CHECK_ARG(d != nullptr, "desc is null");
+    B2_CHECK_ARG(d->batch > 0 && d->num_priors > 0 && d->num_classes > 0, "batch/priors/classes must be > 0");
+    B2_CHECK_LIMIT(d->batch <= 65535, "batch %d > 65535", d->batch);
+    B2_CHECK_LIMIT(d->num_priors <= B200DET_MAX_CANDIDATES, "num_priors %d > %d", d->num_priors, B200DET_MAX_CANDIDATES);
+    B2_CHECK_LIMIT(d->num_classes <= B200DET_MAX_CLASSES, "num_classes %d > %d", d->num_classes, B200DET_MAX_CLASSES);
+    B2_CHECK_ARG(d->loc && d->cls && d->priors, "loc/cls/priors is null");
+    B2_CHECK_ARG((((uintptr_t)d->loc | (uintptr_t)d->priors) & 15) == 0, "loc and priors must be 16-byte aligned");
+    B2_CHECK_ARG(d->topk > 0, "topk must be > 0");
+    return 0;
+}
+
+size_t prior_workspace_bytes(const b200det_prior_desc* d) {
+    PriorWs w;
+    prior_ws_layout(d, nullptr, &w);
+    return w.total_bytes;
+}
+
+int prior_nms_pipeline(const b200det_prior_desc* d, void* ws, size_t ws_bytes, float* out_rows, int32_t* out_index,
+                       int32_t* out_count, int32_t* cand_count, cudaStream_t st) {
+    int rc = prior_validate(d);
+    if (rc) return rc;
+    B2_CHECK_ARG(ws != nullptr && ((uintptr_t)ws & 255) == 0, "workspace must be non-null and 256-byte aligned");
+    B2_CHECK_ARG(out_rows && out_count, "out_rows / out_count is null");
+    PriorWs w;
+    prior_ws_layout(d, ws, &w);
+    if (ws_bytes < w.total_bytes) {
+        set_error("workspace too small: %zu < %zu", ws_bytes, w.total_bytes);
+        return B200DET_EWORKSPACE;
+    }
+    B2_CUDA(cudaMemsetAsync(w.count, 0, w.zero_bytes, st));
+
+    K1pParams p;
+    memset(&p, 0, sizeof(p));
+    p.loc = d->loc; p.cls = d->cls; p.priors = d->priors;
+    p.P = d->num_priors; p.C = d->num_classes; p.n_pad = w.n_pad; p.n_tiles = w.n_tiles;
+    p.class_thresh = d->class_thresh; p.write_dense = d->compat ? 1 : 0;
+    p.box4 = w.box4; p.cc2 = w.cc2; p.orig = w.orig; p.key = w.key[0]; p.pay = w.pay[0];
+    p.tile_count = w.tile_count; p.count = w.count; p.dense_box = w.dense_box; p.dense_label = w.dense_label;
+    const int cc = d->num_classes < kPriMaxCC ? d->num_classes : kPriMaxCC;
+    const size_t smem = (size_t)kPriRows * cc * sizeof(float);
+    dim3 grid(w.n_tiles, d->batch);
+    // 128-bit staging needs every 128-row block to start 16-byte aligned and hold a multiple of 4 floats
+    const bool vec4 = d->num_classes <= kPriMaxCC && d->num_classes % 4 == 0 && ((uintptr_t)d->cls & 15) == 0;
+    if (vec4) {
+        B2_CUDA(cudaFuncSetAttribute(prior_decode_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        prior_decode_filter_kernel<true><<<grid, kPriRows, smem, st>>>(p);
+    } else {
+        B2_CUDA(cudaFuncSetAttribute(prior_decode_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        prior_decode_filter_kernel<false><<<grid, kPriRows, smem, st>>>(p);
+    }
+    B2_LAUNCH_CHECK("prior_decode_filter_kernel");
+    tile_prefix_kernel<<<d->batch, 256, 0, st>>>(w.tile_count, w.tile_prefix, w.n_tiles);
+    B2_LAUNCH_CHECK("tile_prefix_kernel");
+
+    rc = score_sort_launch(w.tile_count, w.count, w.digit_hist, w.key, w.pay, w.n_pad, w.n_tiles, d->batch, st);
+    if (rc) return rc;
+    rc = prior_nms_launch_raw(w.count, w.pay[0], w.box4, w.cc2, w.kbox, w.kpos, w.n_pad, d->nms_thresh, d->topk,
+                              d->compat, w.tile_prefix, w.n_tiles, w.orig, w.dense_box, w.dense_label, d->num_priors,
+                              out_rows, out_index, out_count, d->batch, d->mode_min, st);
+    if (rc) return rc;
+    if (cand_count)
+        B2_CUDA(cudaMemcpyAsync(cand_count, w.count, (size_t)d->batch * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+}  // namespace b200det

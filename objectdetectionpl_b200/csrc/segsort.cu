@@ -1,0 +1,228 @@
+// K2 — per-image (segmented) LSD radix sort of the surviving candidates.
+//
+// Order produced: (class ascending, score descending, candidate index ascending) — i.e. the score
+// order of `(-score).argsort()` (model/YOLOV3.py:317, ties by ascending candidate index = stable),
+// then a stable partition by class so that every (image, class) is one contiguous segment for the
+// class-aware NMS (label_match, YOLOV3.py:324).  The position after the four score passes IS the
+// global score rank; it is carried through the class pass(es) so kept rows can be emitted in the
+// reference's descending-score order without a second sort.
+//
+// Layout: one CTA sorts one 4096-key tile of one image per pass.  Cross-CTA prefix = "recount": a CTA
+// re-reads the digits of the preceding tiles of ITS image (<= a few L2-resident tiles) instead of
+// spinning on other CTAs — no inter-CTA dependency, no forward-progress assumptions, bit-reproducible.
+// Per-image digit totals of all passes come from one up-front histogram kernel (totals are
+// permutation-invariant).  In-tile ranking is the stable warp-match ranking (match.any + per-warp
+// digit counters), 8 bits per pass.
+#include "yolo_ws.cuh"
+
+namespace b200det {
+
+struct SortParams {
+    const uint32_t* tile_count;  // [B][n_tiles] (first pass: tile-sparse input), else unused
+    const uint32_t* count;       // [B]
+    uint32_t* digit_hist;        // [B][kMaxPasses][256]
+    const uint32_t* key_in;
+    const uint32_t* pay_in;
+    const uint32_t* rank_in;
+    uint32_t* key_out;
+    uint32_t* pay_out;
+    uint32_t* rank_out;
+    int n_pad, n_tiles;
+    int pass;                    // index into digit_hist
+    int shift;                   // bit offset of the digit
+    int n_cls_passes;
+};
+
+__device__ __forceinline__ bool sparse_valid(const uint32_t* tile_count_img, int e) {
+    return (uint32_t)(e & (kTile - 1)) < tile_count_img[e >> kTileShift];
+}
+
+// Warp-aggregated shared-memory histogram increment (all 32 lanes must call).
+__device__ __forceinline__ void hist_add(int* hist, uint32_t digit, bool valid) {
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, valid ? digit : 0xFFFFu);
+    if (valid && (peers & lanemask_lt()) == 0) atomicAdd(&hist[digit], __popc(peers));
+}
+
+// Up-front per-image digit totals for every pass (score bytes 0..3 from the key, class digits from
+// the payload).  Input is the tile-sparse K1 output.
+__global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const SortParams p) {
+    __shared__ int h[kMaxPasses][256];
+    const int b = blockIdx.y;
+    const int e0 = blockIdx.x * kSortTile;
+    if (e0 >= p.n_pad) return;
+    const uint32_t* tc = p.tile_count + (size_t)b * p.n_tiles;
+    for (int i = threadIdx.x; i < kMaxPasses * 256; i += kSortThreads) (&h[0][0])[i] = 0;
+    __syncthreads();
+    const size_t img = (size_t)b * p.n_pad;
+    const int npass = kScorePasses + p.n_cls_passes;
+#pragma unroll 4
+    for (int k = 0; k < kSortItems; ++k) {
+        const int e = e0 + k * kSortThreads + threadIdx.x;
+        const bool valid = e < p.n_pad && sparse_valid(tc, e);
+        uint32_t key = 0, pay = 0;
+        if (valid) { key = p.key_in[img + e]; pay = p.pay_in[img + e]; }
+#pragma unroll
+        for (int s = 0; s < kScorePasses; ++s) hist_add(h[s], (key >> (8 * s)) & 0xFFu, valid);
+        hist_add(h[kScorePasses], (pay >> kSlotBits) & 0xFFu, valid);
+        if (npass > kScorePasses + 1) hist_add(h[kScorePasses + 1], (pay >> (kSlotBits + 8)) & 0xFFu, valid);
+    }
+    __syncthreads();
+    uint32_t* g = p.digit_hist + (size_t)b * kMaxPasses * 256;
+    for (int i = threadIdx.x; i < npass * 256; i += kSortThreads) {
+        int v = (&h[0][0])[i];
+        if (v) atomicAdd(&g[i], (uint32_t)v);
+    }
+}
+
+// One radix pass.  FIRST: input is tile-sparse (validity from tile_count), else dense [0, count).
+// SRC: 0 = digit from key, 1 = digit from payload.  RANK: 0 none, 1 = write input position as rank,
+// 2 = carry rank_in -> rank_out.  MOVE_KEY: keys are only moved while score passes remain.
+template <bool FIRST, int SRC, int RANK, bool MOVE_KEY>
+__global__ void __launch_bounds__(kSortThreads) sort_pass_kernel(const SortParams p) {
+    constexpr int NW = kSortThreads / 32;
+    __shared__ int s_pre[256];            // digit counts of the preceding tiles of this image
+    __shared__ int s_warp[NW][256];       // per-warp running digit counters -> destination bases
+    __shared__ int s_scan[33];
+
+    const int b = blockIdx.y;
+    const int e0 = blockIdx.x * kSortTile;
+    const int limit = FIRST ? p.n_pad : (int)p.count[b];
+    if (e0 >= limit) return;
+    const uint32_t* tc = p.tile_count + (size_t)b * p.n_tiles;
+    const size_t img = (size_t)b * p.n_pad;
+    const uint32_t* din = SRC == 0 ? p.key_in : p.pay_in;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    s_pre[tid] = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s_warp[w][tid] = 0;
+    __syncthreads();
+
+    // ---- recount: digits of all elements before this tile -------------------------------------
+    for (int e = tid; e < e0; e += kSortThreads) {       // e0 is a multiple of kSortThreads
+        const bool valid = FIRST ? sparse_valid(tc, e) : true;
+        uint32_t d = 0;
+        if (valid) d = (din[img + e] >> p.shift) & 0xFFu;
+        hist_add(s_pre, d, valid);
+    }
+
+    // ---- load own items (warp-striped: item k of lane l = warp_base + 32k + l) -----------------
+    uint32_t key[kSortItems], pay[kSortItems], rnk[kSortItems];
+    int lrank[kSortItems];               // rank inside the warp's digit run, or -1
+    uint32_t dig[kSortItems];
+    const int wbase = e0 + warp * (32 * kSortItems);
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        const int e = wbase + k * 32 + lane;
+        const bool valid = e < limit && (FIRST ? sparse_valid(tc, e) : true);
+        key[k] = 0; pay[k] = 0; rnk[k] = 0;
+        if (valid) {
+            if (MOVE_KEY || SRC == 0) key[k] = p.key_in[img + e];
+            pay[k] = p.pay_in[img + e];
+            if (RANK == 1) rnk[k] = (uint32_t)e;
+            if (RANK == 2) rnk[k] = p.rank_in[img + e];
+        }
+        const uint32_t src = SRC == 0 ? key[k] : pay[k];
+        dig[k] = (src >> p.shift) & 0xFFu;
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, valid ? dig[k] : 0xFFFFu);
+        int base = 0;
+        if (valid) base = s_warp[warp][dig[k]];
+        __syncwarp();
+        if (valid && (peers & lanemask_lt()) == 0) s_warp[warp][dig[k]] = base + __popc(peers);
+        __syncwarp();
+        lrank[k] = valid ? base + __popc(peers & lanemask_lt()) : -1;
+    }
+    __syncthreads();
+
+    // ---- destination bases: digit_start (image totals) + preceding tiles + preceding warps ------
+    {
+        const uint32_t* tot = p.digit_hist + ((size_t)b * kMaxPasses + p.pass) * 256;
+        int total_unused;
+        const int dstart = block_exclusive_scan((int)tot[tid], s_scan, &total_unused);
+        int run = dstart + s_pre[tid];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const int c = s_warp[w][tid];
+            s_warp[w][tid] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        if (lrank[k] >= 0) {
+            const size_t o = img + (size_t)(s_warp[warp][dig[k]] + lrank[k]);
+            if (MOVE_KEY) p.key_out[o] = key[k];
+            p.pay_out[o] = pay[k];
+            if (RANK != 0) p.rank_out[o] = rnk[k];
+        }
+    }
+}
+
+// Score-only sort (4 passes) for the prior pipeline; the sorted payload ends in pay[0].
+int score_sort_launch(const uint32_t* tile_count, const uint32_t* count, uint32_t* digit_hist, uint32_t* key[2],
+                      uint32_t* pay[2], int n_pad, int n_tiles, int batch, cudaStream_t st) {
+    SortParams p;
+    memset(&p, 0, sizeof(p));
+    p.tile_count = tile_count; p.count = count; p.digit_hist = digit_hist;
+    p.n_pad = n_pad; p.n_tiles = n_tiles; p.n_cls_passes = 0;
+    dim3 grid(ceil_div(n_pad, kSortTile), batch);
+    p.key_in = key[0]; p.pay_in = pay[0];
+    sort_hist_kernel<<<grid, kSortThreads, 0, st>>>(p);
+    B2_LAUNCH_CHECK("sort_hist_kernel");
+    for (int pass = 0; pass < kScorePasses; ++pass) {
+        const int src = pass & 1, dst = src ^ 1;
+        p.key_in = key[src]; p.pay_in = pay[src];
+        p.key_out = key[dst]; p.pay_out = pay[dst];
+        p.pass = pass; p.shift = 8 * pass;
+        if (pass == 0) sort_pass_kernel<true, 0, 0, true><<<grid, kSortThreads, 0, st>>>(p);
+        else if (pass < kScorePasses - 1) sort_pass_kernel<false, 0, 0, true><<<grid, kSortThreads, 0, st>>>(p);
+        else sort_pass_kernel<false, 0, 0, false><<<grid, kSortThreads, 0, st>>>(p);
+        B2_LAUNCH_CHECK("sort_pass_kernel(score)");
+    }
+    return 0;
+}
+
+int yolo_stage_sort(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cudaStream_t st) {
+    int rc = yolo_validate(d, ws, ws_bytes);
+    if (rc) return rc;
+    YoloWs w;
+    yolo_ws_layout(d, ws, &w);
+    SortParams p;
+    memset(&p, 0, sizeof(p));
+    p.tile_count = w.tile_count; p.count = w.count; p.digit_hist = w.digit_hist;
+    p.n_pad = w.n_pad; p.n_tiles = w.n_tiles; p.n_cls_passes = w.n_cls_passes;
+    dim3 grid(ceil_div(w.n_pad, kSortTile), d->batch);
+
+    p.key_in = w.key[0]; p.pay_in = w.pay[0];
+    sort_hist_kernel<<<grid, kSortThreads, 0, st>>>(p);
+    B2_LAUNCH_CHECK("sort_hist_kernel");
+
+    for (int pass = 0; pass < kScorePasses; ++pass) {
+        const int src = pass & 1, dst = src ^ 1;
+        p.key_in = w.key[src]; p.pay_in = w.pay[src];
+        p.key_out = w.key[dst]; p.pay_out = w.pay[dst];
+        p.pass = pass; p.shift = 8 * pass;
+        const bool last_score = pass == kScorePasses - 1;
+        if (pass == 0) sort_pass_kernel<true, 0, 0, true><<<grid, kSortThreads, 0, st>>>(p);
+        else if (!last_score) sort_pass_kernel<false, 0, 0, true><<<grid, kSortThreads, 0, st>>>(p);
+        else sort_pass_kernel<false, 0, 0, false><<<grid, kSortThreads, 0, st>>>(p);
+        B2_LAUNCH_CHECK("sort_pass_kernel(score)");
+    }
+    // after 4 score passes the data sits in buffer 0 (keys are no longer needed)
+    p.key_in = nullptr; p.key_out = nullptr;
+    p.pay_in = w.pay[0]; p.pay_out = w.pay[1]; p.rank_in = nullptr; p.rank_out = w.rank[0];
+    p.pass = kScorePasses; p.shift = kSlotBits;
+    sort_pass_kernel<false, 1, 1, false><<<grid, kSortThreads, 0, st>>>(p);
+    B2_LAUNCH_CHECK("sort_pass_kernel(class lo)");
+    if (w.n_cls_passes == 2) {
+        p.pay_in = w.pay[1]; p.pay_out = w.pay[0]; p.rank_in = w.rank[0]; p.rank_out = w.rank[1];
+        p.pass = kScorePasses + 1; p.shift = kSlotBits + 8;
+        sort_pass_kernel<false, 1, 2, false><<<grid, kSortThreads, 0, st>>>(p);
+        B2_LAUNCH_CHECK("sort_pass_kernel(class hi)");
+    }
+    return 0;
+}
+
+}  // namespace b200det

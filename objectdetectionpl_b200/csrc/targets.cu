@@ -1,0 +1,521 @@
+// K4 — loss-side target assignment.
+//   build_targets_v5        LightningFunc/accuracy.py:472-521  (ordered, scan-based compaction)
+//   v5 matched-row forward  LightningFunc/losses.py:105-123    (gather + D2 decode + GIoU + tobj scatter) + backward
+//   build_targets (v2-v4)   LightningFunc/accuracy.py:305-380  (grid scatter, "highest target row wins")
+//   SSDLoss.match           LightningFunc/losses.py:199-218
+//   RetinaNet assignment    LightningFunc/losses.py:375-403, 423-443
+#include "common.cuh"
+#include "boxmath.cuh"
+
+namespace b200det {
+
+// ================================================================================================
+// T2 — build_targets_v5, one level.  Element e = a*nt + t (anchor-major, target-minor: the order of
+// `t.repeat(na,1,1)[j]`, accuracy.py:490).  Five flags per element: base row kept, and the four
+// neighbour copies (x-left j, y-up k, x-right l, y-down m; accuracy.py:503-506).  Output row of a
+// flagged element = block base + its rank inside the block, blocks laid out [base | j | k | l | m].
+// One 1024-thread CTA makes two passes over the elements: totals, then ranks + writes.
+// ================================================================================================
+struct Tv5Params {
+    const float* targets;   // [nt,6]
+    int nt, na, nx, ny;
+    float anc[B200DET_MAX_ANCHORS][2];
+    int32_t *ob, *oa, *ogj, *ogi, *ocls;
+    float* otbox;
+    float* oanch;
+    int32_t* ocount;
+};
+
+__device__ __forceinline__ float pymod1(float x) {      // torch `x % 1.` (sign of the divisor)
+    float r = fmodf(x, 1.0f);
+    if (r < 0.0f) r += 1.0f;
+    return r;
+}
+
+__device__ __forceinline__ unsigned tv5_flags(const Tv5Params& p, int e, float& gx, float& gy, float& gw, float& gh,
+                                              float& tb, float& tc) {
+    const int a = e / p.nt, t = e - a * p.nt;
+    const float* r = p.targets + (size_t)t * 6;
+    tb = r[0]; tc = r[1];
+    gx = __fmul_rn(r[2], (float)p.nx); gy = __fmul_rn(r[3], (float)p.ny);      // accuracy.py:483,486
+    gw = __fmul_rn(r[4], (float)p.nx); gh = __fmul_rn(r[5], (float)p.ny);
+    const float rw = __fdiv_rn(gw, p.anc[a][0]), rh = __fdiv_rn(gh, p.anc[a][1]);   // accuracy.py:488
+    const float mw = fmaxf(rw, __fdiv_rn(1.0f, rw)), mh = fmaxf(rh, __fdiv_rn(1.0f, rh));
+    if (!(fmaxf(mw, mh) < 4.0f)) return 0u;                                     // accuracy.py:489
+    unsigned f = 1u;
+    const float fx = pymod1(gx), fy = pymod1(gy);
+    if (fx < 0.5f && gx > 1.0f) f |= 2u;                                        // j
+    if (fy < 0.5f && gy > 1.0f) f |= 4u;                                        // k
+    if (fx > 0.5f && gx < __fsub_rn((float)p.nx, 1.0f)) f |= 8u;                // l
+    if (fy > 0.5f && gy < __fsub_rn((float)p.ny, 1.0f)) f |= 16u;               // m
+    return f;
+}
+
+__global__ void __launch_bounds__(1024) build_targets_v5_kernel(const Tv5Params p) {
+    __shared__ int s_wtot[5][32];
+    __shared__ int s_woff[5][32];
+    __shared__ int s_carry[5];
+    __shared__ int s_base[5];
+    const int E = p.na * p.nt;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 5) s_carry[tid] = 0;
+    __syncthreads();
+
+    for (int phase = 0; phase < 2; ++phase) {
+        for (int e0 = 0; e0 < E; e0 += 1024) {
+            const int e = e0 + tid;
+            float gx = 0, gy = 0, gw = 0, gh = 0, tb = 0, tc = 0;
+            const unsigned f = e < E ? tv5_flags(p, e, gx, gy, gw, gh, tb, tc) : 0u;
+            unsigned bal[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) bal[k] = __ballot_sync(0xFFFFFFFFu, (f >> k) & 1u);
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) s_wtot[k][warp] = __popc(bal[k]);
+            }
+            __syncthreads();
+            if (warp < 5) {
+                const int v = s_wtot[warp][lane];
+                int inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                    if (lane >= o) inc += u;
+                }
+                s_woff[warp][lane] = s_carry[warp] + inc - v;
+                __syncwarp();
+                if (lane == 31) s_carry[warp] += inc;
+            }
+            __syncthreads();
+            if (phase == 1 && f) {
+                const int a = e / p.nt;
+                const int ib = (int)tb, ic = (int)tc;                       // .long() truncation, accuracy.py:509
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    if ((f >> k) & 1u) {
+                        const int row = s_base[k] + s_woff[k][warp] + __popc(bal[k] & lanemask_lt());
+                        const float ox = k == 1 ? 0.5f : (k == 3 ? -0.5f : 0.0f);   // off * g, accuracy.py:506
+                        const float oy = k == 2 ? 0.5f : (k == 4 ? -0.5f : 0.0f);
+                        const int gi = (int)__fsub_rn(gx, ox), gj = (int)__fsub_rn(gy, oy);   // accuracy.py:512
+                        p.ob[row] = ib; p.oa[row] = a; p.ogj[row] = gj; p.ogi[row] = gi; p.ocls[row] = ic;
+                        float* tbx = p.otbox + (size_t)row * 4;
+                        tbx[0] = __fsub_rn(gx, (float)gi); tbx[1] = __fsub_rn(gy, (float)gj);   // accuracy.py:517
+                        tbx[2] = gw; tbx[3] = gh;
+                        p.oanch[(size_t)row * 2] = p.anc[a][0];
+                        p.oanch[(size_t)row * 2 + 1] = p.anc[a][1];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (phase == 0) {
+            if (tid == 0) {
+                int run = 0;
+                for (int k = 0; k < 5; ++k) { s_base[k] = run; run += s_carry[k]; s_carry[k] = 0; }
+                p.ocount[0] = run;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ================================================================================================
+// T4 — matched rows of one level: ps = pi[b,a,gj,gi] ; pxy = sigmoid*2-0.5 ; pwh = (sigmoid*2)^2*anch ;
+// giou = bbox_iou_v5(pbox, tbox, xywh, GIoU) ; tobj[cell] = clamp(giou, 0), last row wins.
+// ================================================================================================
+struct MatchParams {
+    const float* pi;
+    int B, na, ny, nx, F;
+    const int32_t *b, *a, *gj, *gi;
+    const float* tbox;
+    const float* anch;
+    int m;
+};
+
+__device__ __forceinline__ long long match_cell(const MatchParams& p, int i) {
+    return (((long long)p.b[i] * p.na + p.a[i]) * p.ny + p.gj[i]) * p.nx + p.gi[i];
+}
+
+__global__ void v5_match_fwd_kernel(const MatchParams p, float* __restrict__ giou, int* __restrict__ tobj_as_int) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.m) return;
+    const long long cell = match_cell(p, i);
+    const float* ps = p.pi + cell * p.F;
+    const float sx = sigmoidf_acc(ps[0]), sy = sigmoidf_acc(ps[1]);
+    const float sw = sigmoidf_acc(ps[2]), sh = sigmoidf_acc(ps[3]);
+    float4 pb;
+    pb.x = __fsub_rn(__fmul_rn(sx, 2.0f), 0.5f);                                    // losses.py:115
+    pb.y = __fsub_rn(__fmul_rn(sy, 2.0f), 0.5f);
+    const float w2 = __fmul_rn(sw, 2.0f), h2 = __fmul_rn(sh, 2.0f);
+    pb.z = __fmul_rn(__fmul_rn(w2, w2), p.anch[(size_t)i * 2]);                     // losses.py:116
+    pb.w = __fmul_rn(__fmul_rn(h2, h2), p.anch[(size_t)i * 2 + 1]);
+    const float4 tb = *reinterpret_cast<const float4*>(p.tbox + (size_t)i * 4);
+    giou[i] = iou_v5_forward(pb, tb, false, B200DET_GIOU);                          // losses.py:118
+    atomicMax(&tobj_as_int[cell], i + 1);                                           // winner = highest row
+}
+
+__global__ void v5_match_tobj_kernel(const MatchParams p, const float* __restrict__ giou, float* __restrict__ tobj) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.m) return;
+    const long long cell = match_cell(p, i);
+    if (reinterpret_cast<const int*>(tobj)[cell] == i + 1) tobj[cell] = fmaxf(giou[i], 0.0f);   // losses.py:123
+}
+
+__global__ void v5_match_bwd_kernel(const MatchParams p, const float* __restrict__ ggiou, float* __restrict__ gpi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.m) return;
+    const long long cell = match_cell(p, i);
+    const float* ps = p.pi + cell * p.F;
+    const float aw = p.anch[(size_t)i * 2], ah = p.anch[(size_t)i * 2 + 1];
+    float s[4];
+    for (int k = 0; k < 4; ++k) s[k] = sigmoidf_acc(ps[k]);
+    float4 pb = make_float4(s[0] * 2.0f - 0.5f, s[1] * 2.0f - 0.5f, (s[2] * 2.0f) * (s[2] * 2.0f) * aw,
+                            (s[3] * 2.0f) * (s[3] * 2.0f) * ah);
+    const float4 tb = *reinterpret_cast<const float4*>(p.tbox + (size_t)i * 4);
+    float g[4];
+    iou_v5_backward(pb, tb, false, B200DET_GIOU, ggiou[i], g);
+    float* gp = gpi + cell * p.F;
+    atomicAdd(gp + 0, g[0] * 2.0f * s[0] * (1.0f - s[0]));
+    atomicAdd(gp + 1, g[1] * 2.0f * s[1] * (1.0f - s[1]));
+    atomicAdd(gp + 2, g[2] * 8.0f * s[2] * s[2] * (1.0f - s[2]) * aw);
+    atomicAdd(gp + 3, g[3] * 8.0f * s[3] * s[3] * (1.0f - s[3]) * ah);
+}
+
+// ================================================================================================
+// T1 — build_targets (YOLOv2..v4).
+// ================================================================================================
+struct BtParams {
+    const float* pred_boxes;   // [B,A,G,G,4]
+    const float* pred_cls;     // [B,A,G,G,C]
+    const float* target;       // [nt,6]
+    const float* anchors;      // [A,2]
+    int B, A, G, C, nt;
+    float ignore_thres;
+    int* winner;               // [B*A*G*G], -1
+    int* tinfo;                // [nt][4]: b, best_n, gj, gi   (wrapped) or -1 when unusable
+    float *iou_scores, *class_mask, *tx, *ty, *tw, *th, *tcls;
+    uint8_t *obj, *noobj;
+    int32_t* status;           // bit0 index guard, bit1 label guard, bit2 negative index out of range
+};
+
+__device__ __forceinline__ bool wrap_index(int& i, int dim) {   // torch advanced indexing wraps negatives
+    if (i < 0) i += dim;
+    return i >= 0;
+}
+
+// pass 1: per target best anchor, guards, winner election, noobj ignore-threshold clearing
+__global__ void build_targets_pass1(const BtParams p) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.nt) return;
+    const float* r = p.target + (size_t)t * 6;
+    const float G = (float)p.G;
+    const float gx = __fmul_rn(r[2], G), gy = __fmul_rn(r[3], G), gw = __fmul_rn(r[4], G), gh = __fmul_rn(r[5], G);
+    int b = (int)r[0], lab = (int)r[1];
+    int gi = (int)gx, gj = (int)gy;                                  // .long(), accuracy.py:337
+    float best = 0.f;
+    int best_n = 0;
+    for (int a = 0; a < p.A; ++a) {                                  // bbox_wh_iou, accuracy.py:297-303
+        const float aw = p.anchors[a * 2], ah = p.anchors[a * 2 + 1];
+        const float inter = __fmul_rn(fminf(aw, gw), fminf(ah, gh));
+        const float uni = __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(aw, ah), 1e-16f), __fmul_rn(gw, gh)), inter);
+        const float v = __fdiv_rn(inter, uni);
+        if (a == 0) { best = v; best_n = 0; }
+        else if (!(v <= best) && (best == best)) { best = v; best_n = a; }
+    }
+    int st = 0;
+    if (b >= p.B || gj >= p.G || gi >= p.G) st |= 1;                 // accuracy.py:340-344 (best_n < A always)
+    if (lab >= p.C) st |= 2;                                         // accuracy.py:365
+    int bw = b, gjw = gj, giw = gi, labw = lab;
+    const bool okb = wrap_index(bw, p.B), okj = wrap_index(gjw, p.G), oki = wrap_index(giw, p.G);
+    const bool okl = wrap_index(labw, p.C);
+    if (!(okb && okj && oki && okl)) st |= 4;
+    if (st) atomicOr(p.status, st);
+    int* ti = p.tinfo + (size_t)t * 4;
+    const bool usable = !(st & 1) && okb && okj && oki;
+    ti[0] = usable ? bw : -1; ti[1] = best_n; ti[2] = gjw; ti[3] = giw;
+    if (usable) {
+        const long long cell = (((long long)bw * p.A + best_n) * p.G + gjw) * p.G + giw;
+        atomicMax(&p.winner[cell], t);
+        // accuracy.py:349-358 — per-target guard only (b, gj, gi upper bounds)
+        for (int a = 0; a < p.A; ++a) {
+            const float aw = p.anchors[a * 2], ah = p.anchors[a * 2 + 1];
+            const float inter = __fmul_rn(fminf(aw, gw), fminf(ah, gh));
+            const float uni = __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(aw, ah), 1e-16f), __fmul_rn(gw, gh)), inter);
+            if (__fdiv_rn(inter, uni) > p.ignore_thres)
+                p.noobj[(((long long)bw * p.A + a) * p.G + gjw) * p.G + giw] = 0;
+        }
+    }
+}
+
+// pass 2: scatter (all-or-nothing on the global guards)
+__global__ void build_targets_pass2(const BtParams p) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.nt) return;
+    const int st = *p.status;
+    if (st & (1 | 4)) return;                                         // accuracy.py:344: skip every scatter
+    const int* ti = p.tinfo + (size_t)t * 4;
+    const int b = ti[0], n = ti[1], gj = ti[2], gi = ti[3];
+    const long long cell = (((long long)b * p.A + n) * p.G + gj) * p.G + gi;
+    p.obj[cell] = 1;                                                  // accuracy.py:345-346
+    p.noobj[cell] = 0;
+    if (st & 2) return;                                               // accuracy.py:367
+    const float* r = p.target + (size_t)t * 6;
+    const float G = (float)p.G;
+    const float gx = __fmul_rn(r[2], G), gy = __fmul_rn(r[3], G), gw = __fmul_rn(r[4], G), gh = __fmul_rn(r[5], G);
+    int lab = (int)r[1];
+    wrap_index(lab, p.C);
+    p.tcls[cell * p.C + lab] = 1.0f;                                  // accuracy.py:374 (multi-hot on duplicates)
+    if (p.winner[cell] != t) return;                                  // highest target row wins
+    p.tx[cell] = __fsub_rn(gx, floorf(gx));                           // accuracy.py:368-372
+    p.ty[cell] = __fsub_rn(gy, floorf(gy));
+    p.tw[cell] = logf(__fadd_rn(__fdiv_rn(gw, p.anchors[n * 2]), 1e-16f));
+    p.th[cell] = logf(__fadd_rn(__fdiv_rn(gh, p.anchors[n * 2 + 1]), 1e-16f));
+    const float* pc = p.pred_cls + cell * p.C;                        // accuracy.py:376
+    float best = pc[0];
+    int besti = 0;
+    for (int c = 1; c < p.C; ++c) {
+        const float v = pc[c];
+        if (!(v <= best) && (best == best)) { best = v; besti = c; }
+    }
+    p.class_mask[cell] = besti == lab ? 1.0f : 0.0f;
+    const float4 pb = *reinterpret_cast<const float4*>(p.pred_boxes + cell * 4);   // accuracy.py:377
+    p.iou_scores[cell] = iou_plus1_eps(cxcywh_to_corners(pb), cxcywh_to_corners(make_float4(gx, gy, gw, gh)));
+}
+
+// ================================================================================================
+// T5 — SSD matching.
+// ================================================================================================
+__device__ __forceinline__ float4 center_to_points(const float4 c) {          // losses.py:172-185
+    return make_float4(fmaxf(__fsub_rn(c.x, __fmul_rn(c.z, 0.5f)), 0.0f), fmaxf(__fsub_rn(c.y, __fmul_rn(c.w, 0.5f)), 0.0f),
+                       fminf(__fadd_rn(c.x, __fmul_rn(c.z, 0.5f)), 1.0f), fminf(__fadd_rn(c.y, __fmul_rn(c.w, 0.5f)), 1.0f));
+}
+
+// per prior: best GT (first max over m) ; per GT: best prior via packed 64-bit atomicMax (iou bits, ~p)
+__global__ void ssd_match_kernel(const float4* __restrict__ priors, int P, const float4* __restrict__ gt, int M,
+                                 float thresh, unsigned long long* __restrict__ gt_best, int32_t* __restrict__ idx,
+                                 uint8_t* __restrict__ matched, int* __restrict__ forced) {
+    extern __shared__ float4 s_gt[];
+    for (int m = threadIdx.x; m < M; m += blockDim.x) s_gt[m] = center_to_points(gt[m]);
+    __syncthreads();
+    const int pidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pidx >= P) return;
+    const float4 d = center_to_points(priors[pidx]);
+    float best = 0.f;
+    int bi = 0;
+    for (int m = 0; m < M; ++m) {
+        const float v = iou_plain(d, s_gt[m]);                                 // losses.py:209
+        if (m == 0) { best = v; bi = 0; }
+        else if (!(v <= best) && (best == best)) { best = v; bi = m; }        // losses.py:214 (max over GTs)
+        const unsigned long long pk = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)pidx);
+        if (v == v) atomicMax(&gt_best[m], pk);                                // losses.py:211 (max over priors)
+    }
+    idx[pidx] = bi;
+    matched[pidx] = best >= thresh ? 1 : 0;                                    // losses.py:215
+    forced[pidx] = -1;
+}
+__global__ void ssd_force_kernel(const unsigned long long* __restrict__ gt_best, int M, int* __restrict__ forced) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const unsigned pidx = 0xFFFFFFFFu - (unsigned)(gt_best[m] & 0xFFFFFFFFull);
+    atomicMax(&forced[pidx], m);                                               // losses.py:216-217: last GT wins
+}
+__global__ void ssd_apply_kernel(const int* __restrict__ forced, int P, int32_t* __restrict__ idx, uint8_t* __restrict__ matched) {
+    const int pidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pidx >= P) return;
+    const int f = forced[pidx];
+    if (f >= 0) { idx[pidx] = f; matched[pidx] = 1; }
+}
+
+// ================================================================================================
+// T6 — RetinaNet assignment.  Per image: ordered list of its target rows, then one thread per anchor.
+// ================================================================================================
+__global__ void __launch_bounds__(1024) group_targets_kernel(const float* __restrict__ targets, int nt,
+                                                             int* __restrict__ list /*[B][nt]*/, int* __restrict__ cnt) {
+    __shared__ int s_scan[33];
+    const int b = blockIdx.x;
+    int base = 0;
+    for (int t0 = 0; t0 < nt; t0 += 1024) {
+        const int t = t0 + threadIdx.x;
+        const int f = (t < nt && targets[(size_t)t * 6] == (float)b) ? 1 : 0;    // losses.py:425 (targets[:,0]==bid)
+        int total;
+        const int ex = block_exclusive_scan(f, s_scan, &total);
+        if (f) list[(size_t)b * nt + base + ex] = t;
+        base += total;
+    }
+    if (threadIdx.x == 0) cnt[b] = base;
+}
+
+__global__ void __launch_bounds__(256) retina_assign_kernel(const float4* __restrict__ anchors, int A,
+                                                            const float* __restrict__ targets, int nt,
+                                                            const int* __restrict__ list, const int* __restrict__ cnt,
+                                                            float img_size, float4* __restrict__ loc, int32_t* __restrict__ cls) {
+    __shared__ float4 s_c[256];     // target corners
+    __shared__ float4 s_x[256];     // target cx,cy,w,h (pixels)
+    __shared__ float s_a[256];      // target area (+1)
+    __shared__ int s_l[256];        // label
+    const int b = blockIdx.y;
+    const int ai = blockIdx.x * blockDim.x + threadIdx.x;
+    const int M = cnt[b];
+    float4 an = make_float4(0.f, 0.f, 1.f, 1.f);
+    if (ai < A) an = anchors[ai];
+    const float4 ac = cxcywh_to_corners(an);                                     // losses.py:373 ('xywh2xyxy')
+    const float aa = __fmul_rn(__fadd_rn(__fsub_rn(ac.z, ac.x), 1.0f), __fadd_rn(__fsub_rn(ac.w, ac.y), 1.0f));
+    float best = 0.f;
+    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+    int bl = 0;
+    bool have = false;
+    for (int m0 = 0; m0 < M; m0 += 256) {
+        const int mm = min(256, M - m0);
+        __syncthreads();
+        if (threadIdx.x < mm) {
+            const float* r = targets + (size_t)list[(size_t)b * nt + m0 + threadIdx.x] * 6;
+            const float4 x = make_float4(__fmul_rn(r[2], img_size), __fmul_rn(r[3], img_size), __fmul_rn(r[4], img_size),
+                                         __fmul_rn(r[5], img_size));             // losses.py:425
+            const float4 c = cxcywh_to_corners(x);
+            s_x[threadIdx.x] = x; s_c[threadIdx.x] = c;
+            s_a[threadIdx.x] = __fmul_rn(__fadd_rn(__fsub_rn(c.z, c.x), 1.0f), __fadd_rn(__fsub_rn(c.w, c.y), 1.0f));
+            s_l[threadIdx.x] = (int)r[1];
+        }
+        __syncthreads();
+        for (int m = 0; m < mm; ++m) {
+            const float4 c = s_c[m];
+            const float iw = fmaxf(__fadd_rn(__fsub_rn(fminf(ac.z, c.z), fmaxf(ac.x, c.x)), 1.0f), 0.0f);   // losses.py:393-397
+            const float ih = fmaxf(__fadd_rn(__fsub_rn(fminf(ac.w, c.w), fmaxf(ac.y, c.y)), 1.0f), 0.0f);
+            const float inter = __fmul_rn(iw, ih);
+            const float v = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, s_a[m]), inter));                       // losses.py:401
+            if (!have || (!(v <= best) && (best == best))) { best = v; bx = s_x[m]; bl = s_l[m]; have = true; }   // :431
+        }
+    }
+    if (ai >= A) return;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    int c = 0;
+    if (have) {
+        o.x = __fdiv_rn(__fsub_rn(bx.x, an.x), an.z);                                                        // losses.py:434
+        o.y = __fdiv_rn(__fsub_rn(bx.y, an.y), an.w);
+        o.z = logf(__fdiv_rn(bx.z, an.z));                                                                    // losses.py:435
+        o.w = logf(__fdiv_rn(bx.w, an.w));
+        c = 1 + bl;                                                                                           // losses.py:437
+        if (best < 0.5f) c = 0;                                                                               // losses.py:439
+        if (best > 0.4f && best < 0.5f) c = -1;                                                               // losses.py:440-441
+    }
+    loc[(size_t)b * A + ai] = o;
+    cls[(size_t)b * A + ai] = c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+int build_targets_v5_launch(const float* targets, int nt, const float* anchors_host, int na, int nx, int ny,
+                            int32_t* ob, int32_t* oa, int32_t* ogj, int32_t* ogi, int32_t* ocls, float* otbox,
+                            float* oanch, int32_t* ocount, cudaStream_t st) {
+    Tv5Params p;
+    memset(&p, 0, sizeof(p));
+    p.targets = targets; p.nt = nt; p.na = na; p.nx = nx; p.ny = ny;
+    for (int a = 0; a < na; ++a) { p.anc[a][0] = anchors_host[a * 2]; p.anc[a][1] = anchors_host[a * 2 + 1]; }
+    p.ob = ob; p.oa = oa; p.ogj = ogj; p.ogi = ogi; p.ocls = ocls; p.otbox = otbox; p.oanch = oanch; p.ocount = ocount;
+    build_targets_v5_kernel<<<1, 1024, 0, st>>>(p);
+    B2_LAUNCH_CHECK("build_targets_v5_kernel");
+    return 0;
+}
+
+int v5_match_fwd_launch(const float* pi, int B, int na, int ny, int nx, int F, const int32_t* b, const int32_t* a,
+                        const int32_t* gj, const int32_t* gi, const float* tbox, const float* anch, int m, float* giou,
+                        float* tobj, cudaStream_t st) {
+    if (m == 0) return 0;
+    MatchParams p{pi, B, na, ny, nx, F, b, a, gj, gi, tbox, anch, m};
+    const int blocks = ceil_div(m, 256);
+    v5_match_fwd_kernel<<<blocks, 256, 0, st>>>(p, giou, reinterpret_cast<int*>(tobj));
+    B2_LAUNCH_CHECK("v5_match_fwd_kernel");
+    v5_match_tobj_kernel<<<blocks, 256, 0, st>>>(p, giou, tobj);
+    B2_LAUNCH_CHECK("v5_match_tobj_kernel");
+    return 0;
+}
+
+int v5_match_bwd_launch(const float* pi, int B, int na, int ny, int nx, int F, const int32_t* b, const int32_t* a,
+                        const int32_t* gj, const int32_t* gi, const float* tbox, const float* anch, int m,
+                        const float* ggiou, float* gpi, cudaStream_t st) {
+    if (m == 0) return 0;
+    MatchParams p{pi, B, na, ny, nx, F, b, a, gj, gi, tbox, anch, m};
+    v5_match_bwd_kernel<<<ceil_div(m, 256), 256, 0, st>>>(p, ggiou, gpi);
+    B2_LAUNCH_CHECK("v5_match_bwd_kernel");
+    return 0;
+}
+
+size_t build_targets_ws_bytes(int B, int A, int G, int nt) {
+    return align_up((size_t)B * A * G * G * 4, 256) + align_up((size_t)(nt > 0 ? nt : 1) * 16, 256);
+}
+
+int build_targets_launch(const float* pred_boxes, const float* pred_cls, const float* target, const float* anchors,
+                         int B, int A, int G, int C, int nt, float ignore_thres, void* ws, float* iou_scores,
+                         float* class_mask, uint8_t* obj, uint8_t* noobj, float* tx, float* ty, float* tw, float* th,
+                         float* tcls, int32_t* status, cudaStream_t st) {
+    const size_t cells = (size_t)B * A * G * G;
+    BtParams p;
+    p.pred_boxes = pred_boxes; p.pred_cls = pred_cls; p.target = target; p.anchors = anchors;
+    p.B = B; p.A = A; p.G = G; p.C = C; p.nt = nt; p.ignore_thres = ignore_thres;
+    p.winner = (int*)ws;
+    p.tinfo = (int*)((char*)ws + align_up(cells * 4, 256));
+    p.iou_scores = iou_scores; p.class_mask = class_mask; p.tx = tx; p.ty = ty; p.tw = tw; p.th = th; p.tcls = tcls;
+    p.obj = obj; p.noobj = noobj; p.status = status;
+    B2_CUDA(cudaMemsetAsync(p.winner, 0xFF, cells * 4, st));                     // accuracy.py:316-324 fills
+    B2_CUDA(cudaMemsetAsync(obj, 0, cells, st));
+    B2_CUDA(cudaMemsetAsync(noobj, 1, cells, st));
+    B2_CUDA(cudaMemsetAsync(class_mask, 0, cells * 4, st));
+    B2_CUDA(cudaMemsetAsync(iou_scores, 0, cells * 4, st));
+    B2_CUDA(cudaMemsetAsync(tx, 0, cells * 4, st));
+    B2_CUDA(cudaMemsetAsync(ty, 0, cells * 4, st));
+    B2_CUDA(cudaMemsetAsync(tw, 0, cells * 4, st));
+    B2_CUDA(cudaMemsetAsync(th, 0, cells * 4, st));
+    B2_CUDA(cudaMemsetAsync(tcls, 0, cells * (size_t)C * 4, st));
+    B2_CUDA(cudaMemsetAsync(status, 0, 4, st));
+    if (nt == 0) return 0;
+    build_targets_pass1<<<ceil_div(nt, 128), 128, 0, st>>>(p);
+    B2_LAUNCH_CHECK("build_targets_pass1");
+    build_targets_pass2<<<ceil_div(nt, 128), 128, 0, st>>>(p);
+    B2_LAUNCH_CHECK("build_targets_pass2");
+    return 0;
+}
+
+size_t ssd_match_ws_bytes(int P, int M) {
+    return align_up((size_t)(M > 0 ? M : 1) * 8, 256) + align_up((size_t)P * 4, 256);
+}
+
+int ssd_match_launch(const float* priors, int P, const float* gt, int M, float thresh, void* ws, int32_t* idx,
+                     uint8_t* matched, cudaStream_t st) {
+    unsigned long long* gt_best = (unsigned long long*)ws;
+    int* forced = (int*)((char*)ws + align_up((size_t)(M > 0 ? M : 1) * 8, 256));
+    B2_CUDA(cudaMemsetAsync(gt_best, 0, (size_t)(M > 0 ? M : 1) * 8, st));
+    const size_t smem = (size_t)M * sizeof(float4);
+    if (smem > 48 * 1024) {
+        set_error("ssd_match: too many ground-truth boxes (%d > 3072)", M);
+        return B200DET_ELIMIT;
+    }
+    ssd_match_kernel<<<ceil_div(P, 256), 256, smem, st>>>((const float4*)priors, P, (const float4*)gt, M, thresh, gt_best,
+                                                          idx, matched, forced);
+    B2_LAUNCH_CHECK("ssd_match_kernel");
+    if (M > 0) {
+        ssd_force_kernel<<<ceil_div(M, 128), 128, 0, st>>>(gt_best, M, forced);
+        B2_LAUNCH_CHECK("ssd_force_kernel");
+        ssd_apply_kernel<<<ceil_div(P, 256), 256, 0, st>>>(forced, P, idx, matched);
+        B2_LAUNCH_CHECK("ssd_apply_kernel");
+    }
+    return 0;
+}
+
+size_t retina_assign_ws_bytes(int B, int nt) {
+    return align_up((size_t)B * (nt > 0 ? nt : 1) * 4, 256) + align_up((size_t)B * 4, 256);
+}
+
+int retina_assign_launch(const float* anchors, int A, const float* targets, int nt, int B, float img_size, void* ws,
+                         float* loc, int32_t* cls, cudaStream_t st) {
+    int* list = (int*)ws;
+    int* cnt = (int*)((char*)ws + align_up((size_t)B * (nt > 0 ? nt : 1) * 4, 256));
+    group_targets_kernel<<<B, 1024, 0, st>>>(targets, nt, list, cnt);
+    B2_LAUNCH_CHECK("group_targets_kernel");
+    dim3 grid(ceil_div(A, 256), B);
+    retina_assign_kernel<<<grid, 256, 0, st>>>((const float4*)anchors, A, targets, nt, list, cnt, img_size, (float4*)loc, cls);
+    B2_LAUNCH_CHECK("retina_assign_kernel");
+    return 0;
+}
+
+}  // namespace b200det

@@ -1,0 +1,363 @@
+// K1 — fused YOLO head decode + confidence filter + class argmax + score key + ordered tile compaction.
+// K0 — decode_box: full decoded map (planar -> rows transpose with the decode formulas).
+//
+// Replaces the view/permute/contiguous/cat/xywh2xyxy/filter/max/score prologue of the reference NMS
+// (model/YOLOV3.py:289-319, YOLOV5.py:173-202) and the inline decode formulas D1/D2
+// (LightningFunc/accuracy.py:412-435,459-466; utils/YoloV5Utils.py:241-248).
+//
+// HBM-bound streaming kernel: every thread owns VEC consecutive cells of one (image, anchor) slab and
+// walks the 5+C planes at stride G*G, so a warp reads 128*VEC contiguous bytes per plane (fully
+// coalesced, 128-bit loads when G*G % 4 == 0), with 8 independent loads in flight per thread.
+// Survivors are compacted IN ORDER inside the CTA's 512-slot tile (ballot-free block scan), so the
+// slot order equals the reference's candidate order and the later stable radix sort breaks score ties
+// by ascending candidate index without any atomically-ordered append.
+#include "yolo_ws.cuh"
+
+namespace b200det {
+
+struct K1Params {
+    const float* head[B200DET_MAX_LEVELS];
+    int G[B200DET_MAX_LEVELS];
+    int GG[B200DET_MAX_LEVELS];
+    int off[B200DET_MAX_LEVELS + 1];
+    float stride[B200DET_MAX_LEVELS];
+    float anc[B200DET_MAX_LEVELS][B200DET_MAX_ANCHORS][2];
+    int nlevels, A, C, N, n_pad, n_tiles;
+    float conf_thres;
+    // outputs
+    float4* box4;
+    float2* cc2;
+    uint32_t* orig;
+    uint32_t* key;
+    uint32_t* pay;
+    uint32_t* tile_count;
+    uint32_t* count;
+    uint32_t* cls_hist;
+};
+
+template <int VEC>
+struct VecLoad;
+template <>
+struct VecLoad<4> {
+    static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
+        float4 t = ldg_stream4(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+};
+template <>
+struct VecLoad<1> {
+    static __device__ __forceinline__ void ld(const float* p, float (&v)[1]) { v[0] = ldg_stream1(p); }
+};
+
+// torch.max(dim) semantics (aten TensorCompareKernel): update when !(v <= best); stop at the first NaN.
+__device__ __forceinline__ void argmax_step(float v, int c, float& best, int& besti) {
+    if (!(v <= best) && (best == best)) { best = v; besti = c; }
+}
+
+template <int VEC, int MODE>
+__global__ void __launch_bounds__(kTile / VEC)
+yolo_decode_filter_kernel(const K1Params p) {
+    constexpr int NT = kTile / VEC;
+    extern __shared__ int s_hist[];          // [C]
+    __shared__ int s_scan[33];
+
+    const int b = blockIdx.y;
+    const int tile = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int n0 = tile * kTile + tid * VEC;
+    const bool in_range = n0 < p.N;          // VEC cells are all in range when the first is (N % VEC == 0)
+
+    for (int c = tid; c < p.C; c += NT) s_hist[c] = 0;
+
+    float box[VEC][4];
+    float conf[VEC], ccf[VEC];
+    int cls[VEC];
+    bool keep[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) keep[v] = false;
+
+    if (in_range) {
+        int lvl = 0;
+#pragma unroll
+        for (int l = 1; l < B200DET_MAX_LEVELS; ++l)
+            if (l < p.nlevels && n0 >= p.off[l]) lvl = l;
+        const int GG = p.GG[lvl];
+        const int rel = n0 - p.off[lvl];
+        const int a = rel / GG;
+        const int cell = rel - a * GG;
+        const int F = 5 + p.C;
+        const float* base = p.head[lvl] + ((size_t)(b * p.A + a) * F) * (size_t)GG + cell;
+
+        float t[5][VEC];
+#pragma unroll
+        for (int f = 0; f < 5; ++f) VecLoad<VEC>::ld(base + (size_t)f * GG, t[f]);
+
+        float best[VEC];
+        int besti[VEC];
+        const float* cp = base + (size_t)5 * GG;
+        {
+            float v0[VEC];
+            VecLoad<VEC>::ld(cp, v0);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) { best[v] = v0[v]; besti[v] = 0; }
+        }
+        int c = 1;
+        constexpr int U = 8;
+        for (; c + U <= p.C; c += U) {
+            float buf[U][VEC];
+#pragma unroll
+            for (int u = 0; u < U; ++u) VecLoad<VEC>::ld(cp + (size_t)(c + u) * GG, buf[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) argmax_step(buf[u][v], c + u, best[v], besti[v]);
+        }
+        for (; c < p.C; ++c) {
+            float buf[VEC];
+            VecLoad<VEC>::ld(cp + (size_t)c * GG, buf);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) argmax_step(buf[v], c, best[v], besti[v]);
+        }
+
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            float cx, cy, w, h, cf, cc;
+            if (MODE == B200DET_DECODE_NONE) {
+                cx = t[0][v]; cy = t[1][v]; w = t[2][v]; h = t[3][v]; cf = t[4][v]; cc = best[v];
+            } else {
+                const int G = p.G[lvl];
+                const int cl = cell + v;
+                const int gy = cl / G;
+                const float gx = (float)(cl - gy * G);
+                const float st = p.stride[lvl];
+                const float aw = p.anc[lvl][a][0], ah = p.anc[lvl][a][1];
+                if (MODE == B200DET_DECODE_YOLO_EXP) {
+                    // accuracy.py:432-435 then *stride (:461)
+                    cx = __fmul_rn(__fadd_rn(sigmoidf_acc(t[0][v]), gx), st);
+                    cy = __fmul_rn(__fadd_rn(sigmoidf_acc(t[1][v]), (float)gy), st);
+                    w = __fmul_rn(__fmul_rn(expf(t[2][v]), aw), st);
+                    h = __fmul_rn(__fmul_rn(expf(t[3][v]), ah), st);
+                } else {
+                    // utils/YoloV5Utils.py:246-247
+                    cx = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sigmoidf_acc(t[0][v]), 2.0f), 0.5f), gx), st);
+                    cy = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sigmoidf_acc(t[1][v]), 2.0f), 0.5f), (float)gy), st);
+                    float sw = __fmul_rn(sigmoidf_acc(t[2][v]), 2.0f);
+                    float sh = __fmul_rn(sigmoidf_acc(t[3][v]), 2.0f);
+                    w = __fmul_rn(__fmul_rn(sw, sw), aw);
+                    h = __fmul_rn(__fmul_rn(sh, sh), ah);
+                }
+                cf = sigmoidf_acc(t[4][v]);
+                cc = sigmoidf_acc(best[v]);   // sigmoid is monotone: argmax taken on the logits
+            }
+            // xywh2xyxy, accuracy.py:289-295 (x/2 == x*0.5 exactly)
+            const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
+            box[v][0] = __fsub_rn(cx, hw);
+            box[v][1] = __fsub_rn(cy, hh);
+            box[v][2] = __fadd_rn(cx, hw);
+            box[v][3] = __fadd_rn(cy, hh);
+            conf[v] = cf; ccf[v] = cc; cls[v] = besti[v];
+            keep[v] = cf >= p.conf_thres;     // model/YOLOV3.py:310 (NaN conf is dropped, as there)
+        }
+    }
+
+    int cnt = 0;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) cnt += keep[v] ? 1 : 0;
+    int total;
+    int ofs = block_exclusive_scan(cnt, s_scan, &total);   // also orders the s_hist zero-fill
+
+    const size_t img = (size_t)b * p.n_pad;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        if (keep[v]) {
+            const uint32_t slot = (uint32_t)(tile * kTile + ofs);
+            const size_t i = img + slot;
+            p.box4[i] = make_float4(box[v][0], box[v][1], box[v][2], box[v][3]);
+            p.cc2[i] = make_float2(conf[v], ccf[v]);
+            p.orig[i] = (uint32_t)(n0 + v);
+            p.key[i] = score_sort_key(__fmul_rn(conf[v], ccf[v]));     // model/YOLOV3.py:315
+            p.pay[i] = ((uint32_t)cls[v] << kSlotBits) | slot;
+            atomicAdd(&s_hist[cls[v]], 1);
+            ++ofs;
+        }
+    }
+    if (tid == 0) {
+        p.tile_count[(size_t)b * p.n_tiles + tile] = (uint32_t)total;
+        if (total) atomicAdd(&p.count[b], (uint32_t)total);
+    }
+    __syncthreads();
+    for (int c = tid; c < p.C; c += NT) {
+        int h = s_hist[c];
+        if (h) atomicAdd(&p.cls_hist[(size_t)b * p.C + c], (uint32_t)h);
+    }
+}
+
+// Exclusive scan of the (image, class) histogram -> class segment offsets.  One CTA per image.
+__global__ void __launch_bounds__(256) seg_scan_kernel(const uint32_t* __restrict__ cls_hist,
+                                                       uint32_t* __restrict__ seg_off, int C) {
+    __shared__ int s_scan[33];
+    const int b = blockIdx.x;
+    int carry = 0;
+    for (int c0 = 0; c0 < C; c0 += 256) {
+        const int c = c0 + threadIdx.x;
+        int v = c < C ? (int)cls_hist[(size_t)b * C + c] : 0;
+        int total;
+        int ex = block_exclusive_scan(v, s_scan, &total);
+        if (c < C) seg_off[(size_t)b * (C + 1) + c] = (uint32_t)(carry + ex);
+        carry += total;
+    }
+    if (threadIdx.x == 0) seg_off[(size_t)b * (C + 1) + C] = (uint32_t)carry;
+}
+
+int yolo_validate(const b200det_yolo_desc* d, const void* ws, size_t ws_bytes) {
+    B2_CHECK_ARG(d != nullptr, "desc is null");
+    B2_CHECK_ARG(d->batch > 0 && d->num_anchors > 0 && d->num_classes > 0, "batch/anchors/classes must be > 0");
+    B2_CHECK_LIMIT(d->num_levels >= 1 && d->num_levels <= B200DET_MAX_LEVELS, "num_levels %d out of [1,%d]",
+                   d->num_levels, B200DET_MAX_LEVELS);
+    B2_CHECK_LIMIT(d->num_anchors <= B200DET_MAX_ANCHORS, "num_anchors %d > %d", d->num_anchors, B200DET_MAX_ANCHORS);
+    B2_CHECK_LIMIT(d->num_classes <= B200DET_MAX_CLASSES, "num_classes %d > %d", d->num_classes, B200DET_MAX_CLASSES);
+    B2_CHECK_LIMIT(d->batch <= 65535, "batch %d > 65535", d->batch);
+    for (int l = 0; l < d->num_levels; ++l) {
+        B2_CHECK_ARG(d->head[l] != nullptr, "head[%d] is null", l);
+        B2_CHECK_ARG(d->grid[l] > 0, "grid[%d] must be > 0", l);
+    }
+    B2_CHECK_ARG(d->decode_mode >= B200DET_DECODE_NONE && d->decode_mode <= B200DET_DECODE_YOLOV5, "bad decode_mode %d",
+                 d->decode_mode);
+    int N, n_pad;
+    B2_CHECK_LIMIT(yolo_counts(d, &N, &n_pad) == 0, "candidates per image out of (0, %d]", B200DET_MAX_CANDIDATES);
+    B2_CHECK_ARG(ws != nullptr, "workspace is null");
+    B2_CHECK_ARG(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
+    YoloWs w;
+    yolo_ws_layout(d, (void*)ws, &w);
+    if (ws_bytes < w.total_bytes) {
+        set_error("workspace too small: %zu < %zu", ws_bytes, w.total_bytes);
+        return B200DET_EWORKSPACE;
+    }
+    return 0;
+}
+
+template <int VEC>
+static int launch_k1(const b200det_yolo_desc* d, const K1Params& p, cudaStream_t st) {
+    dim3 grid(p.n_tiles, d->batch);
+    const size_t smem = (size_t)d->num_classes * sizeof(int);
+    switch (d->decode_mode) {
+        case B200DET_DECODE_NONE:
+            yolo_decode_filter_kernel<VEC, B200DET_DECODE_NONE><<<grid, kTile / VEC, smem, st>>>(p);
+            break;
+        case B200DET_DECODE_YOLO_EXP:
+            yolo_decode_filter_kernel<VEC, B200DET_DECODE_YOLO_EXP><<<grid, kTile / VEC, smem, st>>>(p);
+            break;
+        default:
+            yolo_decode_filter_kernel<VEC, B200DET_DECODE_YOLOV5><<<grid, kTile / VEC, smem, st>>>(p);
+            break;
+    }
+    B2_LAUNCH_CHECK("yolo_decode_filter_kernel");
+    return 0;
+}
+
+int yolo_stage_decode(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cudaStream_t st) {
+    int rc = yolo_validate(d, ws, ws_bytes);
+    if (rc) return rc;
+    YoloWs w;
+    yolo_ws_layout(d, ws, &w);
+    B2_CUDA(cudaMemsetAsync(w.count, 0, w.zero_bytes, st));
+
+    K1Params p;
+    memset(&p, 0, sizeof(p));
+    bool vec4 = true;
+    int off = 0;
+    for (int l = 0; l < d->num_levels; ++l) {
+        p.head[l] = d->head[l];
+        p.G[l] = d->grid[l];
+        p.GG[l] = d->grid[l] * d->grid[l];
+        p.off[l] = off;
+        off += d->num_anchors * p.GG[l];
+        p.stride[l] = d->stride[l];
+        for (int a = 0; a < d->num_anchors; ++a) {
+            p.anc[l][a][0] = d->anchors[l][a][0];
+            p.anc[l][a][1] = d->anchors[l][a][1];
+        }
+        if (p.GG[l] % 4 != 0 || ((uintptr_t)d->head[l] & 15) != 0) vec4 = false;
+    }
+    p.off[d->num_levels] = off;
+    p.nlevels = d->num_levels; p.A = d->num_anchors; p.C = d->num_classes;
+    p.N = w.N; p.n_pad = w.n_pad; p.n_tiles = w.n_tiles;
+    p.conf_thres = d->conf_thres;
+    p.box4 = w.box4; p.cc2 = w.cc2; p.orig = w.orig; p.key = w.key[0]; p.pay = w.pay[0];
+    p.tile_count = w.tile_count; p.count = w.count; p.cls_hist = w.cls_hist;
+
+    rc = vec4 ? launch_k1<4>(d, p, st) : launch_k1<1>(d, p, st);
+    if (rc) return rc;
+    seg_scan_kernel<<<d->batch, 256, 0, st>>>(w.cls_hist, w.seg_off, d->num_classes);
+    B2_LAUNCH_CHECK("seg_scan_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K0 — decode_box: [B, A*(5+C), G, G] planar -> [B, A*G*G, 5+C] rows, decoded.
+// 32 cells x 64 planes per CTA through a padded shared tile: coalesced reads along cells,
+// coalesced writes along fields.
+// ---------------------------------------------------------------------------------------------
+constexpr int kDecCells = 32;
+constexpr int kDecPlanes = 64;
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+decode_box_kernel(const float* __restrict__ head, float* __restrict__ out, int A, int C, int G, float stride,
+                  const float* __restrict__ anchors /*[A,2] device, may be null for MODE NONE*/) {
+    __shared__ float tile[kDecPlanes][kDecCells + 1];
+    const int GG = G * G, F = 5 + C;
+    const int ba = blockIdx.y;                       // b*A + a
+    const int a = ba % A;
+    const int cell0 = blockIdx.x * kDecCells;
+    const int f0 = blockIdx.z * kDecPlanes;
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;   // 32 x 8
+    const int cell = cell0 + lx;
+    const float* src = head + (size_t)ba * F * GG;
+
+    for (int fp = ly; fp < kDecPlanes; fp += 8) {
+        const int f = f0 + fp;
+        float v = 0.f;
+        if (f < F && cell < GG) {
+            v = ldg_stream1(src + (size_t)f * GG + cell);
+            if (MODE != B200DET_DECODE_NONE) {
+                const int gy = cell / G;
+                const float gx = (float)(cell - gy * G);
+                if (MODE == B200DET_DECODE_YOLO_EXP) {
+                    if (f == 0) v = __fmul_rn(__fadd_rn(sigmoidf_acc(v), gx), stride);
+                    else if (f == 1) v = __fmul_rn(__fadd_rn(sigmoidf_acc(v), (float)gy), stride);
+                    else if (f < 4) v = __fmul_rn(__fmul_rn(expf(v), anchors[a * 2 + (f - 2)]), stride);
+                    else v = sigmoidf_acc(v);
+                } else {
+                    float s = sigmoidf_acc(v);
+                    if (f == 0) v = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(s, 2.0f), 0.5f), gx), stride);
+                    else if (f == 1) v = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(s, 2.0f), 0.5f), (float)gy), stride);
+                    else if (f < 4) { float s2 = __fmul_rn(s, 2.0f); v = __fmul_rn(__fmul_rn(s2, s2), anchors[a * 2 + (f - 2)]); }
+                    else v = s;
+                }
+            }
+        }
+        tile[fp][lx] = v;
+    }
+    __syncthreads();
+    const int nf = min(kDecPlanes, F - f0);          // fields of this chunk
+    const int ncell = min(kDecCells, GG - cell0);
+    float* dst = out + ((size_t)ba * GG + cell0) * F + f0;
+    for (int i = threadIdx.x; i < ncell * nf; i += 256) {
+        const int cl = i / nf, f = i - cl * nf;
+        dst[(size_t)cl * F + f] = tile[f][cl];
+    }
+}
+
+int decode_box_launch(const float* head, int B, int A, int C, int G, int mode, const float* anchors_dev, float stride,
+                      float* out, cudaStream_t st) {
+    const int GG = G * G, F = 5 + C;
+    dim3 grid(ceil_div(GG, kDecCells), B * A, ceil_div(F, kDecPlanes));
+    if (mode == B200DET_DECODE_NONE) decode_box_kernel<B200DET_DECODE_NONE><<<grid, 256, 0, st>>>(head, out, A, C, G, stride, anchors_dev);
+    else if (mode == B200DET_DECODE_YOLO_EXP) decode_box_kernel<B200DET_DECODE_YOLO_EXP><<<grid, 256, 0, st>>>(head, out, A, C, G, stride, anchors_dev);
+    else decode_box_kernel<B200DET_DECODE_YOLOV5><<<grid, 256, 0, st>>>(head, out, A, C, G, stride, anchors_dev);
+    B2_LAUNCH_CHECK("decode_box_kernel");
+    return 0;
+}
+
+}  // namespace b200det

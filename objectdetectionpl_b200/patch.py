@@ -1,0 +1,44 @@
+"""Drop-in installation: the same `setattr` monkey-patch idiom the reference uses for its own step
+functions (model/YOLOV5.py:134-150) and the module-global lookups of LightningFunc/losses.py:5-6.
+`LightningFunc/step.py` stays untouched."""
+from __future__ import annotations
+
+from . import boxes, postprocess, targets
+
+
+def install_model(model_cls):
+    """Replace `non_max_suppression` on a reference model class (YOLOv2/3/4/5, SSD, RetinaNet)."""
+    name = model_cls.__name__.lower()
+    if name in ("ssd", "retinanet"):
+        fn = postprocess.prior_non_max_suppression
+    elif name == "yolov2":
+        fn = postprocess.non_max_suppression_v2
+    else:
+        fn = postprocess.non_max_suppression
+    setattr(model_cls, "non_max_suppression", fn)
+    return model_cls
+
+
+def install_losses(losses_module=None, accuracy_module=None):
+    """Patch the target-assignment globals the reference's loss classes resolve at call time
+    (`build_targets_v5`, `bbox_iou_v5`: losses.py:102,118) and the function the RegionLoss classes copy into
+    `self.build_targets` (losses.py:492,654,815 — patch before constructing the criterion)."""
+    if losses_module is not None:
+        losses_module.build_targets_v5 = targets.build_targets_v5
+        losses_module.bbox_iou_v5 = boxes.bbox_iou_v5
+        losses_module.build_targets = targets.build_targets
+        losses_module.bbox_iou = boxes.bbox_iou
+        losses_module.iou = boxes.iou
+    if accuracy_module is not None:
+        accuracy_module.build_targets_v5 = targets.build_targets_v5
+        accuracy_module.bbox_iou_v5 = boxes.bbox_iou_v5
+        accuracy_module.build_targets = targets.build_targets
+        accuracy_module.bbox_iou = boxes.bbox_iou
+        accuracy_module.xywh2xyxy = boxes.xywh2xyxy
+        accuracy_module.iou = boxes.iou
+
+
+def install(*model_classes, losses_module=None, accuracy_module=None):
+    for c in model_classes:
+        install_model(c)
+    install_losses(losses_module, accuracy_module)

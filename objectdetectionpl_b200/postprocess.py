@@ -1,0 +1,202 @@
+"""Detection post-processing with the reference's call signatures.
+
+  non_max_suppression(self, predictions, conf_thres=0.5, nms_thres=0.4)            YOLOv3/v4/v5
+      replaces model/YOLOV5.py:157, YOLOV3.py:273, YOLOV4.py:221
+  non_max_suppression_v2(...)                                                       YOLOv2 (5 anchors)
+      replaces model/YOLOV2.py:159
+  prior_non_max_suppression(self, predictions, topk=100, nms_thresh=0.5, class_thresh=0.45, mode='union')
+      replaces model/SSD.py:249 == model/RetinaNet.py:117
+  decode_box(head, anchors, stride, mode)  — north-star API, restates the inline decode sites D1/D2.
+
+Everything runs on the GPU through libb200det.so; CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+YOLO_FORCED_CONF_THRES = -0.0151   # model/YOLOV5.py:164 — the reference overwrites its conf_thres argument
+
+_DECODE = {None: L.DECODE_NONE, "none": L.DECODE_NONE, "yolo_exp": L.DECODE_YOLO_EXP, "yolov5": L.DECODE_YOLOV5}
+
+
+def _yolo_desc(levels: Sequence[torch.Tensor], num_anchors: int, conf_thres: float, nms_thres: float,
+               decode, anchors, strides) -> L.YoloDesc:
+    if len(levels) == 0 or len(levels) > L.MAX_LEVELS:
+        raise ValueError(f"need 1..{L.MAX_LEVELS} prediction levels, got {len(levels)}")
+    d = L.YoloDesc()
+    first = L.require_cuda(levels[0], "predictions[0]")
+    B = first.shape[0]
+    C = None
+    for i, t in enumerate(levels):
+        L.require_cuda(t, f"predictions[{i}]")
+        if t.device != first.device:
+            raise ValueError("all prediction levels must live on one device")
+        if not t.is_contiguous():
+            raise ValueError(f"predictions[{i}] must be contiguous (the reference .view()s it, model/YOLOV3.py:296)")
+        if t.dim() < 4 or t.shape[0] != B:
+            raise ValueError(f"predictions[{i}] has shape {tuple(t.shape)}; expected [B, A*(5+C), G, G] or [B, A, G, G, 5+C]")
+        G = t.shape[2]                                   # grid_size = prediction.size(2), YOLOV3.py:290 / YOLOV5.py:175
+        per = num_anchors * G * G * B
+        if t.numel() % per:
+            raise ValueError(f"predictions[{i}] of shape {tuple(t.shape)} is not [B, {num_anchors}, 5+C, {G}, {G}] storage")
+        fields = t.numel() // per
+        if C is None:
+            C = fields - 5
+        if fields - 5 != C or C < 1:
+            raise ValueError("all levels must carry the same 5+C fields (C >= 1)")
+        d.head[i] = t.data_ptr()
+        d.grid[i] = G
+    d.batch, d.num_anchors, d.num_classes, d.num_levels = B, num_anchors, C, len(levels)
+    d.decode_mode = _DECODE[decode]
+    if d.decode_mode != L.DECODE_NONE:
+        if anchors is None or strides is None or len(anchors) != len(levels) or len(strides) != len(levels):
+            raise ValueError("decode modes need per-level `anchors` ([A,2] each) and `strides`")
+        for i in range(len(levels)):
+            d.stride[i] = float(strides[i])
+            a = torch.as_tensor(anchors[i], dtype=torch.float32).reshape(-1, 2).cpu()
+            if a.shape[0] != num_anchors:
+                raise ValueError(f"anchors[{i}] must hold {num_anchors} (w,h) pairs")
+            for k in range(num_anchors):
+                d.anchors[i][k][0] = float(a[k, 0])
+                d.anchors[i][k][1] = float(a[k, 1])
+    d.conf_thres, d.nms_thres = float(conf_thres), float(nms_thres)
+    return d
+
+
+def yolo_nms_raw(levels: Sequence[torch.Tensor], num_anchors: int = 3, conf_thres: float = YOLO_FORCED_CONF_THRES,
+                 nms_thres: float = 0.4, decode=None, anchors=None, strides=None, want_index: bool = False):
+    """Enqueue the whole pipeline; returns device tensors (rows [B,n_pad,7], index [B,n_pad]|None, count [B])
+    without synchronising — the building block for benchmarks and CUDA-graph capture."""
+    lib = L.load()
+    d = _yolo_desc(levels, num_anchors, conf_thres, nms_thres, decode, anchors, strides)
+    dev = levels[0].device
+    n, n_pad = ctypes.c_int32(), ctypes.c_int32()
+    L.check(lib.b200det_yolo_num_candidates(ctypes.byref(d), ctypes.byref(n), ctypes.byref(n_pad)), "yolo_num_candidates")
+    ws_bytes = lib.b200det_yolo_workspace_bytes(ctypes.byref(d))
+    with torch.cuda.device(dev):
+        ws = L.workspace(ws_bytes, dev)
+        rows = torch.empty((d.batch, n_pad.value, 7), dtype=torch.float32, device=dev)
+        index = torch.empty((d.batch, n_pad.value), dtype=torch.int32, device=dev) if want_index else None
+        count = torch.empty((d.batch,), dtype=torch.int32, device=dev)
+        L.check(lib.b200det_yolo_nms(ctypes.byref(d), ws.data_ptr(), ws.numel(), rows.data_ptr(),
+                                     index.data_ptr() if want_index else None, count.data_ptr(), L.stream_ptr(dev)),
+                "yolo_nms")
+    return rows, index, count
+
+
+def _yolo_nms(predictions, num_anchors, conf_thres, nms_thres, compat, decode, anchors, strides, return_index):
+    if not isinstance(predictions, (list, tuple)):
+        predictions = [predictions]                      # model/YOLOV3.py:281-282
+    thr = YOLO_FORCED_CONF_THRES if compat else conf_thres
+    rows, index, count = yolo_nms_raw(predictions, num_anchors, thr, nms_thres, decode, anchors, strides, return_index)
+    counts = count.cpu().tolist()                        # the one host sync of the call
+    out: List[Optional[torch.Tensor]] = [rows[b, :k] if k else None for b, k in enumerate(counts)]   # YOLOV3.py:306,333
+    if return_index:
+        return out, [index[b, :k].long() if k else None for b, k in enumerate(counts)]
+    return out
+
+
+def non_max_suppression(self, predictions, conf_thres=0.5, nms_thres=0.4, *, compat=True, decode=None, anchors=None,
+                        strides=None, return_index=False):
+    """Drop-in for YOLOv3/v4/v5 `non_max_suppression` (3 anchors per level).
+
+    Returns a list (one entry per image) of `None` or fp32 `[K,7]` rows
+    `(x1, y1, x2, y2, object_conf, class_score, class_pred)` in descending score order.
+    compat=True (default) reproduces the reference bit-for-bit, including its forced
+    `conf_thres = -0.0151`; compat=False honours `conf_thres`.  Extensions (keyword-only):
+    `decode` in {None,'yolo_exp','yolov5'} with per-level `anchors`/`strides`, `return_index`.
+    """
+    return _yolo_nms(predictions, 3, conf_thres, nms_thres, compat, decode, anchors, strides, return_index)
+
+
+def non_max_suppression_v2(self, predictions, conf_thres=0.5, nms_thres=0.4, *, compat=True, decode=None, anchors=None,
+                           strides=None, return_index=False):
+    """Drop-in for YOLOv2 `non_max_suppression` (5 anchors, model/YOLOV2.py:179-183)."""
+    return _yolo_nms(predictions, 5, conf_thres, nms_thres, compat, decode, anchors, strides, return_index)
+
+
+def prior_nms_raw(loc: torch.Tensor, cls: torch.Tensor, priors: torch.Tensor, topk=100, nms_thresh=0.5,
+                  class_thresh=0.45, mode="union", compat=True, want_index=False):
+    if mode not in ("union", "min"):
+        raise TypeError("Unknown nms mode: %s." % mode)  # model/SSD.py:298-299
+    lib = L.load()
+    L.require_cuda(loc, "loc_preds"); L.require_cuda(cls, "cls_preds"); L.require_cuda(priors, "iou_boxes")
+    if loc.dim() != 3 or loc.shape[2] != 4 or cls.dim() != 3 or cls.shape[:2] != loc.shape[:2] or \
+            tuple(priors.shape) != (loc.shape[1], 4):
+        raise ValueError(f"expected loc [B,P,4], cls [B,P,C], priors [P,4]; got {tuple(loc.shape)}, {tuple(cls.shape)}, "
+                         f"{tuple(priors.shape)}")
+    loc, cls, priors = loc.contiguous(), cls.contiguous(), priors.contiguous()
+    dev = loc.device
+    d = L.PriorDesc()
+    d.batch, d.num_priors, d.num_classes = loc.shape[0], loc.shape[1], cls.shape[2]
+    d.loc, d.cls, d.priors = loc.data_ptr(), cls.data_ptr(), priors.data_ptr()
+    d.topk, d.nms_thresh, d.class_thresh = int(topk), float(nms_thresh), float(class_thresh)
+    d.mode_min, d.compat = int(mode == "min"), int(bool(compat))
+    ws_bytes = lib.b200det_prior_workspace_bytes(ctypes.byref(d))
+    with torch.cuda.device(dev):
+        ws = L.workspace(ws_bytes, dev)
+        rows = torch.empty((d.batch, d.topk, 7), dtype=torch.float32, device=dev)
+        index = torch.empty((d.batch, d.topk), dtype=torch.int32, device=dev) if want_index else None
+        count = torch.empty((2, d.batch), dtype=torch.int32, device=dev)
+        L.check(lib.b200det_prior_nms(ctypes.byref(d), ws.data_ptr(), ws.numel(), rows.data_ptr(),
+                                      index.data_ptr() if want_index else None, count[0].data_ptr(), count[1].data_ptr(),
+                                      L.stream_ptr(dev)), "prior_nms")
+    return rows, index, count
+
+
+def prior_non_max_suppression(self, predictions, topk=100, nms_thresh=0.5, class_thresh=0.45, mode="union", *,
+                              compat=True, return_index=False):
+    """Drop-in for SSD / RetinaNet `non_max_suppression` (model/SSD.py:249, model/RetinaNet.py:117).
+    Priors come from `self.iou_boxes` [P,4].  Returns a list of fp32 `[K,7]` rows
+    `(x1, y1, x2, y2, 0, score, label)`; compat=True reproduces the reference's quirks (the last
+    surviving box is dropped, boxes/labels gathered with score-filtered indices, IndexError when exactly
+    one candidate passes the score threshold)."""
+    loc, cls = predictions
+    rows, index, count = prior_nms_raw(loc, cls, self.iou_boxes, topk, nms_thresh, class_thresh, mode, compat, return_index)
+    c = count.cpu()
+    if compat and bool((c[1] == 1).any()):
+        raise IndexError("too many indices for tensor of dimension 1")   # model/SSD.py:262,266 (0-dim index)
+    kept = c[0].tolist()
+    out = [rows[b, :k] for b, k in enumerate(kept)]
+    if return_index:
+        return out, [index[b, :k].long() for b, k in enumerate(kept)]
+    return out
+
+
+def decode_box(head: torch.Tensor, anchors, stride: float, mode: str = "yolo_exp", num_anchors: Optional[int] = None):
+    """Full decoded map of one level: planar `[B, A*(5+C), G, G]` -> `[B, A*G*G, 5+C]`.
+
+    mode 'yolo_exp' (D1, accuracy.py:412-435,459-466): x=(σ+gx)·stride, w=exp·anchor·stride, σ(conf), σ(cls);
+         `anchors` are the SCALED anchors (grid units) exactly as the reference's callers pass them.
+    mode 'yolov5'  (D2, utils/YoloV5Utils.py:244-248): xy=(2σ-0.5+g)·stride, wh=(2σ)²·anchor (pixel anchors).
+    mode 'none': the planar->rows permute of model/YOLOV3.py:294-300 only.
+    """
+    lib = L.load()
+    L.require_cuda(head, "head")
+    if not head.is_contiguous():
+        raise ValueError("head must be contiguous")
+    m = _DECODE[mode]
+    anc = None
+    if anchors is not None:
+        anc = torch.as_tensor(anchors, dtype=torch.float32).reshape(-1, 2).to(head.device).contiguous()
+        A = anc.shape[0]
+    else:
+        A = num_anchors
+    if A is None:
+        raise ValueError("need `anchors` or `num_anchors`")
+    if m != L.DECODE_NONE and anc is None:
+        raise ValueError("decode modes need anchors")
+    B, G = head.shape[0], head.shape[2]
+    if head.numel() % (B * A * G * G):
+        raise ValueError(f"head of shape {tuple(head.shape)} is not [B, {A}, 5+C, {G}, {G}] storage")
+    F = head.numel() // (B * A * G * G)
+    out = torch.empty((B, A * G * G, F), dtype=torch.float32, device=head.device)
+    with torch.cuda.device(head.device):
+        L.check(lib.b200det_decode_box(head.data_ptr(), B, A, F - 5, G, m, anc.data_ptr() if anc is not None else None,
+                                       float(stride), out.data_ptr(), L.stream_ptr(head.device)), "decode_box")
+    return out

@@ -1,0 +1,160 @@
+"""Loss-side target assignment with the reference's signatures, on the GPU.
+
+  build_targets(pred_boxes, pred_cls, target, anchors, ignore_thres)   LightningFunc/accuracy.py:305
+  build_targets_v5(p, targets, anchors, nl, na)                        LightningFunc/accuracy.py:472
+  v5_match_level(pi, tbox, indices, anch)                              LightningFunc/losses.py:105-123
+  ssd_match(default_boxes, annotations_boxes, match_thresh)            LightningFunc/losses.py:199
+  retina_assign(anchors, targets, batch_size, img_size)                LightningFunc/losses.py:423-443
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+
+def build_targets(pred_boxes, pred_cls, target, anchors, ignore_thres):
+    """Returns the reference's 10-tuple `(iou_scores, class_mask, obj_mask, noobj_mask, tx, ty, tw, th, tcls,
+    tconf)` with identical dtypes (masks uint8).  Duplicate cells: the highest target row wins."""
+    lib = L.load()
+    pb = L.require_cuda(pred_boxes, "pred_boxes").contiguous()
+    pc = L.require_cuda(pred_cls, "pred_cls").contiguous()
+    tg = L.require_cuda(target, "target").contiguous()
+    an = L.require_cuda(torch.as_tensor(anchors, dtype=torch.float32, device=pb.device), "anchors").contiguous()
+    B, A, G = pb.shape[0], pb.shape[1], pb.shape[2]
+    C, nt = pc.shape[-1], tg.shape[0]
+    dev = pb.device
+    f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+    iou_scores, class_mask, tx, ty, tw, th = (f(B, A, G, G) for _ in range(6))
+    tcls = f(B, A, G, G, C)
+    obj = torch.empty((B, A, G, G), dtype=torch.uint8, device=dev)
+    noobj = torch.empty((B, A, G, G), dtype=torch.uint8, device=dev)
+    status = torch.empty((1,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        ws = L.workspace(lib.b200det_build_targets_workspace_bytes(B, A, G, nt), dev)
+        L.check(lib.b200det_build_targets(pb.data_ptr(), pc.data_ptr(), tg.data_ptr() if nt else None, an.data_ptr(), B, A, G, C,
+                                          nt, float(ignore_thres), ws.data_ptr(), ws.numel(), iou_scores.data_ptr(),
+                                          class_mask.data_ptr(), obj.data_ptr(), noobj.data_ptr(), tx.data_ptr(), ty.data_ptr(),
+                                          tw.data_ptr(), th.data_ptr(), tcls.data_ptr(), status.data_ptr(), L.stream_ptr(dev)),
+                "build_targets")
+    return iou_scores, class_mask, obj, noobj, tx, ty, tw, th, tcls, obj.float()
+
+
+def build_targets_v5(p, targets, anchors, nl, na):
+    """Returns `(tcls, tbox, indices, anch)`, four lists of length nl with the reference's dtypes
+    (int64 indices/classes) and row order.  `p[i]` may be a tensor `[B,na,ny,nx,5+C]` or just its shape."""
+    lib = L.load()
+    tg = L.require_cuda(targets, "targets").contiguous()
+    dev = tg.device
+    nt = tg.shape[0]
+    anchors_cpu = torch.as_tensor(anchors).detach().float().cpu().reshape(nl, na, 2)
+    anchors_dev = torch.as_tensor(anchors, dtype=torch.float32, device=dev).reshape(nl, na, 2)
+    cap = max(5 * na * nt, 1)
+    tcls, tbox, indices, anch = [], [], [], []
+    counts = torch.empty((nl,), dtype=torch.int32, device=dev)
+    bufs = []
+    with torch.cuda.device(dev):
+        for i in range(nl):
+            shape = p[i].shape if isinstance(p[i], torch.Tensor) else tuple(p[i])
+            ny, nx = int(shape[2]), int(shape[3])
+            ib = torch.empty((5, cap), dtype=torch.int32, device=dev)      # b, a, gj, gi, cls
+            tb = torch.empty((cap, 4), dtype=torch.float32, device=dev)
+            ac = torch.empty((cap, 2), dtype=torch.float32, device=dev)
+            arr = (ctypes.c_float * (2 * na))(*anchors_cpu[i].reshape(-1).tolist())
+            L.check(lib.b200det_build_targets_v5_level(tg.data_ptr() if nt else None, nt, arr, na, nx, ny, ib[0].data_ptr(),
+                                                       ib[1].data_ptr(), ib[2].data_ptr(), ib[3].data_ptr(), ib[4].data_ptr(),
+                                                       tb.data_ptr(), ac.data_ptr(), counts[i:].data_ptr(), L.stream_ptr(dev)),
+                    "build_targets_v5")
+            bufs.append((ib, tb, ac))
+    ms = counts.cpu().tolist()                                            # one host sync for all levels
+    for i, (ib, tb, ac) in enumerate(bufs):
+        m = ms[i]
+        il = ib[:, :m].long()
+        indices.append((il[0], il[1], il[2], il[3]))
+        tcls.append(il[4])
+        tbox.append(tb[:m])
+        anch.append(ac[:m])
+    del anchors_dev
+    return tcls, tbox, indices, anch
+
+
+class _V5Match(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pi, tbox, b, a, gj, gi, anch):
+        lib = L.load()
+        pid = L.require_cuda(pi.detach(), "pi")
+        if not pid.is_contiguous():
+            raise ValueError("pi must be contiguous [B,na,ny,nx,5+C]")
+        B, na, ny, nx, F = pid.shape
+        m = b.shape[0]
+        dev = pid.device
+        idx = torch.stack((b, a, gj, gi)).to(torch.int32).contiguous()
+        tb = tbox.detach().contiguous().float()
+        ac = anch.detach().contiguous().float()
+        giou = torch.empty((m,), dtype=torch.float32, device=dev)
+        tobj = torch.zeros((B, na, ny, nx), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            L.check(lib.b200det_v5_match_fwd(pid.data_ptr(), B, na, ny, nx, F, idx[0].data_ptr(), idx[1].data_ptr(),
+                                             idx[2].data_ptr(), idx[3].data_ptr(), tb.data_ptr(), ac.data_ptr(), m, giou.data_ptr(),
+                                             tobj.data_ptr(), L.stream_ptr(dev)), "v5_match_fwd")
+        ctx.save_for_backward(pid, idx, tb, ac)
+        ctx.mark_non_differentiable(tobj)
+        return giou, tobj
+
+    @staticmethod
+    def backward(ctx, g_giou, _g_tobj):
+        lib = L.load()
+        pid, idx, tb, ac = ctx.saved_tensors
+        B, na, ny, nx, F = pid.shape
+        m = idx.shape[1]
+        gpi = torch.zeros_like(pid)
+        g = g_giou.contiguous().float()
+        with torch.cuda.device(pid.device):
+            L.check(lib.b200det_v5_match_bwd(pid.data_ptr(), B, na, ny, nx, F, idx[0].data_ptr(), idx[1].data_ptr(),
+                                             idx[2].data_ptr(), idx[3].data_ptr(), tb.data_ptr(), ac.data_ptr(), m, g.data_ptr(),
+                                             gpi.data_ptr(), L.stream_ptr(pid.device)), "v5_match_bwd")
+        return gpi, None, None, None, None, None, None
+
+
+def v5_match_level(pi, tbox, indices, anch):
+    """Fused matched-row path of `MultiScaleRegionLoss_v5.forward` for one level (losses.py:105-123):
+    gather `pi[b,a,gj,gi]`, decode (σ·2−0.5, (σ·2)²·anchor), GIoU against `tbox`, and the objectness target
+    `tobj[b,a,gj,gi] = clamp(giou,0)` (last row wins on duplicate cells).  Returns `(giou[m], tobj[B,na,ny,nx])`;
+    `giou` is differentiable w.r.t. `pi`."""
+    b, a, gj, gi = indices
+    return _V5Match.apply(pi, tbox, b, a, gj, gi, anch)
+
+
+def ssd_match(default_boxes, annotations_boxes, match_thresh=0.5):
+    """`SSDLoss.match` (losses.py:199-218): returns `(box_with_annotation[P] int64, matched[P] bool)`."""
+    lib = L.load()
+    pri = L.require_cuda(default_boxes, "default_boxes").contiguous()
+    gt = L.require_cuda(annotations_boxes, "annotations_boxes").contiguous()
+    P, M = pri.shape[0], gt.shape[0]
+    dev = pri.device
+    idx = torch.empty((P,), dtype=torch.int32, device=dev)
+    matched = torch.empty((P,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        ws = L.workspace(lib.b200det_ssd_match_workspace_bytes(P, M), dev)
+        L.check(lib.b200det_ssd_match(pri.data_ptr(), P, gt.data_ptr() if M else None, M, float(match_thresh), ws.data_ptr(),
+                                      ws.numel(), idx.data_ptr(), matched.data_ptr(), L.stream_ptr(dev)), "ssd_match")
+    return idx.long(), matched.bool()
+
+
+def retina_assign(anchors, targets, batch_size, img_size):
+    """RetinaNet target assignment + encoding (losses.py:423-443): returns
+    `(loc_targets [B,A,4] fp32, cls_targets [B,A] int64)`; cls = 1+label, 0 background (<0.5), −1 ignore (0.4..0.5)."""
+    lib = L.load()
+    an = L.require_cuda(anchors, "anchors").contiguous()
+    tg = L.require_cuda(targets, "targets").contiguous()
+    A, nt, dev = an.shape[0], tg.shape[0], an.device
+    loc = torch.empty((batch_size, A, 4), dtype=torch.float32, device=dev)
+    cls = torch.empty((batch_size, A), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        ws = L.workspace(lib.b200det_retina_assign_workspace_bytes(batch_size, nt), dev)
+        L.check(lib.b200det_retina_assign(an.data_ptr(), A, tg.data_ptr() if nt else None, nt, batch_size, float(img_size),
+                                          ws.data_ptr(), ws.numel(), loc.data_ptr(), cls.data_ptr(), L.stream_ptr(dev)),
+                "retina_assign")
+    return loc, cls.long()
