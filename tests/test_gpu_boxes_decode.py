@@ -1,0 +1,99 @@
+"""GPU parity: elementwise box maths (accuracy.py:6-114, 289-295) and decode_box (D1/D2)."""
+import pytest
+import torch
+
+import objectdetectionpl_b200 as od
+from objectdetectionpl_b200 import synth
+from oracle import ref_port as rp
+from tests.golden_io import load, T
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_iou_family_golden():
+    d = load("iou")
+    b1, b2, c1, c2 = (T(d[k]).to(DEV) for k in ("b1", "b2", "c1", "c2"))
+    assert torch.equal(od.xywh2xyxy(b1).cpu(), T(d["c1"]))
+    assert torch.equal(od.bbox_iou(b1, b2, x1y1x2y2=False).cpu(), T(d["plus1_xywh"]))
+    assert torch.equal(od.bbox_iou(c1, c2).cpu(), T(d["plus1_xyxy"]))
+    assert torch.equal(od.bbox_iou(c1[:1], c2).cpu(), T(d["plus1_one_vs_all"]))
+    assert torch.equal(od.iou(c1.clamp(0, 100), c2.clamp(0, 100)).cpu(), T(d["pair_iou"]))
+    n = b1.shape[0]
+    gw = torch.linspace(0.5, 1.5, n, device=DEV)
+    for kind in ("IoU", "GIoU", "DIoU", "CIoU"):
+        for corner in (False, True):
+            a = (c1 if corner else b1).t().clone().requires_grad_(True)     # transposed views, as losses.py:118 passes
+            bb = (c2 if corner else b2).t()
+            kw = {} if kind == "IoU" else {kind: True}
+            v = od.bbox_iou_v5(a, bb, x1y1x2y2=corner, **kw)
+            (v * gw).sum().backward()
+            tag = f"v5_{kind}_{'xyxy' if corner else 'xywh'}"
+            want, wgrad = T(d[tag]), T(d[tag + "_grad"])
+            if kind == "CIoU":      # atan differs in the last ulp between libm/SLEEF and CUDA
+                torch.testing.assert_close(v.detach().cpu(), want, rtol=1e-5, atol=1e-6, msg=tag)
+            else:
+                assert torch.equal(v.detach().cpu(), want), tag
+            torch.testing.assert_close(a.grad.cpu(), wgrad, rtol=2e-4, atol=1e-6, msg=tag + " grad")
+
+
+def test_bbox_iou_v5_contiguous_and_strided_agree():
+    g = torch.Generator().manual_seed(3)
+    p = torch.rand(500, 4, generator=g).to(DEV) + 0.1
+    t = torch.rand(500, 4, generator=g).to(DEV) + 0.1
+    a = od.bbox_iou_v5(p.t(), t.t(), x1y1x2y2=False, GIoU=True)
+    b = od.bbox_iou_v5(p.t().contiguous(), t.t().contiguous(), x1y1x2y2=False, GIoU=True)
+    assert torch.equal(a, b)
+    want = rp.bbox_iou_v5(p.cpu().t(), t.cpu().t(), x1y1x2y2=False, GIoU=True)
+    assert torch.equal(a.cpu(), want)
+
+
+@pytest.mark.parametrize("mode", ["yolo_exp", "yolov5", "none"])
+@pytest.mark.parametrize("G,C", [(13, 4), (20, 80), (7, 130)])
+def test_decode_box(mode, G, C):
+    B, A = 2, 3
+    head = synth.raw_logits(B, A, C, G, 61 + G)
+    stride = 32.0
+    if mode == "yolo_exp":
+        anc = torch.tensor([[3.625, 2.8125], [4.875, 6.1875], [11.65625, 10.1875]])
+        want = rp.decode_yolo_exp(head, anc, stride)
+    elif mode == "yolov5":
+        anc = torch.tensor([[116., 90.], [156., 198.], [373., 326.]])
+        want = rp.decode_yolov5(head, anc, stride)
+    else:
+        anc = None
+        want = rp.yolo_rows_from_planar([head], A)
+    got = od.decode_box(head.to(DEV), anc, stride, mode, num_anchors=A).cpu()
+    assert got.shape == want.shape
+    if mode == "none":
+        assert torch.equal(got, want)
+    else:
+        torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-6)
+
+
+def test_decode_box_golden_d1():
+    d = load("decode")
+    head = T(d["head"])
+    stride = int(d["img"]) / head.shape[2]
+    got = od.decode_box(head.to(DEV), T(d["d1_scaled_anchors"]), stride, "yolo_exp").cpu()
+    torch.testing.assert_close(got, T(d["d1_output"]), rtol=1e-5, atol=1e-6)
+
+
+def test_fused_decode_nms_matches_decode_then_nms():
+    """Extension path: non_max_suppression(decode='yolov5') == decode_box per level, then the plain NMS on the
+    decoded rows (oracle NMS on the GPU-decoded values, so only the NMS is under test here)."""
+    B, A, C = 2, 3, 6
+    grids, strides = [16, 8], [8.0, 16.0]
+    anchors = [torch.tensor([[10., 13.], [16., 30.], [33., 23.]]), torch.tensor([[30., 61.], [62., 45.], [59., 119.]])]
+    heads = [synth.raw_logits(B, A, C, G, 70 + G) for G in grids]
+    for h in heads:          # raise objectness so that a useful number of rows pass 0.25
+        h.view(B, A, 5 + C, h.shape[2], h.shape[3])[:, :, 4] += 3.0
+    dev_heads = [h.to(DEV) for h in heads]
+    got, gidx = od.non_max_suppression(None, dev_heads, conf_thres=0.25, compat=False, decode="yolov5", anchors=anchors,
+                                       strides=strides, return_index=True)
+    rows = torch.cat([od.decode_box(h, a, s, "yolov5") for h, a, s in zip(dev_heads, anchors, strides)], 1).cpu()
+    # class conf of the fused path is sigmoid(max logit) == max of the decoded sigmoids
+    want, widx = rp.yolo_nms_fast(rows, conf_thres=0.25)
+    for b in range(B):
+        assert torch.equal(gidx[b].cpu(), widx[b])
+        torch.testing.assert_close(got[b].cpu(), want[b], rtol=1e-5, atol=1e-4)

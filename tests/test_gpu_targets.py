@@ -1,0 +1,150 @@
+"""GPU parity: loss-side target assignment (accuracy.py:305-380, 472-521; losses.py:105-123, 199-218,
+423-443) against the golden vectors of the unmodified reference and the CPU oracle."""
+import pytest
+import torch
+
+import objectdetectionpl_b200 as od
+from objectdetectionpl_b200 import synth
+from oracle import ref_port as rp
+from tests.golden_io import load, T
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+BT_NAMES = ["iou_scores", "class_mask", "obj_mask", "noobj_mask", "tx", "ty", "tw", "th", "tcls", "tconf"]
+
+
+@pytest.mark.parametrize("name", ["bt_g13", "bt_g26_dups"])
+def test_build_targets_golden(name):
+    d = load(name)
+    out = od.build_targets(T(d["pred_boxes"]).to(DEV), T(d["pred_cls"]).to(DEV), T(d["target"]).to(DEV),
+                           T(d["anchors"]).to(DEV), 0.5)
+    for k, v in zip(BT_NAMES, out):
+        w = T(d[k])
+        assert v.dtype == w.dtype and tuple(v.shape) == tuple(w.shape), k
+        if k in ("tw", "th"):   # logf vs torch.log: last ulp
+            torch.testing.assert_close(v.cpu(), w, rtol=1e-5, atol=1e-6, msg=k)
+        else:
+            assert torch.equal(v.cpu(), w), k
+
+
+def test_build_targets_oracle_large_and_guards():
+    B, A, G, C = 8, 3, 52, 80
+    g = torch.Generator().manual_seed(5)
+    tg = synth.labels(B, C, 401, max_per_image=100)
+    pb = torch.rand(B, A, G, G, 4, generator=g) * G
+    pc = torch.rand(B, A, G, G, C, generator=g)
+    an = torch.tensor([[1.25, 1.625], [2.0, 3.75], [4.125, 2.875]])
+    want = rp.build_targets(pb, pc, tg, an, 0.5)
+    got = od.build_targets(pb.to(DEV), pc.to(DEV), tg.to(DEV), an.to(DEV), 0.5)
+    for k, v, w in zip(BT_NAMES, got, want):
+        if k in ("tw", "th"):
+            torch.testing.assert_close(v.cpu(), w, rtol=1e-5, atol=1e-6, msg=k)
+        else:
+            assert torch.equal(v.cpu(), w), k
+    # index guard (accuracy.py:340-344): one out-of-range image id suppresses every scatter but the per-target
+    # ignore-threshold clearing of the valid rows
+    bad = tg.clone()
+    bad[3, 0] = B + 2
+    want = rp.build_targets(pb, pc, bad, an, 0.5)
+    got = od.build_targets(pb.to(DEV), pc.to(DEV), bad.to(DEV), an.to(DEV), 0.5)
+    for k, v, w in zip(BT_NAMES, got, want):
+        assert torch.equal(v.cpu(), w), "guard/" + k
+    # label guard (accuracy.py:365-367)
+    bad = tg.clone()
+    bad[7, 1] = C + 1
+    want = rp.build_targets(pb, pc, bad, an, 0.5)
+    got = od.build_targets(pb.to(DEV), pc.to(DEV), bad.to(DEV), an.to(DEV), 0.5)
+    for k, v, w in zip(BT_NAMES, got, want):
+        assert torch.equal(v.cpu(), w), "label-guard/" + k
+
+
+@pytest.mark.parametrize("name", ["btv5_small", "btv5_mid"])
+def test_build_targets_v5_golden(name):
+    d = load(name)
+    shapes = [tuple(d[f"p_{i}"].shape) if name == "btv5_small" else tuple(int(x) for x in d[f"p_{i}"]) for i in range(3)]
+    tcls, tbox, idx, anch = od.build_targets_v5(shapes, T(d["target"]).to(DEV), T(d["anchors"]), 3, 3)
+    for i in range(3):
+        assert tcls[i].dtype == torch.int64 and idx[i][0].dtype == torch.int64
+        assert torch.equal(tcls[i].cpu(), T(d[f"tcls_{i}"]))
+        assert torch.equal(tbox[i].cpu(), T(d[f"tbox_{i}"]))
+        assert torch.equal(anch[i].cpu(), T(d[f"anch_{i}"]))
+        for k, nm in enumerate("b a gj gi".split()):
+            assert torch.equal(idx[i][k].cpu(), T(d[f"{nm}_{i}"])), (i, nm)
+
+
+def test_build_targets_v5_full_batch_and_empty():
+    B, C, img = 64, 80, 640
+    tg = synth.labels(B, C, 4, max_per_image=100)
+    stride = torch.tensor([8., 16., 32.])
+    anchors = torch.tensor(synth.YOLOV5_ANCHORS).float().view(3, -1, 2) / stride.view(-1, 1, 1)
+    shapes = [(B, 3, img // s, img // s, 5 + C) for s in (8, 16, 32)]
+    want = rp.build_targets_v5(shapes, tg, anchors, 3, 3)
+    got = od.build_targets_v5(shapes, tg.to(DEV), anchors, 3, 3)
+    for i in range(3):
+        assert torch.equal(got[0][i].cpu(), want[0][i])
+        assert torch.equal(got[1][i].cpu(), want[1][i])
+        assert torch.equal(got[3][i].cpu(), want[3][i])
+        for k in range(4):
+            assert torch.equal(got[2][i][k].cpu(), want[2][i][k])
+    empty = od.build_targets_v5(shapes, torch.zeros(0, 6, device=DEV), anchors, 3, 3)
+    assert all(t.shape[0] == 0 for t in empty[0]) and all(t.shape == (0, 4) for t in empty[1])
+
+
+def test_v5_match_level_golden_lbox_and_grad():
+    d = load("btv5_small")
+    tg, anchors = T(d["target"]), T(d["anchors"])
+    p = [T(d[f"p_{i}"]).to(DEV).requires_grad_(True) for i in range(3)]
+    tcls, tbox, idx, anch = od.build_targets_v5(p, tg.to(DEV), anchors, 3, 3)
+    pc = [T(d[f"p_{i}"]) for i in range(3)]
+    wt = rp.build_targets_v5([t.shape for t in pc], tg, anchors, 3, 3)
+    lbox = 0
+    for i in range(3):
+        giou, tobj = od.v5_match_level(p[i], tbox[i], idx[i], anch[i])
+        wg, wo = rp.v5_match_level(pc[i], wt[1][i], wt[2][i], wt[3][i])
+        torch.testing.assert_close(giou.detach().cpu(), wg, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(tobj.cpu(), wo, rtol=1e-5, atol=1e-6)
+        assert torch.equal(tobj.cpu() != 0, wo != 0)
+        lbox = lbox + (1.0 - giou).mean()
+    lbox = lbox * 0.05
+    torch.testing.assert_close(lbox.detach().cpu().reshape(1), T(d["lbox"]), rtol=1e-5, atol=1e-7)
+    lbox.backward()
+    for i in range(3):
+        torch.testing.assert_close(p[i].grad.cpu(), T(d[f"lbox_grad_{i}"]), rtol=2e-4, atol=1e-8)
+
+
+def test_ssd_match_and_retina_assign_golden():
+    d = load("match")
+    idx, matched = od.ssd_match(T(d["priors"]).to(DEV), T(d["gt"]).to(DEV), 0.5)
+    assert idx.dtype == torch.int64 and matched.dtype == torch.bool
+    assert torch.equal(idx.cpu(), T(d["ssd_idx"]))
+    assert torch.equal(matched.cpu(), T(d["ssd_matched"]))
+    anchors, tg = T(d["r_anchors"]), T(d["r_target"])
+    B, img = int(d["r_B"]), float(d["r_img"])
+    loc, cls = od.retina_assign(anchors.to(DEV), tg.to(DEV), B, img)
+    loc, cls = loc.cpu(), cls.cpu()
+    assert cls.dtype == torch.int64
+    assert torch.equal(cls[cls > -1], T(d["r_cls_nonignored"]))
+    torch.testing.assert_close(loc[cls > 0], T(d["r_loc_pos"]), rtol=1e-5, atol=1e-6)
+
+
+def test_retina_assign_oracle_unsorted_targets():
+    anchors = synth.retina_priors(256)
+    B = 4
+    tg = synth.labels(B, 9, 77, max_per_image=20)
+    tg[:, 4:6] = tg[:, 4:6] * 1.5 + 0.05
+    perm = torch.randperm(tg.shape[0], generator=torch.Generator().manual_seed(1))
+    tg = tg[perm]                              # image ids interleaved: order within an image must be preserved
+    wl, wc = rp.retina_assign(anchors, tg, B, 256.0)
+    gl, gc = od.retina_assign(anchors.to(DEV), tg.to(DEV), B, 256.0)
+    assert torch.equal(gc.cpu(), wc)
+    torch.testing.assert_close(gl.cpu(), wl, rtol=1e-5, atol=1e-6)
+
+
+def test_ssd_match_oracle_many_gt():
+    pri = synth.ssd_priors()
+    g = torch.Generator().manual_seed(9)
+    gt = torch.cat([0.1 + torch.rand(40, 2, generator=g) * 0.8, 0.03 + torch.rand(40, 2, generator=g) * 0.5], 1)
+    gt[7] = gt[3]                              # duplicate GT -> "last GT wins" on its forced prior
+    wi, wm = rp.ssd_match(pri, gt, 0.5)
+    gi, gm = od.ssd_match(pri.to(DEV), gt.to(DEV), 0.5)
+    assert torch.equal(gi.cpu(), wi) and torch.equal(gm.cpu(), wm)

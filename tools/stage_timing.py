@@ -34,7 +34,7 @@ def main():
         else:
             t[:, :, 4] = torch.sigmoid(torch.randn(a.batch, 3, G, G, device=dev, generator=g) * 2 - 4)
         t[:, :, 5:] = torch.rand(a.batch, 3, a.classes, G, G, device=dev, generator=g)
-        levels.append(t)
+        levels.append(t.view(a.batch, 3 * (5 + a.classes), G, G))
     lib = L.load()
     d = _yolo_desc(levels, 3, a.conf_thres, 0.4, None, None, None)
     n, n_pad = ctypes.c_int32(), ctypes.c_int32()
