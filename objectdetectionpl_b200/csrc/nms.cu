@@ -17,6 +17,8 @@
 //            order (deterministic fp32 order: keeper first, then members by descending score).
 // IoU arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction) and IEEE division so
 // the keep decisions are bit-identical to the reference's fp32 CPU path.
+#include <cuda_fp16.h>
+
 #include "yolo_ws.cuh"
 
 namespace b200det {
@@ -39,6 +41,8 @@ struct NmsParams {
     float4* kbox;               // [B][n_pad]   scratch: keepers' original boxes, per segment
     float* kacc;                // [B][n_pad][5]
     uint32_t* kpos;             // [B][n_pad]
+    uint32_t* chunk_cnt;        // [B][n_chunks] kept rows per 1024 score ranks (VARIANT 0)
+    int n_chunks;
     int n_pad, C;
     float thr;
     // VARIANT 1/2 (prior NMS)
@@ -63,7 +67,11 @@ __device__ __forceinline__ float box_area_plus1(const float4 b) {
     return __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.0f), __fadd_rn(__fsub_rn(b.w, b.y), 1.0f));
 }
 
-// true when the earlier (higher-score) box `a` removes box `b`
+// true when the earlier (higher-score) box `a` removes box `b`.
+// The decision is bit-identical to the reference's fp32 `inter / union > thr` (resp. `!(ovr <= thr)`), but the
+// IEEE division is only executed inside a +-2^-20 guard band around the threshold: outside it the comparison
+// `inter <> thr * den` is provably equivalent (rounding errors of the two products are < 2^-22 relative), and
+// inter == 0 (no overlap: ~90% of all pairs) is decided without touching the divider at all (0/den = +-0).
 template <int VARIANT>
 __device__ __forceinline__ bool removes(const float4 a, const float aa, const float4 b, const float ab, const float thr) {
     const float ix1 = fmaxf(a.x, b.x), iy1 = fmaxf(a.y, b.y);
@@ -71,34 +79,64 @@ __device__ __forceinline__ bool removes(const float4 a, const float aa, const fl
     const float iw = fmaxf(__fadd_rn(__fsub_rn(ix2, ix1), 1.0f), 0.0f);
     const float ih = fmaxf(__fadd_rn(__fsub_rn(iy2, iy1), 1.0f), 0.0f);
     const float inter = __fmul_rn(iw, ih);
-    if (VARIANT == 0) {
-        const float uni = __fadd_rn(__fsub_rn(__fadd_rn(aa, ab), inter), 1e-16f);   // accuracy.py:66
-        return __fdiv_rn(inter, uni) > thr;                                        // YOLOV3.py:323
-    } else if (VARIANT == 1) {
-        const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));    // SSD.py:292
-        return !(ovr <= thr);                                                      // SSD.py:298
-    } else {
-        const float ovr = __fdiv_rn(inter, fminf(ab, aa));                          // SSD.py:294
-        return !(ovr <= thr);
+    float den;
+    if (VARIANT == 0) den = __fadd_rn(__fsub_rn(__fadd_rn(aa, ab), inter), 1e-16f);   // accuracy.py:66
+    else if (VARIANT == 1) den = __fsub_rn(__fadd_rn(aa, ab), inter);                 // SSD.py:292
+    else den = fminf(ab, aa);                                                         // SSD.py:294
+    const bool den_ok = den == den && den != 0.0f;
+    if (inter == 0.0f) {
+        // quotient is +-0 (or NaN when den is 0/NaN)
+        if (VARIANT == 0) return den_ok && thr < 0.0f;          // 0 > thr            (YOLOV3.py:323)
+        return !(den_ok && thr >= 0.0f);                        // !(0 <= thr)        (SSD.py:298)
     }
+    if (den > 0.0f && thr > 0.0f) {
+        const float q = __fmul_rn(thr, den);
+        if (inter > __fmul_rn(q, 1.000001f)) return true;       // ratio > thr*(1+2^-21)  =>  fl(ratio) > thr
+        if (inter < __fmul_rn(q, 0.999999f)) return false;      // ratio < thr*(1-2^-21)  =>  fl(ratio) < thr
+    }
+    const float ratio = __fdiv_rn(inter, den);
+    if (VARIANT == 0) return ratio > thr;
+    return !(ratio <= thr);
 }
 
-template <int VARIANT>
+// Conservative half2 bounds of a corner box for the overlap pre-filter: lo = (x1, y1) rounded DOWN,
+// hi = (x2 + 1, y2 + 1) rounded UP.  The exact test has inter > 0 only if min(hi) > max(lo) holds for these
+// (monotone rounding), so "hmin2(hi_a, hi_b) > hmax2(lo_a, lo_b) in both halves" never misses a pair that the
+// reference arithmetic would count as overlapping; it costs 3 half2 instructions instead of 11 fp32 ones.
+__device__ __forceinline__ uint2 box_bounds_h2(const float4 b) {
+    const __half2 lo = __halves2half2(__float2half_rd(b.x), __float2half_rd(b.y));
+    const __half2 hi = __halves2half2(__float2half_ru(__fadd_ru(b.z, 1.0f)), __float2half_ru(__fadd_ru(b.w, 1.0f)));
+    uint2 r;
+    r.x = *reinterpret_cast<const unsigned*>(&lo);
+    r.y = *reinterpret_cast<const unsigned*>(&hi);
+    return r;
+}
+__device__ __forceinline__ bool may_overlap(const uint2 qa, const uint2 qb) {
+    const __half2 lo = __hmax2(*reinterpret_cast<const __half2*>(&qa.x), *reinterpret_cast<const __half2*>(&qb.x));
+    const __half2 hi = __hmin2(*reinterpret_cast<const __half2*>(&qa.y), *reinterpret_cast<const __half2*>(&qb.y));
+    return __hbgt2(hi, lo);
+}
+
+// FAST: the pre-filter is sound when "no overlap" implies "not removed", i.e. VARIANT 0 with nms_thres >= 0.
+template <int VARIANT, bool FAST>
 __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParams p) {
     __shared__ float4 s_box[kNmsT];
     __shared__ float s_area[kNmsT];
     __shared__ float s_conf[kNmsT];
+    __shared__ uint2 s_q[kNmsT];
     __shared__ unsigned long long s_L[kNmsTriWords];
     __shared__ unsigned long long s_kept[kNmsW];
+    __shared__ unsigned long long s_member[kNmsW];
     __shared__ int s_wpre[kNmsW + 1];
     __shared__ int s_own[kNmsT];
     __shared__ int s_pre[kNmsT];
     __shared__ float4 s_kb[kNmsStage];
     __shared__ float s_ka[kNmsStage];
+    __shared__ uint2 s_kq[kNmsStage];
     __shared__ int s_last_members;
 
     const int b = blockIdx.y;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const size_t img = (size_t)b * p.n_pad;
     int s, e;
     if (VARIANT == 0) {
@@ -128,8 +166,10 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
             s_box[j] = bx;
             s_area[j] = box_area_plus1(bx);
             s_conf[j] = p.cc2[img + slot].x;
+            if (FAST) s_q[j] = box_bounds_h2(bx);
             s_pre[j] = -1;
         }
+        if (tid < kNmsW) s_member[tid] = 0ull;      // 32-row groups past nc are never written by the ballots below
         __syncthreads();
 
         // ---- phase A: against keepers of earlier chunks ----------------------------------------
@@ -139,14 +179,22 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
                 const float4 kb = p.kbox[img + s + kt + tid];
                 s_kb[tid] = kb;
                 s_ka[tid] = box_area_plus1(kb);
+                if (FAST) s_kq[tid] = box_bounds_h2(kb);
             }
             __syncthreads();
             for (int j = tid; j < nc; j += kNmsThreads) {
                 if (s_pre[j] >= 0) continue;
                 const float4 bj = s_box[j];
                 const float aj = s_area[j];
-                for (int k = 0; k < nk; ++k) {
-                    if (removes<VARIANT>(s_kb[k], s_ka[k], bj, aj, thr)) { s_pre[j] = kt + k; break; }
+                if (FAST) {
+                    const uint2 qj = s_q[j];
+                    for (int k = 0; k < nk; ++k) {
+                        if (may_overlap(s_kq[k], qj) && removes<VARIANT>(s_kb[k], s_ka[k], bj, aj, thr)) { s_pre[j] = kt + k; break; }
+                    }
+                } else {
+                    for (int k = 0; k < nk; ++k) {
+                        if (removes<VARIANT>(s_kb[k], s_ka[k], bj, aj, thr)) { s_pre[j] = kt + k; break; }
+                    }
                 }
             }
             __syncthreads();
@@ -160,9 +208,32 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
                 if (s_pre[j] < 0) {
                     const float4 bj = s_box[j];
                     const float aj = s_area[j];
-                    const int iend = min(i0 + 64, j);
-                    for (int i = i0; i < iend; ++i) {
-                        if (removes<VARIANT>(s_box[i], s_area[i], bj, aj, thr)) bits |= 1ull << (i - i0);
+                    const int ni = min(64, j - i0);
+                    if (FAST) {
+                        // pass 1: half2 bounding test, branch-free; pass 2: exact test on the few candidates
+                        const uint2 qj = s_q[j];
+                        unsigned c_lo = 0u, c_hi = 0u;
+                        if (ni == 64) {
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) c_lo |= may_overlap(s_q[i0 + k], qj) ? (1u << k) : 0u;
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) c_hi |= may_overlap(s_q[i0 + 32 + k], qj) ? (1u << k) : 0u;
+                        } else {
+                            for (int k = 0; k < ni; ++k) {
+                                const unsigned m = may_overlap(s_q[i0 + k], qj) ? 1u : 0u;
+                                if (k < 32) c_lo |= m << k; else c_hi |= m << (k - 32);
+                            }
+                        }
+                        unsigned long long cand = ((unsigned long long)c_hi << 32) | c_lo;
+                        while (cand) {
+                            const int k = __ffsll((long long)cand) - 1;
+                            cand &= cand - 1ull;
+                            if (removes<VARIANT>(s_box[i0 + k], s_area[i0 + k], bj, aj, thr)) bits |= 1ull << k;
+                        }
+                    } else {
+                        for (int k = 0; k < ni; ++k) {
+                            if (removes<VARIANT>(s_box[i0 + k], s_area[i0 + k], bj, aj, thr)) bits |= 1ull << k;
+                        }
                     }
                 }
                 s_L[tri_off(j) + w] = bits;
@@ -172,7 +243,6 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
 
         // ---- sweep: exact greedy resolution by warp 0, 32 rows per step -------------------------
         if (tid < 32) {
-            const int lane = tid;
             if (lane < kNmsW) s_kept[lane] = 0ull;
             __syncwarp();
             const int ngroups = (nc + 31) >> 5;
@@ -195,14 +265,14 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
                 }
                 const bool pre = valid && !hit;
                 const unsigned cand = __ballot_sync(0xFFFFFFFFu, pre);
-                unsigned kg = 0;
-                if (cand) {
-                    const int top = 31 - __clz(cand);
-                    for (int sft = 0; sft <= top; ++sft) {
-                        const bool bit = pre && ((m & kg) == 0u);
-                        const unsigned bal = __ballot_sync(0xFFFFFFFFu, bit);
-                        kg = bal & (sft == 31 ? 0xFFFFFFFFu : ((2u << sft) - 1u));
-                    }
+                // lanes whose in-group mask is empty are decided already; only the others need the serial steps
+                const unsigned dep = __ballot_sync(0xFFFFFFFFu, pre && m != 0u);
+                unsigned kg = cand & ~dep;
+                for (unsigned dd = dep; dd; dd &= dd - 1u) {
+                    // every lane below the lowest pending one is final in kg -> that lane can be decided now
+                    const bool bit = pre && ((m & kg) == 0u);
+                    const unsigned bal = __ballot_sync(0xFFFFFFFFu, bit);
+                    kg |= bal & (dd & (0u - dd));
                 }
                 if (lane == 0 && kg) s_kept[wl] |= (unsigned long long)kg << ((g & 1) * 32);
                 __syncwarp();
@@ -216,49 +286,52 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
         __syncthreads();
         const int Kc = s_wpre[kNmsW];
 
-        // ---- owners ------------------------------------------------------------------------------
+        // ---- owners (warp-uniform trip count so that the member bitmap can be built with ballots) ------
         bool any_cross_local = false;
-        for (int j = tid; j < nc; j += kNmsThreads) {
-            int own;
-            bool is_keeper = false;
-            if (s_pre[j] >= 0) {
-                own = s_pre[j];
-                any_cross_local = true;
-            } else {
-                const int wj = j >> 6;
-                const unsigned long long below = (1ull << (j & 63)) - 1ull;
-                if ((s_kept[wj] >> (j & 63)) & 1ull) {
-                    own = Kprev + s_wpre[wj] + __popcll(s_kept[wj] & below);
-                    is_keeper = true;
+        for (int jb = (tid & ~31); jb < nc; jb += kNmsThreads) {
+            const int j = jb + lane;
+            int own = -2;
+            bool is_keeper = false, is_member = false;
+            if (j < nc) {
+                if (s_pre[j] >= 0) {
+                    own = s_pre[j];
+                    any_cross_local = true;
                 } else {
-                    const unsigned long long* row = &s_L[tri_off(j)];
-                    int i = -1;
-                    for (int w = 0; w <= wj; ++w) {
-                        const unsigned long long h = row[w] & s_kept[w];
-                        if (h) { i = (w << 6) + __ffsll((long long)h) - 1; break; }
-                    }
-                    // i >= 0 always: a non-kept, non-presuppressed row was hit by a kept row
-                    if (i >= 0) {
-                        const int wi = i >> 6;
-                        own = Kprev + s_wpre[wi] + __popcll(s_kept[wi] & ((1ull << (i & 63)) - 1ull));
+                    const int wj = j >> 6;
+                    const unsigned long long below = (1ull << (j & 63)) - 1ull;
+                    if ((s_kept[wj] >> (j & 63)) & 1ull) {
+                        own = Kprev + s_wpre[wj] + __popcll(s_kept[wj] & below);
+                        is_keeper = true;
                     } else {
-                        own = -2;
+                        const unsigned long long* row = &s_L[tri_off(j)];
+                        int i = -1;
+                        for (int w = 0; w <= wj; ++w) {
+                            const unsigned long long h = row[w] & s_kept[w];
+                            if (h) { i = (w << 6) + __ffsll((long long)h) - 1; break; }
+                        }
+                        if (i >= 0) {   // always: a non-kept, non-presuppressed row was hit by a kept row
+                            const int wi = i >> 6;
+                            own = Kprev + s_wpre[wi] + __popcll(s_kept[wi] & ((1ull << (i & 63)) - 1ull));
+                            is_member = true;
+                        }
                     }
                 }
+                s_own[j] = own;
+                if (VARIANT == 0) {
+                    if (!is_keeper) p.kpay[img + p.srank[img + c0 + j]] = kNone;
+                }
+                if (is_keeper && !(VARIANT == 0 && single)) {
+                    p.kbox[img + s + own] = s_box[j];
+                    p.kpos[img + s + own] = (uint32_t)(c0 + j);
+                }
             }
-            s_own[j] = own;
-            if (VARIANT == 0) {
-                if (!is_keeper) p.kpay[img + p.srank[img + c0 + j]] = kNone;
-            }
-            if (is_keeper && !(VARIANT == 0 && single)) {
-                p.kbox[img + s + own] = s_box[j];
-                p.kpos[img + s + own] = (uint32_t)(c0 + j);
-            }
+            const unsigned mb = __ballot_sync(0xFFFFFFFFu, is_member);
+            if (lane == 0) reinterpret_cast<unsigned*>(s_member)[jb >> 5] = mb;
         }
         const int any_cross = __syncthreads_or(any_cross_local ? 1 : 0);
 
         if (VARIANT == 0) {
-            // ---- merge sums, pulled per keeper in row order ----------------------------------------
+            // ---- merge sums, pulled per keeper over the member bitmap in row order ------------------
             for (int j = tid; j < nc; j += kNmsThreads) {
                 const int wj = j >> 6;
                 if (s_pre[j] >= 0 || !((s_kept[wj] >> (j & 63)) & 1ull)) continue;
@@ -267,21 +340,28 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
                 const float w0 = s_conf[j];
                 float ax = __fmul_rn(w0, bj.x), ay = __fmul_rn(w0, bj.y);
                 float az = __fmul_rn(w0, bj.z), aw = __fmul_rn(w0, bj.w), ws = w0;
-                for (int m = j + 1; m < nc; ++m) {
-                    if (s_own[m] == kidx) {
-                        const float4 bm = s_box[m];
-                        const float wm = s_conf[m];
-                        ax = __fadd_rn(ax, __fmul_rn(wm, bm.x));
-                        ay = __fadd_rn(ay, __fmul_rn(wm, bm.y));
-                        az = __fadd_rn(az, __fmul_rn(wm, bm.z));
-                        aw = __fadd_rn(aw, __fmul_rn(wm, bm.w));
-                        ws = __fadd_rn(ws, wm);
+                for (int w = wj; w < Wc; ++w) {
+                    unsigned long long mbits = s_member[w];
+                    if (w == wj) mbits &= ~((2ull << (j & 63)) - 1ull);     // rows after j only
+                    while (mbits) {
+                        const int m = (w << 6) + __ffsll((long long)mbits) - 1;
+                        mbits &= mbits - 1ull;
+                        if (s_own[m] == kidx) {
+                            const float4 bm = s_box[m];
+                            const float wm = s_conf[m];
+                            ax = __fadd_rn(ax, __fmul_rn(wm, bm.x));
+                            ay = __fadd_rn(ay, __fmul_rn(wm, bm.y));
+                            az = __fadd_rn(az, __fmul_rn(wm, bm.z));
+                            aw = __fadd_rn(aw, __fmul_rn(wm, bm.w));
+                            ws = __fadd_rn(ws, wm);
+                        }
                     }
                 }
                 if (single) {
                     const uint32_t r = p.srank[img + c0 + j];
                     p.kpay[img + r] = p.spay[img + c0 + j];
                     p.mbox[img + r] = make_float4(__fdiv_rn(ax, ws), __fdiv_rn(ay, ws), __fdiv_rn(az, ws), __fdiv_rn(aw, ws));
+                    atomicAdd(&p.chunk_cnt[(size_t)b * p.n_chunks + (r >> kEmitShift)], 1u);
                 } else {
                     float* acc = p.kacc + (img + s + kidx) * 5;
                     acc[0] = ax; acc[1] = ay; acc[2] = az; acc[3] = aw; acc[4] = ws;
@@ -339,6 +419,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
                 p.kpay[img + r] = p.spay[img + pos];
                 p.mbox[img + r] = make_float4(__fdiv_rn(acc[0], ws), __fdiv_rn(acc[1], ws), __fdiv_rn(acc[2], ws),
                                               __fdiv_rn(acc[3], ws));
+                atomicAdd(&p.chunk_cnt[(size_t)b * p.n_chunks + (r >> kEmitShift)], 1u);
             }
         }
     } else {
@@ -369,44 +450,76 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
     }
 }
 
-// K3b — ordered emit: compact the kept rows of every image in ascending score rank.
+// K3b — ordered emit: compact the kept rows of every image in ascending score rank.  One CTA per 1024 ranks;
+// its output base is the sum of the kept-row counts of the preceding chunks (accumulated by the NMS kernel).
 struct EmitParams {
     const uint32_t* count;
     const uint32_t* kpay;
     const float4* mbox;
     const float2* cc2;
     const uint32_t* orig;
+    const uint32_t* chunk_cnt;
     float* out_rows;       // [B][n_pad][7]
     int32_t* out_index;    // [B][n_pad] or null
     int32_t* out_count;    // [B]
-    int n_pad;
+    int n_pad, n_chunks;
 };
 
-__global__ void __launch_bounds__(1024) yolo_emit_kernel(const EmitParams p) {
+constexpr int kEmitThreads = kEmitChunk / 4;   // 4 consecutive ranks per thread
+
+__global__ void __launch_bounds__(kEmitThreads) yolo_emit_kernel(const EmitParams p) {
     __shared__ int s_scan[33];
-    const int b = blockIdx.x;
+    __shared__ float s_rows[kEmitChunk * 7];    // kept rows of this chunk, packed -> coalesced global stores
+    __shared__ int s_idx[kEmitChunk];
+    const int b = blockIdx.y, c = blockIdx.x, tid = threadIdx.x;
     const size_t img = (size_t)b * p.n_pad;
     const int n = (int)p.count[b];
-    int base = 0;
-    for (int r0 = 0; r0 < n; r0 += 1024) {
-        const int r = r0 + threadIdx.x;
-        uint32_t pay = kNone;
-        if (r < n) pay = p.kpay[img + r];
-        const int flag = pay != kNone ? 1 : 0;
-        int total;
-        const int ex = block_exclusive_scan(flag, s_scan, &total);
-        if (flag) {
-            const uint32_t slot = pay & kSlotMask;
-            const float4 mb = p.mbox[img + r];
-            const float2 cc = p.cc2[img + slot];
-            float* o = p.out_rows + (img + base + ex) * 7;
-            o[0] = mb.x; o[1] = mb.y; o[2] = mb.z; o[3] = mb.w;
-            o[4] = cc.x; o[5] = cc.y; o[6] = (float)(pay >> kSlotBits);     // YOLOV3.py:318-319
-            if (p.out_index) p.out_index[img + base + ex] = (int32_t)p.orig[img + slot];
-        }
-        base += total;
+    const int r0 = c << kEmitShift;
+    if (c > 0 && r0 >= n) return;
+    const uint32_t* cc = p.chunk_cnt + (size_t)b * p.n_chunks;
+    const int upto = c == 0 ? p.n_chunks : c;          // chunk 0 also totals the image
+    int part = 0;
+    for (int t = tid; t < upto; t += kEmitThreads) part += (int)cc[t];
+    int base;
+    block_exclusive_scan(part, s_scan, &base);
+    if (c == 0) {
+        if (tid == 0) p.out_count[b] = base;
+        base = 0;
     }
-    if (threadIdx.x == 0) p.out_count[b] = base;
+    const int r = r0 + tid * 4;
+    uint32_t pay[4] = {kNone, kNone, kNone, kNone};
+    if (r + 3 < n) {
+        const uint4 v = *reinterpret_cast<const uint4*>(p.kpay + img + r);
+        pay[0] = v.x; pay[1] = v.y; pay[2] = v.z; pay[3] = v.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (r + i < n) pay[i] = p.kpay[img + r + i];
+    }
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cnt += pay[i] != kNone ? 1 : 0;
+    int total;
+    int ex = block_exclusive_scan(cnt, s_scan, &total);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (pay[i] != kNone) {
+            const uint32_t slot = pay[i] & kSlotMask;
+            const float4 mb = p.mbox[img + r + i];
+            const float2 cf = p.cc2[img + slot];
+            float* o = s_rows + ex * 7;
+            o[0] = mb.x; o[1] = mb.y; o[2] = mb.z; o[3] = mb.w;
+            o[4] = cf.x; o[5] = cf.y; o[6] = (float)(pay[i] >> kSlotBits);     // YOLOV3.py:318-319
+            if (p.out_index) s_idx[ex] = (int)p.orig[img + slot];
+            ++ex;
+        }
+    }
+    __syncthreads();
+    float* dst = p.out_rows + (img + base) * 7;
+    for (int i = tid; i < total * 7; i += kEmitThreads) dst[i] = s_rows[i];
+    if (p.out_index) {
+        int32_t* di = p.out_index + img + base;
+        for (int i = tid; i < total; i += kEmitThreads) di[i] = s_idx[i];
+    }
 }
 
 int yolo_stage_nms(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -419,10 +532,11 @@ int yolo_stage_nms(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cudaSt
     p.seg_off = w.seg_off; p.count = w.count;
     p.spay = yolo_sorted_pay(w); p.srank = yolo_sorted_rank(w);
     p.box4 = w.box4; p.cc2 = w.cc2; p.kpay = w.kpay; p.mbox = w.mbox;
-    p.kbox = w.kbox; p.kacc = w.kacc; p.kpos = w.kpos;
+    p.kbox = w.kbox; p.kacc = w.kacc; p.kpos = w.kpos; p.chunk_cnt = w.chunk_cnt; p.n_chunks = w.n_chunks;
     p.n_pad = w.n_pad; p.C = w.C; p.thr = d->nms_thres;
     dim3 grid(d->num_classes, d->batch);
-    nms_segment_kernel<0><<<grid, kNmsThreads, 0, st>>>(p);
+    if (d->nms_thres >= 0.0f) nms_segment_kernel<0, true><<<grid, kNmsThreads, 0, st>>>(p);
+    else nms_segment_kernel<0, false><<<grid, kNmsThreads, 0, st>>>(p);
     B2_LAUNCH_CHECK("nms_segment_kernel<0>");
     return 0;
 }
@@ -435,9 +549,10 @@ int yolo_stage_emit(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, float
     YoloWs w;
     yolo_ws_layout(d, ws, &w);
     EmitParams p;
-    p.count = w.count; p.kpay = w.kpay; p.mbox = w.mbox; p.cc2 = w.cc2; p.orig = w.orig;
-    p.out_rows = out_rows; p.out_index = out_index; p.out_count = out_count; p.n_pad = w.n_pad;
-    yolo_emit_kernel<<<d->batch, 1024, 0, st>>>(p);
+    p.count = w.count; p.kpay = w.kpay; p.mbox = w.mbox; p.cc2 = w.cc2; p.orig = w.orig; p.chunk_cnt = w.chunk_cnt;
+    p.out_rows = out_rows; p.out_index = out_index; p.out_count = out_count; p.n_pad = w.n_pad; p.n_chunks = w.n_chunks;
+    dim3 grid(w.n_chunks, d->batch);
+    yolo_emit_kernel<<<grid, kEmitThreads, 0, st>>>(p);
     B2_LAUNCH_CHECK("yolo_emit_kernel");
     return 0;
 }
@@ -454,8 +569,8 @@ int prior_nms_launch_raw(const uint32_t* count, const uint32_t* spay, const floa
     p.orig = orig; p.dense_box = dense_box; p.dense_label = dense_label; p.P = P;
     p.out_rows = out_rows; p.out_index = out_index; p.out_count = out_count;
     dim3 grid(1, batch);
-    if (mode_min) nms_segment_kernel<2><<<grid, kNmsThreads, 0, st>>>(p);
-    else nms_segment_kernel<1><<<grid, kNmsThreads, 0, st>>>(p);
+    if (mode_min) nms_segment_kernel<2, false><<<grid, kNmsThreads, 0, st>>>(p);
+    else nms_segment_kernel<1, false><<<grid, kNmsThreads, 0, st>>>(p);
     B2_LAUNCH_CHECK("nms_segment_kernel<prior>");
     return 0;
 }

@@ -20,7 +20,9 @@ constexpr int kPriMaxCC = 128;     // classes staged per round
 struct PriorWs {
     uint32_t* count;        // [B]   (zeroed)
     uint32_t* digit_hist;   // [B][kMaxPasses][256] (zeroed)
+    uint32_t* ticket;       // [kMaxPasses][B] (zeroed)
     size_t zero_bytes;
+    uint32_t* status;       // [kMaxPasses][B][sort_tiles][256]
     uint32_t* tile_count;   // [B][n_tiles]
     uint32_t* tile_prefix;  // [B][n_tiles]
     float4* box4;           // [B][n_pad]
@@ -46,7 +48,9 @@ static void prior_ws_layout(const b200det_prior_desc* d, void* base, PriorWs* w)
     auto take = [&](size_t bytes) { char* r = p + off; off = align_up(off + bytes, 256); return r; };
     w->count = (uint32_t*)take(B * 4);
     w->digit_hist = (uint32_t*)take(B * kMaxPasses * 256 * 4);
+    w->ticket = (uint32_t*)take((size_t)kMaxPasses * B * 4);
     w->zero_bytes = off;
+    w->status = (uint32_t*)take((size_t)kMaxPasses * B * ceil_div(w->n_pad, kSortTile) * 256 * 4);
     w->tile_count = (uint32_t*)take(B * (size_t)w->n_tiles * 4);
     w->tile_prefix = (uint32_t*)take(B * (size_t)w->n_tiles * 4);
     w->box4 = (float4*)take(B * P * 16);
@@ -193,8 +197,9 @@ __global__ void __launch_bounds__(256) tile_prefix_kernel(const uint32_t* __rest
 }
 
 // from segsort.cu / nms.cu
-int score_sort_launch(const uint32_t* tile_count, const uint32_t* count, uint32_t* digit_hist, uint32_t* key[2],
-                      uint32_t* pay[2], int n_pad, int n_tiles, int batch, cudaStream_t st);
+int score_sort_launch(const uint32_t* tile_count, const uint32_t* count, uint32_t* digit_hist, uint32_t* ticket,
+                      uint32_t* status, uint32_t* key[2], uint32_t* pay[2], int n_pad, int n_tiles, int batch,
+                      cudaStream_t st);
 struct NmsParams;
 int prior_nms_launch_raw(const uint32_t* count, const uint32_t* spay, const float4* box4, const float2* cc2,
                          float4* kbox, uint32_t* kpos, int n_pad, float thr, int topk, int compat,
@@ -257,7 +262,7 @@ int prior_nms_pipeline(const b200det_prior_desc* d, void* ws, size_t ws_bytes, f
     tile_prefix_kernel<<<d->batch, 256, 0, st>>>(w.tile_count, w.tile_prefix, w.n_tiles);
     B2_LAUNCH_CHECK("tile_prefix_kernel");
 
-    rc = score_sort_launch(w.tile_count, w.count, w.digit_hist, w.key, w.pay, w.n_pad, w.n_tiles, d->batch, st);
+    rc = score_sort_launch(w.tile_count, w.count, w.digit_hist, w.ticket, w.status, w.key, w.pay, w.n_pad, w.n_tiles, d->batch, st);
     if (rc) return rc;
     rc = prior_nms_launch_raw(w.count, w.pay[0], w.box4, w.cc2, w.kbox, w.kpos, w.n_pad, d->nms_thresh, d->topk,
                               d->compat, w.tile_prefix, w.n_tiles, w.orig, w.dense_box, w.dense_label, d->num_priors,

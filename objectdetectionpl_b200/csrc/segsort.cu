@@ -7,9 +7,11 @@
 // global score rank; it is carried through the class pass(es) so kept rows can be emitted in the
 // reference's descending-score order without a second sort.
 //
-// Layout: one CTA sorts one 4096-key tile of one image per pass.  Cross-CTA prefix = "recount": a CTA
-// re-reads the digits of the preceding tiles of ITS image (<= a few L2-resident tiles) instead of
-// spinning on other CTAs — no inter-CTA dependency, no forward-progress assumptions, bit-reproducible.
+// Layout: one CTA sorts one 4096-key tile of one image per pass.  The cross-tile prefix of a digit is
+// obtained by decoupled look-back over the preceding tiles OF THE SAME IMAGE (one 32-bit status word per
+// (tile, digit): 2 flag bits + 30-bit count).  Tiles are handed out by a per-(pass, image) ticket counter, so
+// every tile a CTA waits for belongs to a CTA that has already started — no forward-progress assumption on
+// the block scheduler.  The result is independent of timing (counts are integers), i.e. bit-reproducible.
 // Per-image digit totals of all passes come from one up-front histogram kernel (totals are
 // permutation-invariant).  In-tile ranking is the stable warp-match ranking (match.any + per-warp
 // digit counters), 8 bits per pass.
@@ -21,6 +23,9 @@ struct SortParams {
     const uint32_t* tile_count;  // [B][n_tiles] (first pass: tile-sparse input), else unused
     const uint32_t* count;       // [B]
     uint32_t* digit_hist;        // [B][kMaxPasses][256]
+    uint32_t* ticket;            // [kMaxPasses][B]
+    uint32_t* status;            // [kMaxPasses][B][sort_tiles][256]
+    int sort_tiles, B;
     const uint32_t* key_in;
     const uint32_t* pay_in;
     const uint32_t* rank_in;
@@ -37,9 +42,22 @@ __device__ __forceinline__ bool sparse_valid(const uint32_t* tile_count_img, int
     return (uint32_t)(e & (kTile - 1)) < tile_count_img[e >> kTileShift];
 }
 
+// Lanes of the warp holding the same 8-bit digit (all 32 lanes must call).  Built from 8 ballots: the
+// hardware match.any instruction measured ~64 issue cycles per warp on B200, these are plain votes.
+__device__ __forceinline__ unsigned match_digit8(uint32_t digit, bool valid) {
+    unsigned peers = __ballot_sync(0xFFFFFFFFu, valid);
+#pragma unroll
+    for (int bit = 0; bit < 8; ++bit) {
+        const bool one = (digit >> bit) & 1u;
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, one);
+        peers &= one ? bal : ~bal;
+    }
+    return peers;
+}
+
 // Warp-aggregated shared-memory histogram increment (all 32 lanes must call).
 __device__ __forceinline__ void hist_add(int* hist, uint32_t digit, bool valid) {
-    const unsigned peers = __match_any_sync(0xFFFFFFFFu, valid ? digit : 0xFFFFu);
+    const unsigned peers = match_digit8(digit, valid);
     if (valid && (peers & lanemask_lt()) == 0) atomicAdd(&hist[digit], __popc(peers));
 }
 
@@ -52,6 +70,8 @@ __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const SortParam
     if (e0 >= p.n_pad) return;
     const uint32_t* tc = p.tile_count + (size_t)b * p.n_tiles;
     for (int i = threadIdx.x; i < kMaxPasses * 256; i += kSortThreads) (&h[0][0])[i] = 0;
+    for (int ps = 0; ps < kMaxPasses; ++ps)      // look-back words of this (image, tile), all passes
+        p.status[(((size_t)ps * p.B + b) * p.sort_tiles + blockIdx.x) * 256 + threadIdx.x] = 0u;
     __syncthreads();
     const size_t img = (size_t)b * p.n_pad;
     const int npass = kScorePasses + p.n_cls_passes;
@@ -74,72 +94,95 @@ __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const SortParam
     }
 }
 
+__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+constexpr uint32_t kFlagAgg = 1u << 30, kFlagPrefix = 2u << 30, kValMask = (1u << 30) - 1u;
+
 // One radix pass.  FIRST: input is tile-sparse (validity from tile_count), else dense [0, count).
 // SRC: 0 = digit from key, 1 = digit from payload.  RANK: 0 none, 1 = write input position as rank,
 // 2 = carry rank_in -> rank_out.  MOVE_KEY: keys are only moved while score passes remain.
 template <bool FIRST, int SRC, int RANK, bool MOVE_KEY>
 __global__ void __launch_bounds__(kSortThreads) sort_pass_kernel(const SortParams p) {
     constexpr int NW = kSortThreads / 32;
-    __shared__ int s_pre[256];            // digit counts of the preceding tiles of this image
     __shared__ int s_warp[NW][256];       // per-warp running digit counters -> destination bases
     __shared__ int s_scan[33];
+    __shared__ int s_tile;
 
     const int b = blockIdx.y;
-    const int e0 = blockIdx.x * kSortTile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = (int)atomicAdd(&p.ticket[(size_t)p.pass * p.B + b], 1u);
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s_warp[w][tid] = 0;
+    __syncthreads();
+    const int tile = s_tile;
+    const int e0 = tile * kSortTile;
     const int limit = FIRST ? p.n_pad : (int)p.count[b];
     if (e0 >= limit) return;
     const uint32_t* tc = p.tile_count + (size_t)b * p.n_tiles;
     const size_t img = (size_t)b * p.n_pad;
-    const uint32_t* din = SRC == 0 ? p.key_in : p.pay_in;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    s_pre[tid] = 0;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) s_warp[w][tid] = 0;
-    __syncthreads();
-
-    // ---- recount: digits of all elements before this tile -------------------------------------
-    for (int e = tid; e < e0; e += kSortThreads) {       // e0 is a multiple of kSortThreads
-        const bool valid = FIRST ? sparse_valid(tc, e) : true;
-        uint32_t d = 0;
-        if (valid) d = (din[img + e] >> p.shift) & 0xFFu;
-        hist_add(s_pre, d, valid);
-    }
-
-    // ---- load own items (warp-striped: item k of lane l = warp_base + 32k + l) -----------------
+    // ---- load own items (warp-striped: item k of lane l = warp_base + 32k + l) and rank them ---------
     uint32_t key[kSortItems], pay[kSortItems], rnk[kSortItems];
     int lrank[kSortItems];               // rank inside the warp's digit run, or -1
     uint32_t dig[kSortItems];
     const int wbase = e0 + warp * (32 * kSortItems);
+    bool valid[kSortItems];
 #pragma unroll
     for (int k = 0; k < kSortItems; ++k) {
         const int e = wbase + k * 32 + lane;
-        const bool valid = e < limit && (FIRST ? sparse_valid(tc, e) : true);
+        valid[k] = e < limit && (FIRST ? sparse_valid(tc, e) : true);
         key[k] = 0; pay[k] = 0; rnk[k] = 0;
-        if (valid) {
+        if (valid[k]) {
             if (MOVE_KEY || SRC == 0) key[k] = p.key_in[img + e];
             pay[k] = p.pay_in[img + e];
             if (RANK == 1) rnk[k] = (uint32_t)e;
             if (RANK == 2) rnk[k] = p.rank_in[img + e];
         }
+    }
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
         const uint32_t src = SRC == 0 ? key[k] : pay[k];
         dig[k] = (src >> p.shift) & 0xFFu;
-        const unsigned peers = __match_any_sync(0xFFFFFFFFu, valid ? dig[k] : 0xFFFFu);
+        const unsigned peers = match_digit8(dig[k], valid[k]);
         int base = 0;
-        if (valid) base = s_warp[warp][dig[k]];
+        if (valid[k]) base = s_warp[warp][dig[k]];
         __syncwarp();
-        if (valid && (peers & lanemask_lt()) == 0) s_warp[warp][dig[k]] = base + __popc(peers);
+        if (valid[k] && (peers & lanemask_lt()) == 0) s_warp[warp][dig[k]] = base + __popc(peers);
         __syncwarp();
-        lrank[k] = valid ? base + __popc(peers & lanemask_lt()) : -1;
+        lrank[k] = valid[k] ? base + __popc(peers & lanemask_lt()) : -1;
     }
     __syncthreads();
 
-    // ---- destination bases: digit_start (image totals) + preceding tiles + preceding warps ------
+    // ---- per-digit: tile count -> publish -> look back over the preceding tiles of this image ------
     {
+        int cnt = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) cnt += s_warp[w][tid];
+        uint32_t* stat = p.status + (((size_t)p.pass * p.B + b) * p.sort_tiles) * 256 + tid;
+        int excl = 0;
+        if (tile == 0) {
+            st_relaxed(stat, kFlagPrefix | (uint32_t)cnt);
+        } else {
+            st_relaxed(stat + (size_t)tile * 256, kFlagAgg | (uint32_t)cnt);
+            for (int tt = tile - 1; tt >= 0; --tt) {
+                uint32_t v;
+                while (((v = ld_relaxed(stat + (size_t)tt * 256)) >> 30) == 0u) __nanosleep(40);
+                excl += (int)(v & kValMask);
+                if (v & kFlagPrefix) break;
+            }
+            st_relaxed(stat + (size_t)tile * 256, kFlagPrefix | (uint32_t)(excl + cnt));
+        }
+        // destination bases: digit_start (image totals) + preceding tiles + preceding warps
         const uint32_t* tot = p.digit_hist + ((size_t)b * kMaxPasses + p.pass) * 256;
         int total_unused;
         const int dstart = block_exclusive_scan((int)tot[tid], s_scan, &total_unused);
-        int run = dstart + s_pre[tid];
+        int run = dstart + excl;
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
             const int c = s_warp[w][tid];
@@ -161,11 +204,13 @@ __global__ void __launch_bounds__(kSortThreads) sort_pass_kernel(const SortParam
 }
 
 // Score-only sort (4 passes) for the prior pipeline; the sorted payload ends in pay[0].
-int score_sort_launch(const uint32_t* tile_count, const uint32_t* count, uint32_t* digit_hist, uint32_t* key[2],
-                      uint32_t* pay[2], int n_pad, int n_tiles, int batch, cudaStream_t st) {
+int score_sort_launch(const uint32_t* tile_count, const uint32_t* count, uint32_t* digit_hist, uint32_t* ticket,
+                      uint32_t* status, uint32_t* key[2], uint32_t* pay[2], int n_pad, int n_tiles, int batch,
+                      cudaStream_t st) {
     SortParams p;
     memset(&p, 0, sizeof(p));
     p.tile_count = tile_count; p.count = count; p.digit_hist = digit_hist;
+    p.ticket = ticket; p.status = status; p.sort_tiles = ceil_div(n_pad, kSortTile); p.B = batch;
     p.n_pad = n_pad; p.n_tiles = n_tiles; p.n_cls_passes = 0;
     dim3 grid(ceil_div(n_pad, kSortTile), batch);
     p.key_in = key[0]; p.pay_in = pay[0];
@@ -192,6 +237,7 @@ int yolo_stage_sort(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cudaS
     SortParams p;
     memset(&p, 0, sizeof(p));
     p.tile_count = w.tile_count; p.count = w.count; p.digit_hist = w.digit_hist;
+    p.ticket = w.ticket; p.status = w.status; p.sort_tiles = w.sort_tiles; p.B = w.B;
     p.n_pad = w.n_pad; p.n_tiles = w.n_tiles; p.n_cls_passes = w.n_cls_passes;
     dim3 grid(ceil_div(w.n_pad, kSortTile), d->batch);
 

@@ -6,13 +6,18 @@ namespace b200det {
 
 constexpr int kScorePasses = 4;   // 32-bit score key, 8 bits per pass
 constexpr int kMaxPasses = 6;     // + up to two class passes (12-bit class id)
+constexpr int kEmitShift = 10;    // emit chunk = 1024 score ranks
+constexpr int kEmitChunk = 1 << kEmitShift;
 
 struct YoloWs {
     // --- zeroed at the start of every call (one contiguous memset) ---
     uint32_t* count;       // [B]            surviving candidates per image
     uint32_t* cls_hist;    // [B][C]         survivors per (image, class)
     uint32_t* digit_hist;  // [B][kMaxPasses][256] per-image digit totals of every radix pass
+    uint32_t* ticket;      // [kMaxPasses][B]     dynamic tile tickets of the radix passes
+    uint32_t* chunk_cnt;   // [B][n_chunks]       kept rows per 1024 score ranks
     size_t zero_bytes;
+    uint32_t* status;      // [kMaxPasses][B][sort_tiles][256] decoupled look-back words (zeroed by the histogram kernel)
     // --- plain scratch ---
     uint32_t* seg_off;     // [B][C+1]       class segment offsets in the (class, score) order
     uint32_t* tile_count;  // [B][n_tiles]   survivors per candidate tile (tile-sparse layout)
@@ -28,7 +33,7 @@ struct YoloWs {
     float* kacc;           // [B][n_pad][5]  per segment: running merge sums (multi-chunk segments)
     uint32_t* kpos;        // [B][n_pad]     per segment: sorted position of keeper k
     size_t total_bytes;
-    int B, C, N, n_pad, n_tiles, n_cls_passes;
+    int B, C, N, n_pad, n_tiles, n_cls_passes, n_chunks, sort_tiles;
 };
 
 inline int yolo_counts(const b200det_yolo_desc* d, int* n_out, int* n_pad_out) {
@@ -46,13 +51,18 @@ inline void yolo_ws_layout(const b200det_yolo_desc* d, void* base, YoloWs* w) {
     const size_t B = (size_t)d->batch, C = (size_t)d->num_classes, P = (size_t)n_pad;
     w->B = d->batch; w->C = d->num_classes; w->N = N; w->n_pad = n_pad; w->n_tiles = n_pad / kTile;
     w->n_cls_passes = d->num_classes <= 256 ? 1 : 2;
+    w->n_chunks = (n_pad + kEmitChunk - 1) / kEmitChunk;
+    w->sort_tiles = (n_pad + kSortTile - 1) / kSortTile;
     char* p = (char*)base;
     size_t off = 0;
     auto take = [&](size_t bytes) { char* r = p + off; off = align_up(off + bytes, 256); return r; };
     w->count = (uint32_t*)take(B * 4);
     w->cls_hist = (uint32_t*)take(B * C * 4);
     w->digit_hist = (uint32_t*)take(B * kMaxPasses * 256 * 4);
+    w->ticket = (uint32_t*)take((size_t)kMaxPasses * B * 4);
+    w->chunk_cnt = (uint32_t*)take(B * (size_t)w->n_chunks * 4);
     w->zero_bytes = off;
+    w->status = (uint32_t*)take((size_t)kMaxPasses * B * w->sort_tiles * 256 * 4);
     w->seg_off = (uint32_t*)take(B * (C + 1) * 4);
     w->tile_count = (uint32_t*)take(B * (size_t)w->n_tiles * 4);
     w->box4 = (float4*)take(B * P * 16);
