@@ -213,17 +213,16 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
                         // pass 1: half2 bounding test, branch-free; pass 2: exact test on the few candidates
                         const uint2 qj = s_q[j];
                         unsigned c_lo = 0u, c_hi = 0u;
-                        if (ni == 64) {
+                        // all 64 columns of the word are tested (rows >= j hold valid or stale-but-harmless bounds)
+                        // and the columns >= ni are masked off afterwards: no variable-trip-count loop on the diagonal
 #pragma unroll
-                            for (int k = 0; k < 32; ++k) c_lo |= may_overlap(s_q[i0 + k], qj) ? (1u << k) : 0u;
+                        for (int k = 0; k < 32; ++k) c_lo |= may_overlap(s_q[i0 + k], qj) ? (1u << k) : 0u;
+                        if (ni > 32) {
 #pragma unroll
                             for (int k = 0; k < 32; ++k) c_hi |= may_overlap(s_q[i0 + 32 + k], qj) ? (1u << k) : 0u;
-                        } else {
-                            for (int k = 0; k < ni; ++k) {
-                                const unsigned m = may_overlap(s_q[i0 + k], qj) ? 1u : 0u;
-                                if (k < 32) c_lo |= m << k; else c_hi |= m << (k - 32);
-                            }
                         }
+                        if (ni < 32) c_lo &= (1u << ni) - 1u;
+                        else if (ni < 64) c_hi &= (1u << (ni - 32)) - 1u;
                         unsigned long long cand = ((unsigned long long)c_hi << 32) | c_lo;
                         while (cand) {
                             const int k = __ffsll((long long)cand) - 1;
@@ -340,12 +339,14 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
                 const float w0 = s_conf[j];
                 float ax = __fmul_rn(w0, bj.x), ay = __fmul_rn(w0, bj.y);
                 float az = __fmul_rn(w0, bj.z), aw = __fmul_rn(w0, bj.w), ws = w0;
-                for (int w = wj; w < Wc; ++w) {
-                    unsigned long long mbits = s_member[w];
-                    if (w == wj) mbits &= ~((2ull << (j & 63)) - 1ull);     // rows after j only
+                const unsigned* mem32 = reinterpret_cast<const unsigned*>(s_member);
+                const int h0 = j >> 5, nh = (nc + 31) >> 5;
+                for (int h = h0; h < nh; ++h) {
+                    unsigned mbits = mem32[h];
+                    if (h == h0) mbits &= ~((2u << (j & 31)) - 1u);          // rows after j only
                     while (mbits) {
-                        const int m = (w << 6) + __ffsll((long long)mbits) - 1;
-                        mbits &= mbits - 1ull;
+                        const int m = (h << 5) + __ffs((int)mbits) - 1;
+                        mbits &= mbits - 1u;
                         if (s_own[m] == kidx) {
                             const float4 bm = s_box[m];
                             const float wm = s_conf[m];

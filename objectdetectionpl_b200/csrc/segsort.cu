@@ -19,6 +19,8 @@
 
 namespace b200det {
 
+int seg_scan_launch(const uint32_t* cls_hist, uint32_t* seg_off, int C, int batch, cudaStream_t st);
+
 struct SortParams {
     const uint32_t* tile_count;  // [B][n_tiles] (first pass: tile-sparse input), else unused
     const uint32_t* count;       // [B]
@@ -241,6 +243,8 @@ int yolo_stage_sort(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cudaS
     p.n_pad = w.n_pad; p.n_tiles = w.n_tiles; p.n_cls_passes = w.n_cls_passes;
     dim3 grid(ceil_div(w.n_pad, kSortTile), d->batch);
 
+    rc = seg_scan_launch(w.cls_hist, w.seg_off, d->num_classes, d->batch, st);
+    if (rc) return rc;
     p.key_in = w.key[0]; p.pay_in = w.pay[0];
     sort_hist_kernel<<<grid, kSortThreads, 0, st>>>(p);
     B2_LAUNCH_CHECK("sort_hist_kernel");

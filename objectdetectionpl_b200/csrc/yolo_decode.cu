@@ -54,8 +54,8 @@ __device__ __forceinline__ void argmax_step(float v, int c, float& best, int& be
     if (!(v <= best) && (best == best)) { best = v; besti = c; }
 }
 
-template <int VEC, int MODE>
-__global__ void __launch_bounds__(kTile / VEC)
+template <int VEC, int MODE, int U, int MINB>
+__global__ void __launch_bounds__(kTile / VEC, MINB)
 yolo_decode_filter_kernel(const K1Params p) {
     constexpr int NT = kTile / VEC;
     extern __shared__ int s_hist[];          // [C]
@@ -102,7 +102,6 @@ yolo_decode_filter_kernel(const K1Params p) {
             for (int v = 0; v < VEC; ++v) { best[v] = v0[v]; besti[v] = 0; }
         }
         int c = 1;
-        constexpr int U = 8;
         for (; c + U <= p.C; c += U) {
             float buf[U][VEC];
 #pragma unroll
@@ -240,15 +239,17 @@ template <int VEC>
 static int launch_k1(const b200det_yolo_desc* d, const K1Params& p, cudaStream_t st) {
     dim3 grid(p.n_tiles, d->batch);
     const size_t smem = (size_t)d->num_classes * sizeof(int);
+    // U = 8 loads in flight per thread, <= 80 registers (6 CTAs/SM): best of the measured (U, occupancy, cache-hint,
+    // 128/256-bit) variants on B200, all of which sit within 4% of each other (see DESIGN.md, K1 tuning).
     switch (d->decode_mode) {
         case B200DET_DECODE_NONE:
-            yolo_decode_filter_kernel<VEC, B200DET_DECODE_NONE><<<grid, kTile / VEC, smem, st>>>(p);
+            yolo_decode_filter_kernel<VEC, B200DET_DECODE_NONE, 8, 6><<<grid, kTile / VEC, smem, st>>>(p);
             break;
         case B200DET_DECODE_YOLO_EXP:
-            yolo_decode_filter_kernel<VEC, B200DET_DECODE_YOLO_EXP><<<grid, kTile / VEC, smem, st>>>(p);
+            yolo_decode_filter_kernel<VEC, B200DET_DECODE_YOLO_EXP, 8, 5><<<grid, kTile / VEC, smem, st>>>(p);
             break;
         default:
-            yolo_decode_filter_kernel<VEC, B200DET_DECODE_YOLOV5><<<grid, kTile / VEC, smem, st>>>(p);
+            yolo_decode_filter_kernel<VEC, B200DET_DECODE_YOLOV5, 8, 5><<<grid, kTile / VEC, smem, st>>>(p);
             break;
     }
     B2_LAUNCH_CHECK("yolo_decode_filter_kernel");
@@ -286,9 +287,12 @@ int yolo_stage_decode(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cud
     p.box4 = w.box4; p.cc2 = w.cc2; p.orig = w.orig; p.key = w.key[0]; p.pay = w.pay[0];
     p.tile_count = w.tile_count; p.count = w.count; p.cls_hist = w.cls_hist;
 
-    rc = vec4 ? launch_k1<4>(d, p, st) : launch_k1<1>(d, p, st);
-    if (rc) return rc;
-    seg_scan_kernel<<<d->batch, 256, 0, st>>>(w.cls_hist, w.seg_off, d->num_classes);
+    return vec4 ? launch_k1<4>(d, p, st) : launch_k1<1>(d, p, st);
+}
+
+// class segment offsets; launched at the head of the sort stage (only the NMS needs them)
+int seg_scan_launch(const uint32_t* cls_hist, uint32_t* seg_off, int C, int batch, cudaStream_t st) {
+    seg_scan_kernel<<<batch, 256, 0, st>>>(cls_hist, seg_off, C);
     B2_LAUNCH_CHECK("seg_scan_kernel");
     return 0;
 }
