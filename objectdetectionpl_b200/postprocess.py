@@ -156,6 +156,8 @@ def prior_non_max_suppression(self, predictions, topk=100, nms_thresh=0.5, class
     `(x1, y1, x2, y2, 0, score, label)`; compat=True reproduces the reference's quirks (the last
     surviving box is dropped, boxes/labels gathered with score-filtered indices, IndexError when exactly
     one candidate passes the score threshold)."""
+    if mode not in ("union", "min"):
+        raise TypeError("Unknown nms mode: %s." % mode)  # model/SSD.py:298-299
     loc, cls = predictions
     rows, index, count = prior_nms_raw(loc, cls, self.iou_boxes, topk, nms_thresh, class_thresh, mode, compat, return_index)
     c = count.cpu()

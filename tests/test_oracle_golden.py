@@ -169,3 +169,30 @@ def test_ssd_match_and_retina_assign():
     loc, cls = rp.retina_assign(anchors, tg, B, img)
     assert torch.equal(loc[cls > 0], T(d["r_loc_pos"]))
     assert torch.equal(cls[cls > -1], T(d["r_cls_nonignored"]))
+
+
+@pytest.mark.parametrize("name", YOLO_CASES)
+def test_c_oracle_matches_reference(name):
+    """The plain-C restatement (oracle/c/nms_oracle.c, used for full-size GPU parity) against the reference."""
+    from oracle import c_oracle
+    d = load(name)
+    want = unpack_list(d, "out")
+    rows = rp.yolo_rows_from_planar(yolo_levels(d), int(d["A"]))
+    got, gidx = c_oracle.yolo_nms_rows(rows)
+    _, widx = rp.yolo_nms_rows(rows, return_index=True)
+    for i in range(len(want)):
+        assert torch.equal(gidx[i], widx[i])
+        assert_rows_close(got[i], want[i], rtol=1e-6, atol=1e-4, what=f"{name}[{i}]")
+
+
+def test_c_oracle_threshold_and_empty():
+    from oracle import c_oracle
+    lv = synth.yolo_planar(2, 3, 4, [8, 4], 64, 9)
+    rows = rp.yolo_rows_from_planar(lv, 3)
+    got, _ = c_oracle.yolo_nms_rows(rows, conf_thres=2.0)
+    assert got == [None, None]
+    a, ai = c_oracle.yolo_nms_rows(rows, conf_thres=0.5, nms_thres=0.6)
+    b, bi = rp.yolo_nms_rows(rows, conf_thres=0.5, nms_thres=0.6, return_index=True)
+    for i in range(2):
+        assert torch.equal(ai[i], bi[i])
+        assert_rows_close(a[i], b[i], rtol=1e-6, atol=1e-4)
