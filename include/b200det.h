@@ -87,8 +87,10 @@ size_t b200det_yolo_workspace_bytes(const b200det_yolo_desc* d);
 int b200det_yolo_nms(const b200det_yolo_desc* d, void* workspace, size_t workspace_bytes,
                      float* out_rows, int32_t* out_index, int32_t* out_count, void* stream);
 
-/* Stage entry points (the pipeline above is exactly these four calls in order); used by the tests
- * and by profiling.  All operate on the workspace laid out by b200det_yolo_workspace_bytes(). */
+/* Stage entry points (the pipeline above is exactly these five calls in order); used by the tests
+ * and by profiling.  All operate on the workspace laid out by b200det_yolo_workspace_bytes().
+ * reset = one cudaMemsetAsync of the counter header; decode = the fused decode+filter kernel alone. */
+int b200det_yolo_stage_reset(const b200det_yolo_desc* d, void* workspace, size_t workspace_bytes, void* stream);
 int b200det_yolo_stage_decode(const b200det_yolo_desc* d, void* workspace, size_t workspace_bytes, void* stream);
 int b200det_yolo_stage_sort(const b200det_yolo_desc* d, void* workspace, size_t workspace_bytes, void* stream);
 int b200det_yolo_stage_nms(const b200det_yolo_desc* d, void* workspace, size_t workspace_bytes, void* stream);

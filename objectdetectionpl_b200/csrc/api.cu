@@ -18,6 +18,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 // launchers defined in the stage files
+int yolo_stage_reset(const b200det_yolo_desc*, void*, size_t, cudaStream_t);
 int yolo_stage_decode(const b200det_yolo_desc*, void*, size_t, cudaStream_t);
 int yolo_stage_sort(const b200det_yolo_desc*, void*, size_t, cudaStream_t);
 int yolo_stage_nms(const b200det_yolo_desc*, void*, size_t, cudaStream_t);
@@ -72,6 +73,9 @@ size_t b200det_yolo_workspace_bytes(const b200det_yolo_desc* d) {
     return w.total_bytes;
 }
 
+int b200det_yolo_stage_reset(const b200det_yolo_desc* d, void* ws, size_t n, void* st) {
+    return yolo_stage_reset(d, ws, n, (cudaStream_t)st);
+}
 int b200det_yolo_stage_decode(const b200det_yolo_desc* d, void* ws, size_t n, void* st) {
     return yolo_stage_decode(d, ws, n, (cudaStream_t)st);
 }
@@ -88,7 +92,9 @@ int b200det_yolo_stage_emit(const b200det_yolo_desc* d, void* ws, size_t n, floa
 
 int b200det_yolo_nms(const b200det_yolo_desc* d, void* ws, size_t n, float* out_rows, int32_t* out_index,
                      int32_t* out_count, void* st) {
-    int rc = yolo_stage_decode(d, ws, n, (cudaStream_t)st);
+    int rc = yolo_stage_reset(d, ws, n, (cudaStream_t)st);
+    if (rc) return rc;
+    rc = yolo_stage_decode(d, ws, n, (cudaStream_t)st);
     if (rc) return rc;
     rc = yolo_stage_sort(d, ws, n, (cudaStream_t)st);
     if (rc) return rc;

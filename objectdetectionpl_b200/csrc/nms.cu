@@ -73,7 +73,8 @@ __device__ __forceinline__ float box_area_plus1(const float4 b) {
 // `inter <> thr * den` is provably equivalent (rounding errors of the two products are < 2^-22 relative), and
 // inter == 0 (no overlap: ~90% of all pairs) is decided without touching the divider at all (0/den = +-0).
 template <int VARIANT>
-__device__ __forceinline__ bool removes(const float4 a, const float aa, const float4 b, const float ab, const float thr) {
+__device__ __forceinline__ bool removes(const float4 a, const float4 b, const float thr) {
+    const float aa = box_area_plus1(a), ab = box_area_plus1(b);
     const float ix1 = fmaxf(a.x, b.x), iy1 = fmaxf(a.y, b.y);
     const float ix2 = fminf(a.z, b.z), iy2 = fminf(a.w, b.w);
     const float iw = fmaxf(__fadd_rn(__fsub_rn(ix2, ix1), 1.0f), 0.0f);
@@ -99,31 +100,42 @@ __device__ __forceinline__ bool removes(const float4 a, const float aa, const fl
     return !(ratio <= thr);
 }
 
-// Conservative half2 bounds of a corner box for the overlap pre-filter: lo = (x1, y1) rounded DOWN,
-// hi = (x2 + 1, y2 + 1) rounded UP.  The exact test has inter > 0 only if min(hi) > max(lo) holds for these
-// (monotone rounding), so "hmin2(hi_a, hi_b) > hmax2(lo_a, lo_b) in both halves" never misses a pair that the
-// reference arithmetic would count as overlapping; it costs 3 half2 instructions instead of 11 fp32 ones.
-__device__ __forceinline__ uint2 box_bounds_h2(const float4 b) {
+// Conservative half2 summary of a corner box for the pair pre-filter:
+//   lo = (x1, y1) rounded DOWN,  hi = (x2 + 1, y2 + 1) rounded UP,  wh = (w + 1, h + 1) rounded DOWN.
+// With d = hmin2(hi_a, hi_b) - hmax2(lo_a, lo_b) >= (iw, ih) of the exact arithmetic (monotone rounding), a pair can
+// only reach IoU_+1 > thr if  d > thr * max(wh_a, wh_b)  in BOTH axes, because
+//   IoU <= inter / max(area_a, area_b) <= iw / max(w_a + 1, w_b + 1)   (and likewise for ih).
+// `thr2` is thr * (1 - 2^-8) rounded down, which covers the half-precision rounding of the subtraction and product.
+// The test never rejects a pair the reference would remove; it costs 6 half2 instructions instead of ~30 fp32 ones and
+// passes ~1% of random pairs (the plain "do they overlap" test passes ~7%).
+__device__ __forceinline__ uint4 box_bounds_h2(const float4 b) {
     const __half2 lo = __halves2half2(__float2half_rd(b.x), __float2half_rd(b.y));
     const __half2 hi = __halves2half2(__float2half_ru(__fadd_ru(b.z, 1.0f)), __float2half_ru(__fadd_ru(b.w, 1.0f)));
-    uint2 r;
+    const __half2 wh = __halves2half2(__float2half_rd(__fadd_rd(__fsub_rd(b.z, b.x), 1.0f)),
+                                      __float2half_rd(__fadd_rd(__fsub_rd(b.w, b.y), 1.0f)));
+    uint4 r;
     r.x = *reinterpret_cast<const unsigned*>(&lo);
     r.y = *reinterpret_cast<const unsigned*>(&hi);
+    r.z = *reinterpret_cast<const unsigned*>(&wh);
+    r.w = 0u;
     return r;
 }
-__device__ __forceinline__ bool may_overlap(const uint2 qa, const uint2 qb) {
+__device__ __forceinline__ bool may_remove(const uint4 qa, const uint4 qb, const __half2 thr2) {
     const __half2 lo = __hmax2(*reinterpret_cast<const __half2*>(&qa.x), *reinterpret_cast<const __half2*>(&qb.x));
     const __half2 hi = __hmin2(*reinterpret_cast<const __half2*>(&qa.y), *reinterpret_cast<const __half2*>(&qb.y));
-    return __hbgt2(hi, lo);
+    const __half2 m = __hmax2(*reinterpret_cast<const __half2*>(&qa.z), *reinterpret_cast<const __half2*>(&qb.z));
+    const __half2 d = __hsub2(hi, lo);
+    const __half2 zero = __float2half2_rn(0.0f);
+    return __hbgt2(d, __hmax2(__hmul2(thr2, m), zero));
 }
 
 // FAST: the pre-filter is sound when "no overlap" implies "not removed", i.e. VARIANT 0 with nms_thres >= 0.
 template <int VARIANT, bool FAST>
 __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParams p) {
     __shared__ float4 s_box[kNmsT];
-    __shared__ float s_area[kNmsT];
     __shared__ float s_conf[kNmsT];
-    __shared__ uint2 s_q[kNmsT];
+    __shared__ uint2 s_q[kNmsT];        // half2 lo, hi
+    __shared__ unsigned s_qw[kNmsT];    // half2 (w+1, h+1)
     __shared__ unsigned long long s_L[kNmsTriWords];
     __shared__ unsigned long long s_kept[kNmsW];
     __shared__ unsigned long long s_member[kNmsW];
@@ -131,8 +143,8 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
     __shared__ int s_own[kNmsT];
     __shared__ int s_pre[kNmsT];
     __shared__ float4 s_kb[kNmsStage];
-    __shared__ float s_ka[kNmsStage];
     __shared__ uint2 s_kq[kNmsStage];
+    __shared__ unsigned s_kqw[kNmsStage];
     __shared__ int s_last_members;
 
     const int b = blockIdx.y;
@@ -149,6 +161,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
     if (VARIANT == 0 && n <= 0) return;
     const bool single = n <= kNmsT;
     const float thr = p.thr;
+    const __half2 thr2 = __float2half2_rn(0.0f) + __half2half2(__float2half_rd(thr * (1.0f - 0.00390625f)));
 
     int Kprev = 0;          // keepers found in earlier chunks
     int last_k = -1;        // VARIANT 1/2: index of the last keeper so far
@@ -164,9 +177,8 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
             const uint32_t slot = pay & kSlotMask;
             const float4 bx = p.box4[img + slot];
             s_box[j] = bx;
-            s_area[j] = box_area_plus1(bx);
             s_conf[j] = p.cc2[img + slot].x;
-            if (FAST) s_q[j] = box_bounds_h2(bx);
+            if (FAST) { const uint4 q = box_bounds_h2(bx); s_q[j] = make_uint2(q.x, q.y); s_qw[j] = q.z; }
             s_pre[j] = -1;
         }
         if (tid < kNmsW) s_member[tid] = 0ull;      // 32-row groups past nc are never written by the ballots below
@@ -178,22 +190,20 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
             if (tid < nk) {
                 const float4 kb = p.kbox[img + s + kt + tid];
                 s_kb[tid] = kb;
-                s_ka[tid] = box_area_plus1(kb);
-                if (FAST) s_kq[tid] = box_bounds_h2(kb);
+                if (FAST) { const uint4 q = box_bounds_h2(kb); s_kq[tid] = make_uint2(q.x, q.y); s_kqw[tid] = q.z; }
             }
             __syncthreads();
             for (int j = tid; j < nc; j += kNmsThreads) {
                 if (s_pre[j] >= 0) continue;
                 const float4 bj = s_box[j];
-                const float aj = s_area[j];
                 if (FAST) {
-                    const uint2 qj = s_q[j];
+                    const uint4 qj = make_uint4(s_q[j].x, s_q[j].y, s_qw[j], 0u);
                     for (int k = 0; k < nk; ++k) {
-                        if (may_overlap(s_kq[k], qj) && removes<VARIANT>(s_kb[k], s_ka[k], bj, aj, thr)) { s_pre[j] = kt + k; break; }
+                        if (may_remove(make_uint4(s_kq[k].x, s_kq[k].y, s_kqw[k], 0u), qj, thr2) && removes<VARIANT>(s_kb[k], bj, thr)) { s_pre[j] = kt + k; break; }
                     }
                 } else {
                     for (int k = 0; k < nk; ++k) {
-                        if (removes<VARIANT>(s_kb[k], s_ka[k], bj, aj, thr)) { s_pre[j] = kt + k; break; }
+                        if (removes<VARIANT>(s_kb[k], bj, thr)) { s_pre[j] = kt + k; break; }
                     }
                 }
             }
@@ -207,19 +217,18 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
                 unsigned long long bits = 0ull;
                 if (s_pre[j] < 0) {
                     const float4 bj = s_box[j];
-                    const float aj = s_area[j];
-                    const int ni = min(64, j - i0);
+                        const int ni = min(64, j - i0);
                     if (FAST) {
                         // pass 1: half2 bounding test, branch-free; pass 2: exact test on the few candidates
-                        const uint2 qj = s_q[j];
+                        const uint4 qj = make_uint4(s_q[j].x, s_q[j].y, s_qw[j], 0u);
                         unsigned c_lo = 0u, c_hi = 0u;
                         // all 64 columns of the word are tested (rows >= j hold valid or stale-but-harmless bounds)
                         // and the columns >= ni are masked off afterwards: no variable-trip-count loop on the diagonal
 #pragma unroll
-                        for (int k = 0; k < 32; ++k) c_lo |= may_overlap(s_q[i0 + k], qj) ? (1u << k) : 0u;
+                        for (int k = 0; k < 32; ++k) c_lo |= may_remove(make_uint4(s_q[i0 + k].x, s_q[i0 + k].y, s_qw[i0 + k], 0u), qj, thr2) ? (1u << k) : 0u;
                         if (ni > 32) {
 #pragma unroll
-                            for (int k = 0; k < 32; ++k) c_hi |= may_overlap(s_q[i0 + 32 + k], qj) ? (1u << k) : 0u;
+                            for (int k = 0; k < 32; ++k) c_hi |= may_remove(make_uint4(s_q[i0 + 32 + k].x, s_q[i0 + 32 + k].y, s_qw[i0 + 32 + k], 0u), qj, thr2) ? (1u << k) : 0u;
                         }
                         if (ni < 32) c_lo &= (1u << ni) - 1u;
                         else if (ni < 64) c_hi &= (1u << (ni - 32)) - 1u;
@@ -227,11 +236,11 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
                         while (cand) {
                             const int k = __ffsll((long long)cand) - 1;
                             cand &= cand - 1ull;
-                            if (removes<VARIANT>(s_box[i0 + k], s_area[i0 + k], bj, aj, thr)) bits |= 1ull << k;
+                            if (removes<VARIANT>(s_box[i0 + k], bj, thr)) bits |= 1ull << k;
                         }
                     } else {
                         for (int k = 0; k < ni; ++k) {
-                            if (removes<VARIANT>(s_box[i0 + k], s_area[i0 + k], bj, aj, thr)) bits |= 1ull << k;
+                            if (removes<VARIANT>(s_box[i0 + k], bj, thr)) bits |= 1ull << k;
                         }
                     }
                 }
@@ -467,59 +476,64 @@ struct EmitParams {
 };
 
 constexpr int kEmitThreads = kEmitChunk / 4;   // 4 consecutive ranks per thread
+constexpr int kEmitPerCta = 1;                 // chunks per CTA (4 per CTA measured slower: 49 vs 39 us - the kernel is
+                                               // latency-bound per CTA, so more, smaller CTAs win)
 
 __global__ void __launch_bounds__(kEmitThreads) yolo_emit_kernel(const EmitParams p) {
     __shared__ int s_scan[33];
-    __shared__ float s_rows[kEmitChunk * 7];    // kept rows of this chunk, packed -> coalesced global stores
+    __shared__ float s_rows[kEmitChunk * 7];    // kept rows of one chunk, packed -> coalesced global stores
     __shared__ int s_idx[kEmitChunk];
-    const int b = blockIdx.y, c = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int c_first = blockIdx.x * kEmitPerCta;
     const size_t img = (size_t)b * p.n_pad;
     const int n = (int)p.count[b];
-    const int r0 = c << kEmitShift;
-    if (c > 0 && r0 >= n) return;
+    if (c_first > 0 && (c_first << kEmitShift) >= n) return;
     const uint32_t* cc = p.chunk_cnt + (size_t)b * p.n_chunks;
-    const int upto = c == 0 ? p.n_chunks : c;          // chunk 0 also totals the image
+    const int upto = c_first == 0 ? p.n_chunks : c_first;          // the first CTA also totals the image
     int part = 0;
     for (int t = tid; t < upto; t += kEmitThreads) part += (int)cc[t];
     int base;
     block_exclusive_scan(part, s_scan, &base);
-    if (c == 0) {
+    if (c_first == 0) {
         if (tid == 0) p.out_count[b] = base;
         base = 0;
     }
-    const int r = r0 + tid * 4;
-    uint32_t pay[4] = {kNone, kNone, kNone, kNone};
-    if (r + 3 < n) {
-        const uint4 v = *reinterpret_cast<const uint4*>(p.kpay + img + r);
-        pay[0] = v.x; pay[1] = v.y; pay[2] = v.z; pay[3] = v.w;
-    } else {
+    for (int c = c_first; c < c_first + kEmitPerCta && (c << kEmitShift) < n; ++c) {
+        const int r = (c << kEmitShift) + tid * 4;
+        uint32_t pay[4] = {kNone, kNone, kNone, kNone};
+        if (r + 3 < n) {
+            const uint4 v = *reinterpret_cast<const uint4*>(p.kpay + img + r);
+            pay[0] = v.x; pay[1] = v.y; pay[2] = v.z; pay[3] = v.w;
+        } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) if (r + i < n) pay[i] = p.kpay[img + r + i];
-    }
-    int cnt = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) cnt += pay[i] != kNone ? 1 : 0;
-    int total;
-    int ex = block_exclusive_scan(cnt, s_scan, &total);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        if (pay[i] != kNone) {
-            const uint32_t slot = pay[i] & kSlotMask;
-            const float4 mb = p.mbox[img + r + i];
-            const float2 cf = p.cc2[img + slot];
-            float* o = s_rows + ex * 7;
-            o[0] = mb.x; o[1] = mb.y; o[2] = mb.z; o[3] = mb.w;
-            o[4] = cf.x; o[5] = cf.y; o[6] = (float)(pay[i] >> kSlotBits);     // YOLOV3.py:318-319
-            if (p.out_index) s_idx[ex] = (int)p.orig[img + slot];
-            ++ex;
+            for (int i = 0; i < 4; ++i) if (r + i < n) pay[i] = p.kpay[img + r + i];
         }
-    }
-    __syncthreads();
-    float* dst = p.out_rows + (img + base) * 7;
-    for (int i = tid; i < total * 7; i += kEmitThreads) dst[i] = s_rows[i];
-    if (p.out_index) {
-        int32_t* di = p.out_index + img + base;
-        for (int i = tid; i < total; i += kEmitThreads) di[i] = s_idx[i];
+        int cnt = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cnt += pay[i] != kNone ? 1 : 0;
+        int total;
+        int ex = block_exclusive_scan(cnt, s_scan, &total);     // trailing barrier also protects s_rows reuse
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (pay[i] != kNone) {
+                const uint32_t slot = pay[i] & kSlotMask;
+                const float4 mb = p.mbox[img + r + i];
+                const float2 cf = p.cc2[img + slot];
+                float* o = s_rows + ex * 7;
+                o[0] = mb.x; o[1] = mb.y; o[2] = mb.z; o[3] = mb.w;
+                o[4] = cf.x; o[5] = cf.y; o[6] = (float)(pay[i] >> kSlotBits);     // YOLOV3.py:318-319
+                if (p.out_index) s_idx[ex] = (int)p.orig[img + slot];
+                ++ex;
+            }
+        }
+        __syncthreads();
+        float* dst = p.out_rows + (img + base) * 7;
+        for (int i = tid; i < total * 7; i += kEmitThreads) dst[i] = s_rows[i];
+        if (p.out_index) {
+            int32_t* di = p.out_index + img + base;
+            for (int i = tid; i < total; i += kEmitThreads) di[i] = s_idx[i];
+        }
+        base += total;
     }
 }
 
@@ -552,7 +566,7 @@ int yolo_stage_emit(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, float
     EmitParams p;
     p.count = w.count; p.kpay = w.kpay; p.mbox = w.mbox; p.cc2 = w.cc2; p.orig = w.orig; p.chunk_cnt = w.chunk_cnt;
     p.out_rows = out_rows; p.out_index = out_index; p.out_count = out_count; p.n_pad = w.n_pad; p.n_chunks = w.n_chunks;
-    dim3 grid(w.n_chunks, d->batch);
+    dim3 grid(ceil_div(w.n_chunks, kEmitPerCta), d->batch);
     yolo_emit_kernel<<<grid, kEmitThreads, 0, st>>>(p);
     B2_LAUNCH_CHECK("yolo_emit_kernel");
     return 0;

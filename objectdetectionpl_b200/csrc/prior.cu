@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(256) tile_prefix_kernel(const uint32_t* __rest
     }
 }
 
-// from segsort.cu / nms.cu
+// from yolo_decode.cu / segsort.cu / nms.cu
+int zero_fill_launch(void* p, size_t bytes, cudaStream_t st);
 int score_sort_launch(const uint32_t* tile_count, const uint32_t* count, uint32_t* digit_hist, uint32_t* ticket,
                       uint32_t* status, uint32_t* key[2], uint32_t* pay[2], int n_pad, int n_tiles, int batch,
                       cudaStream_t st);
@@ -237,7 +238,8 @@ int prior_nms_pipeline(const b200det_prior_desc* d, void* ws, size_t ws_bytes, f
         set_error("workspace too small: %zu < %zu", ws_bytes, w.total_bytes);
         return B200DET_EWORKSPACE;
     }
-    B2_CUDA(cudaMemsetAsync(w.count, 0, w.zero_bytes, st));
+    rc = zero_fill_launch(w.count, w.zero_bytes, st);
+    if (rc) return rc;
 
     K1pParams p;
     memset(&p, 0, sizeof(p));

@@ -57,12 +57,6 @@ __device__ __forceinline__ unsigned match_digit8(uint32_t digit, bool valid) {
     return peers;
 }
 
-// Warp-aggregated shared-memory histogram increment (all 32 lanes must call).
-__device__ __forceinline__ void hist_add(int* hist, uint32_t digit, bool valid) {
-    const unsigned peers = match_digit8(digit, valid);
-    if (valid && (peers & lanemask_lt()) == 0) atomicAdd(&hist[digit], __popc(peers));
-}
-
 // Up-front per-image digit totals for every pass (score bytes 0..3 from the key, class digits from
 // the payload).  Input is the tile-sparse K1 output.
 __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const SortParams p) {
@@ -83,10 +77,14 @@ __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const SortParam
         const bool valid = e < p.n_pad && sparse_valid(tc, e);
         uint32_t key = 0, pay = 0;
         if (valid) { key = p.key_in[img + e]; pay = p.pay_in[img + e]; }
+        // plain shared-memory atomics: measured 14 us vs 51 us for ballot-aggregated increments on B200
+        if (valid) {
 #pragma unroll
-        for (int s = 0; s < kScorePasses; ++s) hist_add(h[s], (key >> (8 * s)) & 0xFFu, valid);
-        hist_add(h[kScorePasses], (pay >> kSlotBits) & 0xFFu, valid);
-        if (npass > kScorePasses + 1) hist_add(h[kScorePasses + 1], (pay >> (kSlotBits + 8)) & 0xFFu, valid);
+            for (int s = 0; s < kScorePasses; ++s) atomicAdd(&h[s][(key >> (8 * s)) & 0xFFu], 1);
+            atomicAdd(&h[kScorePasses][(pay >> kSlotBits) & 0xFFu], 1);
+            if (npass > kScorePasses + 1) atomicAdd(&h[kScorePasses + 1][(pay >> (kSlotBits + 8)) & 0xFFu], 1);
+        }
+
     }
     __syncthreads();
     uint32_t* g = p.digit_hist + (size_t)b * kMaxPasses * 256;
@@ -204,6 +202,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_pass_kernel(const SortParam
         }
     }
 }
+
 
 // Score-only sort (4 passes) for the prior pipeline; the sorted payload ends in pay[0].
 int score_sort_launch(const uint32_t* tile_count, const uint32_t* count, uint32_t* digit_hist, uint32_t* ticket,

@@ -256,12 +256,33 @@ static int launch_k1(const b200det_yolo_desc* d, const K1Params& p, cudaStream_t
     return 0;
 }
 
+// Zero the counter header of the workspace.  A plain kernel: cudaMemsetAsync of these ~0.4 MB measured 13-15 us
+// between CUDA events on B200, this takes ~3.
+__global__ void __launch_bounds__(256) zero_fill_kernel(uint4* __restrict__ p, size_t n16) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n16) p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+int zero_fill_launch(void* p, size_t bytes, cudaStream_t st) {      // bytes is a multiple of 256 (workspace layout)
+    const size_t n16 = bytes / 16;
+    zero_fill_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, st>>>((uint4*)p, n16);
+    B2_LAUNCH_CHECK("zero_fill_kernel");
+    return 0;
+}
+
+int yolo_stage_reset(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cudaStream_t st) {
+    int rc = yolo_validate(d, ws, ws_bytes);
+    if (rc) return rc;
+    YoloWs w;
+    yolo_ws_layout(d, ws, &w);
+    return zero_fill_launch(w.count, w.zero_bytes, st);
+}
+
 int yolo_stage_decode(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cudaStream_t st) {
     int rc = yolo_validate(d, ws, ws_bytes);
     if (rc) return rc;
     YoloWs w;
     yolo_ws_layout(d, ws, &w);
-    B2_CUDA(cudaMemsetAsync(w.count, 0, w.zero_bytes, st));
 
     K1Params p;
     memset(&p, 0, sizeof(p));

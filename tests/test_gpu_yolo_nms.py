@@ -121,6 +121,7 @@ def test_stage_outputs_sorted_and_segmented():
     nbytes = lib.b200det_yolo_workspace_bytes(ctypes.byref(d))
     ws = torch.zeros(nbytes, dtype=torch.uint8, device=DEV)
     st = torch.cuda.current_stream().cuda_stream
+    L.check(lib.b200det_yolo_stage_reset(ctypes.byref(d), ws.data_ptr(), nbytes, st))
     L.check(lib.b200det_yolo_stage_decode(ctypes.byref(d), ws.data_ptr(), nbytes, st))
     L.check(lib.b200det_yolo_stage_sort(ctypes.byref(d), ws.data_ptr(), nbytes, st))
     torch.cuda.synchronize()

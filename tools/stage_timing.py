@@ -45,6 +45,7 @@ def main():
     cnt = torch.empty(a.batch, dtype=torch.int32, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     stages = [
+        ("reset", lambda: lib.b200det_yolo_stage_reset(ctypes.byref(d), ws.data_ptr(), nb, st)),
         ("decode", lambda: lib.b200det_yolo_stage_decode(ctypes.byref(d), ws.data_ptr(), nb, st)),
         ("sort", lambda: lib.b200det_yolo_stage_sort(ctypes.byref(d), ws.data_ptr(), nb, st)),
         ("nms", lambda: lib.b200det_yolo_stage_nms(ctypes.byref(d), ws.data_ptr(), nb, st)),
