@@ -11,29 +11,15 @@
 // Survivors are compacted IN ORDER inside the CTA's 512-slot tile (ballot-free block scan), so the
 // slot order equals the reference's candidate order and the later stable radix sort breaks score ties
 // by ascending candidate index without any atomically-ordered append.
+#include <stdlib.h>
+
 #include "yolo_ws.cuh"
+#include "yolo_k1.cuh"
 
 namespace b200det {
 
-struct K1Params {
-    const float* head[B200DET_MAX_LEVELS];
-    int G[B200DET_MAX_LEVELS];
-    int GG[B200DET_MAX_LEVELS];
-    int off[B200DET_MAX_LEVELS + 1];
-    float stride[B200DET_MAX_LEVELS];
-    float anc[B200DET_MAX_LEVELS][B200DET_MAX_ANCHORS][2];
-    int nlevels, A, C, N, n_pad, n_tiles;
-    float conf_thres;
-    // outputs
-    float4* box4;
-    float2* cc2;
-    uint32_t* orig;
-    uint32_t* key;
-    uint32_t* pay;
-    uint32_t* tile_count;
-    uint32_t* count;
-    uint32_t* cls_hist;
-};
+bool k1_tma_supported(const K1Params& p);
+int launch_k1_tma(const b200det_yolo_desc* d, const K1Params& p, cudaStream_t st);
 
 template <int VEC>
 struct VecLoad;
@@ -49,17 +35,13 @@ struct VecLoad<1> {
     static __device__ __forceinline__ void ld(const float* p, float (&v)[1]) { v[0] = ldg_stream1(p); }
 };
 
-// torch.max(dim) semantics (aten TensorCompareKernel): update when !(v <= best); stop at the first NaN.
-__device__ __forceinline__ void argmax_step(float v, int c, float& best, int& besti) {
-    if (!(v <= best) && (best == best)) { best = v; besti = c; }
-}
-
 template <int VEC, int MODE, int U, int MINB>
 __global__ void __launch_bounds__(kTile / VEC, MINB)
 yolo_decode_filter_kernel(const K1Params p) {
     constexpr int NT = kTile / VEC;
     extern __shared__ int s_hist[];          // [C]
     __shared__ int s_scan[33];
+    __shared__ K1Stage s_stage;
 
     const int b = blockIdx.y;
     const int tile = blockIdx.x;
@@ -120,42 +102,10 @@ yolo_decode_filter_kernel(const K1Params p) {
 
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            float cx, cy, w, h, cf, cc;
-            if (MODE == B200DET_DECODE_NONE) {
-                cx = t[0][v]; cy = t[1][v]; w = t[2][v]; h = t[3][v]; cf = t[4][v]; cc = best[v];
-            } else {
-                const int G = p.G[lvl];
-                const int cl = cell + v;
-                const int gy = cl / G;
-                const float gx = (float)(cl - gy * G);
-                const float st = p.stride[lvl];
-                const float aw = p.anc[lvl][a][0], ah = p.anc[lvl][a][1];
-                if (MODE == B200DET_DECODE_YOLO_EXP) {
-                    // accuracy.py:432-435 then *stride (:461)
-                    cx = __fmul_rn(__fadd_rn(sigmoidf_acc(t[0][v]), gx), st);
-                    cy = __fmul_rn(__fadd_rn(sigmoidf_acc(t[1][v]), (float)gy), st);
-                    w = __fmul_rn(__fmul_rn(expf(t[2][v]), aw), st);
-                    h = __fmul_rn(__fmul_rn(expf(t[3][v]), ah), st);
-                } else {
-                    // utils/YoloV5Utils.py:246-247
-                    cx = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sigmoidf_acc(t[0][v]), 2.0f), 0.5f), gx), st);
-                    cy = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sigmoidf_acc(t[1][v]), 2.0f), 0.5f), (float)gy), st);
-                    float sw = __fmul_rn(sigmoidf_acc(t[2][v]), 2.0f);
-                    float sh = __fmul_rn(sigmoidf_acc(t[3][v]), 2.0f);
-                    w = __fmul_rn(__fmul_rn(sw, sw), aw);
-                    h = __fmul_rn(__fmul_rn(sh, sh), ah);
-                }
-                cf = sigmoidf_acc(t[4][v]);
-                cc = sigmoidf_acc(best[v]);   // sigmoid is monotone: argmax taken on the logits
-            }
-            // xywh2xyxy, accuracy.py:289-295 (x/2 == x*0.5 exactly)
-            const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
-            box[v][0] = __fsub_rn(cx, hw);
-            box[v][1] = __fsub_rn(cy, hh);
-            box[v][2] = __fadd_rn(cx, hw);
-            box[v][3] = __fadd_rn(cy, hh);
-            conf[v] = cf; ccf[v] = cc; cls[v] = besti[v];
-            keep[v] = cf >= p.conf_thres;     // model/YOLOV3.py:310 (NaN conf is dropped, as there)
+            const float t5[5] = {t[0][v], t[1][v], t[2][v], t[3][v], t[4][v]};
+            k1_finish<MODE>(p, lvl, a, cell + v, t5, best[v], box[v], conf[v], ccf[v]);
+            cls[v] = besti[v];
+            keep[v] = conf[v] >= p.conf_thres;     // model/YOLOV3.py:310 (NaN conf is dropped, as there)
         }
     }
 
@@ -169,13 +119,7 @@ yolo_decode_filter_kernel(const K1Params p) {
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
         if (keep[v]) {
-            const uint32_t slot = (uint32_t)(tile * kTile + ofs);
-            const size_t i = img + slot;
-            p.box4[i] = make_float4(box[v][0], box[v][1], box[v][2], box[v][3]);
-            p.cc2[i] = make_float2(conf[v], ccf[v]);
-            p.orig[i] = (uint32_t)(n0 + v);
-            p.key[i] = score_sort_key(__fmul_rn(conf[v], ccf[v]));     // model/YOLOV3.py:315
-            p.pay[i] = ((uint32_t)cls[v] << kSlotBits) | slot;
+            k1_stage_put(s_stage, ofs, box[v], conf[v], ccf[v], (uint32_t)(n0 + v), cls[v]);
             atomicAdd(&s_hist[cls[v]], 1);
             ++ofs;
         }
@@ -185,6 +129,7 @@ yolo_decode_filter_kernel(const K1Params p) {
         if (total) atomicAdd(&p.count[b], (uint32_t)total);
     }
     __syncthreads();
+    k1_stage_flush<NT>(s_stage, p, img, tile, total, tid);
     for (int c = tid; c < p.C; c += NT) {
         int h = s_hist[c];
         if (h) atomicAdd(&p.cls_hist[(size_t)b * p.C + c], (uint32_t)h);
@@ -308,6 +253,10 @@ int yolo_stage_decode(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cud
     p.box4 = w.box4; p.cc2 = w.cc2; p.orig = w.orig; p.key = w.key[0]; p.pay = w.pay[0];
     p.tile_count = w.tile_count; p.count = w.count; p.cls_hist = w.cls_hist;
 
+    // default: the register-staged LDG kernel; B200DET_K1=tma selects the bulk-async (TMA) pipeline, which is
+    // bit-identical and measured 6% slower on B200 (see yolo_decode_tma.cu)
+    const char* k1 = getenv("B200DET_K1");
+    if (vec4 && k1 && strcmp(k1, "tma") == 0 && k1_tma_supported(p)) return launch_k1_tma(d, p, st);
     return vec4 ? launch_k1<4>(d, p, st) : launch_k1<1>(d, p, st);
 }
 

@@ -157,3 +157,24 @@ def test_no_cpu_fallback():
     levels = synth.yolo_planar(1, 3, 2, [4], 32, 1)
     with pytest.raises(RuntimeError, match="no CPU path"):
         od.non_max_suppression(None, levels)
+
+
+def test_tma_variant_of_k1_is_bit_identical(monkeypatch):
+    """The bulk-async (cp.async.bulk + mbarrier) pipeline variant of the decode kernel (B200DET_K1=tma) must produce
+    exactly the candidates of the default LDG kernel, in all decode modes."""
+    levels = _cuda(synth.yolo_planar(3, 3, 20, [40, 20, 12], 320, 41))          # G*G = 1600, 400, 144: 1-4 runs per tile
+    a, ai = od.non_max_suppression(None, levels, return_index=True)
+    monkeypatch.setenv("B200DET_K1", "tma")
+    b, bi = od.non_max_suppression(None, levels, return_index=True)
+    for x, y, xi, yi in zip(a, b, ai, bi):
+        assert torch.equal(x, y) and torch.equal(xi, yi)
+    heads = [synth.raw_logits(2, 3, 6, G, 80 + G).to(DEV) for G in (16, 12)]
+    for h in heads:
+        h.view(2, 3, 11, h.shape[2], h.shape[3])[:, :, 4] += 3.0
+    kw = dict(conf_thres=0.25, compat=False, decode="yolov5", strides=[8.0, 16.0],
+              anchors=[torch.tensor([[10., 13.], [16., 30.], [33., 23.]]), torch.tensor([[30., 61.], [62., 45.], [59., 119.]])])
+    t = od.non_max_suppression(None, heads, **kw)
+    monkeypatch.delenv("B200DET_K1")
+    l = od.non_max_suppression(None, heads, **kw)
+    for x, y in zip(t, l):
+        assert torch.equal(x, y)
