@@ -100,33 +100,33 @@ __device__ __forceinline__ bool removes(const float4 a, const float4 b, const fl
     return !(ratio <= thr);
 }
 
-// Conservative half2 summary of a corner box for the pair pre-filter:
-//   lo = (x1, y1) rounded DOWN,  hi = (x2 + 1, y2 + 1) rounded UP,  wh = (w + 1, h + 1) rounded DOWN.
+// Conservative half2 summary of a corner box for the pair pre-filter (one 16-byte shared-memory word per row):
+//   lo = (x1, y1) rounded DOWN,  hi = (x2 + 1, y2 + 1) rounded UP,  t = thr' * (w + 1, h + 1) rounded DOWN,
+//   thr' = thr * (1 - 2^-7)  (covers the half-precision rounding of the subtraction below and of the product).
 // With d = hmin2(hi_a, hi_b) - hmax2(lo_a, lo_b) >= (iw, ih) of the exact arithmetic (monotone rounding), a pair can
-// only reach IoU_+1 > thr if  d > thr * max(wh_a, wh_b)  in BOTH axes, because
+// only reach IoU_+1 > thr if  d > max(t_a, t_b)  in BOTH axes, because
 //   IoU <= inter / max(area_a, area_b) <= iw / max(w_a + 1, w_b + 1)   (and likewise for ih).
-// `thr2` is thr * (1 - 2^-8) rounded down, which covers the half-precision rounding of the subtraction and product.
-// The test never rejects a pair the reference would remove; it costs 6 half2 instructions instead of ~30 fp32 ones and
-// passes ~1% of random pairs (the plain "do they overlap" test passes ~7%).
-__device__ __forceinline__ uint4 box_bounds_h2(const float4 b) {
+// The test never rejects a pair the reference would remove (for thr >= 0: degenerate boxes with w + 1 <= 0 only ADD
+// candidates, which the exact test then rejects); it costs 5 half2 instructions + one 128-bit shared load instead of
+// ~30 fp32 instructions and passes ~1% of random pairs (a plain "do they overlap" test passes ~7%).
+__device__ __forceinline__ uint4 box_bounds_h2(const float4 b, const float thr) {
     const __half2 lo = __halves2half2(__float2half_rd(b.x), __float2half_rd(b.y));
     const __half2 hi = __halves2half2(__float2half_ru(__fadd_ru(b.z, 1.0f)), __float2half_ru(__fadd_ru(b.w, 1.0f)));
-    const __half2 wh = __halves2half2(__float2half_rd(__fadd_rd(__fsub_rd(b.z, b.x), 1.0f)),
-                                      __float2half_rd(__fadd_rd(__fsub_rd(b.w, b.y), 1.0f)));
+    const float thr_lo = __fmul_rd(thr, 1.0f - 0.0078125f);
+    const __half2 t = __halves2half2(__float2half_rd(__fmul_rd(thr_lo, __fadd_rd(__fsub_rd(b.z, b.x), 1.0f))),
+                                     __float2half_rd(__fmul_rd(thr_lo, __fadd_rd(__fsub_rd(b.w, b.y), 1.0f))));
     uint4 r;
     r.x = *reinterpret_cast<const unsigned*>(&lo);
     r.y = *reinterpret_cast<const unsigned*>(&hi);
-    r.z = *reinterpret_cast<const unsigned*>(&wh);
+    r.z = *reinterpret_cast<const unsigned*>(&t);
     r.w = 0u;
     return r;
 }
-__device__ __forceinline__ bool may_remove(const uint4 qa, const uint4 qb, const __half2 thr2) {
+__device__ __forceinline__ bool may_remove(const uint4 qa, const uint4 qb) {
     const __half2 lo = __hmax2(*reinterpret_cast<const __half2*>(&qa.x), *reinterpret_cast<const __half2*>(&qb.x));
     const __half2 hi = __hmin2(*reinterpret_cast<const __half2*>(&qa.y), *reinterpret_cast<const __half2*>(&qb.y));
-    const __half2 m = __hmax2(*reinterpret_cast<const __half2*>(&qa.z), *reinterpret_cast<const __half2*>(&qb.z));
-    const __half2 d = __hsub2(hi, lo);
-    const __half2 zero = __float2half2_rn(0.0f);
-    return __hbgt2(d, __hmax2(__hmul2(thr2, m), zero));
+    const __half2 t = __hmax2(*reinterpret_cast<const __half2*>(&qa.z), *reinterpret_cast<const __half2*>(&qb.z));
+    return __hbgt2(__hsub2(hi, lo), t);
 }
 
 // FAST: the pre-filter is sound when "no overlap" implies "not removed", i.e. VARIANT 0 with nms_thres >= 0.
@@ -134,8 +134,8 @@ template <int VARIANT, bool FAST>
 __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParams p) {
     __shared__ float4 s_box[kNmsT];
     __shared__ float s_conf[kNmsT];
-    __shared__ uint2 s_q[kNmsT];        // half2 lo, hi
-    __shared__ unsigned s_qw[kNmsT];    // half2 (w+1, h+1)
+    __shared__ uint2 s_q[kNmsT];        // half2 lo, hi   (see box_bounds_h2; split 8 + 4 bytes: one 128-bit word per row
+    __shared__ unsigned s_qt[kNmsT];    // half2 t         measured slower, 308 vs 295 us)
     __shared__ unsigned long long s_L[kNmsTriWords];
     __shared__ unsigned long long s_kept[kNmsW];
     __shared__ unsigned long long s_member[kNmsW];
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
     __shared__ int s_pre[kNmsT];
     __shared__ float4 s_kb[kNmsStage];
     __shared__ uint2 s_kq[kNmsStage];
-    __shared__ unsigned s_kqw[kNmsStage];
+    __shared__ unsigned s_kqt[kNmsStage];
     __shared__ int s_last_members;
 
     const int b = blockIdx.y;
@@ -161,7 +161,6 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
     if (VARIANT == 0 && n <= 0) return;
     const bool single = n <= kNmsT;
     const float thr = p.thr;
-    const __half2 thr2 = __float2half2_rn(0.0f) + __half2half2(__float2half_rd(thr * (1.0f - 0.00390625f)));
 
     int Kprev = 0;          // keepers found in earlier chunks
     int last_k = -1;        // VARIANT 1/2: index of the last keeper so far
@@ -178,7 +177,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
             const float4 bx = p.box4[img + slot];
             s_box[j] = bx;
             s_conf[j] = p.cc2[img + slot].x;
-            if (FAST) { const uint4 q = box_bounds_h2(bx); s_q[j] = make_uint2(q.x, q.y); s_qw[j] = q.z; }
+            if (FAST) { const uint4 q = box_bounds_h2(bx, thr); s_q[j] = make_uint2(q.x, q.y); s_qt[j] = q.z; }
             s_pre[j] = -1;
         }
         if (tid < kNmsW) s_member[tid] = 0ull;      // 32-row groups past nc are never written by the ballots below
@@ -190,16 +189,16 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
             if (tid < nk) {
                 const float4 kb = p.kbox[img + s + kt + tid];
                 s_kb[tid] = kb;
-                if (FAST) { const uint4 q = box_bounds_h2(kb); s_kq[tid] = make_uint2(q.x, q.y); s_kqw[tid] = q.z; }
+                if (FAST) { const uint4 q = box_bounds_h2(kb, thr); s_kq[tid] = make_uint2(q.x, q.y); s_kqt[tid] = q.z; }
             }
             __syncthreads();
             for (int j = tid; j < nc; j += kNmsThreads) {
                 if (s_pre[j] >= 0) continue;
                 const float4 bj = s_box[j];
                 if (FAST) {
-                    const uint4 qj = make_uint4(s_q[j].x, s_q[j].y, s_qw[j], 0u);
+                    const uint4 qj = make_uint4(s_q[j].x, s_q[j].y, s_qt[j], 0u);
                     for (int k = 0; k < nk; ++k) {
-                        if (may_remove(make_uint4(s_kq[k].x, s_kq[k].y, s_kqw[k], 0u), qj, thr2) && removes<VARIANT>(s_kb[k], bj, thr)) { s_pre[j] = kt + k; break; }
+                        if (may_remove(make_uint4(s_kq[k].x, s_kq[k].y, s_kqt[k], 0u), qj) && removes<VARIANT>(s_kb[k], bj, thr)) { s_pre[j] = kt + k; break; }
                     }
                 } else {
                     for (int k = 0; k < nk; ++k) {
@@ -220,15 +219,15 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
                         const int ni = min(64, j - i0);
                     if (FAST) {
                         // pass 1: half2 bounding test, branch-free; pass 2: exact test on the few candidates
-                        const uint4 qj = make_uint4(s_q[j].x, s_q[j].y, s_qw[j], 0u);
+                        const uint4 qj = make_uint4(s_q[j].x, s_q[j].y, s_qt[j], 0u);
                         unsigned c_lo = 0u, c_hi = 0u;
                         // all 64 columns of the word are tested (rows >= j hold valid or stale-but-harmless bounds)
                         // and the columns >= ni are masked off afterwards: no variable-trip-count loop on the diagonal
 #pragma unroll
-                        for (int k = 0; k < 32; ++k) c_lo |= may_remove(make_uint4(s_q[i0 + k].x, s_q[i0 + k].y, s_qw[i0 + k], 0u), qj, thr2) ? (1u << k) : 0u;
+                        for (int k = 0; k < 32; ++k) c_lo |= may_remove(make_uint4(s_q[i0 + k].x, s_q[i0 + k].y, s_qt[i0 + k], 0u), qj) ? (1u << k) : 0u;
                         if (ni > 32) {
 #pragma unroll
-                            for (int k = 0; k < 32; ++k) c_hi |= may_remove(make_uint4(s_q[i0 + 32 + k].x, s_q[i0 + 32 + k].y, s_qw[i0 + 32 + k], 0u), qj, thr2) ? (1u << k) : 0u;
+                            for (int k = 0; k < 32; ++k) c_hi |= may_remove(make_uint4(s_q[i0 + 32 + k].x, s_q[i0 + 32 + k].y, s_qt[i0 + 32 + k], 0u), qj) ? (1u << k) : 0u;
                         }
                         if (ni < 32) c_lo &= (1u << ni) - 1u;
                         else if (ni < 64) c_hi &= (1u << (ni - 32)) - 1u;
