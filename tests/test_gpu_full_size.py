@@ -92,3 +92,72 @@ def test_config5_dense_crowd_1280():
     ~10% of the candidates above it, clustered boxes -> multi-chunk segments with deep suppression chains."""
     levels = synth.yolo_crowd(4, 3, 5, [160, 80, 40], 1280, seed=5)
     _compare(levels, 3, 4, conf_thres=0.001, compat=False)
+
+
+class _Self:
+    def __init__(self, priors):
+        self.iou_boxes = priors
+
+
+@pytest.mark.parametrize("which", ["ssd300", "retina800"])
+def test_config3_prior_nms_batch32(which):
+    """BASELINE config 3: SSD300 (8 732 priors) and RetinaNet 800x800 (120 087 anchors), 80 classes, batch 32.
+    The whole batch runs on the GPU; 3 images are checked against the oracle (top-100 class-agnostic NMS with the
+    reference's quirks), the rest through properties."""
+    pri = synth.ssd_priors() if which == "ssd300" else synth.retina_priors(800)
+    B, C = 32, 80
+    loc, cls = synth.prior_heads(B, pri.shape[0], C, seed=3, cls_mean=-3.0)
+    got, gidx = od.prior_non_max_suppression(_Self(pri.to(DEV)), (loc.to(DEV), cls.to(DEV)), return_index=True)
+    want, widx = rp.ssd_nms(loc[:3], cls[:3], pri, return_index=True)
+    for b in range(3):
+        g, w = got[b].cpu(), want[b]
+        assert g.shape == w.shape and torch.equal(gidx[b].cpu(), widx[b])
+        assert torch.equal(g[:, 6], w[:, 6]) and torch.equal(g[:, 4], w[:, 4])
+        torch.testing.assert_close(g[:, :4], w[:, :4], rtol=1e-5, atol=1e-4)
+        torch.testing.assert_close(g[:, 5], w[:, 5], rtol=1e-5, atol=1e-6)
+    for b in range(B):
+        g = got[b]
+        assert g.shape[0] <= 99 and g.shape[1] == 7
+        assert bool((g[:-1, 5] >= g[1:, 5]).all()) and bool((g[:, 5] > 0.45).all())
+
+
+def test_config4_targets_batch64():
+    """BASELINE config 4: YOLOv5s training-step target assignment, batch 64, <= 100 labels per image."""
+    B, C, img = 64, 80, 640
+    tg = synth.labels(B, C, seed=4, max_per_image=100)
+    stride = torch.tensor([8., 16., 32.])
+    anchors = torch.tensor(synth.YOLOV5_ANCHORS).float().view(3, -1, 2) / stride.view(-1, 1, 1)
+    g = torch.Generator().manual_seed(44)
+    p = [torch.randn(B, 3, img // s, img // s, 5 + C, generator=g) for s in (8, 16, 32)]
+    want = rp.build_targets_v5([t.shape for t in p], tg, anchors, 3, 3)
+    pd = [t.to(DEV).requires_grad_(True) for t in p]
+    got = od.build_targets_v5(pd, tg.to(DEV), anchors, 3, 3)
+    pc = [t.clone().requires_grad_(True) for t in p]
+    lb_g, lb_w = 0, 0
+    for i in range(3):
+        assert torch.equal(got[0][i].cpu(), want[0][i]) and torch.equal(got[1][i].cpu(), want[1][i])
+        assert all(torch.equal(a.cpu(), b) for a, b in zip(got[2][i], want[2][i]))
+        giou, tobj = od.v5_match_level(pd[i], got[1][i], got[2][i], got[3][i])
+        wg, wo = rp.v5_match_level(pc[i], want[1][i], want[2][i], want[3][i])
+        torch.testing.assert_close(giou.detach().cpu(), wg.detach(), rtol=1e-5, atol=1e-6)
+        # tobj: cells hit by ONE matched row must agree with the oracle; on cells hit by several rows torch's CPU
+        # index_put_ is not ordered once it runs multi-threaded (m > ~10^4), so there the build's published rule is
+        # checked instead: the highest row wins (== the reference's single-threaded "last wins", losses.py:123)
+        bb, aa, gj, gi = (t.cpu() for t in got[2][i])
+        G = p[i].shape[2]
+        cell = ((bb * 3 + aa) * G + gj) * G + gi
+        uniq, inv, cnt = torch.unique(cell, return_inverse=True, return_counts=True)
+        single = cnt[inv] == 1
+        tg_flat, wo_flat = tobj.cpu().flatten(), wo.flatten()
+        torch.testing.assert_close(tg_flat[cell[single]], wo_flat[cell[single]], rtol=1e-5, atol=1e-6)
+        last_row = torch.zeros(uniq.numel(), dtype=torch.long).scatter_reduce_(0, inv, torch.arange(cell.numel()), "amax")
+        torch.testing.assert_close(tg_flat[uniq], wg.detach().clamp(0)[last_row], rtol=1e-5, atol=1e-6)
+        untouched = torch.ones_like(tg_flat, dtype=torch.bool)
+        untouched[uniq] = False
+        assert float(tg_flat[untouched].abs().max()) == 0.0
+        lb_g = lb_g + (1.0 - giou).mean()
+        lb_w = lb_w + (1.0 - wg).mean()
+    lb_g.backward()
+    lb_w.backward()
+    for i in range(3):
+        torch.testing.assert_close(pd[i].grad.cpu(), pc[i].grad, rtol=2e-4, atol=1e-8)
