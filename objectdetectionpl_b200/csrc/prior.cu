@@ -10,6 +10,8 @@
 // rotation so that the 32 lanes of a warp hit 32 different banks (row stride C would otherwise put
 // C%32==0 heads on 1-2 banks).  sigmoid is monotone, so the argmax is taken on the logits and only
 // the winner is squashed (first maximal index on ties, like torch.max).
+#include <stdlib.h>
+
 #include "yolo_ws.cuh"
 
 namespace b200det {
@@ -93,9 +95,13 @@ __device__ __forceinline__ void argmax_rot(float v, int c, float& best, int& bes
     if (take) { best = v; besti = c; }
 }
 
-template <bool VEC4>
+// DIRECT: every thread reads its own row straight from global memory with 128-bit loads (C % 4 == 0).  A warp load
+// touches 32 rows, i.e. 32 different sectors, half of each; the other half is used by the thread's next load and is
+// served by L1.  No shared-memory staging, no barrier and the plain sequential first-max argmax (5 instructions per
+// element instead of ~14 for the staged, rotated scan).
+template <bool VEC4, bool DIRECT>
 __global__ void __launch_bounds__(kPriRows) prior_decode_filter_kernel(const K1pParams p) {
-    extern __shared__ float s_cls[];           // [kPriRows][cc]
+    extern __shared__ float s_cls[];           // [kPriRows][cc] (staged variants)
     __shared__ int s_scan[33];
     const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
     const int C = p.C;
@@ -108,6 +114,43 @@ __global__ void __launch_bounds__(kPriRows) prior_decode_filter_kernel(const K1p
         float best = 0.f;
         int besti = 0;
         bool first = true;
+        if (DIRECT) {
+            if (tid < nrows) {
+                const float4* row = reinterpret_cast<const float4*>(p.cls + ((size_t)b * p.P + p0 + tid) * C);
+                const int n4 = C >> 2;
+                constexpr int U = 5;
+                int c4 = 0;
+                {
+                    const float4 v = __ldg(row);
+                    best = v.x; besti = 0;
+                    if (!(v.y <= best) && (best == best)) { best = v.y; besti = 1; }
+                    if (!(v.z <= best) && (best == best)) { best = v.z; besti = 2; }
+                    if (!(v.w <= best) && (best == best)) { best = v.w; besti = 3; }
+                    c4 = 1;
+                }
+                for (; c4 + U <= n4; c4 += U) {
+                    float4 v[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) v[u] = __ldg(row + c4 + u);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int c = (c4 + u) << 2;
+                        if (!(v[u].x <= best) && (best == best)) { best = v[u].x; besti = c; }
+                        if (!(v[u].y <= best) && (best == best)) { best = v[u].y; besti = c + 1; }
+                        if (!(v[u].z <= best) && (best == best)) { best = v[u].z; besti = c + 2; }
+                        if (!(v[u].w <= best) && (best == best)) { best = v[u].w; besti = c + 3; }
+                    }
+                }
+                for (; c4 < n4; ++c4) {
+                    const float4 v = __ldg(row + c4);
+                    const int c = c4 << 2;
+                    if (!(v.x <= best) && (best == best)) { best = v.x; besti = c; }
+                    if (!(v.y <= best) && (best == best)) { best = v.y; besti = c + 1; }
+                    if (!(v.z <= best) && (best == best)) { best = v.z; besti = c + 2; }
+                    if (!(v.w <= best) && (best == best)) { best = v.w; besti = c + 3; }
+                }
+            }
+        } else
         for (int c0 = 0; c0 < C; c0 += kPriMaxCC) {
             const int cc = min(kPriMaxCC, C - c0);
             __syncthreads();                                  // staging buffer free
@@ -253,12 +296,16 @@ int prior_nms_pipeline(const b200det_prior_desc* d, void* ws, size_t ws_bytes, f
     dim3 grid(w.n_tiles, d->batch);
     // 128-bit staging needs every 128-row block to start 16-byte aligned and hold a multiple of 4 floats
     const bool vec4 = d->num_classes <= kPriMaxCC && d->num_classes % 4 == 0 && ((uintptr_t)d->cls & 15) == 0;
-    if (vec4) {
-        B2_CUDA(cudaFuncSetAttribute(prior_decode_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        prior_decode_filter_kernel<true><<<grid, kPriRows, smem, st>>>(p);
+    const bool direct = d->num_classes % 4 == 0 && ((uintptr_t)d->cls & 15) == 0 &&
+                        !(getenv("B200DET_PRIOR_K1") && strcmp(getenv("B200DET_PRIOR_K1"), "staged") == 0);
+    if (direct) {
+        prior_decode_filter_kernel<true, true><<<grid, kPriRows, 0, st>>>(p);
+    } else if (vec4) {
+        B2_CUDA(cudaFuncSetAttribute(prior_decode_filter_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        prior_decode_filter_kernel<true, false><<<grid, kPriRows, smem, st>>>(p);
     } else {
-        B2_CUDA(cudaFuncSetAttribute(prior_decode_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        prior_decode_filter_kernel<false><<<grid, kPriRows, smem, st>>>(p);
+        B2_CUDA(cudaFuncSetAttribute(prior_decode_filter_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        prior_decode_filter_kernel<false, false><<<grid, kPriRows, smem, st>>>(p);
     }
     B2_LAUNCH_CHECK("prior_decode_filter_kernel");
     tile_prefix_kernel<<<d->batch, 256, 0, st>>>(w.tile_count, w.tile_prefix, w.n_tiles);
