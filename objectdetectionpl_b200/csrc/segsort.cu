@@ -15,11 +15,25 @@
 // Per-image digit totals of all passes come from one up-front histogram kernel (totals are
 // permutation-invariant).  In-tile ranking is the stable warp-match ranking (match.any + per-warp
 // digit counters), 8 bits per pass.
+#include <stdlib.h>
+
 #include "yolo_ws.cuh"
 
 namespace b200det {
 
 int seg_scan_launch(const uint32_t* cls_hist, uint32_t* seg_off, int C, int batch, cudaStream_t st);
+int cluster_sort_capacity();
+int cluster_sort_launch(const uint32_t* tile_count, const uint32_t* count, uint32_t* seg_off, uint32_t* key[2],
+                        uint32_t* pay[2], uint32_t* rank[2], int n_pad, int n_tiles, int C, int n_cls_passes, int batch,
+                        cudaStream_t st);
+
+// The one-launch cluster sort (clustersort.cu) is used whenever an image's slots fit one cluster; B200DET_SORT=global
+// forces the multi-launch sort below (kept for larger images, and as the A/B reference of the tests).
+static bool use_cluster_sort(int n_pad) {
+    const char* e = getenv("B200DET_SORT");
+    if (e && strcmp(e, "global") == 0) return false;
+    return n_pad <= cluster_sort_capacity();
+}
 
 struct SortParams {
     const uint32_t* tile_count;  // [B][n_tiles] (first pass: tile-sparse input), else unused
@@ -208,6 +222,8 @@ __global__ void __launch_bounds__(kSortThreads) sort_pass_kernel(const SortParam
 int score_sort_launch(const uint32_t* tile_count, const uint32_t* count, uint32_t* digit_hist, uint32_t* ticket,
                       uint32_t* status, uint32_t* key[2], uint32_t* pay[2], int n_pad, int n_tiles, int batch,
                       cudaStream_t st) {
+    if (use_cluster_sort(n_pad))
+        return cluster_sort_launch(tile_count, count, nullptr, key, pay, nullptr, n_pad, n_tiles, 0, 0, batch, st);
     SortParams p;
     memset(&p, 0, sizeof(p));
     p.tile_count = tile_count; p.count = count; p.digit_hist = digit_hist;
@@ -235,6 +251,15 @@ int yolo_stage_sort(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cudaS
     if (rc) return rc;
     YoloWs w;
     yolo_ws_layout(d, ws, &w);
+    if (use_cluster_sort(w.n_pad)) {
+        uint32_t* seg_off = w.n_cls_passes == 1 ? w.seg_off : nullptr;
+        if (!seg_off) {
+            rc = seg_scan_launch(w.cls_hist, w.seg_off, d->num_classes, d->batch, st);
+            if (rc) return rc;
+        }
+        return cluster_sort_launch(w.tile_count, w.count, seg_off, w.key, w.pay, w.rank, w.n_pad, w.n_tiles,
+                                   d->num_classes, w.n_cls_passes, d->batch, st);
+    }
     SortParams p;
     memset(&p, 0, sizeof(p));
     p.tile_count = w.tile_count; p.count = w.count; p.digit_hist = w.digit_hist;

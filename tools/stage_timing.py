@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--conf-mode", default="uniform")
     ap.add_argument("--conf-thres", type=float, default=-0.0151)
+    ap.add_argument("--trace-sort", action="store_true", help="per-phase %globaltimer trace of the cluster sort")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     grids = synth.grids_for(a.model, a.img)
@@ -70,6 +71,26 @@ def main():
                img_per_s=a.batch / (total * 1e-6), decode_GBps=head_bytes / (med["decode"] * 1e-6) / 1e9,
                ws_MB=nb / 1e6)
     print(json.dumps(out))
+    if a.trace_sort:
+        CL = 8
+        tr = torch.zeros(a.batch * CL * 64, dtype=torch.int64, device=dev)
+        lib.b200det_debug_set_trace.argtypes = [ctypes.c_void_p]
+        assert lib.b200det_debug_set_trace(tr.data_ptr()) == 0
+        stages[2][1]()
+        torch.cuda.synchronize()
+        lib.b200det_debug_set_trace(None)
+        t = tr.cpu().view(-1, 8, 8)
+        t = t[(t[:, 0, 0] > 0)]
+        t0 = t[:, 0, 0].min()
+        names = ["load", "rank", "scan+csync", "exchange", "scatter", "csync"]
+        print(f"{t.shape[0]} CTAs traced; kernel span {(t[:, :, :7].max() - t0).item() / 1e3:.1f} us")
+        for ps in range(6):
+            if t[:, ps, 0].max() == 0:
+                continue
+            d = (t[:, ps, 1:7] - t[:, ps, 0:6]).double() / 1e3
+            start = (t[:, ps, 0] - t0).double() / 1e3
+            print(f"pass {ps}: start {start.min():6.1f}..{start.max():6.1f} us | " +
+                  " ".join(f"{nm} {d[:, i].mean():5.2f}/{d[:, i].max():5.2f}" for i, nm in enumerate(names)))
 
 
 if __name__ == "__main__":
