@@ -129,6 +129,39 @@ __device__ __forceinline__ bool may_remove(const uint4 qa, const uint4 qb) {
     return __hbgt2(__hsub2(hi, lo), t);
 }
 
+// The same test for 32 consecutive rows of shared memory against one box, as a 32-bit mask.  The ALU pipe is the
+// bottleneck of this kernel (ncu: alu 70 %, fma 16 %), so the per-pair verdicts are not turned into predicates and
+// bit-inserted (HSET2 + ISETP + SEL + IADD3 on the ALU pipe) but accumulated on the FMA pipe: HSET2.BF yields 1.0 / 0.0
+// per axis, `acc = verdict * 2^k + acc` (HFMA2) collects 8 pairs per half in the mantissa of 1024 + v (exact, v < 256),
+// and three byte permutes + one AND per 32 pairs combine the two axes.  Per pair: 3 HMNMX2 + HSET2 (ALU), 2 on the FMA pipe.
+__device__ __forceinline__ unsigned may_remove_mask32(const uint2* __restrict__ q, const unsigned* __restrict__ qt,
+                                                      const uint4 qj) {
+    const __half2 lo_j = *reinterpret_cast<const __half2*>(&qj.x);
+    const __half2 hi_j = *reinterpret_cast<const __half2*>(&qj.y);
+    const __half2 t_j = *reinterpret_cast<const __half2*>(&qj.z);
+    unsigned u[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        __half2 acc = __floats2half2_rn(1024.0f, 1024.0f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint2 qa = q[g * 8 + k];
+            const unsigned ta = qt[g * 8 + k];
+            const __half2 lo = __hmax2(*reinterpret_cast<const __half2*>(&qa.x), lo_j);
+            const __half2 hi = __hmin2(*reinterpret_cast<const __half2*>(&qa.y), hi_j);
+            const __half2 t = __hmax2(*reinterpret_cast<const __half2*>(&ta), t_j);
+            const __half2 verdict = __hgt2(__hsub2(hi, lo), t);                 // 1.0 where the axis passes
+            const float w = (float)(1 << k);
+            acc = __hfma2(verdict, __floats2half2_rn(w, w), acc);
+        }
+        u[g] = *reinterpret_cast<const unsigned*>(&acc);
+    }
+    // byte 0 / byte 2 of u[g] = the 8 verdicts of the x / y axis
+    const unsigned ra = __byte_perm(u[0], u[1], 0x6240);     // x bits 0..15 | y bits 0..15 << 16
+    const unsigned rb = __byte_perm(u[2], u[3], 0x6240);     // x bits 16..31 | y bits 16..31 << 16
+    return __byte_perm(ra, rb, 0x5410) & __byte_perm(ra, rb, 0x7632);
+}
+
 // FAST: the pre-filter is sound when "no overlap" implies "not removed", i.e. VARIANT 0 with nms_thres >= 0.
 template <int VARIANT, bool FAST>
 __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParams p) {
@@ -146,6 +179,10 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
     __shared__ uint2 s_kq[kNmsStage];
     __shared__ unsigned s_kqt[kNmsStage];
     __shared__ int s_last_members;
+    __shared__ uint32_t s_mlist[kNmsT];     // members of in-chunk clusters in ascending row order: owner index << 10 | row
+    __shared__ uint16_t s_olist[kNmsT];     // keeper rows of this chunk that own at least one member (any order)
+    __shared__ int s_mpre[kNmsT / 32 + 1];  // exclusive prefix of the member bitmap's popcounts
+    __shared__ int s_ocount;
 
     const int b = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -181,6 +218,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
             s_pre[j] = -1;
         }
         if (tid < kNmsW) s_member[tid] = 0ull;      // 32-row groups past nc are never written by the ballots below
+        if (tid == 0) s_ocount = 0;
         __syncthreads();
 
         // ---- phase A: against keepers of earlier chunks ----------------------------------------
@@ -223,12 +261,8 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
                         unsigned c_lo = 0u, c_hi = 0u;
                         // all 64 columns of the word are tested (rows >= j hold valid or stale-but-harmless bounds)
                         // and the columns >= ni are masked off afterwards: no variable-trip-count loop on the diagonal
-#pragma unroll
-                        for (int k = 0; k < 32; ++k) c_lo |= may_remove(make_uint4(s_q[i0 + k].x, s_q[i0 + k].y, s_qt[i0 + k], 0u), qj) ? (1u << k) : 0u;
-                        if (ni > 32) {
-#pragma unroll
-                            for (int k = 0; k < 32; ++k) c_hi |= may_remove(make_uint4(s_q[i0 + 32 + k].x, s_q[i0 + 32 + k].y, s_qt[i0 + 32 + k], 0u), qj) ? (1u << k) : 0u;
-                        }
+                        c_lo = may_remove_mask32(s_q + i0, s_qt + i0, qj);
+                        if (ni > 32) c_hi = may_remove_mask32(s_q + i0 + 32, s_qt + i0 + 32, qj);
                         if (ni < 32) c_lo &= (1u << ni) - 1u;
                         else if (ni < 64) c_hi &= (1u << (ni - 32)) - 1u;
                         unsigned long long cand = ((unsigned long long)c_hi << 32) | c_lo;
@@ -320,6 +354,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
                             const int wi = i >> 6;
                             own = Kprev + s_wpre[wi] + __popcll(s_kept[wi] & ((1ull << (i & 63)) - 1ull));
                             is_member = true;
+                            s_pre[i] = -2;      // keeper row i owns members (still < 0 = "not pre-suppressed")
                         }
                     }
                 }
@@ -338,24 +373,62 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
         const int any_cross = __syncthreads_or(any_cross_local ? 1 : 0);
 
         if (VARIANT == 0) {
-            // ---- merge sums, pulled per keeper over the member bitmap in row order ------------------
+            // ---- merge sums (YOLOV3.py:327-329): keeper first, then its members by descending score ----------
+            // Most keepers own nothing and finish at once; the keepers that own members are compacted so that a few
+            // full warps walk the (short, ordered) member list instead of every keeper scanning the member bitmap.
+            const unsigned* mem32 = reinterpret_cast<const unsigned*>(s_member);
+            const int nh = (nc + 31) >> 5;
+            if (tid < 32) {
+                const int c = lane < nh ? __popc(mem32[lane]) : 0;
+                int inc = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                if (lane <= kNmsT / 32) s_mpre[lane] = inc - c;
+            }
+            __syncthreads();
+            auto finish = [&](const int j, const int kidx, const float ax, const float ay, const float az, const float aw,
+                              const float ws) {
+                if (single) {
+                    const uint32_t r = p.srank[img + c0 + j];
+                    p.kpay[img + r] = p.spay[img + c0 + j];
+                    p.mbox[img + r] = make_float4(__fdiv_rn(ax, ws), __fdiv_rn(ay, ws), __fdiv_rn(az, ws), __fdiv_rn(aw, ws));
+                    atomicAdd(&p.chunk_cnt[(size_t)b * p.n_chunks + (r >> kEmitShift)], 1u);
+                } else {
+                    float* acc = p.kacc + (img + s + kidx) * 5;
+                    acc[0] = ax; acc[1] = ay; acc[2] = az; acc[3] = aw; acc[4] = ws;
+                }
+            };
             for (int j = tid; j < nc; j += kNmsThreads) {
-                const int wj = j >> 6;
-                if (s_pre[j] >= 0 || !((s_kept[wj] >> (j & 63)) & 1ull)) continue;
-                const int kidx = s_own[j];
-                const float4 bj = s_box[j];
-                const float w0 = s_conf[j];
-                float ax = __fmul_rn(w0, bj.x), ay = __fmul_rn(w0, bj.y);
-                float az = __fmul_rn(w0, bj.z), aw = __fmul_rn(w0, bj.w), ws = w0;
-                const unsigned* mem32 = reinterpret_cast<const unsigned*>(s_member);
-                const int h0 = j >> 5, nh = (nc + 31) >> 5;
-                for (int h = h0; h < nh; ++h) {
-                    unsigned mbits = mem32[h];
-                    if (h == h0) mbits &= ~((2u << (j & 31)) - 1u);          // rows after j only
-                    while (mbits) {
-                        const int m = (h << 5) + __ffs((int)mbits) - 1;
-                        mbits &= mbits - 1u;
-                        if (s_own[m] == kidx) {
+                const unsigned mw = mem32[j >> 5];
+                if ((mw >> (j & 31)) & 1u) {
+                    s_mlist[s_mpre[j >> 5] + __popc(mw & ((1u << (j & 31)) - 1u))] = ((uint32_t)s_own[j] << 10) | (uint32_t)j;
+                } else if (s_pre[j] < 0 && ((s_kept[j >> 6] >> (j & 63)) & 1ull)) {
+                    if (s_pre[j] == -2) {
+                        s_olist[atomicAdd(&s_ocount, 1)] = (uint16_t)j;
+                    } else {
+                        const float4 bj = s_box[j];
+                        const float w0 = s_conf[j];
+                        finish(j, s_own[j], __fmul_rn(w0, bj.x), __fmul_rn(w0, bj.y), __fmul_rn(w0, bj.z), __fmul_rn(w0, bj.w), w0);
+                    }
+                }
+            }
+            __syncthreads();
+            {
+                const int M = s_mpre[nh], no = s_ocount;
+                for (int t = tid; t < no; t += kNmsThreads) {
+                    const int j = s_olist[t];
+                    const uint32_t kidx = (uint32_t)s_own[j];
+                    const float4 bj = s_box[j];
+                    const float w0 = s_conf[j];
+                    float ax = __fmul_rn(w0, bj.x), ay = __fmul_rn(w0, bj.y);
+                    float az = __fmul_rn(w0, bj.z), aw = __fmul_rn(w0, bj.w), ws = w0;
+                    for (int u = 0; u < M; ++u) {
+                        const uint32_t v = s_mlist[u];
+                        if ((v >> 10) == kidx) {
+                            const int m = (int)(v & 1023u);
                             const float4 bm = s_box[m];
                             const float wm = s_conf[m];
                             ax = __fadd_rn(ax, __fmul_rn(wm, bm.x));
@@ -365,15 +438,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
                             ws = __fadd_rn(ws, wm);
                         }
                     }
-                }
-                if (single) {
-                    const uint32_t r = p.srank[img + c0 + j];
-                    p.kpay[img + r] = p.spay[img + c0 + j];
-                    p.mbox[img + r] = make_float4(__fdiv_rn(ax, ws), __fdiv_rn(ay, ws), __fdiv_rn(az, ws), __fdiv_rn(aw, ws));
-                    atomicAdd(&p.chunk_cnt[(size_t)b * p.n_chunks + (r >> kEmitShift)], 1u);
-                } else {
-                    float* acc = p.kacc + (img + s + kidx) * 5;
-                    acc[0] = ax; acc[1] = ay; acc[2] = az; acc[3] = aw; acc[4] = ws;
+                    finish(j, (int)kidx, ax, ay, az, aw, ws);
                 }
             }
             if (any_cross) {
