@@ -28,6 +28,7 @@ constexpr int kNmsThreads = 256;
 constexpr int kNmsW = kNmsT / 64;          // mask words per full row
 constexpr int kNmsTriWords = 32 * kNmsW * (kNmsW + 1);   // packed lower-triangular rows
 constexpr int kNmsStage = 256;             // earlier keepers staged per phase-A round
+constexpr int kNmsRounds = 12;             // parallel fixed-point rounds before the serial sweep takes over
 
 struct NmsParams {
     const uint32_t* seg_off;    // [B][C+1]     VARIANT 0
@@ -162,15 +163,28 @@ __device__ __forceinline__ unsigned may_remove_mask32(const uint2* __restrict__ 
     return __byte_perm(ra, rb, 0x5410) & __byte_perm(ra, rb, 0x7632);
 }
 
+// Development aid: phase timestamps of the first chunk of every segment CTA (see tools/stage_timing.py --trace-nms).
+__device__ unsigned long long* g_nms_trace = nullptr;
+__device__ __forceinline__ void nms_stamp(unsigned long long* tr, int point) {
+#ifdef B200DET_NMS_TRACE          // compiled out by default: the extra live pointer costs ~15 % of the kernel
+    if (tr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        tr[point] = t;
+    }
+#endif
+}
+
 // FAST: the pre-filter is sound when "no overlap" implies "not removed", i.e. VARIANT 0 with nms_thres >= 0.
 template <int VARIANT, bool FAST>
-__global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParams p) {
+__global__ void __launch_bounds__(kNmsThreads, 5) nms_segment_kernel(const NmsParams p) {
     __shared__ float4 s_box[kNmsT];
     __shared__ float s_conf[kNmsT];
     __shared__ uint2 s_q[kNmsT];        // half2 lo, hi   (see box_bounds_h2; split 8 + 4 bytes: one 128-bit word per row
     __shared__ unsigned s_qt[kNmsT];    // half2 t         measured slower, 308 vs 295 us)
     __shared__ unsigned long long s_L[kNmsTriWords];
     __shared__ unsigned long long s_kept[kNmsW];
+    __shared__ __align__(16) uint2 s_state[kNmsT / 32];   // per 32-row group: x = kept rows, y = decided rows
     __shared__ unsigned long long s_member[kNmsW];
     __shared__ int s_wpre[kNmsW + 1];
     __shared__ int s_own[kNmsT];
@@ -180,9 +194,9 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
     __shared__ unsigned s_kqt[kNmsStage];
     __shared__ int s_last_members;
     __shared__ uint32_t s_mlist[kNmsT];     // members of in-chunk clusters in ascending row order: owner index << 10 | row
-    __shared__ uint16_t s_olist[kNmsT];     // keeper rows of this chunk that own at least one member (any order)
+    __shared__ int16_t s_next[kNmsT];       // member list position of the next member of the same cluster, or -1
+    __shared__ int16_t s_first[kNmsT];      // per in-chunk keeper ordinal: list position of its first member, or -1
     __shared__ int s_mpre[kNmsT / 32 + 1];  // exclusive prefix of the member bitmap's popcounts
-    __shared__ int s_ocount;
 
     const int b = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -199,6 +213,12 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
     const bool single = n <= kNmsT;
     const float thr = p.thr;
 
+#ifdef B200DET_NMS_TRACE
+    unsigned long long* tr = (VARIANT == 0 && g_nms_trace) ? g_nms_trace + ((size_t)b * gridDim.x + blockIdx.x) * 8 : nullptr;
+#else
+    unsigned long long* tr = nullptr;
+#endif
+    nms_stamp(tr, 0);
     int Kprev = 0;          // keepers found in earlier chunks
     int last_k = -1;        // VARIANT 1/2: index of the last keeper so far
     if (tid == 0) s_last_members = 0;
@@ -216,9 +236,9 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
             s_conf[j] = p.cc2[img + slot].x;
             if (FAST) { const uint4 q = box_bounds_h2(bx, thr); s_q[j] = make_uint2(q.x, q.y); s_qt[j] = q.z; }
             s_pre[j] = -1;
+            s_first[j] = -1;
         }
         if (tid < kNmsW) s_member[tid] = 0ull;      // 32-row groups past nc are never written by the ballots below
-        if (tid == 0) s_ocount = 0;
         __syncthreads();
 
         // ---- phase A: against keepers of earlier chunks ----------------------------------------
@@ -247,10 +267,21 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
             __syncthreads();
         }
 
+        if (c0 == s) nms_stamp(tr, 1);
         // ---- phase B: lower-triangular overlap masks inside the chunk --------------------------
-        for (int w = 0; w < Wc; ++w) {
+        // One task = (mask word w, 32-row group g >= 2w).  The tasks are dealt round-robin to the warps: looping over
+        // the words with rows striped over the CTA leaves the high warps idle for the later words (6 task slots for
+        // warps 0-1 vs 2 for warps 6-7 at ~315 rows), which showed up as barrier stalls.
+        const int ngroups_b = (nc + 31) >> 5;
+        int n_tasks = 0;
+        for (int w = 0; w < Wc; ++w) n_tasks += ngroups_b - 2 * w;
+        for (int t = tid >> 5; t < n_tasks; t += kNmsThreads / 32) {
+            int w = 0, rem = t;
+            while (rem >= ngroups_b - 2 * w) { rem -= ngroups_b - 2 * w; ++w; }
             const int i0 = w << 6;
-            for (int j = i0 + tid; j < nc; j += kNmsThreads) {
+            {
+                const int j = ((2 * w + rem) << 5) + lane;
+                if (j >= nc) continue;
                 unsigned long long bits = 0ull;
                 if (s_pre[j] < 0) {
                     const float4 bj = s_box[j];
@@ -282,43 +313,90 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
         }
         __syncthreads();
 
-        // ---- sweep: exact greedy resolution by warp 0, 32 rows per step -------------------------
-        if (tid < 32) {
-            if (lane < kNmsW) s_kept[lane] = 0ull;
-            __syncwarp();
-            const int ngroups = (nc + 31) >> 5;
-            for (int g = 0; g < ngroups; ++g) {
+        if (c0 == s) nms_stamp(tr, 2);
+        // ---- greedy resolution ------------------------------------------------------------------------------
+        // Row j is kept iff no KEPT earlier row has a bit in its mask.  The masks are lower-triangular, so the solution
+        // is unique and can be reached as a fixed point in parallel: a row is decided once one kept row hits it
+        // (removed) or every row in its mask is decided and not kept (kept).  Dependency chains are short on real
+        // inputs (a few rounds for the whole CTA, instead of one warp walking the rows 32 at a time while seven wait);
+        // kept/decided bits of a 32-row group live in one 64-bit word so that a reader sees a consistent pair, and the
+        // serial sweep below finishes adversarial chains after kNmsRounds rounds.
+        {
+            for (int g = tid >> 5; g < kNmsT / 32; g += kNmsThreads / 32) {
                 const int j = (g << 5) + lane;
-                const int wl = g >> 1;                       // word holding this group
-                const bool valid = j < nc && s_pre[j] < 0;
-                bool hit = false;
-                unsigned m = 0;
-                if (valid) {
-                    const unsigned long long* row = &s_L[tri_off(j)];
-                    for (int w = 0; w < wl; ++w) hit |= (row[w] & s_kept[w]) != 0ull;
-                    const unsigned long long lw = row[wl];
-                    if (g & 1) {
-                        hit |= (lw & s_kept[wl] & 0xFFFFFFFFull) != 0ull;
-                        m = (unsigned)(lw >> 32);
-                    } else {
-                        m = (unsigned)lw;
-                    }
-                }
-                const bool pre = valid && !hit;
-                const unsigned cand = __ballot_sync(0xFFFFFFFFu, pre);
-                // lanes whose in-group mask is empty are decided already; only the others need the serial steps
-                const unsigned dep = __ballot_sync(0xFFFFFFFFu, pre && m != 0u);
-                unsigned kg = cand & ~dep;
-                for (unsigned dd = dep; dd; dd &= dd - 1u) {
-                    // every lane below the lowest pending one is final in kg -> that lane can be decided now
-                    const bool bit = pre && ((m & kg) == 0u);
-                    const unsigned bal = __ballot_sync(0xFFFFFFFFu, bit);
-                    kg |= bal & (dd & (0u - dd));
-                }
-                if (lane == 0 && kg) s_kept[wl] |= (unsigned long long)kg << ((g & 1) * 32);
-                __syncwarp();
+                const unsigned dec = __ballot_sync(0xFFFFFFFFu, j >= nc || s_pre[j] >= 0);   // nothing to decide
+                if (lane == 0) s_state[g] = make_uint2(0u, dec);
             }
-            if (lane == 0) {
+            __syncthreads();
+            int undecided = 1;
+            for (int round = 0; round < kNmsRounds && undecided; ++round) {
+                bool left = false;
+                for (int g = tid >> 5; g < ngroups_b; g += kNmsThreads / 32) {
+                    const int j = (g << 5) + lane;
+                    const uint2 mine = s_state[g];
+                    if (mine.y == 0xFFFFFFFFu) continue;                       // warp-uniform: group fully decided
+                    bool now_kept = false, now_dec = false;
+                    if (!((mine.y >> lane) & 1u)) {
+                        const unsigned long long* row = &s_L[tri_off(j)];
+                        const int wl = j >> 6;
+                        bool hit = false, pend = false;
+                        for (int w = 0; w <= wl; ++w) {
+                            const unsigned long long m = row[w];
+                            const uint4 st = *reinterpret_cast<const uint4*>(&s_state[2 * w]);   // {kept, dec} x 2 groups
+                            const unsigned long long kept = ((unsigned long long)st.z << 32) | st.x;
+                            const unsigned long long dec = ((unsigned long long)st.w << 32) | st.y;
+                            hit |= (m & kept) != 0ull;
+                            pend |= (m & ~dec) != 0ull;
+                        }
+                        now_kept = !hit && !pend;
+                        now_dec = hit || !pend;
+                    }
+                    const unsigned kb = __ballot_sync(0xFFFFFFFFu, now_kept);
+                    const unsigned db = __ballot_sync(0xFFFFFFFFu, now_dec);
+                    if (lane == 0 && db) s_state[g] = make_uint2(mine.x | kb, mine.y | db);
+                    left |= (mine.y | db) != 0xFFFFFFFFu;
+                }
+                undecided = __syncthreads_or(left ? 1 : 0);
+            }
+            if (tid < kNmsW) s_kept[tid] = ((unsigned long long)s_state[2 * tid + 1].x << 32) | s_state[2 * tid].x;
+            __syncthreads();
+            if (undecided && tid < 32) {
+                if (lane < kNmsW) s_kept[lane] = 0ull;
+                __syncwarp();
+                const int ngroups = (nc + 31) >> 5;
+                for (int g = 0; g < ngroups; ++g) {
+                    const int j = (g << 5) + lane;
+                    const int wl = g >> 1;                       // word holding this group
+                    const bool valid = j < nc && s_pre[j] < 0;
+                    bool hit = false;
+                    unsigned m = 0;
+                    if (valid) {
+                        const unsigned long long* row = &s_L[tri_off(j)];
+                        for (int w = 0; w < wl; ++w) hit |= (row[w] & s_kept[w]) != 0ull;
+                        const unsigned long long lw = row[wl];
+                        if (g & 1) {
+                            hit |= (lw & s_kept[wl] & 0xFFFFFFFFull) != 0ull;
+                            m = (unsigned)(lw >> 32);
+                        } else {
+                            m = (unsigned)lw;
+                        }
+                    }
+                    const bool pre = valid && !hit;
+                    const unsigned cand = __ballot_sync(0xFFFFFFFFu, pre);
+                    // lanes whose in-group mask is empty are decided already; only the others need the serial steps
+                    const unsigned dep = __ballot_sync(0xFFFFFFFFu, pre && m != 0u);
+                    unsigned kg = cand & ~dep;
+                    for (unsigned dd = dep; dd; dd &= dd - 1u) {
+                        // every lane below the lowest pending one is final in kg -> that lane can be decided now
+                        const bool bit = pre && ((m & kg) == 0u);
+                        const unsigned bal = __ballot_sync(0xFFFFFFFFu, bit);
+                        kg |= bal & (dd & (0u - dd));
+                    }
+                    if (lane == 0 && kg) s_kept[wl] |= (unsigned long long)kg << ((g & 1) * 32);
+                    __syncwarp();
+                }
+            }
+            if (tid == 0) {
                 int run = 0;
                 for (int w = 0; w < kNmsW; ++w) { s_wpre[w] = run; run += (w < Wc) ? __popcll(s_kept[w]) : 0; }
                 s_wpre[kNmsW] = run;
@@ -327,6 +405,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
         __syncthreads();
         const int Kc = s_wpre[kNmsW];
 
+        if (c0 == s) nms_stamp(tr, 3);
         // ---- owners (warp-uniform trip count so that the member bitmap can be built with ballots) ------
         bool any_cross_local = false;
         for (int jb = (tid & ~31); jb < nc; jb += kNmsThreads) {
@@ -354,7 +433,6 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
                             const int wi = i >> 6;
                             own = Kprev + s_wpre[wi] + __popcll(s_kept[wi] & ((1ull << (i & 63)) - 1ull));
                             is_member = true;
-                            s_pre[i] = -2;      // keeper row i owns members (still < 0 = "not pre-suppressed")
                         }
                     }
                 }
@@ -373,6 +451,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
         const int any_cross = __syncthreads_or(any_cross_local ? 1 : 0);
 
         if (VARIANT == 0) {
+            if (c0 == s) nms_stamp(tr, 4);
             // ---- merge sums (YOLOV3.py:327-329): keeper first, then its members by descending score ----------
             // Most keepers own nothing and finish at once; the keepers that own members are compacted so that a few
             // full warps walk the (short, ordered) member list instead of every keeper scanning the member bitmap.
@@ -403,43 +482,40 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
             };
             for (int j = tid; j < nc; j += kNmsThreads) {
                 const unsigned mw = mem32[j >> 5];
-                if ((mw >> (j & 31)) & 1u) {
+                if ((mw >> (j & 31)) & 1u)
                     s_mlist[s_mpre[j >> 5] + __popc(mw & ((1u << (j & 31)) - 1u))] = ((uint32_t)s_own[j] << 10) | (uint32_t)j;
-                } else if (s_pre[j] < 0 && ((s_kept[j >> 6] >> (j & 63)) & 1ull)) {
-                    if (s_pre[j] == -2) {
-                        s_olist[atomicAdd(&s_ocount, 1)] = (uint16_t)j;
-                    } else {
-                        const float4 bj = s_box[j];
-                        const float w0 = s_conf[j];
-                        finish(j, s_own[j], __fmul_rn(w0, bj.x), __fmul_rn(w0, bj.y), __fmul_rn(w0, bj.z), __fmul_rn(w0, bj.w), w0);
-                    }
-                }
             }
             __syncthreads();
-            {
-                const int M = s_mpre[nh], no = s_ocount;
-                for (int t = tid; t < no; t += kNmsThreads) {
-                    const int j = s_olist[t];
-                    const uint32_t kidx = (uint32_t)s_own[j];
-                    const float4 bj = s_box[j];
-                    const float w0 = s_conf[j];
-                    float ax = __fmul_rn(w0, bj.x), ay = __fmul_rn(w0, bj.y);
-                    float az = __fmul_rn(w0, bj.z), aw = __fmul_rn(w0, bj.w), ws = w0;
-                    for (int u = 0; u < M; ++u) {
-                        const uint32_t v = s_mlist[u];
-                        if ((v >> 10) == kidx) {
-                            const int m = (int)(v & 1023u);
-                            const float4 bm = s_box[m];
-                            const float wm = s_conf[m];
-                            ax = __fadd_rn(ax, __fmul_rn(wm, bm.x));
-                            ay = __fadd_rn(ay, __fmul_rn(wm, bm.y));
-                            az = __fadd_rn(az, __fmul_rn(wm, bm.z));
-                            aw = __fadd_rn(aw, __fmul_rn(wm, bm.w));
-                            ws = __fadd_rn(ws, wm);
-                        }
-                    }
-                    finish(j, (int)kidx, ax, ay, az, aw, ws);
+            const int M = s_mpre[nh];
+            // every member finds its successor in its cluster (and whether it is the first): M independent compares
+            for (int t = tid; t < M; t += kNmsThreads) {
+                const uint32_t own_t = s_mlist[t] >> 10;
+                bool has_prev = false;
+                int next = -1;
+                for (int u = 0; u < t; ++u) has_prev |= (s_mlist[u] >> 10) == own_t;
+                for (int u = M - 1; u > t; --u) if ((s_mlist[u] >> 10) == own_t) next = u;
+                s_next[t] = (int16_t)next;
+                if (!has_prev) s_first[own_t - (uint32_t)Kprev] = (int16_t)t;
+            }
+            __syncthreads();
+            for (int j = tid; j < nc; j += kNmsThreads) {
+                if (s_pre[j] >= 0 || !((s_kept[j >> 6] >> (j & 63)) & 1ull)) continue;
+                const int kidx = s_own[j];
+                const float4 bj = s_box[j];
+                const float w0 = s_conf[j];
+                float ax = __fmul_rn(w0, bj.x), ay = __fmul_rn(w0, bj.y);
+                float az = __fmul_rn(w0, bj.z), aw = __fmul_rn(w0, bj.w), ws = w0;
+                for (int t = s_first[kidx - Kprev]; t >= 0; t = s_next[t]) {
+                    const int m = (int)(s_mlist[t] & 1023u);
+                    const float4 bm = s_box[m];
+                    const float wm = s_conf[m];
+                    ax = __fadd_rn(ax, __fmul_rn(wm, bm.x));
+                    ay = __fadd_rn(ay, __fmul_rn(wm, bm.y));
+                    az = __fadd_rn(az, __fmul_rn(wm, bm.z));
+                    aw = __fadd_rn(aw, __fmul_rn(wm, bm.w));
+                    ws = __fadd_rn(ws, wm);
                 }
+                finish(j, kidx, ax, ay, az, aw, ws);
             }
             if (any_cross) {
                 // rows of this chunk owned by keepers of earlier chunks
@@ -481,6 +557,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(const NmsParam
         }
         Kprev += Kc;
         __syncthreads();   // kacc / kbox writes of this chunk are visible to the next one (same CTA)
+        if (c0 == s) nms_stamp(tr, 5);
     }
 
     if (VARIANT == 0) {
@@ -655,3 +732,8 @@ int prior_nms_launch_raw(const uint32_t* count, const uint32_t* spay, const floa
 }
 
 }  // namespace b200det
+
+extern "C" int b200det_debug_set_nms_trace(void* dev_ptr) {
+    unsigned long long* p = (unsigned long long*)dev_ptr;
+    return (int)cudaMemcpyToSymbol(b200det::g_nms_trace, &p, sizeof(p));
+}

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--conf-mode", default="uniform")
     ap.add_argument("--conf-thres", type=float, default=-0.0151)
     ap.add_argument("--trace-sort", action="store_true", help="per-phase %globaltimer trace of the cluster sort")
+    ap.add_argument("--trace-nms", action="store_true", help="per-phase %globaltimer trace of the NMS kernel")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     grids = synth.grids_for(a.model, a.img)
@@ -71,6 +72,21 @@ def main():
                img_per_s=a.batch / (total * 1e-6), decode_GBps=head_bytes / (med["decode"] * 1e-6) / 1e9,
                ws_MB=nb / 1e6)
     print(json.dumps(out))
+    if a.trace_nms:
+        tr = torch.zeros(a.batch * a.classes * 8, dtype=torch.int64, device=dev)
+        lib.b200det_debug_set_nms_trace.argtypes = [ctypes.c_void_p]
+        assert lib.b200det_debug_set_nms_trace(tr.data_ptr()) == 0
+        stages[3][1]()
+        torch.cuda.synchronize()
+        lib.b200det_debug_set_nms_trace(None)
+        t = tr.cpu().view(-1, 8)
+        t = t[t[:, 0] > 0]
+        t0 = t[:, 0].min()
+        names = ["load", "phaseB", "sweep", "owners", "merge"]
+        d = (t[:, 1:6] - t[:, 0:5]).double() / 1e3
+        life = (t[:, 5] - t[:, 0]).double() / 1e3
+        print(f"{t.shape[0]} CTAs; span {(t[:, 5].max() - t0).item() / 1e3:.1f} us; CTA life mean {life.mean():.1f} max {life.max():.1f} us")
+        print(" ".join(f"{nm} {d[:, i].mean():5.2f}/{d[:, i].max():5.2f}" for i, nm in enumerate(names)))
     if a.trace_sort:
         CL = 8
         tr = torch.zeros(a.batch * CL * 64, dtype=torch.int64, device=dev)
