@@ -2,19 +2,21 @@
 post-processing and target-assignment hot path of Leyan529/ObjectDetectionPL.
 
 Public names mirror the reference (LightningFunc/accuracy.py, model/*.py::non_max_suppression):
-    non_max_suppression, non_max_suppression_v2, prior_non_max_suppression, decode_box,
+    non_max_suppression, non_max_suppression_host (pinned host input, copy/compute overlap), non_max_suppression_v2,
+    prior_non_max_suppression, decode_box,
     xywh2xyxy, bbox_iou, iou, bbox_iou_v5, build_targets, build_targets_v5, v5_match_level,
     ssd_match, retina_assign, install (drop-in monkey patch), dist (image-sharded multi-GPU glue).
 The CUDA library is loaded lazily on first use; importing the package needs neither a GPU nor the .so.
 """
 from .boxes import bbox_iou, bbox_iou_v5, iou, xywh2xyxy
-from .postprocess import (decode_box, non_max_suppression, non_max_suppression_v2, prior_non_max_suppression,
+from .postprocess import (decode_box, non_max_suppression, non_max_suppression_host, non_max_suppression_v2,
+                          prior_non_max_suppression,
                           prior_nms_raw, yolo_nms_raw, YOLO_FORCED_CONF_THRES)
 from .targets import build_targets, build_targets_v5, retina_assign, ssd_match, v5_match_level
 from .patch import install, install_losses, install_model
 from . import dist, synth
 
-__all__ = ["non_max_suppression", "non_max_suppression_v2", "prior_non_max_suppression", "decode_box", "xywh2xyxy",
+__all__ = ["non_max_suppression", "non_max_suppression_host", "non_max_suppression_v2", "prior_non_max_suppression", "decode_box", "xywh2xyxy",
            "bbox_iou", "iou", "bbox_iou_v5", "build_targets", "build_targets_v5", "v5_match_level", "ssd_match",
            "retina_assign", "install", "install_losses", "install_model", "dist", "synth", "yolo_nms_raw", "prior_nms_raw",
            "YOLO_FORCED_CONF_THRES"]

@@ -114,6 +114,83 @@ def non_max_suppression(self, predictions, conf_thres=0.5, nms_thres=0.4, *, com
     return _yolo_nms(predictions, 3, conf_thres, nms_thres, compat, decode, anchors, strides, return_index)
 
 
+class _HostPipe:
+    """Buffers and streams of the host-input pipeline for one (device, head shapes, chunk) configuration."""
+
+    def __init__(self, dev, shapes, chunk, n_pad):
+        self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.dev_in = [[torch.empty((chunk,) + tuple(sh[1:]), dtype=torch.float32, device=dev) for sh in shapes]
+                       for _ in range(2)]
+        B = shapes[0][0]
+        self.host_rows = torch.empty((B, n_pad, 7), dtype=torch.float32).pin_memory()
+        self.host_index = torch.empty((B, n_pad), dtype=torch.int32).pin_memory()
+        self.host_count = torch.empty((B,), dtype=torch.int32).pin_memory()
+
+
+_host_pipes = {}
+
+
+def non_max_suppression_host(self, predictions, conf_thres=0.5, nms_thres=0.4, *, compat=True, num_anchors=3,
+                             device=None, chunk_images=8, decode=None, anchors=None, strides=None, return_index=False):
+    """`non_max_suppression` for predictions that live in HOST memory (pinned memory for full PCIe speed).
+
+    Same arguments and the same rows as `non_max_suppression` (model/YOLOV5.py:157); the batch is cut into chunks of
+    `chunk_images` images and the three legs run on separate streams, so the host->device copy of chunk k+1 overlaps
+    the CUDA pipeline of chunk k and the device->host copy of chunk k-1 (every image is independent).
+    Returns a list of `None` / fp32 `[K,7]` HOST tensors: views into a pinned buffer that is reused by the next call
+    with the same shapes (clone them to keep them)."""
+    if not isinstance(predictions, (list, tuple)):
+        predictions = [predictions]
+    for i, t in enumerate(predictions):
+        if not isinstance(t, torch.Tensor) or t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise TypeError(f"predictions[{i}] must be a contiguous fp32 HOST tensor (use non_max_suppression for CUDA tensors)")
+    if not torch.cuda.is_available():
+        raise RuntimeError("b200det has no CPU path: non_max_suppression_host needs a CUDA device to run on")
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    B = predictions[0].shape[0]
+    chunk = max(1, min(int(chunk_images), B))
+    thr = YOLO_FORCED_CONF_THRES if compat else conf_thres
+    n_pad = None
+    shapes = tuple(tuple(t.shape) for t in predictions)
+    key = (dev.index, shapes, chunk, num_anchors)
+    pipe = _host_pipes.get(key)
+    nchunks = (B + chunk - 1) // chunk
+    ev_in = [torch.cuda.Event() for _ in range(nchunks)]
+    ev_done = [torch.cuda.Event() for _ in range(nchunks)]
+    keep = []
+    with torch.cuda.device(dev):
+        for c in range(nchunks):
+            lo, hi = c * chunk, min(B, (c + 1) * chunk)
+            if pipe is None:
+                G = sum(num_anchors * t.shape[2] * t.shape[2] for t in predictions)
+                n_pad = (G + L.TILE - 1) // L.TILE * L.TILE
+                pipe = _host_pipes[key] = _HostPipe(dev, shapes, chunk, n_pad)
+            dst = [t[:hi - lo] for t in pipe.dev_in[c & 1]]
+            with torch.cuda.stream(pipe.s_in):
+                if c >= 2:
+                    pipe.s_in.wait_event(ev_done[c - 2])            # the pipeline is done with this input buffer
+                for d_, t in zip(dst, predictions):
+                    d_.copy_(t[lo:hi], non_blocking=True)
+                ev_in[c].record(pipe.s_in)
+            with torch.cuda.stream(pipe.s_cmp):
+                pipe.s_cmp.wait_event(ev_in[c])
+                rows, index, count = yolo_nms_raw(dst, num_anchors, thr, nms_thres, decode, anchors, strides, return_index)
+                ev_done[c].record(pipe.s_cmp)
+            with torch.cuda.stream(pipe.s_out):
+                pipe.s_out.wait_event(ev_done[c])
+                pipe.host_rows[lo:hi].copy_(rows, non_blocking=True)
+                pipe.host_count[lo:hi].copy_(count, non_blocking=True)
+                if return_index:
+                    pipe.host_index[lo:hi].copy_(index, non_blocking=True)
+            keep.append((rows, index, count))                        # alive until the copies have run
+        pipe.s_out.synchronize()
+    counts = pipe.host_count.tolist()
+    out: List[Optional[torch.Tensor]] = [pipe.host_rows[b, :k] if k else None for b, k in enumerate(counts)]
+    if return_index:
+        return out, [pipe.host_index[b, :k].long() if k else None for b, k in enumerate(counts)]
+    return out
+
+
 def non_max_suppression_v2(self, predictions, conf_thres=0.5, nms_thres=0.4, *, compat=True, decode=None, anchors=None,
                            strides=None, return_index=False):
     """Drop-in for YOLOv2 `non_max_suppression` (5 anchors, model/YOLOV2.py:179-183)."""
