@@ -194,8 +194,10 @@ __global__ void __launch_bounds__(kNmsThreads, 5) nms_segment_kernel(const NmsPa
     __shared__ unsigned s_kqt[kNmsStage];
     __shared__ int s_last_members;
     __shared__ uint32_t s_mlist[kNmsT];     // members of in-chunk clusters in ascending row order: owner index << 10 | row
+    __shared__ unsigned s_nzw[kNmsT];       // per row: which of its mask words are non-zero (most rows: none)
     __shared__ int16_t s_next[kNmsT];       // member list position of the next member of the same cluster, or -1
     __shared__ int16_t s_first[kNmsT];      // per in-chunk keeper ordinal: list position of its first member, or -1
+    __shared__ int16_t s_last[kNmsT];       // ... of its last member so far (while the chains are built)
     __shared__ int s_mpre[kNmsT / 32 + 1];  // exclusive prefix of the member bitmap's popcounts
 
     const int b = blockIdx.y;
@@ -237,6 +239,8 @@ __global__ void __launch_bounds__(kNmsThreads, 5) nms_segment_kernel(const NmsPa
             if (FAST) { const uint4 q = box_bounds_h2(bx, thr); s_q[j] = make_uint2(q.x, q.y); s_qt[j] = q.z; }
             s_pre[j] = -1;
             s_first[j] = -1;
+            s_last[j] = -1;
+            s_nzw[j] = 0u;
         }
         if (tid < kNmsW) s_member[tid] = 0ull;      // 32-row groups past nc are never written by the ballots below
         __syncthreads();
@@ -309,6 +313,7 @@ __global__ void __launch_bounds__(kNmsThreads, 5) nms_segment_kernel(const NmsPa
                     }
                 }
                 s_L[tri_off(j) + w] = bits;
+                if (bits) atomicOr(&s_nzw[j], 1u << w);
             }
         }
         __syncthreads();
@@ -324,8 +329,11 @@ __global__ void __launch_bounds__(kNmsThreads, 5) nms_segment_kernel(const NmsPa
         {
             for (int g = tid >> 5; g < kNmsT / 32; g += kNmsThreads / 32) {
                 const int j = (g << 5) + lane;
-                const unsigned dec = __ballot_sync(0xFFFFFFFFu, j >= nc || s_pre[j] >= 0);   // nothing to decide
-                if (lane == 0) s_state[g] = make_uint2(0u, dec);
+                const bool live = j < nc && s_pre[j] < 0;
+                const bool free_row = live && s_nzw[j] == 0u;                  // overlaps no earlier row: kept
+                const unsigned kept0 = __ballot_sync(0xFFFFFFFFu, free_row);
+                const unsigned dec0 = __ballot_sync(0xFFFFFFFFu, !live || free_row);
+                if (lane == 0) s_state[g] = make_uint2(kept0, dec0);
             }
             __syncthreads();
             int undecided = 1;
@@ -338,9 +346,9 @@ __global__ void __launch_bounds__(kNmsThreads, 5) nms_segment_kernel(const NmsPa
                     bool now_kept = false, now_dec = false;
                     if (!((mine.y >> lane) & 1u)) {
                         const unsigned long long* row = &s_L[tri_off(j)];
-                        const int wl = j >> 6;
                         bool hit = false, pend = false;
-                        for (int w = 0; w <= wl; ++w) {
+                        for (unsigned nz = s_nzw[j]; nz; nz &= nz - 1u) {
+                            const int w = __ffs((int)nz) - 1;
                             const unsigned long long m = row[w];
                             const uint4 st = *reinterpret_cast<const uint4*>(&s_state[2 * w]);   // {kept, dec} x 2 groups
                             const unsigned long long kept = ((unsigned long long)st.z << 32) | st.x;
@@ -425,7 +433,8 @@ __global__ void __launch_bounds__(kNmsThreads, 5) nms_segment_kernel(const NmsPa
                     } else {
                         const unsigned long long* row = &s_L[tri_off(j)];
                         int i = -1;
-                        for (int w = 0; w <= wj; ++w) {
+                        for (unsigned nz = s_nzw[j]; nz; nz &= nz - 1u) {
+                            const int w = __ffs((int)nz) - 1;
                             const unsigned long long h = row[w] & s_kept[w];
                             if (h) { i = (w << 6) + __ffsll((long long)h) - 1; break; }
                         }
@@ -487,15 +496,26 @@ __global__ void __launch_bounds__(kNmsThreads, 5) nms_segment_kernel(const NmsPa
             }
             __syncthreads();
             const int M = s_mpre[nh];
-            // every member finds its successor in its cluster (and whether it is the first): M independent compares
-            for (int t = tid; t < M; t += kNmsThreads) {
-                const uint32_t own_t = s_mlist[t] >> 10;
-                bool has_prev = false;
-                int next = -1;
-                for (int u = 0; u < t; ++u) has_prev |= (s_mlist[u] >> 10) == own_t;
-                for (int u = M - 1; u > t; --u) if ((s_mlist[u] >> 10) == own_t) next = u;
-                s_next[t] = (int16_t)next;
-                if (!has_prev) s_first[own_t - (uint32_t)Kprev] = (int16_t)t;
+            // chain the members of every cluster in list (= row) order: one warp walks the list 32 entries at a time;
+            // the predecessor of an entry is the closest lower lane with the same owner, else the owner's last entry
+            // of the earlier steps (s_last)
+            if (tid < 32) {
+                for (int t0 = 0; t0 < M; t0 += 32) {
+                    const int t = t0 + lane;
+                    const bool valid = t < M;
+                    const int o = valid ? (int)(s_mlist[t] >> 10) - Kprev : -1 - lane;     // distinct dummies
+                    if (valid) s_next[t] = -1;
+                    const unsigned peers = __match_any_sync(0xFFFFFFFFu, o);
+                    const unsigned lower = peers & lanemask_lt();
+                    __syncwarp();
+                    if (valid) {
+                        const int prev = lower ? t0 + 31 - __clz((int)lower) : (int)s_last[o];
+                        if (prev >= 0) s_next[prev] = (int16_t)t;
+                        else s_first[o] = (int16_t)t;
+                        if ((peers >> lane) <= 1u) s_last[o] = (int16_t)t;                // highest lane of the group
+                    }
+                    __syncwarp();
+                }
             }
             __syncthreads();
             for (int j = tid; j < nc; j += kNmsThreads) {
