@@ -105,6 +105,9 @@ class ClockSampler:
         if self.ok:
             self.t = threading.Thread(target=self._run, daemon=True)
             self.t.start()
+            t0 = time.time()
+            while not self.samples and time.time() - t0 < 2.0:      # the first NVML query can take a while
+                time.sleep(0.001)
         return self
 
     def __exit__(self, *a):
@@ -308,7 +311,7 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak()
         achieved = head_bytes / (k1_us * 1e-6) / 1e9
-        launches = 1 + 1 + 1 + 1 + 1                           # zero-fill; K1; cluster sort; NMS; emit
+        launches = 1 + 1 + 1 + 1                               # K1; cluster sort; NMS; emit (the reset stage launches nothing)
         traffic = None
         tp = os.path.join(ROOT, "profiles", "k1_traffic.json")   # dram__bytes_read+write of one K1 launch (ncu --set full)
         if os.path.exists(tp):

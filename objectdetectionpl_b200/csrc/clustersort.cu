@@ -30,7 +30,10 @@ static_assert(kCsCap % kTile == 0, "CTA capacity must cover whole candidate tile
 
 struct ClusterSortParams {
     const uint32_t* tile_count;   // [B][n_tiles]
-    const uint32_t* count;        // [B]
+    uint32_t* count;              // [B]  read, or (count_from_tiles) written: sum of the image's tile counts
+    uint32_t* chunk_cnt;          // [B][n_chunks] zeroed here for the NMS stage when count_from_tiles
+    int n_chunks;
+    int count_from_tiles;
     uint32_t* seg_off;            // [B][C+1] or null (score-only sort / C > 256)
     uint32_t* key[2];
     uint32_t* pay[2];
@@ -226,8 +229,19 @@ __global__ void __launch_bounds__(kCsThreads, 2) cluster_sort_kernel(const Clust
     const int crank = CL == 1 ? 0 : (int)blockIdx.x;     // cluster dims are (CL, 1, 1) and gridDim.x == CL
     const int tid = threadIdx.x;
     const size_t img = (size_t)b * p.n_pad;
-    const int n = (int)p.count[b];
     const uint32_t* tc = p.tile_count + (size_t)b * p.n_tiles;
+    int n;
+    if (p.count_from_tiles) {
+        int part = 0;
+        for (int t = tid; t < p.n_tiles; t += kCsThreads) part += (int)tc[t];
+        block_exclusive_scan(part, sm.scan, &n);
+        if (crank == 0) {
+            if (tid == 0) p.count[b] = (uint32_t)n;
+            for (int i = tid; i < p.n_chunks; i += kCsThreads) p.chunk_cnt[(size_t)b * p.n_chunks + i] = 0u;
+        }
+    } else {
+        n = (int)p.count[b];
+    }
     unsigned long long* tr = g_cs_trace ? g_cs_trace + ((size_t)(b * CL + crank) * 8) * 8 : nullptr;
 
     for (int i = tid; i < kCsWarps * 256; i += kCsThreads) (&sm.tab[0][0])[i] = make_uint2(0u, 0u);
@@ -275,13 +289,14 @@ static int cluster_sort_launch_cl(const ClusterSortParams& p, int batch, cudaStr
 
 // One-launch sort of every image's candidates.  n_cls_passes = 0: score order only, result in pay[0];
 // otherwise (class, score) order in yolo_sorted_pay / yolo_sorted_rank and, when seg_off != null, the class offsets.
-int cluster_sort_launch(const uint32_t* tile_count, const uint32_t* count, uint32_t* seg_off, uint32_t* key[2],
-                        uint32_t* pay[2], uint32_t* rank[2], int n_pad, int n_tiles, int C, int n_cls_passes, int batch,
-                        cudaStream_t st) {
+int cluster_sort_launch(const uint32_t* tile_count, uint32_t* count, bool count_from_tiles, uint32_t* chunk_cnt,
+                        int n_chunks, uint32_t* seg_off, uint32_t* key[2], uint32_t* pay[2], uint32_t* rank[2], int n_pad,
+                        int n_tiles, int C, int n_cls_passes, int batch, cudaStream_t st) {
     B2_CHECK_LIMIT(n_pad <= cluster_sort_capacity(), "cluster sort: %d slots per image > %d", n_pad, cluster_sort_capacity());
     ClusterSortParams p;
     memset(&p, 0, sizeof(p));
     p.tile_count = tile_count; p.count = count; p.seg_off = seg_off;
+    p.count_from_tiles = count_from_tiles ? 1 : 0; p.chunk_cnt = chunk_cnt; p.n_chunks = n_chunks;
     for (int i = 0; i < 2; ++i) { p.key[i] = key[i]; p.pay[i] = pay[i]; p.rank[i] = rank ? rank[i] : nullptr; }
     p.n_pad = n_pad; p.n_tiles = n_tiles; p.C = C; p.n_cls_passes = n_cls_passes;
     if (n_pad <= kCsCap) return cluster_sort_launch_cl<1>(p, batch, st);

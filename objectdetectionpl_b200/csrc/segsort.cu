@@ -23,9 +23,9 @@ namespace b200det {
 
 int seg_scan_launch(const uint32_t* cls_hist, uint32_t* seg_off, int C, int batch, cudaStream_t st);
 int cluster_sort_capacity();
-int cluster_sort_launch(const uint32_t* tile_count, const uint32_t* count, uint32_t* seg_off, uint32_t* key[2],
-                        uint32_t* pay[2], uint32_t* rank[2], int n_pad, int n_tiles, int C, int n_cls_passes, int batch,
-                        cudaStream_t st);
+int cluster_sort_launch(const uint32_t* tile_count, uint32_t* count, bool count_from_tiles, uint32_t* chunk_cnt,
+                        int n_chunks, uint32_t* seg_off, uint32_t* key[2], uint32_t* pay[2], uint32_t* rank[2], int n_pad,
+                        int n_tiles, int C, int n_cls_passes, int batch, cudaStream_t st);
 
 // The one-launch cluster sort (clustersort.cu) is used whenever an image's slots fit one cluster; B200DET_SORT=global
 // forces the multi-launch sort below (kept for larger images, and as the A/B reference of the tests).
@@ -34,6 +34,8 @@ static bool use_cluster_sort(int n_pad) {
     if (e && strcmp(e, "global") == 0) return false;
     return n_pad <= cluster_sort_capacity();
 }
+
+bool yolo_fast_path(const YoloWs& w) { return use_cluster_sort(w.n_pad) && w.n_cls_passes == 1; }
 
 struct SortParams {
     const uint32_t* tile_count;  // [B][n_tiles] (first pass: tile-sparse input), else unused
@@ -223,7 +225,8 @@ int score_sort_launch(const uint32_t* tile_count, const uint32_t* count, uint32_
                       uint32_t* status, uint32_t* key[2], uint32_t* pay[2], int n_pad, int n_tiles, int batch,
                       cudaStream_t st) {
     if (use_cluster_sort(n_pad))
-        return cluster_sort_launch(tile_count, count, nullptr, key, pay, nullptr, n_pad, n_tiles, 0, 0, batch, st);
+        return cluster_sort_launch(tile_count, const_cast<uint32_t*>(count), false, nullptr, 0, nullptr, key, pay, nullptr, n_pad,
+                                   n_tiles, 0, 0, batch, st);
     SortParams p;
     memset(&p, 0, sizeof(p));
     p.tile_count = tile_count; p.count = count; p.digit_hist = digit_hist;
@@ -257,8 +260,9 @@ int yolo_stage_sort(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cudaS
             rc = seg_scan_launch(w.cls_hist, w.seg_off, d->num_classes, d->batch, st);
             if (rc) return rc;
         }
-        return cluster_sort_launch(w.tile_count, w.count, seg_off, w.key, w.pay, w.rank, w.n_pad, w.n_tiles,
-                                   d->num_classes, w.n_cls_passes, d->batch, st);
+        const bool fast = yolo_fast_path(w);      // then count / chunk_cnt were not prepared by reset + decode
+        return cluster_sort_launch(w.tile_count, w.count, fast, fast ? w.chunk_cnt : nullptr, w.n_chunks, seg_off, w.key,
+                                   w.pay, w.rank, w.n_pad, w.n_tiles, d->num_classes, w.n_cls_passes, d->batch, st);
     }
     SortParams p;
     memset(&p, 0, sizeof(p));

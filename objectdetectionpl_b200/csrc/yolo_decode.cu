@@ -120,17 +120,17 @@ yolo_decode_filter_kernel(const K1Params p) {
     for (int v = 0; v < VEC; ++v) {
         if (keep[v]) {
             k1_stage_put(s_stage, ofs, box[v], conf[v], ccf[v], (uint32_t)(n0 + v), cls[v]);
-            atomicAdd(&s_hist[cls[v]], 1);
+            if (p.cls_hist) atomicAdd(&s_hist[cls[v]], 1);
             ++ofs;
         }
     }
     if (tid == 0) {
         p.tile_count[(size_t)b * p.n_tiles + tile] = (uint32_t)total;
-        if (total) atomicAdd(&p.count[b], (uint32_t)total);
+        if (total && p.count) atomicAdd(&p.count[b], (uint32_t)total);
     }
     __syncthreads();
     k1_stage_flush<NT>(s_stage, p, img, tile, total, tid);
-    for (int c = tid; c < p.C; c += NT) {
+    if (p.cls_hist) for (int c = tid; c < p.C; c += NT) {
         int h = s_hist[c];
         if (h) atomicAdd(&p.cls_hist[(size_t)b * p.C + c], (uint32_t)h);
     }
@@ -220,6 +220,7 @@ int yolo_stage_reset(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cuda
     if (rc) return rc;
     YoloWs w;
     yolo_ws_layout(d, ws, &w);
+    if (yolo_fast_path(w)) return 0;          // the cluster sort produces count / seg_off / zeroed chunk counters itself
     return zero_fill_launch(w.count, w.zero_bytes, st);
 }
 
@@ -252,6 +253,7 @@ int yolo_stage_decode(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cud
     p.conf_thres = d->conf_thres;
     p.box4 = w.box4; p.cc2 = w.cc2; p.orig = w.orig; p.key = w.key[0]; p.pay = w.pay[0];
     p.tile_count = w.tile_count; p.count = w.count; p.cls_hist = w.cls_hist;
+    if (yolo_fast_path(w)) { p.count = nullptr; p.cls_hist = nullptr; }      // see yolo_stage_reset
 
     // default: the register-staged LDG kernel; B200DET_K1=tma selects the bulk-async (TMA) pipeline, which is
     // bit-identical and measured 6% slower on B200 (see yolo_decode_tma.cu)

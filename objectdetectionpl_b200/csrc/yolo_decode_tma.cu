@@ -244,11 +244,11 @@ __global__ void __launch_bounds__(kTile / CPT + 32, CTAS) yolo_decode_filter_tma
         }
         if (tid == 0) {
             p.tile_count[(size_t)b * p.n_tiles + tile] = (uint32_t)total;
-            if (total) atomicAdd(&p.count[b], (uint32_t)total);
+            if (total && p.count) atomicAdd(&p.count[b], (uint32_t)total);
         }
         consumer_sync<kTmaConsumers>();
         k1_stage_flush<kTmaConsumers>(s_cand, p, img, tile, total, tid);
-        for (int c = tid; c < p.C; c += kTmaConsumers) {
+        if (p.cls_hist) for (int c = tid; c < p.C; c += kTmaConsumers) {
             const int h = s_hist[c];
             if (h) atomicAdd(&p.cls_hist[(size_t)b * p.C + c], (uint32_t)h);
         }

@@ -85,4 +85,9 @@ inline const uint32_t* yolo_sorted_rank(const YoloWs& w) { return w.n_cls_passes
 
 int yolo_validate(const b200det_yolo_desc* d, const void* ws, size_t ws_bytes);
 
+// True when the sort stage is the one-launch cluster sort AND it derives everything the later stages need (count,
+// class offsets, zeroed chunk counters) itself: then the reset stage launches nothing and the decode kernel skips its
+// global counter atomics.  (segsort.cu)
+bool yolo_fast_path(const YoloWs& w);
+
 }  // namespace b200det
