@@ -642,19 +642,20 @@ constexpr int kEmitPerCta = 1;                 // chunks per CTA (4 per CTA meas
 
 __global__ void __launch_bounds__(kEmitThreads) yolo_emit_kernel(const EmitParams p) {
     __shared__ int s_scan[33];
-    __shared__ float s_rows[kEmitChunk * 7];    // kept rows of one chunk, packed -> coalesced global stores
+    __shared__ __align__(16) float s_rows[kEmitChunk * 7 + 4];    // kept rows of one chunk, packed (+ alignment shift)
     __shared__ int s_idx[kEmitChunk];
-    const int b = blockIdx.y, tid = threadIdx.x;
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     const int c_first = blockIdx.x * kEmitPerCta;
     const size_t img = (size_t)b * p.n_pad;
     const int n = (int)p.count[b];
     if (c_first > 0 && (c_first << kEmitShift) >= n) return;
     const uint32_t* cc = p.chunk_cnt + (size_t)b * p.n_chunks;
+    // output base = kept rows of the preceding chunks; every warp sums them on its own (no block barrier)
     const int upto = c_first == 0 ? p.n_chunks : c_first;          // the first CTA also totals the image
-    int part = 0;
-    for (int t = tid; t < upto; t += kEmitThreads) part += (int)cc[t];
-    int base;
-    block_exclusive_scan(part, s_scan, &base);
+    int base = 0;
+    for (int t = lane; t < upto; t += 32) base += (int)cc[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) base += __shfl_xor_sync(0xFFFFFFFFu, base, o);
     if (c_first == 0) {
         if (tid == 0) p.out_count[b] = base;
         base = 0;
@@ -669,27 +670,58 @@ __global__ void __launch_bounds__(kEmitThreads) yolo_emit_kernel(const EmitParam
 #pragma unroll
             for (int i = 0; i < 4; ++i) if (r + i < n) pay[i] = p.kpay[img + r + i];
         }
+        // gathers issued before the scan so that their latency overlaps it
+        float4 mb[4];
+        float2 cf[4];
+        int og[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (pay[i] != kNone) {
+                const uint32_t slot = pay[i] & kSlotMask;
+                mb[i] = p.mbox[img + r + i];
+                cf[i] = p.cc2[img + slot];
+                og[i] = p.out_index ? (int)p.orig[img + slot] : 0;
+            }
+        }
         int cnt = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) cnt += pay[i] != kNone ? 1 : 0;
         int total;
         int ex = block_exclusive_scan(cnt, s_scan, &total);     // trailing barrier also protects s_rows reuse
+        // rows are staged with the same alignment (mod 4 floats) as their place in the output, so the copy below
+        // moves whole aligned float4 words
+        const size_t gfloat = (img + (size_t)base) * 7;
+        const int sh = (int)(gfloat & 3);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (pay[i] != kNone) {
-                const uint32_t slot = pay[i] & kSlotMask;
-                const float4 mb = p.mbox[img + r + i];
-                const float2 cf = p.cc2[img + slot];
-                float* o = s_rows + ex * 7;
-                o[0] = mb.x; o[1] = mb.y; o[2] = mb.z; o[3] = mb.w;
-                o[4] = cf.x; o[5] = cf.y; o[6] = (float)(pay[i] >> kSlotBits);     // YOLOV3.py:318-319
-                if (p.out_index) s_idx[ex] = (int)p.orig[img + slot];
+                float* o = s_rows + sh + ex * 7;
+                o[0] = mb[i].x; o[1] = mb[i].y; o[2] = mb[i].z; o[3] = mb[i].w;
+                o[4] = cf[i].x; o[5] = cf[i].y; o[6] = (float)(pay[i] >> kSlotBits);     // YOLOV3.py:318-319
+                if (p.out_index) s_idx[ex] = og[i];
                 ++ex;
             }
         }
         __syncthreads();
-        float* dst = p.out_rows + (img + base) * 7;
-        for (int i = tid; i < total * 7; i += kEmitThreads) dst[i] = s_rows[i];
+        {
+            const int nfl = total * 7;                            // floats to write
+            float4* dst4 = reinterpret_cast<float4*>(p.out_rows + (gfloat - sh));
+            const float4* src4 = reinterpret_cast<const float4*>(s_rows);
+            const int nvec = (sh + nfl + 3) >> 2;
+            for (int i = tid; i < nvec; i += kEmitThreads) {
+                const float4 v = src4[i];
+                const int f0 = i * 4 - sh;                        // index of v.x among the chunk's floats
+                if (f0 >= 0 && f0 + 3 < nfl) {
+                    dst4[i] = v;
+                } else {
+                    float* d = reinterpret_cast<float*>(dst4 + i);
+                    if (f0 >= 0 && f0 < nfl) d[0] = v.x;
+                    if (f0 + 1 >= 0 && f0 + 1 < nfl) d[1] = v.y;
+                    if (f0 + 2 >= 0 && f0 + 2 < nfl) d[2] = v.z;
+                    if (f0 + 3 >= 0 && f0 + 3 < nfl) d[3] = v.w;
+                }
+            }
+        }
         if (p.out_index) {
             int32_t* di = p.out_index + img + base;
             for (int i = tid; i < total; i += kEmitThreads) di[i] = s_idx[i];
@@ -722,6 +754,7 @@ int yolo_stage_emit(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, float
     int rc = yolo_validate(d, ws, ws_bytes);
     if (rc) return rc;
     B2_CHECK_ARG(out_rows && out_count, "out_rows / out_count is null");
+    B2_CHECK_ARG(((uintptr_t)out_rows & 15) == 0, "out_rows must be 16-byte aligned");
     YoloWs w;
     yolo_ws_layout(d, ws, &w);
     EmitParams p;
