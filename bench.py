@@ -173,12 +173,33 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Keep fd 1 for the ONE JSON line: libraries that write to the C stdout (NCCL prints its version there) are
+    pointed at stderr for the rest of the run."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_json(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
     args = parse()
     rank, world, local = dist_env()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -343,7 +364,7 @@ def main():
             line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
                                     "sample": f"{done} image of the same batch (25200 candidates, all survive), no warm-up, "
                                               "torch-CPU port of the reference loop with all host threads"}
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     if world > 1:
         dist.destroy_process_group()
 
