@@ -219,6 +219,33 @@ int b200det_retina_assign(const float* anchors, int32_t num_anchors, const float
                           int32_t num_targets, int32_t batch, float img_size, void* workspace,
                           size_t workspace_bytes, float* loc_targets, int32_t* cls_targets, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * M1 — true-positive matching of detections against labels.  Replaces `get_batch_statistics(outputs,
+ * targets, iou_threshold)` (LightningFunc/accuracy.py:116-154, called from LightningFunc/step.py:95).
+ *   rows       detection rows of 7 floats (x1,y1,x2,y2,conf,cls_conf,label); image b owns rows
+ *              [row_start[b], row_start[b] + count[b])  (row units; row_start int64 on the device) — covers both the
+ *              padded [B,n_pad,7] output of b200det_yolo_nms (row_start[b] = b*n_pad) and a packed concatenation;
+ *   targets    [num_targets,6] = (image, label, x1, y1, x2, y2) exactly as the reference passes them;
+ *   tp         out, indexed like rows: 1.0 for a true positive, else 0.0;  max_count >= max(count) sizes the grid.
+ * ---------------------------------------------------------------------------------------------- */
+size_t b200det_batch_statistics_workspace_bytes(int32_t batch, int32_t num_targets);
+int b200det_batch_statistics(const float* rows, const int64_t* row_start, const int32_t* count, int32_t batch,
+                             int32_t max_count, const float* targets, int32_t num_targets, float iou_threshold,
+                             void* ws, size_t ws_bytes, float* tp, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * M2 — per-class precision / recall / AP / F1.  Replaces `ap_per_class(tp, conf, pred_cls, target_cls)`
+ * with `compute_ap` (LightningFunc/accuracy.py:207-287, called from LightningFunc/step.py:115).
+ *   tp, conf, pred_cls   [num_pred] fp32 (tp != 0 counts as a true positive; labels as floats, like the rows);
+ *   classes, n_gt        [num_classes] int32: np.unique(target_cls) and the label count of each (device);
+ *   p, r, ap, f1         [num_classes] fp64 out.  Ties in conf are ordered by position (numpy's argsort is unstable).
+ * Limits: num_pred <= 2^30; class ids that are not integers in [0, 2^30) match no evaluated class.
+ * ---------------------------------------------------------------------------------------------- */
+size_t b200det_ap_per_class_workspace_bytes(int32_t num_pred);
+int b200det_ap_per_class(const float* tp, const float* conf, const float* pred_cls, int32_t num_pred,
+                         const int32_t* classes, const int32_t* n_gt, int32_t num_classes, void* ws, size_t ws_bytes,
+                         double* p, double* r, double* ap, double* f1, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

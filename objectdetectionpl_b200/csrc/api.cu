@@ -47,6 +47,13 @@ int ssd_match_launch(const float*, int, const float*, int, float, void*, int32_t
 size_t retina_assign_ws_bytes(int, int);
 int retina_assign_launch(const float*, int, const float*, int, int, float, void*, float*, int32_t*, cudaStream_t);
 
+size_t batch_statistics_ws_bytes(int, int);
+int batch_statistics_launch(const float*, const long long*, const int*, int, int, const float*, int, float, void*, float*,
+                            cudaStream_t);
+size_t ap_per_class_ws_bytes(int);
+int ap_per_class_launch(const float*, const float*, const float*, int, const int*, const int*, int, void*, double*, double*,
+                        double*, double*, cudaStream_t);
+
 }  // namespace b200det
 
 using namespace b200det;
@@ -254,6 +261,42 @@ int b200det_retina_assign(const float* anchors, int32_t A, const float* targets,
         return B200DET_EWORKSPACE;
     }
     return retina_assign_launch(anchors, A, targets, nt, B, img_size, ws, loc, cls, (cudaStream_t)st);
+}
+
+size_t b200det_batch_statistics_workspace_bytes(int32_t B, int32_t nt) {
+    if (B <= 0 || nt < 0) return 0;
+    return batch_statistics_ws_bytes(B, nt);
+}
+int b200det_batch_statistics(const float* rows, const int64_t* row_start, const int32_t* count, int32_t B, int32_t max_count,
+                             const float* targets, int32_t nt, float thr, void* ws, size_t ws_bytes, float* tp, void* st) {
+    B2_CHECK_ARG(B > 0 && nt >= 0 && max_count >= 0, "bad sizes");
+    B2_CHECK_LIMIT(B <= 65535, "batch %d > 65535", B);
+    B2_CHECK_ARG(row_start && count && ws && (nt == 0 || targets) && (max_count == 0 || (rows && tp)), "null argument");
+    if (ws_bytes < batch_statistics_ws_bytes(B, nt)) {
+        set_error("workspace too small");
+        return B200DET_EWORKSPACE;
+    }
+    return batch_statistics_launch(rows, (const long long*)row_start, count, B, max_count, targets, nt, thr, ws, tp,
+                                   (cudaStream_t)st);
+}
+
+size_t b200det_ap_per_class_workspace_bytes(int32_t n) {
+    if (n < 0 || n > (1 << 30)) return 0;
+    return ap_per_class_ws_bytes(n);
+}
+int b200det_ap_per_class(const float* tp, const float* conf, const float* pred_cls, int32_t n, const int32_t* classes,
+                         const int32_t* n_gt, int32_t num_classes, void* ws, size_t ws_bytes, double* p, double* r, double* ap,
+                         double* f1, void* st) {
+    B2_CHECK_ARG(n >= 0 && num_classes >= 0, "bad sizes");
+    B2_CHECK_LIMIT(n <= (1 << 30), "num_pred %d > 2^30", n);
+    B2_CHECK_LIMIT(num_classes <= 65535, "num_classes %d > 65535", num_classes);
+    B2_CHECK_ARG(ws && (n == 0 || (tp && conf && pred_cls)) && (num_classes == 0 || (classes && n_gt && p && r && ap && f1)),
+                 "null argument");
+    if (ws_bytes < ap_per_class_ws_bytes(n)) {
+        set_error("workspace too small");
+        return B200DET_EWORKSPACE;
+    }
+    return ap_per_class_launch(tp, conf, pred_cls, n, classes, n_gt, num_classes, ws, p, r, ap, f1, (cudaStream_t)st);
 }
 
 }  // extern "C"

@@ -254,15 +254,26 @@ int yolo_stage_sort(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cudaS
     if (rc) return rc;
     YoloWs w;
     yolo_ws_layout(d, ws, &w);
+    return class_score_sort(w, yolo_fast_path(w), st);
+}
+
+// (class asc, score desc, index asc) sort of the tile-sparse (key, payload) pairs described by `w` (also used by the
+// AP kernels of metrics.cu with a hand-filled YoloWs).  `fast`: count / chunk_cnt are derived here (yolo_fast_path).
+int class_score_sort(const YoloWs& w, bool fast, cudaStream_t st) {
+    int rc = 0;
+    struct { int num_classes, batch; } dd = {w.C, w.B};
+    const auto* d = &dd;
     if (use_cluster_sort(w.n_pad)) {
         uint32_t* seg_off = w.n_cls_passes == 1 ? w.seg_off : nullptr;
         if (!seg_off) {
             rc = seg_scan_launch(w.cls_hist, w.seg_off, d->num_classes, d->batch, st);
             if (rc) return rc;
         }
-        const bool fast = yolo_fast_path(w);      // then count / chunk_cnt were not prepared by reset + decode
-        return cluster_sort_launch(w.tile_count, w.count, fast, fast ? w.chunk_cnt : nullptr, w.n_chunks, seg_off, w.key,
-                                   w.pay, w.rank, w.n_pad, w.n_tiles, d->num_classes, w.n_cls_passes, d->batch, st);
+        uint32_t* key[2] = {w.key[0], w.key[1]};
+        uint32_t* pay[2] = {w.pay[0], w.pay[1]};
+        uint32_t* rank[2] = {w.rank[0], w.rank[1]};
+        return cluster_sort_launch(w.tile_count, w.count, fast, fast ? w.chunk_cnt : nullptr, w.n_chunks, seg_off, key,
+                                   pay, rank, w.n_pad, w.n_tiles, d->num_classes, w.n_cls_passes, d->batch, st);
     }
     SortParams p;
     memset(&p, 0, sizeof(p));

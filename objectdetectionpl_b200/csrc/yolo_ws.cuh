@@ -89,5 +89,7 @@ int yolo_validate(const b200det_yolo_desc* d, const void* ws, size_t ws_bytes);
 // class offsets, zeroed chunk counters) itself: then the reset stage launches nothing and the decode kernel skips its
 // global counter atomics.  (segsort.cu)
 bool yolo_fast_path(const YoloWs& w);
+int class_score_sort(const YoloWs& w, bool fast, cudaStream_t st);
+int zero_fill_launch(void* p, size_t bytes, cudaStream_t st);
 
 }  // namespace b200det

@@ -3,7 +3,7 @@ functions (model/YOLOV5.py:134-150) and the module-global lookups of LightningFu
 `LightningFunc/step.py` stays untouched."""
 from __future__ import annotations
 
-from . import boxes, postprocess, targets
+from . import boxes, metrics, postprocess, targets
 
 
 def install_model(model_cls):
@@ -38,7 +38,17 @@ def install_losses(losses_module=None, accuracy_module=None):
         accuracy_module.iou = boxes.iou
 
 
-def install(*model_classes, losses_module=None, accuracy_module=None):
+def install_metrics(step_module=None, accuracy_module=None):
+    """Patch the test-time metrics: `LightningFunc/step.py:11` binds `get_batch_statistics` and `ap_per_class` into its own
+    namespace at import, so both modules are patched."""
+    for m in (step_module, accuracy_module):
+        if m is not None:
+            m.get_batch_statistics = metrics.get_batch_statistics
+            m.ap_per_class = metrics.ap_per_class
+
+
+def install(*model_classes, losses_module=None, accuracy_module=None, step_module=None):
     for c in model_classes:
         install_model(c)
     install_losses(losses_module, accuracy_module)
+    install_metrics(step_module, accuracy_module)

@@ -227,6 +227,46 @@ def match_cases():
     _save("match", **d)
 
 
+def metrics_cases():
+    """get_batch_statistics + ap_per_class of the unmodified reference (accuracy.py:116-154, 207-287) on the output of
+    its own NMS; the labels are jittered copies of some detections (so that there are true positives, duplicates aiming
+    at the same label, and labels nobody reaches) plus unrelated boxes."""
+    acc = rh.accuracy()
+    nms = rh.yolo_nms(5)
+    for name, B, C, grids, img, seed in (("metrics_small", 3, 4, [10, 5], 80, 81), ("metrics_mid", 6, 12, [20, 10, 5], 160, 82)):
+        lv = synth.yolo_planar(B, 3, C, grids, img, seed, v5_view=True)
+        dets = nms(None, [t.clone() for t in lv])
+        dets[1] = None                                   # an image without detections (accuracy.py:122-123)
+        g = torch.Generator().manual_seed(seed)
+        tg = []
+        for b, d in enumerate(dets):
+            if d is None:
+                tg.append(torch.tensor([[b, 1.0, 5.0, 5.0, 30.0, 30.0]]))
+                continue
+            if b == B - 1:
+                continue                                 # an image without labels (:133-135)
+            k = min(8, d.shape[0])
+            pick = d[torch.randperm(d.shape[0], generator=g)[:k]]
+            box = pick[:, :4] + torch.randn(k, 4, generator=g) * 2.5
+            lab = pick[:, 6:7].clone()
+            lab[0] = (lab[0] + 1) % C                    # one label with the wrong class
+            rnd = torch.rand(3, 4, generator=g) * img * 0.5
+            rnd[:, 2:] += rnd[:, :2] + 4
+            tg.append(torch.cat([torch.full((k, 1), float(b)), lab, box], 1))
+            tg.append(torch.cat([torch.full((3, 1), float(b)), torch.randint(0, C, (3, 1), generator=g).float(), rnd], 1))
+        tg = torch.cat(tg)
+        stats = acc.get_batch_statistics(dets, tg, 0.5)
+        tp, sc, lb = [np.concatenate(x, 0) for x in zip(*stats)]
+        labels = tg[:, 1].tolist()
+        p, r, ap, f1, cls = acc.ap_per_class(tp, sc, lb, labels)
+        d = dict(targets=_np(tg), thr=np.array(0.5), tp=tp, scores=sc, labels=lb, target_cls=np.array(labels),
+                 p=p, r=r, ap=ap, f1=f1, classes=cls, n_stats=np.array(len(stats)))
+        _pack_list("dets", dets, d)
+        for i, st in enumerate(stats):
+            d[f"stat_tp_{i}"] = st[0]
+        _save(name, **d)
+
+
 def main():
     if not rh.available():
         sys.exit("reference tree not present; golden vectors can only be generated in the build container")
@@ -238,6 +278,7 @@ def main():
     build_targets_v5_cases()
     decode_cases()
     match_cases()
+    metrics_cases()
 
 
 if __name__ == "__main__":

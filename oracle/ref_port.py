@@ -522,3 +522,81 @@ def retina_assign(anchors: torch.Tensor, targets: torch.Tensor, batch_size: int,
         locs.append(loc)
         clss.append(cls)
     return torch.stack(locs), torch.stack(clss)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# M1 / M2 — detection metrics: true-positive matching and per-class average precision
+# ---------------------------------------------------------------------------------------------------------
+
+def get_batch_statistics(outputs, targets: torch.Tensor, iou_threshold: float):
+    """Restates LightningFunc/accuracy.py:116-154.
+
+    Per image with detections (`None` entries are skipped, :122-123): walk the rows in their given order; a row whose
+    label (last column, :128) occurs among the image's target labels (:146) is compared with ALL target boxes of the
+    image through the +1 IoU (:149, accuracy.py:39, corners); the first maximal target (:149 `.max(0)`) is claimed
+    when `iou >= iou_threshold` and nobody claimed it before (:150-152).  The walk stops once every target is
+    claimed (:142-143) — which changes nothing, later rows could only hit claimed targets.
+    Returns `[tp float64 [K], scores (column 4) [K], labels (column 6) [K]]` per image, as numpy like the reference."""
+    import numpy as np
+    res = []
+    for i, out in enumerate(outputs):
+        if out is None:
+            continue
+        boxes, scores, labels = out[:, :4], out[:, 4], out[:, -1]
+        tp = np.zeros(boxes.shape[0])
+        ann = targets[targets[:, 0] == i][:, 1:]
+        if len(ann):
+            t_labels, t_boxes = ann[:, 0], ann[:, 1:]
+            claimed = []
+            for k in range(boxes.shape[0]):
+                if len(claimed) == len(ann):
+                    break
+                if not bool((t_labels == labels[k]).any()):
+                    continue
+                v, idx = bbox_iou_plus1(boxes[k].unsqueeze(0), t_boxes).max(0)
+                if bool(v >= iou_threshold) and int(idx) not in claimed:
+                    tp[k] = 1
+                    claimed.append(int(idx))
+        res.append([tp, scores.cpu().numpy(), labels.cpu().numpy()])
+    return res
+
+
+def compute_ap(recall, precision):
+    """Restates accuracy.py:262-287: sentinels, precision envelope from the right, sum of Δrecall · precision."""
+    import numpy as np
+    mrec = np.concatenate(([0.0], recall, [1.0]))
+    mpre = np.concatenate(([0.0], precision, [0.0]))
+    mpre = np.maximum.accumulate(mpre[::-1])[::-1]                  # :277-278 (right-to-left running maximum)
+    step = np.where(mrec[1:] != mrec[:-1])[0]                       # :282
+    return np.sum((mrec[step + 1] - mrec[step]) * mpre[step + 1])   # :285
+
+
+def ap_per_class(tp, conf, pred_cls, target_cls):
+    """Restates accuracy.py:207-260.  Detections ordered by descending `conf` (:221; numpy's default argsort is
+    unstable — ties are ordered by ascending position here); per class of `target_cls` (:225): cumulative TP / FP
+    in that order, recall = tpc / (n_gt + 1e-16), precision = tpc / (tpc + fpc), their last values, AP by
+    `compute_ap`; a class without predictions scores 0 (:238-241).  Returns p, r, ap, f1 (float64), classes int32."""
+    import numpy as np
+    tp, conf, pred_cls = np.asarray(tp), np.asarray(conf), np.asarray(pred_cls)
+    order = np.argsort(-conf, kind="stable")
+    tp, conf, pred_cls = tp[order], conf[order], pred_cls[order]
+    classes = np.unique(target_cls)
+    ap, p, r = [], [], []
+    for c in classes:
+        sel = pred_cls == c
+        n_gt = (np.asarray(target_cls) == c).sum()
+        n_p = sel.sum()
+        if n_p == 0 and n_gt == 0:
+            continue
+        if n_p == 0 or n_gt == 0:
+            ap.append(0); r.append(0); p.append(0)
+            continue
+        fpc = (1 - tp[sel]).cumsum()
+        tpc = tp[sel].cumsum()
+        recall = tpc / (n_gt + 1e-16)
+        precision = tpc / (tpc + fpc)
+        r.append(recall[-1]); p.append(precision[-1])
+        ap.append(compute_ap(recall, precision))
+    p, r, ap = np.array(p), np.array(r), np.array(ap)
+    f1 = 2 * p * r / (p + r + 1e-16)
+    return p, r, ap, f1, classes.astype("int32")

@@ -196,3 +196,22 @@ def test_c_oracle_threshold_and_empty():
     for i in range(2):
         assert torch.equal(ai[i], bi[i])
         assert_rows_close(a[i], b[i], rtol=1e-6, atol=1e-4)
+
+
+# ---- metrics: get_batch_statistics / ap_per_class -------------------------------------------------
+@pytest.mark.parametrize("name", ["metrics_small", "metrics_mid"])
+def test_metrics_oracle_against_reference_vectors(name):
+    import numpy as np
+    d = load(name)
+    dets = unpack_list(d, "dets")
+    tg = T(d["targets"])
+    stats = rp.get_batch_statistics(dets, tg, float(d["thr"]))
+    assert len(stats) == int(d["n_stats"])
+    for i, st in enumerate(stats):
+        assert st[0].dtype == np.float64 and np.array_equal(st[0], d[f"stat_tp_{i}"])
+    tp, sc, lb = [np.concatenate(x, 0) for x in zip(*stats)]
+    assert np.array_equal(tp, d["tp"]) and np.array_equal(sc, d["scores"]) and np.array_equal(lb, d["labels"])
+    p, r, ap, f1, cls = rp.ap_per_class(tp, sc, lb, d["target_cls"].tolist())
+    assert np.array_equal(cls, d["classes"]) and cls.dtype == np.int32
+    for got, want in ((p, d["p"]), (r, d["r"]), (ap, d["ap"]), (f1, d["f1"])):
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)

@@ -69,7 +69,8 @@ def test_install_patches_the_reference_seams(rh):
     saved = [(c, c.non_max_suppression) for c in classes + [ssd, ret]]
     losses, acc = rh.losses(), rh.accuracy()
     saved_l = {k: getattr(losses, k) for k in ("build_targets_v5", "bbox_iou_v5", "build_targets", "bbox_iou", "iou")}
-    saved_a = {k: getattr(acc, k) for k in ("build_targets_v5", "bbox_iou_v5", "build_targets", "bbox_iou", "xywh2xyxy", "iou")}
+    saved_a = {k: getattr(acc, k) for k in ("build_targets_v5", "bbox_iou_v5", "build_targets", "bbox_iou", "xywh2xyxy", "iou",
+                                            "get_batch_statistics", "ap_per_class")}
     try:
         od.install(*classes, ssd, ret, losses_module=losses, accuracy_module=acc)
         assert classes[0].non_max_suppression is od.non_max_suppression_v2
@@ -77,6 +78,7 @@ def test_install_patches_the_reference_seams(rh):
         assert ssd.non_max_suppression is od.prior_non_max_suppression and ret.non_max_suppression is od.prior_non_max_suppression
         assert losses.build_targets_v5 is od.build_targets_v5 and losses.bbox_iou_v5 is od.bbox_iou_v5
         assert acc.xywh2xyxy is od.xywh2xyxy
+        assert acc.get_batch_statistics is od.get_batch_statistics and acc.ap_per_class is od.ap_per_class
         # a criterion built after install() picks the replacement up (losses.py:654)
         crit = losses.RegionLoss_v3([(1, 1)] * 3, torch.nn.BCELoss, torch.nn.MSELoss, torch.nn.BCELoss, 4)
         assert crit.build_targets is od.build_targets
@@ -87,3 +89,32 @@ def test_install_patches_the_reference_seams(rh):
             setattr(losses, k, v)
         for k, v in saved_a.items():
             setattr(acc, k, v)
+
+
+@pytest.mark.parametrize("seed", [231, 232])
+def test_metrics_live(rh, seed):
+    import numpy as np
+    acc = rh.accuracy()
+    lv = synth.yolo_planar(3, 3, 5, [10, 5], 80, seed, v5_view=True)
+    dets = rp.yolo_nms(lv, num_anchors=3)
+    g = torch.Generator().manual_seed(seed)
+    tg = []
+    for b, d in enumerate(dets):
+        pick = d[torch.randperm(d.shape[0], generator=g)[:7]]
+        tg.append(torch.cat([torch.full((7, 1), float(b)), pick[:, 6:7], pick[:, :4] + torch.randn(7, 4, generator=g) * 3], 1))
+    tg = torch.cat(tg)
+    want = acc.get_batch_statistics(dets, tg, 0.5)
+    got = rp.get_batch_statistics(dets, tg, 0.5)
+    for a, b in zip(got, want):
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    tp, sc, lb = [np.concatenate(x, 0) for x in zip(*want)]
+    for a, b in zip(rp.ap_per_class(tp, sc, lb, tg[:, 1].tolist()), acc.ap_per_class(tp, sc, lb, tg[:, 1].tolist())):
+        np.testing.assert_allclose(a, b, rtol=1e-12, atol=0)
+
+
+def test_install_metrics_patches_step_namespace(rh):
+    import objectdetectionpl_b200 as od
+    acc = rh.accuracy()
+    ns = types.SimpleNamespace(get_batch_statistics=acc.get_batch_statistics, ap_per_class=acc.ap_per_class)
+    od.install_metrics(step_module=ns)
+    assert ns.get_batch_statistics is od.get_batch_statistics and ns.ap_per_class is od.ap_per_class

@@ -73,6 +73,27 @@ def main():
     anc = synth.retina_priors(600).to(DEV)
     tg32 = synth.labels(32, C, 6).to(DEV)
     out.append(dict(cfg="T6: RetinaNet assign A=67995 B=32", us=timed(lambda: od.retina_assign(anc, tg32, 32, 600.0))))
+    # M1 / M2: metrics on the headline NMS output (64 images, ~19.6 k kept rows each, <= 100 labels per image)
+    lv = [t.to(DEV) for t in synth.yolo_planar(64, 3, 80, [80, 40, 20], 640, 1234, v5_view=True, tie_free=False)]
+    rows, _, count = od.yolo_nms_raw(lv, 3)
+    del lv
+    n_pad = rows.shape[1]
+    row_start = torch.arange(64, device=DEV, dtype=torch.int64) * n_pad
+    tgm = synth.labels(64, 80, 4).to(DEV)
+    tgm[:, 2:4] = tgm[:, 2:4] * 640
+    tgm[:, 4:6] = tgm[:, 2:4] + tgm[:, 4:6] * 640
+    us = timed(lambda: od.batch_statistics_raw(rows, row_start, count, n_pad, tgm, 0.5))
+    kept = int(count.sum())
+    out.append(dict(cfg="M1: get_batch_statistics on the headline NMS output (device-resident)", us=us, detections=kept,
+                    labels=int(tgm.shape[0]), det_per_s=kept / (us * 1e-6)))
+    tp = od.batch_statistics_raw(rows, row_start, count, n_pad, tgm, 0.5)
+    mask = torch.arange(n_pad, device=DEV)[None, :] < count[:, None]
+    tpf, conf, cls = tp[mask], rows[..., 4][mask], rows[..., 6][mask]
+    classes = torch.arange(80, device=DEV, dtype=torch.int32)
+    n_gt = torch.bincount(tgm[:, 1].long(), minlength=80).int()
+    us = timed(lambda: od.ap_per_class_device(tpf, conf, cls, classes, n_gt))
+    out.append(dict(cfg="M2: ap_per_class over the same detections, 80 classes (device-resident)", us=us, detections=kept,
+                    det_per_s=kept / (us * 1e-6)))
     for o in out:
         print(json.dumps(o))
 
