@@ -230,17 +230,31 @@ __global__ void __launch_bounds__(kNmsThreads, 5) nms_segment_kernel(const NmsPa
         const int Wc = (nc + 63) >> 6;
 
         // ---- load the chunk ----------------------------------------------------------------
-        for (int j = tid; j < nc; j += kNmsThreads) {
-            const uint32_t pay = p.spay[img + c0 + j];
-            const uint32_t slot = pay & kSlotMask;
-            const float4 bx = p.box4[img + slot];
-            s_box[j] = bx;
-            s_conf[j] = p.cc2[img + slot].x;
-            if (FAST) { const uint4 q = box_bounds_h2(bx, thr); s_q[j] = make_uint2(q.x, q.y); s_qt[j] = q.z; }
-            s_pre[j] = -1;
-            s_first[j] = -1;
-            s_last[j] = -1;
-            s_nzw[j] = 0u;
+        // both rows of a thread are fetched together: payload -> slot -> box is a chain of two L2 round trips, and a
+        // row-at-a-time loop would walk it twice back to back
+        {
+            static_assert(kNmsT <= 2 * kNmsThreads, "a thread loads at most two rows of a chunk");
+            const int j0 = tid, j1 = tid + kNmsThreads;
+            uint32_t slot0 = 0, slot1 = 0;
+            if (j0 < nc) slot0 = p.spay[img + c0 + j0] & kSlotMask;
+            if (j1 < nc) slot1 = p.spay[img + c0 + j1] & kSlotMask;
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+            float f0 = 0.f, f1 = 0.f;
+            if (j0 < nc) { b0 = p.box4[img + slot0]; f0 = p.cc2[img + slot0].x; }
+            if (j1 < nc) { b1 = p.box4[img + slot1]; f1 = p.cc2[img + slot1].x; }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = h ? j1 : j0;
+                if (j >= nc) continue;
+                const float4 bx = h ? b1 : b0;
+                s_box[j] = bx;
+                s_conf[j] = h ? f1 : f0;
+                if (FAST) { const uint4 q = box_bounds_h2(bx, thr); s_q[j] = make_uint2(q.x, q.y); s_qt[j] = q.z; }
+                s_pre[j] = -1;
+                s_first[j] = -1;
+                s_last[j] = -1;
+                s_nzw[j] = 0u;
+            }
         }
         if (tid < kNmsW) s_member[tid] = 0ull;      // 32-row groups past nc are never written by the ballots below
         __syncthreads();

@@ -20,13 +20,19 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--conf-mode", default="uniform")
     ap.add_argument("--conf-thres", type=float, default=-0.0151)
+    ap.add_argument("--crowd", action="store_true", help="BASELINE config 5 shard: synth.yolo_crowd 1280x1280, 5 classes, conf_thres 0.001")
     ap.add_argument("--trace-sort", action="store_true", help="per-phase %globaltimer trace of the cluster sort")
     ap.add_argument("--trace-nms", action="store_true", help="per-phase %globaltimer trace of the NMS kernel")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
+    if a.crowd:
+        a.img, a.classes, a.conf_thres = 1280, 5, 0.001
     grids = synth.grids_for(a.model, a.img)
     g = torch.Generator(device=dev).manual_seed(1)
     levels = []
+    if a.crowd:
+        levels = [t.to(dev) for t in synth.yolo_crowd(a.batch, 3, 5, grids, 1280, seed=5)]
+        grids = []
     for G in grids:   # generated on device for speed: same distributions as synth.yolo_planar
         t = torch.empty(a.batch, 3, 5 + a.classes, G, G, device=dev)
         t[:, :, 0:2] = torch.rand(a.batch, 3, 2, G, G, device=dev, generator=g) * a.img
