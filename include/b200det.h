@@ -246,6 +246,21 @@ int b200det_ap_per_class(const float* tp, const float* conf, const float* pred_c
                          const int32_t* classes, const int32_t* n_gt, int32_t num_classes, void* ws, size_t ws_bytes,
                          double* p, double* r, double* ap, double* f1, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * M3 — test-time statistics of one YOLOv2..v4 level.  Replaces the body of `get_yolo_statistics(self, output,
+ * target)` (LightningFunc/accuracy.py:382-470, called from LightningFunc/step.py:99) for one head tensor:
+ * D1 decode (:412-435), build_targets on the decoded map (:437-443), the six metrics (:447-457) and the decoded map
+ * `output` (:459-466).
+ *   head            planar [B, A, 5+C, G, G] raw logits;  scaled_anchors [A,2] device = anchors / stride (:427);
+ *   out_rows        [B, A*G*G, 5+C] out: (x, y, w, h) * stride, sigmoid(conf), sigmoid(cls)   (the reference's `output`)
+ *   metrics         [6] fp32 out (device): cls_acc, recall50, recall75, precision, conf_obj, conf_noobj.
+ * ---------------------------------------------------------------------------------------------- */
+size_t b200det_yolo_statistics_workspace_bytes(int32_t batch, int32_t num_anchors, int32_t grid, int32_t num_targets);
+int b200det_yolo_statistics_level(const float* head, int32_t batch, int32_t num_anchors, int32_t num_classes, int32_t grid,
+                                  const float* scaled_anchors, float stride, const float* target, int32_t num_targets,
+                                  float ignore_thres, void* ws, size_t ws_bytes, float* out_rows, float* metrics,
+                                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,13 +14,14 @@ from .postprocess import (decode_box, non_max_suppression, non_max_suppression_h
                           prior_non_max_suppression,
                           prior_nms_raw, yolo_nms_raw, YOLO_FORCED_CONF_THRES)
 from .targets import build_targets, build_targets_v5, retina_assign, ssd_match, v5_match_level
-from .metrics import ap_per_class, ap_per_class_device, batch_statistics_raw, get_batch_statistics
+from .metrics import (ap_per_class, ap_per_class_device, batch_statistics_raw, get_batch_statistics, get_yolo_statistics,
+                      yolo_statistics_level)
 from .patch import install, install_losses, install_metrics, install_model
 from . import dist, synth
 
 __all__ = ["non_max_suppression", "non_max_suppression_host", "non_max_suppression_v2", "prior_non_max_suppression", "decode_box", "xywh2xyxy",
            "bbox_iou", "iou", "bbox_iou_v5", "build_targets", "build_targets_v5", "v5_match_level", "ssd_match",
-           "retina_assign", "get_batch_statistics", "ap_per_class", "batch_statistics_raw", "ap_per_class_device", "install",
+           "retina_assign", "get_batch_statistics", "get_yolo_statistics", "yolo_statistics_level", "ap_per_class", "batch_statistics_raw", "ap_per_class_device", "install",
            "install_losses", "install_metrics", "install_model", "dist", "synth", "yolo_nms_raw", "prior_nms_raw",
            "YOLO_FORCED_CONF_THRES"]
 __version__ = "0.1.0"

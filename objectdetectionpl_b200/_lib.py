@@ -67,6 +67,8 @@ SIGNATURES = {
     "b200det_retina_assign": (_i32, [_vp, _i32, _vp, _i32, _i32, _f, _vp, _sz, _vp, _vp, _vp]),
     "b200det_batch_statistics_workspace_bytes": (_sz, [_i32, _i32]),
     "b200det_batch_statistics": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _i32, _f, _vp, _sz, _vp, _vp]),
+    "b200det_yolo_statistics_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "b200det_yolo_statistics_level": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _f, _vp, _i32, _f, _vp, _sz, _vp, _vp, _vp]),
     "b200det_ap_per_class_workspace_bytes": (_sz, [_i32]),
     "b200det_ap_per_class": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
 }

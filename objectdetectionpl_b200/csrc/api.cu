@@ -50,6 +50,9 @@ int retina_assign_launch(const float*, int, const float*, int, int, float, void*
 size_t batch_statistics_ws_bytes(int, int);
 int batch_statistics_launch(const float*, const long long*, const int*, int, int, const float*, int, float, void*, float*,
                             cudaStream_t);
+size_t yolo_statistics_ws_bytes(int, int, int, int);
+int yolo_statistics_launch(const float*, int, int, int, int, const float*, float, const float*, int, float, void*, float*,
+                           float*, cudaStream_t);
 size_t ap_per_class_ws_bytes(int);
 int ap_per_class_launch(const float*, const float*, const float*, int, const int*, const int*, int, void*, double*, double*,
                         double*, double*, cudaStream_t);
@@ -278,6 +281,24 @@ int b200det_batch_statistics(const float* rows, const int64_t* row_start, const 
     }
     return batch_statistics_launch(rows, (const long long*)row_start, count, B, max_count, targets, nt, thr, ws, tp,
                                    (cudaStream_t)st);
+}
+
+size_t b200det_yolo_statistics_workspace_bytes(int32_t B, int32_t A, int32_t G, int32_t nt) {
+    if (B <= 0 || A <= 0 || G <= 0 || nt < 0) return 0;
+    return yolo_statistics_ws_bytes(B, A, G, nt);
+}
+int b200det_yolo_statistics_level(const float* head, int32_t B, int32_t A, int32_t C, int32_t G, const float* scaled_anchors,
+                                  float stride, const float* target, int32_t nt, float ignore_thres, void* ws,
+                                  size_t ws_bytes, float* out_rows, float* metrics, void* st) {
+    B2_CHECK_ARG(B > 0 && A > 0 && C > 0 && G > 0 && nt >= 0, "bad sizes");
+    B2_CHECK_ARG(head && scaled_anchors && ws && out_rows && metrics && (nt == 0 || target), "null argument");
+    B2_CHECK_LIMIT((long long)B * A <= 65535, "B*A %lld > 65535", (long long)B * A);
+    if (ws_bytes < yolo_statistics_ws_bytes(B, A, G, nt)) {
+        set_error("workspace too small");
+        return B200DET_EWORKSPACE;
+    }
+    return yolo_statistics_launch(head, B, A, C, G, scaled_anchors, stride, target, nt, ignore_thres, ws, out_rows, metrics,
+                                  (cudaStream_t)st);
 }
 
 size_t b200det_ap_per_class_workspace_bytes(int32_t n) {

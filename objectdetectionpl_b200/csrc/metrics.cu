@@ -358,4 +358,113 @@ int ap_per_class_launch(const float* tp, const float* conf, const float* pred_cl
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// M3 — get_yolo_statistics for one level (LightningFunc/accuracy.py:382-470, the YOLOv2..v4 test step, step.py:99):
+// D1 decode of the planar head, build_targets on the decoded map, six scalar metrics, and the decoded map itself.
+// ------------------------------------------------------------------------------------------------------------------
+int decode_box_launch(const float*, int, int, int, int, int, const float*, float, float*, cudaStream_t);
+size_t build_targets_ws_bytes(int, int, int, int);
+int build_targets_launch_ex(const float*, int, const float*, int, const float*, const float*, int, int, int, int, int, float,
+                            void*, float*, float*, uint8_t*, uint8_t*, float*, float*, float*, float*, float*, int32_t*,
+                            cudaStream_t);
+
+struct YsWs {
+    double* acc;          // [8] n_obj, n_noobj, sum class_mask[obj], sum conf[obj], sum conf[noobj], sum conf50, sum iou50*det, sum iou75*det
+    int32_t* status;      // build_targets guard bits
+    float* iou_scores;    // [cells]
+    float* class_mask;    // [cells]
+    uint8_t* obj;         // [cells]
+    uint8_t* noobj;       // [cells]
+    void* bt_ws;
+    size_t bytes;
+};
+static YsWs ys_layout(void* base, int B, int A, int G, int nt) {
+    YsWs w;
+    const size_t cells = (size_t)B * A * G * G;
+    char* p = (char*)base;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* r = p + off; off = align_up(off + bytes, 256); return r; };
+    w.acc = (double*)take(8 * 8);
+    w.status = (int32_t*)take(4);
+    w.iou_scores = (float*)take(cells * 4);
+    w.class_mask = (float*)take(cells * 4);
+    w.obj = (uint8_t*)take(cells);
+    w.noobj = (uint8_t*)take(cells);
+    w.bt_ws = take(build_targets_ws_bytes(B, A, G, nt));
+    w.bytes = off;
+    return w;
+}
+size_t yolo_statistics_ws_bytes(int B, int A, int G, int nt) { return ys_layout(nullptr, B, A, G, nt).bytes; }
+
+// One pass over the cells: the eight sums of accuracy.py:447-457, and the boxes of the decoded rows scaled from grid
+// units to pixels (`pred_boxes.view(...) * self.stride`, :461) now that build_targets has read them.
+__global__ void __launch_bounds__(256) ys_reduce_kernel(float* __restrict__ rows, int F, long long cells, float stride,
+                                                        const float* __restrict__ iou_scores, const float* __restrict__ class_mask,
+                                                        const uint8_t* __restrict__ obj, const uint8_t* __restrict__ noobj,
+                                                        double* __restrict__ acc) {
+    __shared__ double s_red[8][8];
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long c = (long long)blockIdx.x * 256 + threadIdx.x; c < cells; c += (long long)gridDim.x * 256) {
+        float* r = rows + c * F;
+        const float conf = r[4];
+        r[0] = __fmul_rn(r[0], stride); r[1] = __fmul_rn(r[1], stride);
+        r[2] = __fmul_rn(r[2], stride); r[3] = __fmul_rn(r[3], stride);
+        const bool o = obj[c] != 0, no = noobj[c] != 0;
+        const float cm = class_mask[c], iou = iou_scores[c];
+        const float conf50 = conf > 0.5f ? 1.0f : 0.0f;                       // :450
+        const float det = conf50 * cm * (o ? 1.0f : 0.0f);                    // :453 (tconf = obj_mask.float())
+        if (o) { a[0] += 1.0; a[2] += cm; a[3] += conf; }
+        if (no) { a[1] += 1.0; a[4] += conf; }
+        a[5] += conf50;
+        a[6] += (iou > 0.5f ? 1.0f : 0.0f) * det;                             // :451, :454-455
+        a[7] += (iou > 0.75f ? 1.0f : 0.0f) * det;                            // :452, :456
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        double v = a[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if ((threadIdx.x & 31) == 0) s_red[k][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += s_red[threadIdx.x][w];
+        atomicAdd(&acc[threadIdx.x], v);
+    }
+}
+
+// metrics[6] = cls_acc, recall50, recall75, precision, conf_obj, conf_noobj  (the order of batch_metrics, :468)
+__global__ void ys_final_kernel(const double* __restrict__ acc, float* __restrict__ metrics) {
+    const float n_obj = (float)acc[0];
+    metrics[0] = 100.0f * (float)(acc[2] / acc[0]);                           // mean over an empty selection is NaN, as in torch
+    metrics[1] = (float)acc[6] / (n_obj + 1e-16f);
+    metrics[2] = (float)acc[7] / (n_obj + 1e-16f);
+    metrics[3] = (float)acc[6] / ((float)acc[5] + 1e-16f);
+    metrics[4] = (float)(acc[3] / acc[0]);
+    metrics[5] = (float)(acc[4] / acc[1]);
+}
+
+int yolo_statistics_launch(const float* head, int B, int A, int C, int G, const float* scaled_anchors, float stride,
+                           const float* target, int nt, float ignore_thres, void* ws, float* out_rows, float* metrics,
+                           cudaStream_t st) {
+    YsWs w = ys_layout(ws, B, A, G, nt);
+    const int F = 5 + C;
+    const long long cells = (long long)B * A * G * G;
+    // decoded map in GRID units first (stride 1): x = sigma + gx, w = exp * anchor  (:412-435)
+    int rc = decode_box_launch(head, B, A, C, G, B200DET_DECODE_YOLO_EXP, scaled_anchors, 1.0f, out_rows, st);
+    if (rc) return rc;
+    rc = build_targets_launch_ex(out_rows, F, out_rows + 5, F, target, scaled_anchors, B, A, G, C, nt, ignore_thres, w.bt_ws,
+                                 w.iou_scores, w.class_mask, w.obj, w.noobj, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                 w.status, st);
+    if (rc) return rc;
+    B2_CUDA(cudaMemsetAsync(w.acc, 0, 64, st));
+    const int grid = (int)((cells + 255) / 256 < 148 * 8 ? (cells + 255) / 256 : 148 * 8);
+    ys_reduce_kernel<<<grid, 256, 0, st>>>(out_rows, F, cells, stride, w.iou_scores, w.class_mask, w.obj, w.noobj, w.acc);
+    B2_LAUNCH_CHECK("ys_reduce_kernel");
+    ys_final_kernel<<<1, 1, 0, st>>>(w.acc, metrics);
+    B2_LAUNCH_CHECK("ys_final_kernel");
+    return 0;
+}
+
 }  // namespace b200det

@@ -185,8 +185,9 @@ __global__ void v5_match_bwd_kernel(const MatchParams p, const float* __restrict
 // T1 — build_targets (YOLOv2..v4).
 // ================================================================================================
 struct BtParams {
-    const float* pred_boxes;   // [B,A,G,G,4]
-    const float* pred_cls;     // [B,A,G,G,C]
+    const float* pred_boxes;   // [B,A,G,G,4]   (cell stride box_ld floats; 4 = dense)
+    const float* pred_cls;     // [B,A,G,G,C]   (cell stride cls_ld floats; C = dense)
+    int box_ld, cls_ld;
     const float* target;       // [nt,6]
     const float* anchors;      // [A,2]
     int B, A, G, C, nt;
@@ -264,13 +265,15 @@ __global__ void build_targets_pass2(const BtParams p) {
     const float gx = __fmul_rn(r[2], G), gy = __fmul_rn(r[3], G), gw = __fmul_rn(r[4], G), gh = __fmul_rn(r[5], G);
     int lab = (int)r[1];
     wrap_index(lab, p.C);
-    p.tcls[cell * p.C + lab] = 1.0f;                                  // accuracy.py:374 (multi-hot on duplicates)
+    if (p.tcls) p.tcls[cell * p.C + lab] = 1.0f;                      // accuracy.py:374 (multi-hot on duplicates)
     if (p.winner[cell] != t) return;                                  // highest target row wins
-    p.tx[cell] = __fsub_rn(gx, floorf(gx));                           // accuracy.py:368-372
-    p.ty[cell] = __fsub_rn(gy, floorf(gy));
-    p.tw[cell] = logf(__fadd_rn(__fdiv_rn(gw, p.anchors[n * 2]), 1e-16f));
-    p.th[cell] = logf(__fadd_rn(__fdiv_rn(gh, p.anchors[n * 2 + 1]), 1e-16f));
-    const float* pc = p.pred_cls + cell * p.C;                        // accuracy.py:376
+    if (p.tx) {                                                       // (the statistics path does not need the regression targets)
+        p.tx[cell] = __fsub_rn(gx, floorf(gx));                       // accuracy.py:368-372
+        p.ty[cell] = __fsub_rn(gy, floorf(gy));
+        p.tw[cell] = logf(__fadd_rn(__fdiv_rn(gw, p.anchors[n * 2]), 1e-16f));
+        p.th[cell] = logf(__fadd_rn(__fdiv_rn(gh, p.anchors[n * 2 + 1]), 1e-16f));
+    }
+    const float* pc = p.pred_cls + cell * p.cls_ld;                   // accuracy.py:376
     float best = pc[0];
     int besti = 0;
     for (int c = 1; c < p.C; ++c) {
@@ -278,7 +281,13 @@ __global__ void build_targets_pass2(const BtParams p) {
         if (!(v <= best) && (best == best)) { best = v; besti = c; }
     }
     p.class_mask[cell] = besti == lab ? 1.0f : 0.0f;
-    const float4 pb = *reinterpret_cast<const float4*>(p.pred_boxes + cell * 4);   // accuracy.py:377
+    float4 pb;                                                        // accuracy.py:377
+    if (p.box_ld == 4) {
+        pb = *reinterpret_cast<const float4*>(p.pred_boxes + cell * 4);
+    } else {
+        const float* q = p.pred_boxes + cell * p.box_ld;
+        pb = make_float4(q[0], q[1], q[2], q[3]);
+    }
     p.iou_scores[cell] = iou_plus1_eps(cxcywh_to_corners(pb), cxcywh_to_corners(make_float4(gx, gy, gw, gh)));
 }
 
@@ -445,13 +454,29 @@ size_t build_targets_ws_bytes(int B, int A, int G, int nt) {
     return align_up((size_t)B * A * G * G * 4, 256) + align_up((size_t)(nt > 0 ? nt : 1) * 16, 256);
 }
 
+int build_targets_launch_ex(const float* pred_boxes, int box_ld, const float* pred_cls, int cls_ld, const float* target,
+                            const float* anchors, int B, int A, int G, int C, int nt, float ignore_thres, void* ws,
+                            float* iou_scores, float* class_mask, uint8_t* obj, uint8_t* noobj, float* tx, float* ty,
+                            float* tw, float* th, float* tcls, int32_t* status, cudaStream_t st);
+
 int build_targets_launch(const float* pred_boxes, const float* pred_cls, const float* target, const float* anchors,
                          int B, int A, int G, int C, int nt, float ignore_thres, void* ws, float* iou_scores,
                          float* class_mask, uint8_t* obj, uint8_t* noobj, float* tx, float* ty, float* tw, float* th,
                          float* tcls, int32_t* status, cudaStream_t st) {
+    return build_targets_launch_ex(pred_boxes, 4, pred_cls, C, target, anchors, B, A, G, C, nt, ignore_thres, ws, iou_scores,
+                                   class_mask, obj, noobj, tx, ty, tw, th, tcls, status, st);
+}
+
+// box_ld / cls_ld: floats between consecutive cells of pred_boxes / pred_cls (so both can be columns of one decoded
+// [cells, 5+C] row array); tx, ty, tw, th (all four or none) and tcls may be null when the caller does not need them.
+int build_targets_launch_ex(const float* pred_boxes, int box_ld, const float* pred_cls, int cls_ld, const float* target,
+                            const float* anchors, int B, int A, int G, int C, int nt, float ignore_thres, void* ws,
+                            float* iou_scores, float* class_mask, uint8_t* obj, uint8_t* noobj, float* tx, float* ty,
+                            float* tw, float* th, float* tcls, int32_t* status, cudaStream_t st) {
     const size_t cells = (size_t)B * A * G * G;
     BtParams p;
     p.pred_boxes = pred_boxes; p.pred_cls = pred_cls; p.target = target; p.anchors = anchors;
+    p.box_ld = box_ld; p.cls_ld = cls_ld;
     p.B = B; p.A = A; p.G = G; p.C = C; p.nt = nt; p.ignore_thres = ignore_thres;
     p.winner = (int*)ws;
     p.tinfo = (int*)((char*)ws + align_up(cells * 4, 256));
@@ -462,11 +487,13 @@ int build_targets_launch(const float* pred_boxes, const float* pred_cls, const f
     B2_CUDA(cudaMemsetAsync(noobj, 1, cells, st));
     B2_CUDA(cudaMemsetAsync(class_mask, 0, cells * 4, st));
     B2_CUDA(cudaMemsetAsync(iou_scores, 0, cells * 4, st));
-    B2_CUDA(cudaMemsetAsync(tx, 0, cells * 4, st));
-    B2_CUDA(cudaMemsetAsync(ty, 0, cells * 4, st));
-    B2_CUDA(cudaMemsetAsync(tw, 0, cells * 4, st));
-    B2_CUDA(cudaMemsetAsync(th, 0, cells * 4, st));
-    B2_CUDA(cudaMemsetAsync(tcls, 0, cells * (size_t)C * 4, st));
+    if (tx) {
+        B2_CUDA(cudaMemsetAsync(tx, 0, cells * 4, st));
+        B2_CUDA(cudaMemsetAsync(ty, 0, cells * 4, st));
+        B2_CUDA(cudaMemsetAsync(tw, 0, cells * 4, st));
+        B2_CUDA(cudaMemsetAsync(th, 0, cells * 4, st));
+    }
+    if (tcls) B2_CUDA(cudaMemsetAsync(tcls, 0, cells * (size_t)C * 4, st));
     B2_CUDA(cudaMemsetAsync(status, 0, 4, st));
     if (nt == 0) return 0;
     build_targets_pass1<<<ceil_div(nt, 128), 128, 0, st>>>(p);

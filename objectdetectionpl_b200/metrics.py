@@ -3,7 +3,9 @@
   get_batch_statistics(outputs, targets, iou_threshold)      replaces LightningFunc/accuracy.py:116-154
   ap_per_class(tp, conf, pred_cls, target_cls)               replaces LightningFunc/accuracy.py:207-260 (+ compute_ap :262)
 
-Both return numpy objects of the reference's shapes and dtypes, so `LightningFunc/step.py:95,115` runs unchanged;
+  get_yolo_statistics(self, output, target)                  replaces LightningFunc/accuracy.py:382-470 (YOLOv2..v4 test step)
+
+They return numpy objects of the reference's shapes and dtypes, so `LightningFunc/step.py:95,99,115` runs unchanged;
 `batch_statistics_raw` / `ap_per_class_device` are the device-resident building blocks (no host sync).
 """
 from __future__ import annotations
@@ -114,3 +116,64 @@ def ap_per_class(tp, conf, pred_cls, target_cls, device=None):
                                        torch.as_tensor(n_gt.astype(np.int32), device=dev))
     res = torch.stack([p, r, ap, f1]).cpu().numpy()
     return res[0], res[1], res[2], res[3], classes.astype("int32")
+
+
+def yolo_statistics_level(head: torch.Tensor, scaled_anchors: torch.Tensor, stride: float, target: torch.Tensor,
+                          ignore_thres: float):
+    """One level of `get_yolo_statistics` on the device: returns `(metrics fp32 [6], output [B, A*G*G, 5+C])` where
+    metrics = (cls_acc, recall50, recall75, precision, conf_obj, conf_noobj) and `output` is the decoded map
+    (boxes in pixels).  No host sync."""
+    lib = L.load()
+    L.require_cuda(head, "output")
+    if not head.is_contiguous():
+        raise ValueError("output must be contiguous (the reference .view()s it, accuracy.py:406)")
+    dev = head.device
+    an = scaled_anchors.to(dev, torch.float32).contiguous()
+    tg = target.to(dev, torch.float32).contiguous()
+    A, B, G = int(an.shape[0]), int(head.shape[0]), int(head.shape[2])
+    if head.numel() % (B * A * G * G):
+        raise ValueError(f"output of shape {tuple(head.shape)} is not [B, {A}*(5+C), {G}, {G}] storage")
+    F = head.numel() // (B * A * G * G)
+    nt = int(tg.shape[0])
+    rows = torch.empty((B, A * G * G, F), dtype=torch.float32, device=dev)
+    metrics = torch.empty((6,), dtype=torch.float32, device=dev)
+    nb = lib.b200det_yolo_statistics_workspace_bytes(B, A, G, nt)
+    with torch.cuda.device(dev):
+        ws = L.workspace(nb, dev)
+        L.check(lib.b200det_yolo_statistics_level(head.data_ptr(), B, A, F - 5, G, an.data_ptr(), float(stride),
+                                                  tg.data_ptr() if nt else None, nt, float(ignore_thres), ws.data_ptr(),
+                                                  ws.numel(), rows.data_ptr(), metrics.data_ptr(), L.stream_ptr(dev)),
+                "yolo_statistics_level")
+    return metrics, rows
+
+
+def get_yolo_statistics(self, output, target):
+    """Drop-in for `get_yolo_statistics` (accuracy.py:382): `{grid_size: [cls_acc, recall50, recall75, precision,
+    conf_obj, conf_noobj (0-dim numpy), output (CPU tensor [B, A*G*G, 5+C])]}` per level.  Reads `self.anchors`,
+    `self.anch_masks`, `self.num_classes`, `self.img_size`, `self.ignore_thres` and leaves the attributes the reference
+    sets behind (`num_anchors`, `grid_size`, `stride`, `scaled_anchors`)."""
+    batch_metrics = {}
+    if type(output) != list:
+        output = [output]
+    for i, x in enumerate(output):
+        if self.anch_masks is not None:                                   # YOLOv4 (:388-389)
+            anchors = [self.anchors[m] for m in self.anch_masks[i]]
+        elif len(self.anchors) == 3:                                      # YOLOv3 (:394-395)
+            anchors = self.anchors[i]
+        else:                                                             # YOLOv2 (:396-397)
+            anchors = self.anchors
+        self.num_anchors = len(anchors)
+        g = x.size(2)
+        self.grid_size = g
+        self.stride = self.img_size / g                                   # :422
+        scaled = torch.tensor([(a_w / self.stride, a_h / self.stride) for a_w, a_h in anchors], dtype=torch.float32,
+                              device=x.device)                            # :427 (python-float division, then fp32)
+        self.scaled_anchors = scaled
+        if x.numel() // (x.size(0) * self.num_anchors * g * g) != self.num_classes + 5:
+            raise RuntimeError(f"shape '{[x.size(0), self.num_anchors, self.num_classes + 5, g, g]}' is invalid for input "
+                               f"of size {x.numel()}")                    # the reference's .view() error (:405-406)
+        m, rows = yolo_statistics_level(x, scaled, self.stride, target, self.ignore_thres)
+        mh = m.cpu().numpy()
+        batch_metrics[g] = [mh[0], mh[1], mh[2], mh[3], mh[4], mh[5], rows.cpu()]
+        batch_metrics[g][:6] = [np.asarray(v) for v in batch_metrics[g][:6]]
+    return batch_metrics

@@ -16,6 +16,8 @@ def install_model(model_cls):
     else:
         fn = postprocess.non_max_suppression
     setattr(model_cls, "non_max_suppression", fn)
+    if name in ("yolov2", "yolov3", "yolov4"):
+        setattr(model_cls, "get_yolo_statistics", metrics.get_yolo_statistics)     # step.py:99 (model/YOLOV3.py:252)
     return model_cls
 
 

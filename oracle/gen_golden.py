@@ -267,6 +267,75 @@ def metrics_cases():
         _save(name, **d)
 
 
+def yolo_stats_cases():
+    """get_yolo_statistics of the unmodified reference (accuracy.py:382-470): a YOLOv3-like three-level call (per-level
+    anchor lists), a YOLOv2-like single head (5 anchors) and a YOLOv4-like call through `anch_masks`; the heads are
+    shifted so that a good share of the confidences passes 0.5, and labels repeat cells."""
+    acc = rh.accuracy()
+    C, img, B = 4, 416, 2
+    tg = synth.labels(B, C, 94, max_per_image=12)
+    tg = torch.cat([tg, tg[:5]])                                     # duplicate rows: same cell, last one wins
+
+    def plant(h, A, G, anchors_px):
+        """Make every anchor of the label's cell predict the label (box, class, confidence) for every second label, so
+        that the IoU / precision / recall sums are non-trivial."""
+        v = h.view(B, A, 5 + C, G, G)
+        stride = img / G
+        for t in tg[::2]:
+            b, lab = int(t[0]), int(t[1])
+            gx, gy, gw, gh = (t[2:] * G).tolist()
+            gi, gj = int(gx), int(gy)
+            if not (0 <= gi < G and 0 <= gj < G):
+                continue
+            fx = min(max(gx - gi, 1e-3), 1 - 1e-3)
+            fy = min(max(gy - gj, 1e-3), 1 - 1e-3)
+            for a in range(A):
+                aw, ah = anchors_px[a][0] / stride, anchors_px[a][1] / stride
+                v[b, a, 0, gj, gi] = float(np.log(fx / (1 - fx)))
+                v[b, a, 1, gj, gi] = float(np.log(fy / (1 - fy)))
+                v[b, a, 2, gj, gi] = float(np.log(gw / aw))
+                v[b, a, 3, gj, gi] = float(np.log(gh / ah))
+                v[b, a, 4, gj, gi] = 4.0
+                v[b, a, 5:, gj, gi] = -5.0
+                v[b, a, 5 + lab, gj, gi] = 5.0
+        return h
+
+    a3 = [[(116, 90), (156, 198), (373, 326)], [(30, 61), (62, 45), (59, 119)], [(10, 13), (16, 30), (33, 23)]]
+    heads = []
+    for lvl, (G, seed) in enumerate(((13, 91), (26, 92), (52, 93))):
+        h = synth.raw_logits(B, 3, C, G, seed)
+        h.view(B, 3, 5 + C, G, G)[:, :, 4] += 3.5
+        heads.append(plant(h, 3, G, a3[lvl]))
+    s3 = types.SimpleNamespace(anch_masks=None, anchors=a3, num_classes=C, img_size=img, ignore_thres=0.5)
+    bm3 = acc.get_yolo_statistics(s3, [h.clone() for h in heads], tg)
+    d = dict(target=_np(tg), img=np.array(img), C=np.array(C))
+    for G, h in zip((13, 26, 52), heads):
+        d[f"v3_head_{G}"] = _np(h)
+        d[f"v3_metrics_{G}"] = np.array([float(x) for x in bm3[G][:6]], np.float64)
+        d[f"v3_output_{G}"] = _np(bm3[G][6])
+    d["v3_anchors"] = np.array(a3, np.float32)
+    # YOLOv2: one head, 5 anchors in one flat list (accuracy.py:396-397)
+    a2 = [(1.3221, 1.73145), (3.19275, 4.00944), (5.05587, 8.09892), (9.47112, 4.84053), (11.2364, 10.0071)]
+    h2 = synth.raw_logits(B, 5, C, 13, 95)
+    h2.view(B, 5, 5 + C, 13, 13)[:, :, 4] += 3.5
+    plant(h2, 5, 13, [(w * 32, h_ * 32) for w, h_ in a2])
+    s2 = types.SimpleNamespace(anch_masks=None, anchors=a2, num_classes=C, img_size=img, ignore_thres=0.5)
+    bm2 = acc.get_yolo_statistics(s2, h2.clone(), tg)
+    d["v2_head"], d["v2_anchors"] = _np(h2), np.array(a2, np.float32)
+    d["v2_metrics"] = np.array([float(x) for x in bm2[13][:6]], np.float64)
+    d["v2_output"] = _np(bm2[13][6])
+    # YOLOv4: flat anchor list + masks (accuracy.py:388-389)
+    flat = np.array([(12, 16), (19, 36), (40, 28), (36, 75), (76, 55), (72, 146), (142, 110), (192, 243), (459, 401)], np.float32)
+    masks = [[6, 7, 8], [3, 4, 5], [0, 1, 2]]
+    s4 = types.SimpleNamespace(anch_masks=masks, anchors=flat, num_classes=C, img_size=img, ignore_thres=0.5)
+    bm4 = acc.get_yolo_statistics(s4, [h.clone() for h in heads[:2]], tg)
+    d["v4_anchors"], d["v4_masks"] = flat, np.array(masks)
+    for G in (13, 26):
+        d[f"v4_metrics_{G}"] = np.array([float(x) for x in bm4[G][:6]], np.float64)
+        d[f"v4_output_{G}"] = _np(bm4[G][6])
+    _save("yolo_stats", **d)
+
+
 def main():
     if not rh.available():
         sys.exit("reference tree not present; golden vectors can only be generated in the build container")
@@ -279,6 +348,7 @@ def main():
     decode_cases()
     match_cases()
     metrics_cases()
+    yolo_stats_cases()
 
 
 if __name__ == "__main__":

@@ -600,3 +600,48 @@ def ap_per_class(tp, conf, pred_cls, target_cls):
     p, r, ap = np.array(p), np.array(r), np.array(ap)
     f1 = 2 * p * r / (p + r + 1e-16)
     return p, r, ap, f1, classes.astype("int32")
+
+
+def get_yolo_statistics(selfobj, output, target: torch.Tensor):
+    """Restates LightningFunc/accuracy.py:382-470 (test-time statistics of YOLOv2..v4, one entry per level).
+    `selfobj` provides anchors / anch_masks / num_classes / img_size / ignore_thres like the Lightning module.
+    Per level: D1 decode in grid units (:402-435), `build_targets` on it (:437-443), then
+      cls_acc = 100·mean(class_mask[obj]), conf_obj = mean(conf[obj]), conf_noobj = mean(conf[noobj]),
+      precision = Σ iou50·det / (Σ conf50 + 1e-16), recall50/75 = Σ iou50/75·det / (Σ obj + 1e-16),
+      det = conf50 · class_mask · tconf (:447-457), and `output` = the decoded map with boxes · stride (:459-466).
+    Returns {grid: [cls_acc, recall50, recall75, precision, conf_obj, conf_noobj (numpy 0-dim), output tensor]}."""
+    res = {}
+    if not isinstance(output, list):
+        output = [output]
+    for i, head in enumerate(output):
+        if selfobj.anch_masks is not None:
+            anchors = [selfobj.anchors[m] for m in selfobj.anch_masks[i]]
+        elif len(selfobj.anchors) == 3:
+            anchors = selfobj.anchors[i]
+        else:
+            anchors = selfobj.anchors
+        g = head.size(2)
+        stride = selfobj.img_size / g
+        scaled = torch.tensor([(aw / stride, ah / stride) for aw, ah in anchors], dtype=F32)
+        dec = decode_yolo_exp(head, scaled, 1.0)                       # grid units: stride applied at the end (:461)
+        b, a, c = head.shape[0], len(anchors), selfobj.num_classes
+        pred_boxes = dec[..., :4].reshape(b, a, g, g, 4)
+        pred_conf = dec[..., 4].reshape(b, a, g, g)
+        pred_cls = dec[..., 5:].reshape(b, a, g, g, c)
+        iou_scores, class_mask, obj, noobj, _, _, _, _, _, tconf = build_targets(pred_boxes, pred_cls, target, scaled,
+                                                                                 selfobj.ignore_thres)
+        obj, noobj = obj.bool(), noobj.bool()
+        cls_acc = 100 * class_mask[obj].mean()
+        conf_obj = pred_conf[obj].mean()
+        conf_noobj = pred_conf[noobj].mean()
+        conf50 = (pred_conf > 0.5).float()
+        iou50 = (iou_scores > 0.5).float()
+        iou75 = (iou_scores > 0.75).float()
+        det = conf50 * class_mask * tconf
+        precision = torch.sum(iou50 * det) / (conf50.sum() + 1e-16)
+        recall50 = torch.sum(iou50 * det) / (obj.sum() + 1e-16)
+        recall75 = torch.sum(iou75 * det) / (obj.sum() + 1e-16)
+        out = torch.cat((dec[..., :4] * stride, dec[..., 4:]), -1)
+        res[g] = [cls_acc.numpy(), recall50.numpy(), recall75.numpy(), precision.numpy(), conf_obj.numpy(),
+                  conf_noobj.numpy(), out]
+    return res

@@ -108,3 +108,63 @@ def test_ap_per_class_perfect_and_empty():
     assert c.tolist() == [0, 3]
     np.testing.assert_allclose([p[0], r[0], ap[0]], [1.0, 1.0, 1.0], rtol=1e-12)
     assert p[1] == 0 and r[1] == 0 and ap[1] == 0 and f1[1] == 0           # class without predictions (accuracy.py:238)
+
+
+# ---- get_yolo_statistics: decoded map within 1e-5 relative (sigmoid / exp), metrics within 1e-5 ------
+def _stats_self(kind, d):
+    import types
+    C, img = int(d["C"]), int(d["img"])
+    if kind == "v3":
+        anchors = [[tuple(map(float, a)) for a in lvl] for lvl in d["v3_anchors"]]
+        return types.SimpleNamespace(anch_masks=None, anchors=anchors, num_classes=C, img_size=img, ignore_thres=0.5)
+    if kind == "v2":
+        return types.SimpleNamespace(anch_masks=None, anchors=[tuple(map(float, a)) for a in d["v2_anchors"]], num_classes=C,
+                                     img_size=img, ignore_thres=0.5)
+    return types.SimpleNamespace(anch_masks=d["v4_masks"].tolist(), anchors=d["v4_anchors"], num_classes=C, img_size=img,
+                                 ignore_thres=0.5)
+
+
+def _check_stats(bm, G, want_metrics, want_output):
+    got = [float(x) for x in bm[G][:6]]
+    np.testing.assert_allclose(got, want_metrics, rtol=1e-5, atol=1e-6)
+    assert not bm[G][6].is_cuda and bm[G][6].shape == want_output.shape
+    torch.testing.assert_close(bm[G][6], want_output, rtol=1e-5, atol=1e-5)
+    assert all(isinstance(x, np.ndarray) and x.shape == () for x in bm[G][:6])
+
+
+def test_yolo_statistics_golden_reference_vectors():
+    d = load("yolo_stats")
+    tg = T(d["target"]).to(DEV)
+    heads = [T(d[f"v3_head_{G}"]).to(DEV) for G in (13, 26, 52)]
+    for kind, hs, grids in (("v3", heads, (13, 26, 52)), ("v4", heads[:2], (13, 26))):
+        s = _stats_self(kind, d)
+        bm = od.get_yolo_statistics(s, [h.clone() for h in hs], tg)
+        assert sorted(bm) == sorted(grids)
+        for G in grids:
+            _check_stats(bm, G, d[f"{kind}_metrics_{G}"], T(d[f"{kind}_output_{G}"]))
+        assert s.num_anchors == 3 and s.grid_size == grids[-1]
+    bm = od.get_yolo_statistics(_stats_self("v2", d), T(d["v2_head"]).to(DEV), tg)      # single tensor (accuracy.py:386)
+    _check_stats(bm, 13, d["v2_metrics"], T(d["v2_output"]))
+
+
+@pytest.mark.parametrize("B,C,G,seed", [(4, 20, 13, 1), (8, 80, 26, 2), (2, 3, 52, 3)])
+def test_yolo_statistics_against_oracle(B, C, G, seed):
+    import types
+    head = synth.raw_logits(B, 3, C, G, seed)
+    head.view(B, 3, 5 + C, G, G)[:, :, 4] += 3.0
+    tg = synth.labels(B, C, seed + 10, max_per_image=20)
+    anchors = [[(116, 90), (156, 198), (373, 326)]] * 3
+    mk = lambda: types.SimpleNamespace(anch_masks=None, anchors=anchors, num_classes=C, img_size=416, ignore_thres=0.5)
+    want = rp.get_yolo_statistics(mk(), [head.clone()], tg)
+    got = od.get_yolo_statistics(mk(), [head.to(DEV)], tg.to(DEV))
+    _check_stats(got, G, [float(x) for x in want[G][:6]], want[G][6])
+
+
+def test_yolo_statistics_no_targets_gives_nan_means():
+    import types
+    head = synth.raw_logits(2, 3, 4, 13, 5).to(DEV)
+    s = types.SimpleNamespace(anch_masks=None, anchors=[[(116, 90), (156, 198), (373, 326)]] * 3, num_classes=4, img_size=416,
+                              ignore_thres=0.5)
+    bm = od.get_yolo_statistics(s, [head], torch.zeros(0, 6, device=DEV))
+    m = [float(x) for x in bm[13][:6]]
+    assert np.isnan(m[0]) and np.isnan(m[4]) and m[1] == 0 and m[2] == 0 and m[3] == 0      # mean over an empty selection

@@ -215,3 +215,32 @@ def test_metrics_oracle_against_reference_vectors(name):
     assert np.array_equal(cls, d["classes"]) and cls.dtype == np.int32
     for got, want in ((p, d["p"]), (r, d["r"]), (ap, d["ap"]), (f1, d["f1"])):
         np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
+
+
+# ---- get_yolo_statistics ---------------------------------------------------------------------------
+def _stats_self(kind, d):
+    import types
+    C, img = int(d["C"]), int(d["img"])
+    if kind == "v3":
+        anchors = [[tuple(map(float, a)) for a in lvl] for lvl in d["v3_anchors"]]
+        return types.SimpleNamespace(anch_masks=None, anchors=anchors, num_classes=C, img_size=img, ignore_thres=0.5)
+    if kind == "v2":
+        return types.SimpleNamespace(anch_masks=None, anchors=[tuple(map(float, a)) for a in d["v2_anchors"]], num_classes=C,
+                                     img_size=img, ignore_thres=0.5)
+    return types.SimpleNamespace(anch_masks=d["v4_masks"].tolist(), anchors=d["v4_anchors"], num_classes=C, img_size=img,
+                                 ignore_thres=0.5)
+
+
+def test_yolo_statistics_oracle_against_reference_vectors():
+    import numpy as np
+    d = load("yolo_stats")
+    tg = T(d["target"])
+    heads = [T(d[f"v3_head_{G}"]) for G in (13, 26, 52)]
+    for kind, hs, grids in (("v3", heads, (13, 26, 52)), ("v4", heads[:2], (13, 26))):
+        bm = rp.get_yolo_statistics(_stats_self(kind, d), [h.clone() for h in hs], tg)
+        for G in grids:
+            np.testing.assert_allclose([float(x) for x in bm[G][:6]], d[f"{kind}_metrics_{G}"], rtol=1e-6, atol=1e-7)
+            assert torch.equal(bm[G][6], T(d[f"{kind}_output_{G}"]))
+    bm = rp.get_yolo_statistics(_stats_self("v2", d), T(d["v2_head"]), tg)
+    np.testing.assert_allclose([float(x) for x in bm[13][:6]], d["v2_metrics"], rtol=1e-6, atol=1e-7)
+    assert torch.equal(bm[13][6], T(d["v2_output"]))

@@ -94,6 +94,19 @@ def main():
     us = timed(lambda: od.ap_per_class_device(tpf, conf, cls, classes, n_gt))
     out.append(dict(cfg="M2: ap_per_class over the same detections, 80 classes (device-resident)", us=us, detections=kept,
                     det_per_s=kept / (us * 1e-6)))
+    # M3: get_yolo_statistics, YOLOv3 416 COCO heads, batch 64 (device-resident form, per level)
+    import types
+    a3 = [[(116, 90), (156, 198), (373, 326)], [(30, 61), (62, 45), (59, 119)], [(10, 13), (16, 30), (33, 23)]]
+    tgs = synth.labels(64, 80, 4).to(DEV)
+    for lvl, G in enumerate((13, 26, 52)):
+        head = synth.raw_logits(64, 3, 80, G, 7).to(DEV)
+        stride = 416 / G
+        sc = torch.tensor([(w / stride, h / stride) for w, h in a3[lvl]], device=DEV)
+        us = timed(lambda: od.yolo_statistics_level(head, sc, stride, tgs, 0.5))
+        nbytes = head.numel() * 4
+        out.append(dict(cfg=f"M3: get_yolo_statistics level G={G} B=64 C=80 (decode + build_targets + metrics, device-resident)",
+                        us=us, head_MB=nbytes / 1e6, GBps_read_plus_write=2 * nbytes / (us * 1e-6) / 1e9))
+        del head
     for o in out:
         print(json.dumps(o))
 
