@@ -220,6 +220,26 @@ int b200det_retina_assign(const float* anchors, int32_t num_anchors, const float
                           size_t workspace_bytes, float* loc_targets, int32_t* cls_targets, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * T4' — the per-level loss terms of `MultiScaleRegionLoss_v5.forward` (LightningFunc/losses.py:98-152) fused
+ * (SURVEY §8f row 2): matched-row gather + D2 decode + GIoU (:105-119), objectness target scatter (:123), class
+ * focal-BCE over the matched rows (:127-133) and objectness focal-BCE over every cell (:137; FocalLoss :37-64 around
+ * BCEWithLogitsLoss with pos_weight 1).
+ *   fwd: giou[m], tobj[B,na,ny,nx] (zero-filled here), sums[3] fp64 (device) = sum(1-giou), sum FL_obj, sum FL_cls;
+ *        the means are sums / m, / cells, / (m*C).  with_cls = 0 skips the class term (nc == 1, :127).
+ *   bwd: gpi (zero-filled by the caller) += d/dpi of  g_box*sum(1-giou) + g_obj*sum FL_obj + g_cls*sum FL_cls
+ *        (tobj is treated as a constant: `giou.detach()`, :123).
+ * ---------------------------------------------------------------------------------------------- */
+int b200det_v5_loss_fwd(const float* pi, int32_t batch, int32_t na, int32_t ny, int32_t nx, int32_t fields,
+                        const int32_t* b, const int32_t* a, const int32_t* gj, const int32_t* gi, const int32_t* tcls,
+                        const float* tbox, const float* anch, int32_t m, float cp, float cn, float gamma, float alpha,
+                        int32_t with_cls, float* giou, float* tobj, double* sums, void* stream);
+int b200det_v5_loss_bwd(const float* pi, int32_t batch, int32_t na, int32_t ny, int32_t nx, int32_t fields,
+                        const int32_t* b, const int32_t* a, const int32_t* gj, const int32_t* gi, const int32_t* tcls,
+                        const float* tbox, const float* anch, int32_t m, float cp, float cn, float gamma, float alpha,
+                        int32_t with_cls, const float* tobj, float g_box, float g_obj, float g_cls, float* gpi,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * M1 — true-positive matching of detections against labels.  Replaces `get_batch_statistics(outputs,
  * targets, iou_threshold)` (LightningFunc/accuracy.py:116-154, called from LightningFunc/step.py:95).
  *   rows       detection rows of 7 floats (x1,y1,x2,y2,conf,cls_conf,label); image b owns rows

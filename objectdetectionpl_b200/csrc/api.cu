@@ -39,6 +39,12 @@ int v5_match_fwd_launch(const float*, int, int, int, int, int, const int32_t*, c
                         const int32_t*, const float*, const float*, int, float*, float*, cudaStream_t);
 int v5_match_bwd_launch(const float*, int, int, int, int, int, const int32_t*, const int32_t*, const int32_t*,
                         const int32_t*, const float*, const float*, int, const float*, float*, cudaStream_t);
+int v5_loss_fwd_launch(const float*, int, int, int, int, int, const int32_t*, const int32_t*, const int32_t*, const int32_t*,
+                       const int32_t*, const float*, const float*, int, float, float, float, float, int, float*, float*,
+                       double*, cudaStream_t);
+int v5_loss_bwd_launch(const float*, int, int, int, int, int, const int32_t*, const int32_t*, const int32_t*, const int32_t*,
+                       const int32_t*, const float*, const float*, int, float, float, float, float, int, const float*, float,
+                       float, float, float*, cudaStream_t);
 size_t build_targets_ws_bytes(int, int, int, int);
 int build_targets_launch(const float*, const float*, const float*, const float*, int, int, int, int, int, float, void*,
                          float*, float*, uint8_t*, uint8_t*, float*, float*, float*, float*, float*, int32_t*, cudaStream_t);
@@ -213,6 +219,27 @@ int b200det_v5_match_bwd(const float* pi, int32_t B, int32_t na, int32_t ny, int
     B2_CHECK_ARG(m == 0 || (pi && b && a && gj && gi && tbox && anch && ggiou && gpi), "null argument");
     B2_CHECK_ARG(((uintptr_t)tbox & 15) == 0, "tbox must be 16-byte aligned");
     return v5_match_bwd_launch(pi, B, na, ny, nx, F, b, a, gj, gi, tbox, anch, m, ggiou, gpi, (cudaStream_t)st);
+}
+
+int b200det_v5_loss_fwd(const float* pi, int32_t B, int32_t na, int32_t ny, int32_t nx, int32_t F, const int32_t* b,
+                        const int32_t* a, const int32_t* gj, const int32_t* gi, const int32_t* tcls, const float* tbox,
+                        const float* anch, int32_t m, float cp, float cn, float gamma, float alpha, int32_t with_cls,
+                        float* giou, float* tobj, double* sums, void* st) {
+    B2_CHECK_ARG(B > 0 && na > 0 && ny > 0 && nx > 0 && m >= 0 && F >= 5, "bad sizes");
+    B2_CHECK_ARG(pi && tobj && sums && (m == 0 || (b && a && gj && gi && tcls && tbox && anch && giou)), "null argument");
+    B2_CHECK_ARG(((uintptr_t)tbox & 15) == 0 && ((uintptr_t)sums & 7) == 0, "tbox must be 16-byte, sums 8-byte aligned");
+    return v5_loss_fwd_launch(pi, B, na, ny, nx, F, b, a, gj, gi, tcls, tbox, anch, m, cp, cn, gamma, alpha, with_cls, giou,
+                              tobj, sums, (cudaStream_t)st);
+}
+int b200det_v5_loss_bwd(const float* pi, int32_t B, int32_t na, int32_t ny, int32_t nx, int32_t F, const int32_t* b,
+                        const int32_t* a, const int32_t* gj, const int32_t* gi, const int32_t* tcls, const float* tbox,
+                        const float* anch, int32_t m, float cp, float cn, float gamma, float alpha, int32_t with_cls,
+                        const float* tobj, float g_box, float g_obj, float g_cls, float* gpi, void* st) {
+    B2_CHECK_ARG(B > 0 && na > 0 && ny > 0 && nx > 0 && m >= 0 && F >= 5, "bad sizes");
+    B2_CHECK_ARG(pi && tobj && gpi && (m == 0 || (b && a && gj && gi && tcls && tbox && anch)), "null argument");
+    B2_CHECK_ARG(((uintptr_t)tbox & 15) == 0, "tbox must be 16-byte aligned");
+    return v5_loss_bwd_launch(pi, B, na, ny, nx, F, b, a, gj, gi, tcls, tbox, anch, m, cp, cn, gamma, alpha, with_cls, tobj,
+                              g_box, g_obj, g_cls, gpi, (cudaStream_t)st);
 }
 
 size_t b200det_build_targets_workspace_bytes(int32_t B, int32_t A, int32_t G, int32_t nt) {

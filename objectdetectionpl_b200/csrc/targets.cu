@@ -450,6 +450,149 @@ int v5_match_bwd_launch(const float* pi, int B, int na, int ny, int nx, int F, c
     return 0;
 }
 
+// ================================================================================================
+// T4' — the three per-level loss terms of MultiScaleRegionLoss_v5.forward (losses.py:105-137) in one op:
+//   lbox = mean(1 - giou)                              (:119)
+//   lobj = mean(FL(pi[..., 4], tobj))                   (:137, FocalLoss(BCEWithLogits) :37-64, gamma 1.5, alpha 0.25)
+//   lcls = mean(FL(ps[:, 5:], onehot(tcls) cp / cn))    (:131-133)
+// Forward leaves sums[3] (fp64): sum(1 - giou), sum FL_obj over all cells, sum FL_cls over the m x C matched logits;
+// backward takes the three upstream scalars already divided by the element counts.
+// ================================================================================================
+__device__ __forceinline__ float focal_bce(const float x, const float t, const float gamma, const float alpha) {
+    const float ls = fminf(x, 0.0f) - log1pf(expf(-fabsf(x)));                    // log_sigmoid(x)
+    const float bce = (1.0f - t) * x - ls;                                         // BCEWithLogits, pos_weight = 1
+    const float pr = sigmoidf_acc(x);
+    const float p_t = t * pr + (1.0f - t) * (1.0f - pr);                           // losses.py:54
+    const float af = t * alpha + (1.0f - t) * (1.0f - alpha);                      // :55
+    return bce * (af * powf(1.0f - p_t, gamma));                                   // :56-57
+}
+__device__ __forceinline__ float focal_bce_grad(const float x, const float t, const float gamma, const float alpha) {
+    const float ls = fminf(x, 0.0f) - log1pf(expf(-fabsf(x)));
+    const float bce = (1.0f - t) * x - ls;
+    const float pr = sigmoidf_acc(x);
+    const float p_t = t * pr + (1.0f - t) * (1.0f - pr);
+    const float af = t * alpha + (1.0f - t) * (1.0f - alpha);
+    const float q = 1.0f - p_t;
+    const float mf = powf(q, gamma);
+    const float dpt = (2.0f * t - 1.0f) * pr * (1.0f - pr);
+    const float dmf = q > 0.0f ? -gamma * powf(q, gamma - 1.0f) * dpt : 0.0f;
+    return af * ((pr - t) * mf + bce * dmf);
+}
+
+__device__ __forceinline__ void block_add_double(double v, double* target) {
+    __shared__ double s_part[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_part[w];
+        atomicAdd(target, t);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) v5_loss_rows_fwd_kernel(const MatchParams p, const int32_t* __restrict__ tcls,
+                                                               const float* __restrict__ giou, float cp, float cn,
+                                                               float gamma, float alpha, int with_cls, double* __restrict__ sums) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double box = 0.0, cls = 0.0;
+    if (i < p.m) {
+        box = (double)(1.0f - giou[i]);
+        if (with_cls) {
+            const float* ps = p.pi + match_cell(p, i) * p.F + 5;
+            const int lab = tcls[i];
+            for (int c = 0; c < p.F - 5; ++c) cls += (double)focal_bce(ps[c], c == lab ? cp : cn, gamma, alpha);
+        }
+    }
+    block_add_double(box, sums + 0);
+    block_add_double(cls, sums + 2);
+}
+
+__global__ void __launch_bounds__(256) v5_loss_obj_fwd_kernel(const float* __restrict__ pi, int F, long long cells,
+                                                              const float* __restrict__ tobj, float gamma, float alpha,
+                                                              double* __restrict__ sums) {
+    double acc = 0.0;
+    for (long long c = (long long)blockIdx.x * 256 + threadIdx.x; c < cells; c += (long long)gridDim.x * 256)
+        acc += (double)focal_bce(pi[c * F + 4], tobj[c], gamma, alpha);
+    block_add_double(acc, sums + 1);
+}
+
+__global__ void __launch_bounds__(256) v5_loss_obj_bwd_kernel(const float* __restrict__ pi, int F, long long cells,
+                                                              const float* __restrict__ tobj, float gamma, float alpha,
+                                                              float g_obj, float* __restrict__ gpi) {
+    for (long long c = (long long)blockIdx.x * 256 + threadIdx.x; c < cells; c += (long long)gridDim.x * 256)
+        gpi[c * F + 4] = g_obj * focal_bce_grad(pi[c * F + 4], tobj[c], gamma, alpha);   // the only writer of column 4
+}
+
+__global__ void __launch_bounds__(256) v5_loss_rows_bwd_kernel(const MatchParams p, const int32_t* __restrict__ tcls, float cp,
+                                                               float cn, float gamma, float alpha, int with_cls, float g_box,
+                                                               float g_cls, float* __restrict__ gpi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.m) return;
+    const long long cell = match_cell(p, i);
+    const float* ps = p.pi + cell * p.F;
+    float* gp = gpi + cell * p.F;
+    const float aw = p.anch[(size_t)i * 2], ah = p.anch[(size_t)i * 2 + 1];
+    float s[4];
+    for (int k = 0; k < 4; ++k) s[k] = sigmoidf_acc(ps[k]);
+    const float4 pb = make_float4(s[0] * 2.0f - 0.5f, s[1] * 2.0f - 0.5f, (s[2] * 2.0f) * (s[2] * 2.0f) * aw,
+                                  (s[3] * 2.0f) * (s[3] * 2.0f) * ah);
+    const float4 tb = *reinterpret_cast<const float4*>(p.tbox + (size_t)i * 4);
+    float g[4];
+    iou_v5_backward(pb, tb, false, B200DET_GIOU, -g_box, g);                        // d(1 - giou) = -d giou
+    atomicAdd(gp + 0, g[0] * 2.0f * s[0] * (1.0f - s[0]));
+    atomicAdd(gp + 1, g[1] * 2.0f * s[1] * (1.0f - s[1]));
+    atomicAdd(gp + 2, g[2] * 8.0f * s[2] * s[2] * (1.0f - s[2]) * aw);
+    atomicAdd(gp + 3, g[3] * 8.0f * s[3] * s[3] * (1.0f - s[3]) * ah);
+    if (with_cls) {
+        const int lab = tcls[i];
+        for (int c = 0; c < p.F - 5; ++c)
+            atomicAdd(gp + 5 + c, g_cls * focal_bce_grad(ps[5 + c], c == lab ? cp : cn, gamma, alpha));
+    }
+}
+
+int v5_loss_fwd_launch(const float* pi, int B, int na, int ny, int nx, int F, const int32_t* b, const int32_t* a,
+                       const int32_t* gj, const int32_t* gi, const int32_t* tcls, const float* tbox, const float* anch, int m,
+                       float cp, float cn, float gamma, float alpha, int with_cls, float* giou, float* tobj, double* sums,
+                       cudaStream_t st) {
+    const long long cells = (long long)B * na * ny * nx;
+    B2_CUDA(cudaMemsetAsync(sums, 0, 3 * sizeof(double), st));
+    B2_CUDA(cudaMemsetAsync(tobj, 0, (size_t)cells * 4, st));                      // torch.zeros_like(pi[..., 0])  (:107)
+    MatchParams p{pi, B, na, ny, nx, F, b, a, gj, gi, tbox, anch, m};
+    if (m > 0) {
+        const int blocks = ceil_div(m, 256);
+        v5_match_fwd_kernel<<<blocks, 256, 0, st>>>(p, giou, reinterpret_cast<int*>(tobj));
+        B2_LAUNCH_CHECK("v5_match_fwd_kernel");
+        v5_match_tobj_kernel<<<blocks, 256, 0, st>>>(p, giou, tobj);
+        B2_LAUNCH_CHECK("v5_match_tobj_kernel");
+        v5_loss_rows_fwd_kernel<<<blocks, 256, 0, st>>>(p, tcls, giou, cp, cn, gamma, alpha, with_cls, sums);
+        B2_LAUNCH_CHECK("v5_loss_rows_fwd_kernel");
+    }
+    const int grid = (int)((cells + 255) / 256 < 148 * 8 ? (cells + 255) / 256 : 148 * 8);
+    v5_loss_obj_fwd_kernel<<<grid, 256, 0, st>>>(pi, F, cells, tobj, gamma, alpha, sums);
+    B2_LAUNCH_CHECK("v5_loss_obj_fwd_kernel");
+    return 0;
+}
+
+// gpi must be zero-filled by the caller; g_* are the upstream gradients of the three means divided by their counts
+int v5_loss_bwd_launch(const float* pi, int B, int na, int ny, int nx, int F, const int32_t* b, const int32_t* a,
+                       const int32_t* gj, const int32_t* gi, const int32_t* tcls, const float* tbox, const float* anch, int m,
+                       float cp, float cn, float gamma, float alpha, int with_cls, const float* tobj, float g_box, float g_obj,
+                       float g_cls, float* gpi, cudaStream_t st) {
+    const long long cells = (long long)B * na * ny * nx;
+    const int grid = (int)((cells + 255) / 256 < 148 * 8 ? (cells + 255) / 256 : 148 * 8);
+    v5_loss_obj_bwd_kernel<<<grid, 256, 0, st>>>(pi, F, cells, tobj, gamma, alpha, g_obj, gpi);
+    B2_LAUNCH_CHECK("v5_loss_obj_bwd_kernel");
+    if (m > 0) {
+        MatchParams p{pi, B, na, ny, nx, F, b, a, gj, gi, tbox, anch, m};
+        v5_loss_rows_bwd_kernel<<<ceil_div(m, 256), 256, 0, st>>>(p, tcls, cp, cn, gamma, alpha, with_cls, g_box, g_cls, gpi);
+        B2_LAUNCH_CHECK("v5_loss_rows_bwd_kernel");
+    }
+    return 0;
+}
+
 size_t build_targets_ws_bytes(int B, int A, int G, int nt) {
     return align_up((size_t)B * A * G * G * 4, 256) + align_up((size_t)(nt > 0 ? nt : 1) * 16, 256);
 }

@@ -3,6 +3,7 @@
   build_targets(pred_boxes, pred_cls, target, anchors, ignore_thres)   LightningFunc/accuracy.py:305
   build_targets_v5(p, targets, anchors, nl, na)                        LightningFunc/accuracy.py:472
   v5_match_level(pi, tbox, indices, anch)                              LightningFunc/losses.py:105-123
+  v5_loss_level(...) / v5_loss(output, target, anchors, nl, na, nc)    LightningFunc/losses.py:98-152 (fused loss terms)
   ssd_match(default_boxes, annotations_boxes, match_thresh)            LightningFunc/losses.py:199
   retina_assign(anchors, targets, batch_size, img_size)                LightningFunc/losses.py:423-443
 """
@@ -125,6 +126,80 @@ def v5_match_level(pi, tbox, indices, anch):
     `giou` is differentiable w.r.t. `pi`."""
     b, a, gj, gi = indices
     return _V5Match.apply(pi, tbox, b, a, gj, gi, anch)
+
+
+class _V5LossLevel(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pi, tbox, b, a, gj, gi, anch, tcls, cp, cn, gamma, alpha, with_cls):
+        lib = L.load()
+        pid = L.require_cuda(pi.detach(), "pi")
+        if not pid.is_contiguous():
+            raise ValueError("pi must be contiguous [B,na,ny,nx,5+C]")
+        B, na, ny, nx, F = pid.shape
+        m = int(b.shape[0])
+        dev = pid.device
+        idx = torch.stack((b, a, gj, gi, tcls)).to(torch.int32).contiguous() if m else torch.zeros((5, 0), dtype=torch.int32, device=dev)
+        tb = tbox.detach().contiguous().float()
+        ac = anch.detach().contiguous().float()
+        giou = torch.empty((max(m, 1),), dtype=torch.float32, device=dev)
+        tobj = torch.empty((B, na, ny, nx), dtype=torch.float32, device=dev)
+        sums = torch.empty((3,), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            L.check(lib.b200det_v5_loss_fwd(pid.data_ptr(), B, na, ny, nx, F, idx[0].data_ptr(), idx[1].data_ptr(),
+                                            idx[2].data_ptr(), idx[3].data_ptr(), idx[4].data_ptr(), tb.data_ptr(), ac.data_ptr(),
+                                            m, cp, cn, gamma, alpha, int(with_cls), giou.data_ptr(), tobj.data_ptr(),
+                                            sums.data_ptr(), L.stream_ptr(dev)), "v5_loss_fwd")
+        cells = B * na * ny * nx
+        n_box, n_cls = max(m, 1), max(m * (F - 5), 1)
+        means = (sums / torch.tensor([n_box, cells, n_cls], dtype=torch.float64, device=dev)).float()
+        ctx.save_for_backward(pid, idx, tb, ac, tobj)
+        ctx.cfg = (cp, cn, gamma, alpha, int(with_cls), m, cells, n_box, n_cls)
+        ctx.mark_non_differentiable(tobj)
+        return means[0], means[1], means[2], tobj
+
+    @staticmethod
+    def backward(ctx, g_box, g_obj, g_cls, _g_tobj):
+        lib = L.load()
+        pid, idx, tb, ac, tobj = ctx.saved_tensors
+        cp, cn, gamma, alpha, with_cls, m, cells, n_box, n_cls = ctx.cfg
+        B, na, ny, nx, F = pid.shape
+        gpi = torch.zeros_like(pid)
+        g = torch.stack((g_box, g_obj, g_cls)).double().cpu().tolist()     # three upstream scalars (one sync in backward)
+        with torch.cuda.device(pid.device):
+            L.check(lib.b200det_v5_loss_bwd(pid.data_ptr(), B, na, ny, nx, F, idx[0].data_ptr(), idx[1].data_ptr(),
+                                            idx[2].data_ptr(), idx[3].data_ptr(), idx[4].data_ptr(), tb.data_ptr(), ac.data_ptr(),
+                                            m, cp, cn, gamma, alpha, with_cls, tobj.data_ptr(), g[0] / n_box, g[1] / cells,
+                                            g[2] / n_cls, gpi.data_ptr(), L.stream_ptr(pid.device)), "v5_loss_bwd")
+        return (gpi,) + (None,) * 12
+
+
+def v5_loss_level(pi, tbox, indices, anch, tcls, cp=1.0, cn=0.0, gamma=1.5, alpha=0.25, with_cls=True):
+    """The three loss terms of one level of `MultiScaleRegionLoss_v5.forward` (losses.py:105-137), fused and
+    differentiable w.r.t. `pi`: returns `(mean(1 - giou), mean FL(pi[...,4], tobj), mean FL(ps[:,5:], class targets), tobj)`.
+    With no matched rows the first and third are 0 (the reference skips them, :110)."""
+    b, a, gj, gi = indices
+    return _V5LossLevel.apply(pi, tbox, b, a, gj, gi, anch, tcls, float(cp), float(cn), float(gamma), float(alpha), bool(with_cls))
+
+
+def v5_loss(output, target, anchors, nl, na, nc, cp=1.0, cn=0.0, gamma=1.5, alpha=0.25):
+    """`MultiScaleRegionLoss_v5.forward` (losses.py:98-152, reduction 'mean', label smoothing 0, focal gamma 1.5) on top of
+    `build_targets_v5` + `v5_loss_level`.  `anchors` are the criterion's scaled anchors `[nl, na, 2]` (:95-96).
+    Returns the reference's metrics dict of shape-[1] tensors: loss, Localization, Classification, Conf_obj."""
+    dev = output[0].device
+    lcls = torch.zeros(1, device=dev); lbox = torch.zeros(1, device=dev); lobj = torch.zeros(1, device=dev)
+    tcls, tbox, indices, anch = build_targets_v5(output, target, anchors, nl, na)
+    for i, pi in enumerate(output):
+        nb = indices[i][0].shape[0]
+        t_box, t_obj, t_cls, _ = v5_loss_level(pi, tbox[i], indices[i], anch[i], tcls[i], cp, cn, gamma, alpha, nc > 1)
+        if nb:
+            lbox = lbox + t_box                                           # :119
+            if nc > 1:
+                lcls = lcls + t_cls                                       # :131
+        lobj = lobj + t_obj                                               # :137
+    lbox = lbox * 0.05
+    lobj = lobj * 1.0
+    lcls = lcls * 0.58
+    return {"loss": lbox + lobj + lcls, "Localization": lbox, "Classification": lcls, "Conf_obj": lobj}
 
 
 def ssd_match(default_boxes, annotations_boxes, match_thresh=0.5):

@@ -336,6 +336,38 @@ def yolo_stats_cases():
     _save("yolo_stats", **d)
 
 
+def v5_loss_cases():
+    """MultiScaleRegionLoss_v5 forward + backward of the unmodified reference (losses.py:68-152): metrics and the
+    gradient w.r.t. every head level."""
+    losses = rh.losses()
+    B, C, img = 2, 4, 160
+    anchors_px = [list(map(float, a)) for a in synth.YOLOV5_ANCHORS]
+    crit = losses.MultiScaleRegionLoss_v5(anchors_px, None, None, None, None, C, img)
+    g = torch.Generator().manual_seed(101)
+    p = [torch.randn(B, 3, img // s, img // s, 5 + C, generator=g).requires_grad_(True) for s in (8, 16, 32)]
+    tg = synth.labels(B, C, 102, max_per_image=7)
+    tg = torch.cat([tg, tg[:3]])                                       # duplicate labels: same cells claimed twice
+    m = crit(p, tg)
+    m["loss"].backward()
+    d = dict(target=_np(tg), C=np.array(C), img=np.array(img), anchors_scaled=_np(crit.anchors),
+             metrics=np.array([float(m[k]) for k in ("loss", "Localization", "Classification", "Conf_obj")], np.float64))
+    for i, t in enumerate(p):
+        d[f"p_{i}"] = _np(t)
+        d[f"grad_{i}"] = _np(t.grad)
+    # single-class criterion: the class term is skipped (losses.py:127)
+    crit1 = losses.MultiScaleRegionLoss_v5(anchors_px, None, None, None, None, 1, img)
+    p1 = [torch.randn(B, 3, img // s, img // s, 6, generator=g).requires_grad_(True) for s in (8, 16, 32)]
+    tg1 = tg.clone(); tg1[:, 1] = 0
+    m1 = crit1(p1, tg1)
+    m1["loss"].backward()
+    d["metrics_1c"] = np.array([float(m1[k]) for k in ("loss", "Localization", "Classification", "Conf_obj")], np.float64)
+    for i, t in enumerate(p1):
+        d[f"p1c_{i}"] = _np(t)
+        d[f"grad1c_{i}"] = _np(t.grad)
+    d["target_1c"] = _np(tg1)
+    _save("v5_loss", **d)
+
+
 def main():
     if not rh.available():
         sys.exit("reference tree not present; golden vectors can only be generated in the build container")
@@ -349,6 +381,7 @@ def main():
     match_cases()
     metrics_cases()
     yolo_stats_cases()
+    v5_loss_cases()
 
 
 if __name__ == "__main__":

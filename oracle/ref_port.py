@@ -645,3 +645,41 @@ def get_yolo_statistics(selfobj, output, target: torch.Tensor):
         res[g] = [cls_acc.numpy(), recall50.numpy(), recall75.numpy(), precision.numpy(), conf_obj.numpy(),
                   conf_noobj.numpy(), out]
     return res
+
+
+def focal_bce_with_logits(pred: torch.Tensor, true: torch.Tensor, gamma: float = 1.5, alpha: float = 0.25) -> torch.Tensor:
+    """FocalLoss(nn.BCEWithLogitsLoss(pos_weight=1, reduction='mean'), gamma) — LightningFunc/losses.py:37-64:
+    elementwise BCE-with-logits times alpha_factor · (1 - p_t)^gamma, then the mean."""
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(pred, true, reduction="none")
+    prob = torch.sigmoid(pred)
+    p_t = true * prob + (1 - true) * (1 - prob)                       # :54
+    alpha_factor = true * alpha + (1 - true) * (1 - alpha)            # :55
+    return (loss * (alpha_factor * (1.0 - p_t) ** gamma)).mean()      # :56-60
+
+
+def v5_loss(output, target: torch.Tensor, anchors: torch.Tensor, nl: int, na: int, nc: int):
+    """Restates MultiScaleRegionLoss_v5.forward (losses.py:98-152; reduction 'mean', label smoothing 0 => cp, cn = 1, 0;
+    focal gamma 1.5).  `anchors` = the criterion's `self.anchors` ([nl, na, 2], pixel anchors / stride, :95-96).
+    Differentiable through torch autograd; returns the metrics dict."""
+    lcls, lbox, lobj = torch.zeros(1), torch.zeros(1), torch.zeros(1)
+    tcls, tbox, indices, anch = build_targets_v5([tuple(p.shape) for p in output], target, anchors, nl, na)
+    for i, pi in enumerate(output):
+        b, a, gj, gi = indices[i]
+        tobj = torch.zeros_like(pi[..., 0])
+        nb = b.shape[0]
+        if nb:
+            ps = pi[b, a, gj, gi]                                                          # :111
+            pxy = ps[:, :2].sigmoid() * 2. - 0.5                                           # :115
+            pwh = (ps[:, 2:4].sigmoid() * 2) ** 2 * anch[i]                                # :116
+            giou = bbox_iou_v5(torch.cat((pxy, pwh), 1).t(), tbox[i].t(), x1y1x2y2=False, GIoU=True)   # :118
+            lbox = lbox + (1.0 - giou).mean()                                              # :119
+            tobj[b, a, gj, gi] = giou.detach().clamp(0).type(tobj.dtype)                   # :123 (gr = 1)
+            if nc > 1:
+                t = torch.full_like(ps[:, 5:], 0.0)                                        # :128 (cn)
+                t[range(nb), tcls[i]] = 1.0                                                # :129 (cp)
+                lcls = lcls + focal_bce_with_logits(ps[:, 5:], t)                          # :131
+        lobj = lobj + focal_bce_with_logits(pi[..., 4], tobj)                              # :137
+    lbox = lbox * 0.05
+    lobj = lobj * 1.0
+    lcls = lcls * 0.58
+    return {"loss": lbox + lobj + lcls, "Localization": lbox, "Classification": lcls, "Conf_obj": lobj}

@@ -148,3 +148,51 @@ def test_ssd_match_oracle_many_gt():
     wi, wm = rp.ssd_match(pri, gt, 0.5)
     gi, gm = od.ssd_match(pri.to(DEV), gt.to(DEV), 0.5)
     assert torch.equal(gi.cpu(), wi) and torch.equal(gm.cpu(), wm)
+
+
+# ---- fused v5 loss terms (losses.py:98-152): values and gradients within 1e-5 relative -----------------
+@pytest.mark.parametrize("tag,nc", [("", 4), ("1c", 1)])
+def test_v5_loss_golden_reference_vectors(tag, nc):
+    import numpy as np
+    from tests.golden_io import load, T
+    d = load("v5_loss")
+    pk, gk, tk, mk = (("p_", "grad_", "target", "metrics") if not tag else ("p1c_", "grad1c_", "target_1c", "metrics_1c"))
+    p = [T(d[f"{pk}{i}"]).to(DEV).requires_grad_(True) for i in range(3)]
+    m = od.v5_loss(p, T(d[tk]).to(DEV), T(d["anchors_scaled"]).to(DEV), 3, 3, nc)
+    assert all(m[k].shape == (1,) for k in m)
+    m["loss"].backward()
+    got = [float(m[k].detach()) for k in ("loss", "Localization", "Classification", "Conf_obj")]
+    np.testing.assert_allclose(got, d[mk], rtol=1e-5, atol=1e-7)
+    for i in range(3):
+        torch.testing.assert_close(p[i].grad.cpu(), T(d[f"{gk}{i}"]), rtol=1e-4, atol=2e-8)
+
+
+@pytest.mark.parametrize("B,C,img,seed", [(4, 20, 320, 1), (8, 80, 640, 2)])
+def test_v5_loss_against_oracle_autograd(B, C, img, seed):
+    from oracle import ref_port as rp
+    g = torch.Generator().manual_seed(seed)
+    p_cpu = [torch.randn(B, 3, img // s, img // s, 5 + C, generator=g) for s in (8, 16, 32)]
+    tg = synth.labels(B, C, seed + 20, max_per_image=30)
+    stride = torch.tensor([8., 16., 32.])
+    anchors = torch.tensor(synth.YOLOV5_ANCHORS).float().view(3, -1, 2) / stride.view(-1, 1, 1)
+    pw = [t.clone().requires_grad_(True) for t in p_cpu]
+    want = rp.v5_loss(pw, tg, anchors, 3, 3, C)
+    want["loss"].backward()
+    pg = [t.to(DEV).requires_grad_(True) for t in p_cpu]
+    got = od.v5_loss(pg, tg.to(DEV), anchors.to(DEV), 3, 3, C)
+    got["loss"].backward()
+    for k in want:
+        torch.testing.assert_close(got[k].detach().cpu(), want[k].detach(), rtol=1e-5, atol=1e-7)
+    for a, b in zip(pg, pw):
+        torch.testing.assert_close(a.grad.cpu(), b.grad, rtol=1e-4, atol=2e-8)
+
+
+def test_v5_loss_without_targets():
+    from oracle import ref_port as rp
+    p_cpu = [torch.randn(2, 3, 8, 8, 9), torch.randn(2, 3, 4, 4, 9)]
+    anchors = torch.tensor([[[1.25, 1.6], [2.0, 3.75], [4.1, 2.9]], [[1.9, 3.8], [3.9, 2.8], [3.7, 7.4]]])
+    tg = torch.zeros(0, 6)
+    want = rp.v5_loss([t.clone() for t in p_cpu], tg, anchors, 2, 3, 4)
+    got = od.v5_loss([t.to(DEV) for t in p_cpu], tg.to(DEV), anchors.to(DEV), 2, 3, 4)
+    for k in want:
+        torch.testing.assert_close(got[k].cpu(), want[k], rtol=1e-5, atol=1e-7)

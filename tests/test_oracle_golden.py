@@ -244,3 +244,18 @@ def test_yolo_statistics_oracle_against_reference_vectors():
     bm = rp.get_yolo_statistics(_stats_self("v2", d), T(d["v2_head"]), tg)
     np.testing.assert_allclose([float(x) for x in bm[13][:6]], d["v2_metrics"], rtol=1e-6, atol=1e-7)
     assert torch.equal(bm[13][6], T(d["v2_output"]))
+
+
+# ---- fused v5 loss terms ------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,nc", [("", 4), ("1c", 1)])
+def test_v5_loss_oracle_against_reference_vectors(tag, nc):
+    import numpy as np
+    d = load("v5_loss")
+    pk, gk, tk, mk = (("p_", "grad_", "target", "metrics") if not tag else ("p1c_", "grad1c_", "target_1c", "metrics_1c"))
+    p = [T(d[f"{pk}{i}"]).clone().requires_grad_(True) for i in range(3)]
+    m = rp.v5_loss(p, T(d[tk]), T(d["anchors_scaled"]), 3, 3, nc)
+    m["loss"].backward()
+    got = [float(m[k].detach()) for k in ("loss", "Localization", "Classification", "Conf_obj")]
+    np.testing.assert_allclose(got, d[mk], rtol=1e-6, atol=1e-7)
+    for i in range(3):
+        torch.testing.assert_close(p[i].grad, T(d[f"{gk}{i}"]), rtol=1e-5, atol=1e-8)

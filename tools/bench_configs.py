@@ -59,6 +59,14 @@ def main():
     out.append(dict(cfg="4: YOLOv5s build_targets_v5 (3 levels, incl. 1 host sync)", us=us_bt, nt=int(tg.shape[0]),
                     rows=[int(t.shape[0]) for t in tcls]))
     out.append(dict(cfg="4: v5 matched-row GIoU fwd+bwd (3 levels, through autograd)", us=us_m))
+
+    def loss_fwd_bwd():
+        for t in p:
+            t.grad = None
+        od.v5_loss(p, tg, anchors.to(DEV), 3, 3, C)["loss"].backward()
+    us_l = timed(loss_fwd_bwd)
+    out.append(dict(cfg="4: fused v5 loss (build_targets_v5 + box/obj/cls terms) fwd+bwd, 3 levels, B=64 C=80", us=us_l,
+                    head_MB=sum(t.numel() for t in p) * 4 / 1e6))
     del p
     an3 = torch.tensor([[1.25, 1.625], [2.0, 3.75], [4.125, 2.875]], device=DEV)
     for G in (13, 26, 52):
