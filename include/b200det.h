@@ -49,6 +49,11 @@ extern "C" {
 #define B200DET_DECODE_YOLO_EXP 1  /* D1: sigmoid xy + grid, exp wh * anchor, * stride (accuracy.py:412-435,461) */
 #define B200DET_DECODE_YOLOV5 2    /* D2: (2s-0.5+grid)*stride, (2s)^2*anchor (utils/YoloV5Utils.py:244-248)    */
 
+/* memory layout of the head levels */
+#define B200DET_LAYOUT_PLANAR 0         /* [B, A, 5+C, G, G]: what every reference NMS reads (model/YOLOV3.py:294-300)  */
+#define B200DET_LAYOUT_CHANNELS_LAST 1  /* [B, A, G, G, 5+C]: what YOLOv5's Yolo_Layers really writes (model/YOLOV5.py:96);
+                                           same candidate order, no permute copy                    */
+
 int b200det_version(void);
 const char* b200det_last_error(void);
 
@@ -71,6 +76,7 @@ typedef struct b200det_yolo_desc {
                                                         (grid units), D2 pixel anchors                 */
     float conf_thres;                                /* keep rows with conf >= conf_thres              */
     float nms_thres;                                 /* suppress when IoU_+1 > nms_thres               */
+    int32_t layout;                                  /* B200DET_LAYOUT_* (0 = planar)                  */
 } b200det_yolo_desc;
 
 /* candidates per image N = sum_l A*G_l^2; per-image regions are padded to n_pad = roundup(N, TILE) */

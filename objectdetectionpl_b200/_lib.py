@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libb200det.so")
 
 MAX_LEVELS, MAX_ANCHORS, MAX_CLASSES, MAX_CANDIDATES, TILE = 8, 16, 4095, 1 << 20, 512
 DECODE_NONE, DECODE_YOLO_EXP, DECODE_YOLOV5 = 0, 1, 2
+LAYOUT_PLANAR, LAYOUT_CHANNELS_LAST = 0, 1
 IOU, GIOU, DIOU, CIOU = 0, 1, 2, 3
 
 
@@ -21,7 +22,7 @@ class YoloDesc(Structure):
     _fields_ = [("batch", c_int32), ("num_anchors", c_int32), ("num_classes", c_int32), ("num_levels", c_int32),
                 ("head", c_void_p * MAX_LEVELS), ("grid", c_int32 * MAX_LEVELS), ("decode_mode", c_int32),
                 ("stride", c_float * MAX_LEVELS), ("anchors", ((c_float * 2) * MAX_ANCHORS) * MAX_LEVELS),
-                ("conf_thres", c_float), ("nms_thres", c_float)]
+                ("conf_thres", c_float), ("nms_thres", c_float), ("layout", c_int32)]
 
 
 class PriorDesc(Structure):

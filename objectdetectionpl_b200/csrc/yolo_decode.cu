@@ -18,6 +18,7 @@
 
 namespace b200det {
 
+int launch_k1_rows(const b200det_yolo_desc* d, const K1Params& p, cudaStream_t st);
 bool k1_tma_supported(const K1Params& p);
 int launch_k1_tma(const b200det_yolo_desc* d, const K1Params& p, cudaStream_t st);
 
@@ -156,6 +157,7 @@ __global__ void __launch_bounds__(256) seg_scan_kernel(const uint32_t* __restric
 int yolo_validate(const b200det_yolo_desc* d, const void* ws, size_t ws_bytes) {
     B2_CHECK_ARG(d != nullptr, "desc is null");
     B2_CHECK_ARG(d->batch > 0 && d->num_anchors > 0 && d->num_classes > 0, "batch/anchors/classes must be > 0");
+    B2_CHECK_ARG(d->layout == B200DET_LAYOUT_PLANAR || d->layout == B200DET_LAYOUT_CHANNELS_LAST, "bad layout %d", d->layout);
     B2_CHECK_LIMIT(d->num_levels >= 1 && d->num_levels <= B200DET_MAX_LEVELS, "num_levels %d out of [1,%d]",
                    d->num_levels, B200DET_MAX_LEVELS);
     B2_CHECK_LIMIT(d->num_anchors <= B200DET_MAX_ANCHORS, "num_anchors %d > %d", d->num_anchors, B200DET_MAX_ANCHORS);
@@ -255,6 +257,7 @@ int yolo_stage_decode(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cud
     p.tile_count = w.tile_count; p.count = w.count; p.cls_hist = w.cls_hist;
     if (yolo_fast_path(w)) { p.count = nullptr; p.cls_hist = nullptr; }      // see yolo_stage_reset
 
+    if (d->layout == B200DET_LAYOUT_CHANNELS_LAST) return launch_k1_rows(d, p, st);
     // default: the register-staged LDG kernel; B200DET_K1=tma selects the bulk-async (TMA) pipeline, which is
     // bit-identical and measured 6% slower on B200 (see yolo_decode_tma.cu)
     const char* k1 = getenv("B200DET_K1");

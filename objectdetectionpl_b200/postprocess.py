@@ -24,8 +24,11 @@ YOLO_FORCED_CONF_THRES = -0.0151   # model/YOLOV5.py:164 — the reference overw
 _DECODE = {None: L.DECODE_NONE, "none": L.DECODE_NONE, "yolo_exp": L.DECODE_YOLO_EXP, "yolov5": L.DECODE_YOLOV5}
 
 
+_LAYOUT = {None: L.LAYOUT_PLANAR, "planar": L.LAYOUT_PLANAR, "channels_last": L.LAYOUT_CHANNELS_LAST}
+
+
 def _yolo_desc(levels: Sequence[torch.Tensor], num_anchors: int, conf_thres: float, nms_thres: float,
-               decode, anchors, strides) -> L.YoloDesc:
+               decode, anchors, strides, layout=None) -> L.YoloDesc:
     if len(levels) == 0 or len(levels) > L.MAX_LEVELS:
         raise ValueError(f"need 1..{L.MAX_LEVELS} prediction levels, got {len(levels)}")
     d = L.YoloDesc()
@@ -65,15 +68,23 @@ def _yolo_desc(levels: Sequence[torch.Tensor], num_anchors: int, conf_thres: flo
                 d.anchors[i][k][0] = float(a[k, 0])
                 d.anchors[i][k][1] = float(a[k, 1])
     d.conf_thres, d.nms_thres = float(conf_thres), float(nms_thres)
+    if layout not in _LAYOUT:
+        raise ValueError(f"layout must be 'planar' or 'channels_last', got {layout!r}")
+    d.layout = _LAYOUT[layout]
+    if d.layout == L.LAYOUT_CHANNELS_LAST:
+        for i, t in enumerate(levels):
+            if t.dim() != 5 or t.shape[1] != num_anchors or t.shape[2] != t.shape[3] or t.shape[4] != C + 5:
+                raise ValueError(f"layout='channels_last' needs predictions[{i}] of shape [B, {num_anchors}, G, G, 5+C], "
+                                 f"got {tuple(t.shape)}")
     return d
 
 
 def yolo_nms_raw(levels: Sequence[torch.Tensor], num_anchors: int = 3, conf_thres: float = YOLO_FORCED_CONF_THRES,
-                 nms_thres: float = 0.4, decode=None, anchors=None, strides=None, want_index: bool = False):
+                 nms_thres: float = 0.4, decode=None, anchors=None, strides=None, want_index: bool = False, layout=None):
     """Enqueue the whole pipeline; returns device tensors (rows [B,n_pad,7], index [B,n_pad]|None, count [B])
     without synchronising — the building block for benchmarks and CUDA-graph capture."""
     lib = L.load()
-    d = _yolo_desc(levels, num_anchors, conf_thres, nms_thres, decode, anchors, strides)
+    d = _yolo_desc(levels, num_anchors, conf_thres, nms_thres, decode, anchors, strides, layout)
     dev = levels[0].device
     n, n_pad = ctypes.c_int32(), ctypes.c_int32()
     L.check(lib.b200det_yolo_num_candidates(ctypes.byref(d), ctypes.byref(n), ctypes.byref(n_pad)), "yolo_num_candidates")
@@ -89,11 +100,11 @@ def yolo_nms_raw(levels: Sequence[torch.Tensor], num_anchors: int = 3, conf_thre
     return rows, index, count
 
 
-def _yolo_nms(predictions, num_anchors, conf_thres, nms_thres, compat, decode, anchors, strides, return_index):
+def _yolo_nms(predictions, num_anchors, conf_thres, nms_thres, compat, decode, anchors, strides, return_index, layout=None):
     if not isinstance(predictions, (list, tuple)):
         predictions = [predictions]                      # model/YOLOV3.py:281-282
     thr = YOLO_FORCED_CONF_THRES if compat else conf_thres
-    rows, index, count = yolo_nms_raw(predictions, num_anchors, thr, nms_thres, decode, anchors, strides, return_index)
+    rows, index, count = yolo_nms_raw(predictions, num_anchors, thr, nms_thres, decode, anchors, strides, return_index, layout)
     counts = count.cpu().tolist()                        # the one host sync of the call
     out: List[Optional[torch.Tensor]] = [rows[b, :k] if k else None for b, k in enumerate(counts)]   # YOLOV3.py:306,333
     if return_index:
@@ -102,16 +113,19 @@ def _yolo_nms(predictions, num_anchors, conf_thres, nms_thres, compat, decode, a
 
 
 def non_max_suppression(self, predictions, conf_thres=0.5, nms_thres=0.4, *, compat=True, decode=None, anchors=None,
-                        strides=None, return_index=False):
+                        strides=None, return_index=False, layout=None):
     """Drop-in for YOLOv3/v4/v5 `non_max_suppression` (3 anchors per level).
 
     Returns a list (one entry per image) of `None` or fp32 `[K,7]` rows
     `(x1, y1, x2, y2, object_conf, class_score, class_pred)` in descending score order.
     compat=True (default) reproduces the reference bit-for-bit, including its forced
     `conf_thres = -0.0151`; compat=False honours `conf_thres`.  Extensions (keyword-only):
-    `decode` in {None,'yolo_exp','yolov5'} with per-level `anchors`/`strides`, `return_index`.
+    `decode` in {None,'yolo_exp','yolov5'} with per-level `anchors`/`strides`, `return_index`, and
+    `layout='channels_last'`: the levels are read as what their `[B, A, G, G, 5+C]` shape says (the layout YOLOv5's
+    head really writes, model/YOLOV5.py:96) instead of the reference's planar re-interpretation of the same bytes
+    (YOLOV5.py:178-183) — same result as the default on the permuted tensor, without the permute copy.
     """
-    return _yolo_nms(predictions, 3, conf_thres, nms_thres, compat, decode, anchors, strides, return_index)
+    return _yolo_nms(predictions, 3, conf_thres, nms_thres, compat, decode, anchors, strides, return_index, layout)
 
 
 class _HostPipe:

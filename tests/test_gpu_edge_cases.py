@@ -126,3 +126,30 @@ def test_output_views_do_not_alias_the_input_and_input_is_untouched():
     od.non_max_suppression(None, lv)
     for a, b in zip(lv, before):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("layout", ["planar", "channels_last"])
+def test_arbitrary_bit_patterns_terminate(layout):
+    """Heads made of random bit patterns (NaN, inf, denormals, huge / negative sizes) must run to completion in both
+    layouts and give the same rows in both (the reference itself loops forever on w <= -1)."""
+    dev = torch.device(DEV)
+    g = torch.Generator(device=dev).manual_seed(11)
+    for it, (B, A, C, grids) in enumerate([(2, 3, 20, [20, 10, 5]), (2, 3, 4, [40, 20, 10]), (1, 3, 80, [40, 20])]):
+        levels = []
+        for G in grids:
+            bits = torch.randint(-2**31, 2**31 - 1, (B, A, 5 + C, G, G), device=dev, generator=g, dtype=torch.int64).to(torch.int32)
+            v = bits.view(torch.float32).clone()
+            if it % 2:
+                v[:, :, 4:] = torch.rand(B, A, 1 + C, G, G, device=dev, generator=g)
+            levels.append(v)
+        planar = [v.reshape(v.shape[0], -1, v.shape[3], v.shape[4]) for v in levels]
+        rows_p, _, count_p = od.yolo_nms_raw(planar, A)
+        if layout == "channels_last":
+            cl = [v.permute(0, 1, 3, 4, 2).contiguous() for v in levels]
+            rows, _, count = od.yolo_nms_raw(cl, A, layout="channels_last")
+            torch.cuda.synchronize()
+            assert torch.equal(count, count_p)
+            for b, k in enumerate(count.tolist()):
+                assert torch.equal(rows[b, :k].view(torch.int32), rows_p[b, :k].view(torch.int32))     # bit patterns (NaN-safe)
+        torch.cuda.synchronize()
+        assert int(count_p.min()) >= 0

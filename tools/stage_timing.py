@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--conf-mode", default="uniform")
     ap.add_argument("--conf-thres", type=float, default=-0.0151)
+    ap.add_argument("--layout", default="planar", choices=["planar", "channels_last"])
     ap.add_argument("--crowd", action="store_true", help="BASELINE config 5 shard: synth.yolo_crowd 1280x1280, 5 classes, conf_thres 0.001")
     ap.add_argument("--trace-sort", action="store_true", help="per-phase %globaltimer trace of the cluster sort")
     ap.add_argument("--trace-nms", action="store_true", help="per-phase %globaltimer trace of the NMS kernel")
@@ -44,7 +45,9 @@ def main():
         t[:, :, 5:] = torch.rand(a.batch, 3, a.classes, G, G, device=dev, generator=g)
         levels.append(t.view(a.batch, 3 * (5 + a.classes), G, G))
     lib = L.load()
-    d = _yolo_desc(levels, 3, a.conf_thres, 0.4, None, None, None)
+    if a.layout == "channels_last":
+        levels = [t.view(a.batch, 3, 5 + a.classes, t.shape[2], t.shape[3]).permute(0, 1, 3, 4, 2).contiguous() for t in levels]
+    d = _yolo_desc(levels, 3, a.conf_thres, 0.4, None, None, None, a.layout)
     n, n_pad = ctypes.c_int32(), ctypes.c_int32()
     lib.b200det_yolo_num_candidates(ctypes.byref(d), ctypes.byref(n), ctypes.byref(n_pad))
     nb = lib.b200det_yolo_workspace_bytes(ctypes.byref(d))
