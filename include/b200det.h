@@ -182,6 +182,12 @@ int b200det_build_targets_v5_level(const float* targets, int32_t num_targets, co
 /* Matched-row forward: pi [B,na,ny,nx,5+C] channels-last (losses.py:112), rows from the call above.
  *   giou[m]; tobj[B,na,ny,nx] must be zero-filled by the caller, receives clamp(giou,0) with
  *   "last row wins" on duplicate cells (losses.py:123). */
+/* all levels in one launch (one CTA per level): per-level host arrays nx/ny [nl], anchors [nl][na][2], and host
+ * arrays of the nl device output pointers; count_out [nl] (device).  Same rows as nl calls of the _level entry. */
+int b200det_build_targets_v5(const float* targets, int32_t num_targets, int32_t num_levels, const float* anchors_host,
+                             int32_t num_anchors, const int32_t* nx_host, const int32_t* ny_host, int32_t* const* out_b,
+                             int32_t* const* out_a, int32_t* const* out_gj, int32_t* const* out_gi, int32_t* const* out_cls,
+                             float* const* out_tbox, float* const* out_anch, int32_t* count_out, void* stream);
 int b200det_v5_match_fwd(const float* pi, int32_t batch, int32_t num_anchors, int32_t ny, int32_t nx,
                          int32_t fields, const int32_t* b, const int32_t* a, const int32_t* gj,
                          const int32_t* gi, const float* tbox, const float* anch, int32_t m, float* giou,
@@ -232,8 +238,9 @@ int b200det_retina_assign(const float* anchors, int32_t num_anchors, const float
  * BCEWithLogitsLoss with pos_weight 1).
  *   fwd: giou[m], tobj[B,na,ny,nx] (zero-filled here), sums[3] fp64 (device) = sum(1-giou), sum FL_obj, sum FL_cls;
  *        the means are sums / m, / cells, / (m*C).  with_cls = 0 skips the class term (nc == 1, :127).
- *   bwd: gpi (zero-filled by the caller) += d/dpi of  g_box*sum(1-giou) + g_obj*sum FL_obj + g_cls*sum FL_cls
- *        (tobj is treated as a constant: `giou.detach()`, :123).
+ *   bwd: gpi (zero-filled by the caller) += d/dpi of  g3[0]*inv_nbox*sum(1-giou) + g3[1]*inv_cells*sum FL_obj +
+ *        g3[2]*inv_ncls*sum FL_cls, g3 = the three upstream gradients on the DEVICE (no host sync in backward);
+ *        tobj is treated as a constant (`giou.detach()`, :123).
  * ---------------------------------------------------------------------------------------------- */
 int b200det_v5_loss_fwd(const float* pi, int32_t batch, int32_t na, int32_t ny, int32_t nx, int32_t fields,
                         const int32_t* b, const int32_t* a, const int32_t* gj, const int32_t* gi, const int32_t* tcls,
@@ -242,8 +249,8 @@ int b200det_v5_loss_fwd(const float* pi, int32_t batch, int32_t na, int32_t ny, 
 int b200det_v5_loss_bwd(const float* pi, int32_t batch, int32_t na, int32_t ny, int32_t nx, int32_t fields,
                         const int32_t* b, const int32_t* a, const int32_t* gj, const int32_t* gi, const int32_t* tcls,
                         const float* tbox, const float* anch, int32_t m, float cp, float cn, float gamma, float alpha,
-                        int32_t with_cls, const float* tobj, float g_box, float g_obj, float g_cls, float* gpi,
-                        void* stream);
+                        int32_t with_cls, const float* tobj, const float* g3, float inv_nbox, float inv_cells,
+                        float inv_ncls, float* gpi, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * M1 — true-positive matching of detections against labels.  Replaces `get_batch_statistics(outputs,

@@ -58,12 +58,14 @@ SIGNATURES = {
     "b200det_bbox_iou_v5_bwd": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
     "b200det_build_targets_v5_level": (_i32, [_vp, _i32, POINTER(_f), _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
                                               _vp, _vp, _vp]),
+    "b200det_build_targets_v5": (_i32, [_vp, _i32, _i32, POINTER(_f), _i32, POINTER(_i32), POINTER(_i32)] +
+                                 [POINTER(_vp)] * 7 + [_vp, _vp]),
     "b200det_v5_match_fwd": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "b200det_v5_match_bwd": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "b200det_v5_loss_fwd": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f, _f, _f, _f,
                                    _i32, _vp, _vp, _vp, _vp]),
     "b200det_v5_loss_bwd": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f, _f, _f, _f,
-                                   _i32, _vp, _f, _f, _f, _vp, _vp]),
+                                   _i32, _vp, _vp, _f, _f, _f, _vp, _vp]),
     "b200det_build_targets_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "b200det_build_targets": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f, _vp, _sz] + [_vp] * 10 + [_vp]),
     "b200det_ssd_match_workspace_bytes": (_sz, [_i32, _i32]),

@@ -35,6 +35,9 @@ int bbox_iou_v5_bwd_launch(const float*, long long, long long, const float*, lon
                            const float*, float*, cudaStream_t);
 int build_targets_v5_launch(const float*, int, const float*, int, int, int, int32_t*, int32_t*, int32_t*, int32_t*,
                             int32_t*, float*, float*, int32_t*, cudaStream_t);
+int build_targets_v5_multi_launch(const float*, int, int, const float*, int, const int32_t*, const int32_t*, int32_t* const*,
+                                  int32_t* const*, int32_t* const*, int32_t* const*, int32_t* const*, float* const*,
+                                  float* const*, int32_t*, cudaStream_t);
 int v5_match_fwd_launch(const float*, int, int, int, int, int, const int32_t*, const int32_t*, const int32_t*,
                         const int32_t*, const float*, const float*, int, float*, float*, cudaStream_t);
 int v5_match_bwd_launch(const float*, int, int, int, int, int, const int32_t*, const int32_t*, const int32_t*,
@@ -43,8 +46,8 @@ int v5_loss_fwd_launch(const float*, int, int, int, int, int, const int32_t*, co
                        const int32_t*, const float*, const float*, int, float, float, float, float, int, float*, float*,
                        double*, cudaStream_t);
 int v5_loss_bwd_launch(const float*, int, int, int, int, int, const int32_t*, const int32_t*, const int32_t*, const int32_t*,
-                       const int32_t*, const float*, const float*, int, float, float, float, float, int, const float*, float,
-                       float, float, float*, cudaStream_t);
+                       const int32_t*, const float*, const float*, int, float, float, float, float, int, const float*,
+                       const float*, float, float, float, float*, cudaStream_t);
 size_t build_targets_ws_bytes(int, int, int, int);
 int build_targets_launch(const float*, const float*, const float*, const float*, int, int, int, int, int, float, void*,
                          float*, float*, uint8_t*, uint8_t*, float*, float*, float*, float*, float*, int32_t*, cudaStream_t);
@@ -204,6 +207,19 @@ int b200det_build_targets_v5_level(const float* targets, int32_t nt, const float
     return build_targets_v5_launch(targets, nt, anchors_host, na, nx, ny, ob, oa, ogj, ogi, ocls, otbox, oanch, ocount,
                                    (cudaStream_t)st);
 }
+int b200det_build_targets_v5(const float* targets, int32_t nt, int32_t nl, const float* anchors_host, int32_t na,
+                             const int32_t* nx_host, const int32_t* ny_host, int32_t* const* ob, int32_t* const* oa,
+                             int32_t* const* ogj, int32_t* const* ogi, int32_t* const* ocls, float* const* otbox,
+                             float* const* oanch, int32_t* ocount, void* st) {
+    B2_CHECK_ARG(nt >= 0 && na > 0 && nl > 0, "bad sizes");
+    B2_CHECK_LIMIT(na <= B200DET_MAX_ANCHORS && nl <= B200DET_MAX_LEVELS, "num_anchors %d / levels %d beyond the limits", na, nl);
+    B2_CHECK_ARG(anchors_host && nx_host && ny_host && ob && oa && ogj && ogi && ocls && otbox && oanch && ocount && (nt == 0 || targets),
+                 "null argument");
+    B2_CHECK_LIMIT((long long)nt * na < (1ll << 30), "too many targets");
+    for (int l = 0; l < nl; ++l) B2_CHECK_ARG(nx_host[l] > 0 && ny_host[l] > 0, "bad grid of level %d", l);
+    return build_targets_v5_multi_launch(targets, nt, nl, anchors_host, na, nx_host, ny_host, ob, oa, ogj, ogi, ocls, otbox,
+                                         oanch, ocount, (cudaStream_t)st);
+}
 int b200det_v5_match_fwd(const float* pi, int32_t B, int32_t na, int32_t ny, int32_t nx, int32_t F, const int32_t* b,
                          const int32_t* a, const int32_t* gj, const int32_t* gi, const float* tbox, const float* anch,
                          int32_t m, float* giou, float* tobj, void* st) {
@@ -234,12 +250,13 @@ int b200det_v5_loss_fwd(const float* pi, int32_t B, int32_t na, int32_t ny, int3
 int b200det_v5_loss_bwd(const float* pi, int32_t B, int32_t na, int32_t ny, int32_t nx, int32_t F, const int32_t* b,
                         const int32_t* a, const int32_t* gj, const int32_t* gi, const int32_t* tcls, const float* tbox,
                         const float* anch, int32_t m, float cp, float cn, float gamma, float alpha, int32_t with_cls,
-                        const float* tobj, float g_box, float g_obj, float g_cls, float* gpi, void* st) {
+                        const float* tobj, const float* g3, float inv_nbox, float inv_cells, float inv_ncls, float* gpi,
+                        void* st) {
     B2_CHECK_ARG(B > 0 && na > 0 && ny > 0 && nx > 0 && m >= 0 && F >= 5, "bad sizes");
-    B2_CHECK_ARG(pi && tobj && gpi && (m == 0 || (b && a && gj && gi && tcls && tbox && anch)), "null argument");
+    B2_CHECK_ARG(pi && tobj && gpi && g3 && (m == 0 || (b && a && gj && gi && tcls && tbox && anch)), "null argument");
     B2_CHECK_ARG(((uintptr_t)tbox & 15) == 0, "tbox must be 16-byte aligned");
     return v5_loss_bwd_launch(pi, B, na, ny, nx, F, b, a, gj, gi, tcls, tbox, anch, m, cp, cn, gamma, alpha, with_cls, tobj,
-                              g_box, g_obj, g_cls, gpi, (cudaStream_t)st);
+                              g3, inv_nbox, inv_cells, inv_ncls, gpi, (cudaStream_t)st);
 }
 
 size_t b200det_build_targets_workspace_bytes(int32_t B, int32_t A, int32_t G, int32_t nt) {

@@ -56,19 +56,22 @@ def build_targets_v5(p, targets, anchors, nl, na):
     tcls, tbox, indices, anch = [], [], [], []
     counts = torch.empty((nl,), dtype=torch.int32, device=dev)
     bufs = []
+    nxs, nys = (ctypes.c_int32 * nl)(), (ctypes.c_int32 * nl)()
+    ptrs = [(ctypes.c_void_p * nl)() for _ in range(7)]                  # b, a, gj, gi, cls, tbox, anch per level
+    for i in range(nl):
+        shape = p[i].shape if isinstance(p[i], torch.Tensor) else tuple(p[i])
+        nys[i], nxs[i] = int(shape[2]), int(shape[3])
+        ib = torch.empty((5, cap), dtype=torch.int32, device=dev)        # b, a, gj, gi, cls
+        tb = torch.empty((cap, 4), dtype=torch.float32, device=dev)
+        ac = torch.empty((cap, 2), dtype=torch.float32, device=dev)
+        for k in range(5):
+            ptrs[k][i] = ib[k].data_ptr()
+        ptrs[5][i], ptrs[6][i] = tb.data_ptr(), ac.data_ptr()
+        bufs.append((ib, tb, ac))
+    arr = (ctypes.c_float * (2 * na * nl))(*anchors_cpu.reshape(-1).tolist())
     with torch.cuda.device(dev):
-        for i in range(nl):
-            shape = p[i].shape if isinstance(p[i], torch.Tensor) else tuple(p[i])
-            ny, nx = int(shape[2]), int(shape[3])
-            ib = torch.empty((5, cap), dtype=torch.int32, device=dev)      # b, a, gj, gi, cls
-            tb = torch.empty((cap, 4), dtype=torch.float32, device=dev)
-            ac = torch.empty((cap, 2), dtype=torch.float32, device=dev)
-            arr = (ctypes.c_float * (2 * na))(*anchors_cpu[i].reshape(-1).tolist())
-            L.check(lib.b200det_build_targets_v5_level(tg.data_ptr() if nt else None, nt, arr, na, nx, ny, ib[0].data_ptr(),
-                                                       ib[1].data_ptr(), ib[2].data_ptr(), ib[3].data_ptr(), ib[4].data_ptr(),
-                                                       tb.data_ptr(), ac.data_ptr(), counts[i:].data_ptr(), L.stream_ptr(dev)),
-                    "build_targets_v5")
-            bufs.append((ib, tb, ac))
+        L.check(lib.b200det_build_targets_v5(tg.data_ptr() if nt else None, nt, nl, arr, na, nxs, nys, *ptrs, counts.data_ptr(),
+                                             L.stream_ptr(dev)), "build_targets_v5")     # one launch, one CTA per level
     ms = counts.cpu().tolist()                                            # one host sync for all levels
     for i, (ib, tb, ac) in enumerate(bufs):
         m = ms[i]
@@ -164,12 +167,12 @@ class _V5LossLevel(torch.autograd.Function):
         cp, cn, gamma, alpha, with_cls, m, cells, n_box, n_cls = ctx.cfg
         B, na, ny, nx, F = pid.shape
         gpi = torch.zeros_like(pid)
-        g = torch.stack((g_box, g_obj, g_cls)).double().cpu().tolist()     # three upstream scalars (one sync in backward)
+        g3 = torch.stack((g_box, g_obj, g_cls)).float().contiguous()      # stays on the device: no sync in backward
         with torch.cuda.device(pid.device):
             L.check(lib.b200det_v5_loss_bwd(pid.data_ptr(), B, na, ny, nx, F, idx[0].data_ptr(), idx[1].data_ptr(),
                                             idx[2].data_ptr(), idx[3].data_ptr(), idx[4].data_ptr(), tb.data_ptr(), ac.data_ptr(),
-                                            m, cp, cn, gamma, alpha, with_cls, tobj.data_ptr(), g[0] / n_box, g[1] / cells,
-                                            g[2] / n_cls, gpi.data_ptr(), L.stream_ptr(pid.device)), "v5_loss_bwd")
+                                            m, cp, cn, gamma, alpha, with_cls, tobj.data_ptr(), g3.data_ptr(), 1.0 / n_box,
+                                            1.0 / cells, 1.0 / n_cls, gpi.data_ptr(), L.stream_ptr(pid.device)), "v5_loss_bwd")
         return (gpi,) + (None,) * 12
 
 
