@@ -178,3 +178,26 @@ def test_tma_variant_of_k1_is_bit_identical(monkeypatch):
     l = od.non_max_suppression(None, heads, **kw)
     for x, y in zip(t, l):
         assert torch.equal(x, y)
+
+
+def test_pipeline_is_cuda_graph_capturable():
+    """The library never allocates or synchronises (include/b200det.h), so the four launches of a step can be captured
+    once and replayed; the replay must reproduce the eager result for new head values in the same buffers."""
+    levels = _cuda(synth.yolo_planar(4, 3, 20, [20, 10, 5], 160, 55))
+    static = [t.clone() for t in levels]
+    od.yolo_nms_raw(static, 3, want_index=True)                       # warm-up: one-time function attributes, workspace
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        rows, index, count = od.yolo_nms_raw(static, 3, want_index=True)
+    for seed in (56, 57):
+        fresh = _cuda(synth.yolo_planar(4, 3, 20, [20, 10, 5], 160, seed))
+        for dst, src in zip(static, fresh):
+            dst.copy_(src)
+        g.replay()
+        torch.cuda.synchronize()
+        want_rows, want_index, want_count = od.yolo_nms_raw(fresh, 3, want_index=True)
+        torch.cuda.synchronize()
+        assert torch.equal(count, want_count)
+        for b, k in enumerate(count.tolist()):
+            assert torch.equal(rows[b, :k], want_rows[b, :k]) and torch.equal(index[b, :k], want_index[b, :k])
