@@ -189,12 +189,19 @@ __global__ void __launch_bounds__(kNmsThreads, 5) nms_segment_kernel(const NmsPa
     __shared__ int s_wpre[kNmsW + 1];
     __shared__ int s_own[kNmsT];
     __shared__ int s_pre[kNmsT];
-    __shared__ float4 s_kb[kNmsStage];
-    __shared__ uint2 s_kq[kNmsStage];
-    __shared__ unsigned s_kqt[kNmsStage];
+    // phase-A staging (keepers of earlier chunks) lives in the mask triangle: phase A of a chunk is over before phase B
+    // writes the triangle, and the triangle of the previous chunk is dead by then.  (Shared memory per CTA decides the
+    // carve-out: 5 CTAs x <= 39 KB fit the 196 KB setting and leave 32 KB of L1 for the box gathers; 42 KB per CTA measured
+    // 248 vs 238 us.)
+    static_assert(kNmsStage * (16 + 8 + 4) <= kNmsTriWords * 8, "phase-A staging must fit the mask triangle");
+    float4* const s_kb = reinterpret_cast<float4*>(s_L);
+    uint2* const s_kq = reinterpret_cast<uint2*>(s_L + kNmsStage * 2);
+    unsigned* const s_kqt = reinterpret_cast<unsigned*>(s_L + kNmsStage * 3);
     __shared__ int s_last_members;
     __shared__ uint32_t s_mlist[kNmsT];     // members of in-chunk clusters in ascending row order: owner index << 10 | row
     __shared__ unsigned s_nzw[kNmsT];       // per row: which of its mask words are non-zero (most rows: none)
+    __shared__ uint32_t s_pay[kNmsT];       // sorted payload of the row   } fetched with the boxes, so that the owner / merge
+    __shared__ uint32_t s_rank[kNmsT];      // score rank of the row       } phases do not wait on L2 again (VARIANT 0)
     __shared__ int16_t s_next[kNmsT];       // member list position of the next member of the same cluster, or -1
     __shared__ int16_t s_first[kNmsT];      // per in-chunk keeper ordinal: list position of its first member, or -1
     __shared__ int16_t s_last[kNmsT];       // ... of its last member so far (while the chains are built)
@@ -236,8 +243,12 @@ __global__ void __launch_bounds__(kNmsThreads, 5) nms_segment_kernel(const NmsPa
             static_assert(kNmsT <= 2 * kNmsThreads, "a thread loads at most two rows of a chunk");
             const int j0 = tid, j1 = tid + kNmsThreads;
             uint32_t slot0 = 0, slot1 = 0;
-            if (j0 < nc) slot0 = p.spay[img + c0 + j0] & kSlotMask;
-            if (j1 < nc) slot1 = p.spay[img + c0 + j1] & kSlotMask;
+            if (j0 < nc) { const uint32_t v = p.spay[img + c0 + j0]; slot0 = v & kSlotMask; s_pay[j0] = v; }
+            if (j1 < nc) { const uint32_t v = p.spay[img + c0 + j1]; slot1 = v & kSlotMask; s_pay[j1] = v; }
+            if (VARIANT == 0) {
+                if (j0 < nc) s_rank[j0] = p.srank[img + c0 + j0];
+                if (j1 < nc) s_rank[j1] = p.srank[img + c0 + j1];
+            }
             float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
             float f0 = 0.f, f1 = 0.f;
             if (j0 < nc) { b0 = p.box4[img + slot0]; f0 = p.cc2[img + slot0].x; }
@@ -461,7 +472,7 @@ __global__ void __launch_bounds__(kNmsThreads, 5) nms_segment_kernel(const NmsPa
                 }
                 s_own[j] = own;
                 if (VARIANT == 0) {
-                    if (!is_keeper) p.kpay[img + p.srank[img + c0 + j]] = kNone;
+                    if (!is_keeper) p.kpay[img + s_rank[j]] = kNone;
                 }
                 if (is_keeper && !(VARIANT == 0 && single)) {
                     p.kbox[img + s + own] = s_box[j];
@@ -494,8 +505,8 @@ __global__ void __launch_bounds__(kNmsThreads, 5) nms_segment_kernel(const NmsPa
             auto finish = [&](const int j, const int kidx, const float ax, const float ay, const float az, const float aw,
                               const float ws) {
                 if (single) {
-                    const uint32_t r = p.srank[img + c0 + j];
-                    p.kpay[img + r] = p.spay[img + c0 + j];
+                    const uint32_t r = s_rank[j];
+                    p.kpay[img + r] = s_pay[j];
                     p.mbox[img + r] = make_float4(__fdiv_rn(ax, ws), __fdiv_rn(ay, ws), __fdiv_rn(az, ws), __fdiv_rn(aw, ws));
                     atomicAdd(&p.chunk_cnt[(size_t)b * p.n_chunks + (r >> kEmitShift)], 1u);
                 } else {
