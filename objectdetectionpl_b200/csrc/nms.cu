@@ -177,7 +177,7 @@ __device__ __forceinline__ void nms_stamp(unsigned long long* tr, int point) {
 
 // FAST: the pre-filter is sound when "no overlap" implies "not removed", i.e. VARIANT 0 with nms_thres >= 0.
 template <int VARIANT, bool FAST>
-__global__ void __launch_bounds__(kNmsThreads, 5) nms_segment_kernel(const NmsParams p) {
+__global__ void __launch_bounds__(kNmsThreads, 6) nms_segment_kernel(const NmsParams p) {
     __shared__ float4 s_box[kNmsT];
     __shared__ float s_conf[kNmsT];
     __shared__ uint2 s_q[kNmsT];        // half2 lo, hi   (see box_bounds_h2; split 8 + 4 bytes: one 128-bit word per row
@@ -199,9 +199,10 @@ __global__ void __launch_bounds__(kNmsThreads, 5) nms_segment_kernel(const NmsPa
     unsigned* const s_kqt = reinterpret_cast<unsigned*>(s_L + kNmsStage * 3);
     __shared__ int s_last_members;
     __shared__ uint32_t s_mlist[kNmsT];     // members of in-chunk clusters in ascending row order: owner index << 10 | row
-    __shared__ unsigned s_nzw[kNmsT];       // per row: which of its mask words are non-zero (most rows: none)
-    __shared__ uint32_t s_pay[kNmsT];       // sorted payload of the row   } fetched with the boxes, so that the owner / merge
-    __shared__ uint32_t s_rank[kNmsT];      // score rank of the row       } phases do not wait on L2 again (VARIANT 0)
+    __shared__ __align__(4) uint8_t s_nzw[kNmsT];   // per row: which of its mask words are non-zero (most rows: none)
+    static_assert(kNmsW <= 8, "one byte of non-zero-word flags per row");
+    __shared__ uint32_t s_rank[kNmsT];      // score rank of the row, fetched with the boxes so that the owner / merge phases
+                                            // do not wait on L2 for it again (VARIANT 0)
     __shared__ int16_t s_next[kNmsT];       // member list position of the next member of the same cluster, or -1
     __shared__ int16_t s_first[kNmsT];      // per in-chunk keeper ordinal: list position of its first member, or -1
     __shared__ int16_t s_last[kNmsT];       // ... of its last member so far (while the chains are built)
@@ -243,8 +244,8 @@ __global__ void __launch_bounds__(kNmsThreads, 5) nms_segment_kernel(const NmsPa
             static_assert(kNmsT <= 2 * kNmsThreads, "a thread loads at most two rows of a chunk");
             const int j0 = tid, j1 = tid + kNmsThreads;
             uint32_t slot0 = 0, slot1 = 0;
-            if (j0 < nc) { const uint32_t v = p.spay[img + c0 + j0]; slot0 = v & kSlotMask; s_pay[j0] = v; }
-            if (j1 < nc) { const uint32_t v = p.spay[img + c0 + j1]; slot1 = v & kSlotMask; s_pay[j1] = v; }
+            if (j0 < nc) slot0 = p.spay[img + c0 + j0] & kSlotMask;
+            if (j1 < nc) slot1 = p.spay[img + c0 + j1] & kSlotMask;
             if (VARIANT == 0) {
                 if (j0 < nc) s_rank[j0] = p.srank[img + c0 + j0];
                 if (j1 < nc) s_rank[j1] = p.srank[img + c0 + j1];
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(kNmsThreads, 5) nms_segment_kernel(const NmsPa
                     }
                 }
                 s_L[tri_off(j) + w] = bits;
-                if (bits) atomicOr(&s_nzw[j], 1u << w);
+                if (bits) atomicOr(reinterpret_cast<unsigned*>(s_nzw) + (j >> 2), (1u << w) << (8 * (j & 3)));
             }
         }
         __syncthreads();
@@ -506,7 +507,7 @@ __global__ void __launch_bounds__(kNmsThreads, 5) nms_segment_kernel(const NmsPa
                               const float ws) {
                 if (single) {
                     const uint32_t r = s_rank[j];
-                    p.kpay[img + r] = s_pay[j];
+                    p.kpay[img + r] = p.spay[img + c0 + j];
                     p.mbox[img + r] = make_float4(__fdiv_rn(ax, ws), __fdiv_rn(ay, ws), __fdiv_rn(az, ws), __fdiv_rn(aw, ws));
                     atomicAdd(&p.chunk_cnt[(size_t)b * p.n_chunks + (r >> kEmitShift)], 1u);
                 } else {
