@@ -18,6 +18,7 @@
 // IoU arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction) and IEEE division so
 // the keep decisions are bit-identical to the reference's fp32 CPU path.
 #include <cuda_fp16.h>
+#include <limits.h>
 
 #include "yolo_ws.cuh"
 
@@ -272,6 +273,13 @@ __global__ void __launch_bounds__(kNmsThreads, 6) nms_segment_kernel(const NmsPa
         __syncthreads();
 
         // ---- phase A: against keepers of earlier chunks ----------------------------------------
+        // FAST: one task = 32 rows x 32 staged keepers, through the same vectorised bound test as phase B, dealt round-robin
+        // to the warps; the owner of a row is the LOWEST keeper index that removes it (atomicMin), rows already owned after
+        // an earlier stage are skipped.  (The row-per-thread loop over all keepers it replaces made large segments — few
+        // classes, dense crowds — crawl: 930 us for the config-5 shard.)
+        if (FAST && Kprev > 0) {
+            for (int j = tid; j < nc; j += kNmsThreads) s_own[j] = INT_MAX;      // s_own doubles as the hit slot until the owners phase
+        }
         for (int kt = 0; kt < Kprev; kt += kNmsStage) {
             const int nk = min(kNmsStage, Kprev - kt);
             if (tid < nk) {
@@ -280,15 +288,31 @@ __global__ void __launch_bounds__(kNmsThreads, 6) nms_segment_kernel(const NmsPa
                 if (FAST) { const uint4 q = box_bounds_h2(kb, thr); s_kq[tid] = make_uint2(q.x, q.y); s_kqt[tid] = q.z; }
             }
             __syncthreads();
-            for (int j = tid; j < nc; j += kNmsThreads) {
-                if (s_pre[j] >= 0) continue;
-                const float4 bj = s_box[j];
-                if (FAST) {
+            if (FAST) {
+                const int nkb = (nk + 31) >> 5, ngr = (nc + 31) >> 5;
+                for (int t = tid >> 5; t < ngr * nkb; t += kNmsThreads / 32) {
+                    const int g = t / nkb, kb0 = (t - g * nkb) << 5;
+                    const int j = (g << 5) + lane;
+                    const bool active = j < nc && s_pre[j] < 0;
+                    if (!__any_sync(0xFFFFFFFFu, active)) continue;
+                    if (!active) continue;
+                    const float4 bj = s_box[j];
                     const uint4 qj = make_uint4(s_q[j].x, s_q[j].y, s_qt[j], 0u);
-                    for (int k = 0; k < nk; ++k) {
-                        if (may_remove(make_uint4(s_kq[k].x, s_kq[k].y, s_kqt[k], 0u), qj) && removes<VARIANT>(s_kb[k], bj, thr)) { s_pre[j] = kt + k; break; }
+                    unsigned cand = may_remove_mask32(s_kq + kb0, s_kqt + kb0, qj);
+                    if (nk - kb0 < 32) cand &= (1u << (nk - kb0)) - 1u;                   // stale entries past the stage
+                    while (cand) {
+                        const int k = __ffs((int)cand) - 1;
+                        cand &= cand - 1u;
+                        if (removes<VARIANT>(s_kb[kb0 + k], bj, thr)) { atomicMin(&s_own[j], kt + kb0 + k); break; }
                     }
-                } else {
+                }
+                __syncthreads();
+                for (int j = tid; j < nc; j += kNmsThreads)
+                    if (s_pre[j] < 0 && s_own[j] != INT_MAX) s_pre[j] = s_own[j];
+            } else {
+                for (int j = tid; j < nc; j += kNmsThreads) {
+                    if (s_pre[j] >= 0) continue;
+                    const float4 bj = s_box[j];
                     for (int k = 0; k < nk; ++k) {
                         if (removes<VARIANT>(s_kb[k], bj, thr)) { s_pre[j] = kt + k; break; }
                     }
