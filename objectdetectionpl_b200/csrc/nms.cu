@@ -28,7 +28,7 @@ constexpr int kNmsT = 384;                 // rows per chunk (384: 6 CTAs/SM; 51
 constexpr int kNmsThreads = 256;
 constexpr int kNmsW = kNmsT / 64;          // mask words per full row
 constexpr int kNmsTriWords = 32 * kNmsW * (kNmsW + 1);   // packed lower-triangular rows
-constexpr int kNmsStage = 256;             // earlier keepers staged per phase-A round
+constexpr int kNmsStage = 384;             // earlier keepers staged per phase-A round (fills the aliased mask triangle exactly)
 constexpr int kNmsRounds = 12;             // parallel fixed-point rounds before the serial sweep takes over
 
 struct NmsParams {
@@ -282,10 +282,10 @@ __global__ void __launch_bounds__(kNmsThreads, 6) nms_segment_kernel(const NmsPa
         }
         for (int kt = 0; kt < Kprev; kt += kNmsStage) {
             const int nk = min(kNmsStage, Kprev - kt);
-            if (tid < nk) {
-                const float4 kb = p.kbox[img + s + kt + tid];
-                s_kb[tid] = kb;
-                if (FAST) { const uint4 q = box_bounds_h2(kb, thr); s_kq[tid] = make_uint2(q.x, q.y); s_kqt[tid] = q.z; }
+            for (int i = tid; i < nk; i += kNmsThreads) {
+                const float4 kb = p.kbox[img + s + kt + i];
+                s_kb[i] = kb;
+                if (FAST) { const uint4 q = box_bounds_h2(kb, thr); s_kq[i] = make_uint2(q.x, q.y); s_kqt[i] = q.z; }
             }
             __syncthreads();
             if (FAST) {
