@@ -177,8 +177,10 @@ __device__ __forceinline__ void nms_stamp(unsigned long long* tr, int point) {
 }
 
 // FAST: the pre-filter is sound when "no overlap" implies "not removed", i.e. VARIANT 0 with nms_thres >= 0.
-template <int VARIANT, bool FAST>
-__global__ void __launch_bounds__(kNmsThreads, 6) nms_segment_kernel(const NmsParams p) {
+// NT threads per CTA: 256 for the usual ~300-row segments (6 CTAs/SM); 512 when the average segment is longer than a chunk
+// (few classes, dense crowds): there are then few CTAs and the phase-A / phase-B warp tasks of a segment are the parallelism.
+template <int VARIANT, bool FAST, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 6 : 3) nms_segment_kernel(const NmsParams p) {
     __shared__ float4 s_box[kNmsT];
     __shared__ float s_conf[kNmsT];
     __shared__ uint2 s_q[kNmsT];        // half2 lo, hi   (see box_bounds_h2; split 8 + 4 bytes: one 128-bit word per row
@@ -242,8 +244,8 @@ __global__ void __launch_bounds__(kNmsThreads, 6) nms_segment_kernel(const NmsPa
         // both rows of a thread are fetched together: payload -> slot -> box is a chain of two L2 round trips, and a
         // row-at-a-time loop would walk it twice back to back
         {
-            static_assert(kNmsT <= 2 * kNmsThreads, "a thread loads at most two rows of a chunk");
-            const int j0 = tid, j1 = tid + kNmsThreads;
+            static_assert(kNmsT <= 2 * NT, "a thread loads at most two rows of a chunk");
+            const int j0 = tid, j1 = tid + NT;
             uint32_t slot0 = 0, slot1 = 0;
             if (j0 < nc) slot0 = p.spay[img + c0 + j0] & kSlotMask;
             if (j1 < nc) slot1 = p.spay[img + c0 + j1] & kSlotMask;
@@ -278,11 +280,11 @@ __global__ void __launch_bounds__(kNmsThreads, 6) nms_segment_kernel(const NmsPa
         // an earlier stage are skipped.  (The row-per-thread loop over all keepers it replaces made large segments — few
         // classes, dense crowds — crawl: 930 us for the config-5 shard.)
         if (FAST && Kprev > 0) {
-            for (int j = tid; j < nc; j += kNmsThreads) s_own[j] = INT_MAX;      // s_own doubles as the hit slot until the owners phase
+            for (int j = tid; j < nc; j += NT) s_own[j] = INT_MAX;      // s_own doubles as the hit slot until the owners phase
         }
         for (int kt = 0; kt < Kprev; kt += kNmsStage) {
             const int nk = min(kNmsStage, Kprev - kt);
-            for (int i = tid; i < nk; i += kNmsThreads) {
+            for (int i = tid; i < nk; i += NT) {
                 const float4 kb = p.kbox[img + s + kt + i];
                 s_kb[i] = kb;
                 if (FAST) { const uint4 q = box_bounds_h2(kb, thr); s_kq[i] = make_uint2(q.x, q.y); s_kqt[i] = q.z; }
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(kNmsThreads, 6) nms_segment_kernel(const NmsPa
             __syncthreads();
             if (FAST) {
                 const int nkb = (nk + 31) >> 5, ngr = (nc + 31) >> 5;
-                for (int t = tid >> 5; t < ngr * nkb; t += kNmsThreads / 32) {
+                for (int t = tid >> 5; t < ngr * nkb; t += NT / 32) {
                     const int g = t / nkb, kb0 = (t - g * nkb) << 5;
                     const int j = (g << 5) + lane;
                     const bool active = j < nc && s_pre[j] < 0;
@@ -307,10 +309,10 @@ __global__ void __launch_bounds__(kNmsThreads, 6) nms_segment_kernel(const NmsPa
                     }
                 }
                 __syncthreads();
-                for (int j = tid; j < nc; j += kNmsThreads)
+                for (int j = tid; j < nc; j += NT)
                     if (s_pre[j] < 0 && s_own[j] != INT_MAX) s_pre[j] = s_own[j];
             } else {
-                for (int j = tid; j < nc; j += kNmsThreads) {
+                for (int j = tid; j < nc; j += NT) {
                     if (s_pre[j] >= 0) continue;
                     const float4 bj = s_box[j];
                     for (int k = 0; k < nk; ++k) {
@@ -329,7 +331,7 @@ __global__ void __launch_bounds__(kNmsThreads, 6) nms_segment_kernel(const NmsPa
         const int ngroups_b = (nc + 31) >> 5;
         int n_tasks = 0;
         for (int w = 0; w < Wc; ++w) n_tasks += ngroups_b - 2 * w;
-        for (int t = tid >> 5; t < n_tasks; t += kNmsThreads / 32) {
+        for (int t = tid >> 5; t < n_tasks; t += NT / 32) {
             int w = 0, rem = t;
             while (rem >= ngroups_b - 2 * w) { rem -= ngroups_b - 2 * w; ++w; }
             const int i0 = w << 6;
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(kNmsThreads, 6) nms_segment_kernel(const NmsPa
         // kept/decided bits of a 32-row group live in one 64-bit word so that a reader sees a consistent pair, and the
         // serial sweep below finishes adversarial chains after kNmsRounds rounds.
         {
-            for (int g = tid >> 5; g < kNmsT / 32; g += kNmsThreads / 32) {
+            for (int g = tid >> 5; g < kNmsT / 32; g += NT / 32) {
                 const int j = (g << 5) + lane;
                 const bool live = j < nc && s_pre[j] < 0;
                 const bool free_row = live && s_nzw[j] == 0u;                  // overlaps no earlier row: kept
@@ -389,7 +391,7 @@ __global__ void __launch_bounds__(kNmsThreads, 6) nms_segment_kernel(const NmsPa
             int undecided = 1;
             for (int round = 0; round < kNmsRounds && undecided; ++round) {
                 bool left = false;
-                for (int g = tid >> 5; g < ngroups_b; g += kNmsThreads / 32) {
+                for (int g = tid >> 5; g < ngroups_b; g += NT / 32) {
                     const int j = (g << 5) + lane;
                     const uint2 mine = s_state[g];
                     if (mine.y == 0xFFFFFFFFu) continue;                       // warp-uniform: group fully decided
@@ -466,7 +468,7 @@ __global__ void __launch_bounds__(kNmsThreads, 6) nms_segment_kernel(const NmsPa
         if (c0 == s) nms_stamp(tr, 3);
         // ---- owners (warp-uniform trip count so that the member bitmap can be built with ballots) ------
         bool any_cross_local = false;
-        for (int jb = (tid & ~31); jb < nc; jb += kNmsThreads) {
+        for (int jb = (tid & ~31); jb < nc; jb += NT) {
             const int j = jb + lane;
             int own = -2;
             bool is_keeper = false, is_member = false;
@@ -539,7 +541,7 @@ __global__ void __launch_bounds__(kNmsThreads, 6) nms_segment_kernel(const NmsPa
                     acc[0] = ax; acc[1] = ay; acc[2] = az; acc[3] = aw; acc[4] = ws;
                 }
             };
-            for (int j = tid; j < nc; j += kNmsThreads) {
+            for (int j = tid; j < nc; j += NT) {
                 const unsigned mw = mem32[j >> 5];
                 if ((mw >> (j & 31)) & 1u)
                     s_mlist[s_mpre[j >> 5] + __popc(mw & ((1u << (j & 31)) - 1u))] = ((uint32_t)s_own[j] << 10) | (uint32_t)j;
@@ -568,7 +570,7 @@ __global__ void __launch_bounds__(kNmsThreads, 6) nms_segment_kernel(const NmsPa
                 }
             }
             __syncthreads();
-            for (int j = tid; j < nc; j += kNmsThreads) {
+            for (int j = tid; j < nc; j += NT) {
                 if (s_pre[j] >= 0 || !((s_kept[j >> 6] >> (j & 63)) & 1ull)) continue;
                 const int kidx = s_own[j];
                 const float4 bj = s_box[j];
@@ -589,7 +591,7 @@ __global__ void __launch_bounds__(kNmsThreads, 6) nms_segment_kernel(const NmsPa
             }
             if (any_cross) {
                 // rows of this chunk owned by keepers of earlier chunks
-                for (int kidx = tid; kidx < Kprev; kidx += kNmsThreads) {
+                for (int kidx = tid; kidx < Kprev; kidx += NT) {
                     float* acc = p.kacc + (img + s + kidx) * 5;
                     float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f, ws = 0.f;
                     bool loaded = false;
@@ -618,7 +620,7 @@ __global__ void __launch_bounds__(kNmsThreads, 6) nms_segment_kernel(const NmsPa
             }
             if (last_k >= 0) {
                 int cnt = 0;
-                for (int j = tid; j < nc; j += kNmsThreads) {
+                for (int j = tid; j < nc; j += NT) {
                     const bool is_keeper = s_pre[j] < 0 && ((s_kept[j >> 6] >> (j & 63)) & 1ull);
                     if (!is_keeper && s_own[j] == last_k) ++cnt;
                 }
@@ -632,7 +634,7 @@ __global__ void __launch_bounds__(kNmsThreads, 6) nms_segment_kernel(const NmsPa
 
     if (VARIANT == 0) {
         if (!single) {
-            for (int kidx = tid; kidx < Kprev; kidx += kNmsThreads) {
+            for (int kidx = tid; kidx < Kprev; kidx += NT) {
                 const float* acc = p.kacc + (img + s + kidx) * 5;
                 const uint32_t pos = p.kpos[img + s + kidx];
                 const uint32_t r = p.srank[img + pos];
@@ -648,7 +650,7 @@ __global__ void __launch_bounds__(kNmsThreads, 6) nms_segment_kernel(const NmsPa
         if (p.compat && K > 0 && s_last_members == 0) K -= 1;          // SSD.py:277-278
         if (tid == 0) p.out_count[b] = K;
         const uint32_t* tp = p.tile_prefix + (size_t)b * p.n_tiles;
-        for (int kidx = tid; kidx < K; kidx += kNmsThreads) {
+        for (int kidx = tid; kidx < K; kidx += NT) {
             const uint32_t pos = p.kpos[img + kidx];
             const uint32_t pay = p.spay[img + pos];
             const uint32_t slot = pay & kSlotMask;
@@ -793,8 +795,14 @@ int yolo_stage_nms(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cudaSt
     p.kbox = w.kbox; p.kacc = w.kacc; p.kpos = w.kpos; p.chunk_cnt = w.chunk_cnt; p.n_chunks = w.n_chunks;
     p.n_pad = w.n_pad; p.C = w.C; p.thr = d->nms_thres;
     dim3 grid(d->num_classes, d->batch);
-    if (d->nms_thres >= 0.0f) nms_segment_kernel<0, true><<<grid, kNmsThreads, 0, st>>>(p);
-    else nms_segment_kernel<0, false><<<grid, kNmsThreads, 0, st>>>(p);
+    // candidates per (image, class) on average, if everything survived: longer than a chunk -> the wide variant
+    const bool wide = w.N / d->num_classes > kNmsT;
+    if (d->nms_thres >= 0.0f) {
+        if (wide) nms_segment_kernel<0, true, 512><<<grid, 512, 0, st>>>(p);
+        else nms_segment_kernel<0, true, kNmsThreads><<<grid, kNmsThreads, 0, st>>>(p);
+    } else {
+        nms_segment_kernel<0, false, kNmsThreads><<<grid, kNmsThreads, 0, st>>>(p);
+    }
     B2_LAUNCH_CHECK("nms_segment_kernel<0>");
     return 0;
 }
@@ -828,8 +836,8 @@ int prior_nms_launch_raw(const uint32_t* count, const uint32_t* spay, const floa
     p.orig = orig; p.dense_box = dense_box; p.dense_label = dense_label; p.P = P;
     p.out_rows = out_rows; p.out_index = out_index; p.out_count = out_count;
     dim3 grid(1, batch);
-    if (mode_min) nms_segment_kernel<2, false><<<grid, kNmsThreads, 0, st>>>(p);
-    else nms_segment_kernel<1, false><<<grid, kNmsThreads, 0, st>>>(p);
+    if (mode_min) nms_segment_kernel<2, false, kNmsThreads><<<grid, kNmsThreads, 0, st>>>(p);
+    else nms_segment_kernel<1, false, kNmsThreads><<<grid, kNmsThreads, 0, st>>>(p);
     B2_LAUNCH_CHECK("nms_segment_kernel<prior>");
     return 0;
 }
