@@ -590,24 +590,71 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 6 : 3) nms_segment_kernel(cons
                 finish(j, kidx, ax, ay, az, aw, ws);
             }
             if (any_cross) {
-                // rows of this chunk owned by keepers of earlier chunks
-                for (int kidx = tid; kidx < Kprev; kidx += NT) {
-                    float* acc = p.kacc + (img + s + kidx) * 5;
-                    float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f, ws = 0.f;
-                    bool loaded = false;
-                    for (int m = 0; m < nc; ++m) {
-                        if (s_own[m] == kidx) {
-                            if (!loaded) { ax = acc[0]; ay = acc[1]; az = acc[2]; aw = acc[3]; ws = acc[4]; loaded = true; }
-                            const float4 bm = s_box[m];
-                            const float wm = s_conf[m];
-                            ax = __fadd_rn(ax, __fmul_rn(wm, bm.x));
-                            ay = __fadd_rn(ay, __fmul_rn(wm, bm.y));
-                            az = __fadd_rn(az, __fmul_rn(wm, bm.z));
-                            aw = __fadd_rn(aw, __fmul_rn(wm, bm.w));
-                            ws = __fadd_rn(ws, wm);
-                        }
+                // Rows of this chunk owned by keepers of earlier chunks add to those keepers' running sums (in row order,
+                // per owner).  The rows are compacted, sorted by (owner, row) with a bitonic network in the — now free —
+                // mask triangle, and the first row of every owner run walks its run.  (Every earlier keeper scanning all
+                // rows of the chunk was 27 % of the kernel on the dense-crowd configuration.)
+                __syncthreads();                                            // in-chunk merge is done with s_member / s_mpre
+                unsigned long long* s_x = s_L;                              // keys: owner << 32 | row
+                unsigned* xbits = reinterpret_cast<unsigned*>(s_member);
+                for (int g = tid >> 5; g < kNmsT / 32; g += NT / 32) {
+                    const int j = (g << 5) + lane;
+                    const unsigned bal = __ballot_sync(0xFFFFFFFFu, j < nc && s_pre[j] >= 0);
+                    if (lane == 0) xbits[g] = bal;
+                }
+                __syncthreads();
+                if (tid < 32) {
+                    const int c = lane < kNmsT / 32 ? __popc(xbits[lane]) : 0;
+                    int inc = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                        if (lane >= o) inc += t;
                     }
-                    if (loaded) { acc[0] = ax; acc[1] = ay; acc[2] = az; acc[3] = aw; acc[4] = ws; }
+                    if (lane <= kNmsT / 32) s_mpre[lane] = inc - c;
+                }
+                __syncthreads();
+                const int Mx = s_mpre[kNmsT / 32];
+                int P = 32;
+                while (P < Mx) P <<= 1;                                       // <= 512
+                for (int i = tid; i < P; i += NT) s_x[i] = ~0ull;
+                __syncthreads();
+                for (int j = tid; j < nc; j += NT) {
+                    if (s_pre[j] >= 0) {
+                        const unsigned bw = xbits[j >> 5];
+                        s_x[s_mpre[j >> 5] + __popc(bw & ((1u << (j & 31)) - 1u))] = ((unsigned long long)(unsigned)s_pre[j] << 32) | (unsigned)j;
+                    }
+                }
+                __syncthreads();
+                for (int k = 2; k <= P; k <<= 1) {
+                    for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                        for (int i = tid; i < P; i += NT) {
+                            const int l = i ^ jj;
+                            if (l > i) {
+                                const unsigned long long a = s_x[i], bq = s_x[l];
+                                const bool up = (i & k) == 0;
+                                if ((a > bq) == up) { s_x[i] = bq; s_x[l] = a; }
+                            }
+                        }
+                        __syncthreads();
+                    }
+                }
+                for (int t = tid; t < Mx; t += NT) {
+                    const unsigned kidx = (unsigned)(s_x[t] >> 32);
+                    if (t > 0 && (unsigned)(s_x[t - 1] >> 32) == kidx) continue;             // not the first row of its owner
+                    float* acc = p.kacc + (img + s + kidx) * 5;
+                    float ax = acc[0], ay = acc[1], az = acc[2], aw = acc[3], ws = acc[4];
+                    for (int u = t; u < Mx && (unsigned)(s_x[u] >> 32) == kidx; ++u) {
+                        const int m = (int)(unsigned)s_x[u];
+                        const float4 bm = s_box[m];
+                        const float wm = s_conf[m];
+                        ax = __fadd_rn(ax, __fmul_rn(wm, bm.x));
+                        ay = __fadd_rn(ay, __fmul_rn(wm, bm.y));
+                        az = __fadd_rn(az, __fmul_rn(wm, bm.z));
+                        aw = __fadd_rn(aw, __fmul_rn(wm, bm.w));
+                        ws = __fadd_rn(ws, wm);
+                    }
+                    acc[0] = ax; acc[1] = ay; acc[2] = az; acc[3] = aw; acc[4] = ws;
                 }
             }
         } else {
