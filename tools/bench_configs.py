@@ -30,6 +30,12 @@ def main():
     out.append(dict(cfg="2: yolov3 416 C=80 B=64 decode+NMS (device-resident, no host sync)", us=us, img_per_s=64 / (us * 1e-6),
                     head_MB=nbytes / 1e6))
     del lv
+    # cfg 5: dense-crowd shard (64 of the 512 images: one GPU's share), 1280x1280, 5 classes, conf_thres 0.001
+    lv = [t.to(DEV) for t in synth.yolo_crowd(64, 3, 5, [160, 80, 40], 1280, seed=5)]
+    us = timed(lambda: od.yolo_nms_raw(lv, 3, conf_thres=0.001))
+    out.append(dict(cfg="5: dense-crowd shard, yolov5l 1280 C=5 B=64/GPU, conf_thres 0.001 (~10k pre-NMS boxes/image), decode+NMS",
+                    us=us, img_per_s=64 / (us * 1e-6), head_MB=sum(t.numel() for t in lv) * 4 / 1e6))
+    del lv
     # cfg 3: SSD300 / RetinaNet 800, batch 32
     for name, pri in (("3a: SSD300 P=8732", synth.ssd_priors()), ("3b: RetinaNet800 P=120087", synth.retina_priors(800))):
         loc, cls = synth.prior_heads(32, pri.shape[0], 80, 3)
