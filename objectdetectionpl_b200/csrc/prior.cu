@@ -241,6 +241,9 @@ __global__ void __launch_bounds__(256) tile_prefix_kernel(const uint32_t* __rest
 
 // from yolo_decode.cu / segsort.cu / nms.cu
 int zero_fill_launch(void* p, size_t bytes, cudaStream_t st);
+bool topk_select_supported(int k);
+int topk_select_launch(const uint32_t* tile_count, const uint32_t* key, const uint32_t* pay, uint32_t* pay_out, int n_pad,
+                       int n_tiles, int k, int batch, cudaStream_t st);
 int score_sort_launch(const uint32_t* tile_count, const uint32_t* count, uint32_t* digit_hist, uint32_t* ticket,
                       uint32_t* status, uint32_t* key[2], uint32_t* pay[2], int n_pad, int n_tiles, int batch,
                       cudaStream_t st);
@@ -311,7 +314,13 @@ int prior_nms_pipeline(const b200det_prior_desc* d, void* ws, size_t ws_bytes, f
     tile_prefix_kernel<<<d->batch, 256, 0, st>>>(w.tile_count, w.tile_prefix, w.n_tiles);
     B2_LAUNCH_CHECK("tile_prefix_kernel");
 
-    rc = score_sort_launch(w.tile_count, w.count, w.digit_hist, w.ticket, w.status, w.key, w.pay, w.n_pad, w.n_tiles, d->batch, st);
+    // only the topk best-scoring candidates reach the NMS (SSD.py:273): radix select instead of a full sort
+    // (B200DET_TOPK=sort keeps the full sort, the A/B reference of the tests)
+    const char* tk = getenv("B200DET_TOPK");
+    if (topk_select_supported(d->topk) && !(tk && strcmp(tk, "sort") == 0))
+        rc = topk_select_launch(w.tile_count, w.key[0], w.pay[0], w.pay[0], w.n_pad, w.n_tiles, d->topk, d->batch, st);
+    else
+        rc = score_sort_launch(w.tile_count, w.count, w.digit_hist, w.ticket, w.status, w.key, w.pay, w.n_pad, w.n_tiles, d->batch, st);
     if (rc) return rc;
     rc = prior_nms_launch_raw(w.count, w.pay[0], w.box4, w.cc2, w.kbox, w.kpos, w.n_pad, d->nms_thresh, d->topk,
                               d->compat, w.tile_prefix, w.n_tiles, w.orig, w.dense_box, w.dense_label, d->num_priors,

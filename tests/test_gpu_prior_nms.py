@@ -5,6 +5,7 @@ import torch
 
 import objectdetectionpl_b200 as od
 from objectdetectionpl_b200 import synth
+from objectdetectionpl_b200.postprocess import prior_nms_raw
 from oracle import ref_port as rp
 from tests.golden_io import load, T, unpack_list, SSD_CASES
 
@@ -75,3 +76,31 @@ def test_quirks_zero_and_one_candidate():
     assert out[0].shape == (1, 7) and out[0][0, 6].item() == 1.0
     with pytest.raises(TypeError):
         od.prior_non_max_suppression(_Self(pri), (loc, cls), mode="bogus")
+
+
+# ---- radix-select top-k (topk.cu) against the full score sort it replaces ------------------------------------------------
+@pytest.mark.parametrize("P,C,B,topk,quant,mean", [
+    (8732, 21, 4, 100, None, -1.0),        # SSD300-like: thousands of candidates per image
+    (30000, 8, 3, 100, None, 1.0),         # nearly every prior is a candidate
+    (5000, 4, 3, 100, 0.5, 0.0),           # logits quantised to 0.5: massive score ties, the tie order decides the top-k
+    (600, 3, 3, 200, None, -3.5),          # fewer candidates than topk
+    (4000, 5, 2, 1, None, 0.0),            # topk = 1
+    (9000, 6, 2, 1000, 0.25, 0.5),         # large topk with ties
+])
+def test_topk_select_equals_full_sort(P, C, B, topk, quant, mean, monkeypatch):
+    g = torch.Generator().manual_seed(P + topk)
+    pri = torch.rand(P, 4, generator=g) * 0.5 + 0.1
+    loc = torch.randn(B, P, 4, generator=g) * 0.2
+    cls = torch.randn(B, P, C, generator=g) * 2 + mean
+    if quant:
+        cls = torch.round(cls / quant) * quant
+    args = (loc.to(DEV), cls.to(DEV), pri.to(DEV))
+    got = prior_nms_raw(*args, topk=topk, want_index=True, compat=False)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("B200DET_TOPK", "sort")
+    want = prior_nms_raw(*args, topk=topk, want_index=True, compat=False)
+    torch.cuda.synchronize()
+    assert torch.equal(got[2], want[2])
+    for b, k in enumerate(got[2][0].tolist()):
+        assert torch.equal(got[1][b, :k], want[1][b, :k]), f"image {b}: kept priors differ"
+        assert torch.equal(got[0][b, :k], want[0][b, :k]), f"image {b}: rows differ"

@@ -1,0 +1,26 @@
+"""Wall-clock latency of the public API call (host overhead + GPU + the one count sync) for small batches."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import objectdetectionpl_b200 as od
+from objectdetectionpl_b200 import synth
+dev = torch.device("cuda:0")
+for B, C, mode, thr in ((1, 20, "uniform", 0.5), (1, 80, "sparse", 0.25), (8, 80, "sparse", 0.25), (64, 80, "uniform", 0.5)):
+    lv = [t.to(dev) for t in synth.yolo_planar(B, 3, C, [80, 40, 20], 640, 3, conf_mode=mode, v5_view=True, tie_free=False)]
+    kw = dict(compat=(mode == "uniform"), conf_thres=thr)
+    for _ in range(5):
+        od.non_max_suppression(None, lv, **kw)
+    torch.cuda.synchronize()
+    n = 50
+    t0 = time.perf_counter()
+    for _ in range(n):
+        out = od.non_max_suppression(None, lv, **kw)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / n
+    t0 = time.perf_counter()
+    for _ in range(n):
+        od.yolo_nms_raw(lv, 3, od.YOLO_FORCED_CONF_THRES if mode == "uniform" else thr)
+    torch.cuda.synchronize()
+    dr = (time.perf_counter() - t0) / n
+    print(f"B={B} C={C} {mode}: non_max_suppression {dt * 1e6:.0f} us/call, yolo_nms_raw (no sync, no list) {dr * 1e6:.0f} us/call, "
+          f"kept {sum(o.shape[0] for o in out if o is not None)}")
