@@ -36,9 +36,14 @@ struct VecLoad<1> {
     static __device__ __forceinline__ void ld(const float* p, float (&v)[1]) { v[0] = ldg_stream1(p); }
 };
 
-template <int VEC, int MODE, int U, int MINB>
-__global__ void __launch_bounds__(kTile / VEC, MINB)
+// One CTA = one 512-candidate tile of one level; one thread = 4 consecutive cells.  Tiles of a level whose planes keep
+// 4-cell groups aligned (G*G % 4 == 0, 16-byte aligned head) use 128-bit loads; the others (13x13 ...) read the same four
+// cells with scalar loads — a per-tile, CTA-uniform choice, so a YOLOv3/v4 call (13, 26, 52) streams 94 % of its bytes
+// through the vector path instead of dropping the whole launch to the scalar one (measured 100 us for 232 MB before).
+template <int MODE, int U, int MINB>
+__global__ void __launch_bounds__(kTile / 4, MINB)
 yolo_decode_filter_kernel(const K1Params p) {
+    constexpr int VEC = 4;
     constexpr int NT = kTile / VEC;
     extern __shared__ int s_hist[];          // [C]
     __shared__ int s_scan[33];
@@ -47,10 +52,18 @@ yolo_decode_filter_kernel(const K1Params p) {
     const int b = blockIdx.y;
     const int tile = blockIdx.x;
     const int tid = threadIdx.x;
-    const int n0 = tile * kTile + tid * VEC;
-    const bool in_range = n0 < p.N;          // VEC cells are all in range when the first is (N % VEC == 0)
+    int lvl = 0;
+#pragma unroll
+    for (int l = 1; l < B200DET_MAX_LEVELS; ++l)
+        if (l < p.nlevels && tile >= p.tile_off[l]) lvl = l;
+    const int GG = p.GG[lvl];
+    const int lvl_n = p.A * GG;                                  // candidates of this level
+    const int rel0 = (tile - p.tile_off[lvl]) * kTile + tid * VEC;
+    const int n0 = p.off[lvl] + rel0;                            // candidate index of the thread's first cell
+    const int F = 5 + p.C;
+    const bool vec_tile = (GG & 3) == 0 && (((uintptr_t)p.head[lvl]) & 15) == 0;
 
-    for (int c = tid; c < p.C; c += NT) s_hist[c] = 0;
+    if (p.cls_hist) for (int c = tid; c < p.C; c += NT) s_hist[c] = 0;
 
     float box[VEC][4];
     float conf[VEC], ccf[VEC];
@@ -59,54 +72,93 @@ yolo_decode_filter_kernel(const K1Params p) {
 #pragma unroll
     for (int v = 0; v < VEC; ++v) keep[v] = false;
 
-    if (in_range) {
-        int lvl = 0;
-#pragma unroll
-        for (int l = 1; l < B200DET_MAX_LEVELS; ++l)
-            if (l < p.nlevels && n0 >= p.off[l]) lvl = l;
-        const int GG = p.GG[lvl];
-        const int rel = n0 - p.off[lvl];
-        const int a = rel / GG;
-        const int cell = rel - a * GG;
-        const int F = 5 + p.C;
-        const float* base = p.head[lvl] + ((size_t)(b * p.A + a) * F) * (size_t)GG + cell;
+    if (vec_tile) {
+        if (rel0 < lvl_n) {                  // the 4 cells are all in range and in one plane row (lvl_n % 4 == 0)
+            const int a = rel0 / GG;
+            const int cell = rel0 - a * GG;
+            const float* base = p.head[lvl] + ((size_t)(b * p.A + a) * F) * (size_t)GG + cell;
 
-        float t[5][VEC];
+            float t[5][VEC];
 #pragma unroll
-        for (int f = 0; f < 5; ++f) VecLoad<VEC>::ld(base + (size_t)f * GG, t[f]);
+            for (int f = 0; f < 5; ++f) VecLoad<VEC>::ld(base + (size_t)f * GG, t[f]);
 
-        float best[VEC];
-        int besti[VEC];
-        const float* cp = base + (size_t)5 * GG;
-        {
-            float v0[VEC];
-            VecLoad<VEC>::ld(cp, v0);
+            float best[VEC];
+            int besti[VEC];
+            const float* cp = base + (size_t)5 * GG;
+            {
+                float v0[VEC];
+                VecLoad<VEC>::ld(cp, v0);
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) { best[v] = v0[v]; besti[v] = 0; }
-        }
-        int c = 1;
-        for (; c + U <= p.C; c += U) {
-            float buf[U][VEC];
+                for (int v = 0; v < VEC; ++v) { best[v] = v0[v]; besti[v] = 0; }
+            }
+            int c = 1;
+            for (; c + U <= p.C; c += U) {
+                float buf[U][VEC];
 #pragma unroll
-            for (int u = 0; u < U; ++u) VecLoad<VEC>::ld(cp + (size_t)(c + u) * GG, buf[u]);
+                for (int u = 0; u < U; ++u) VecLoad<VEC>::ld(cp + (size_t)(c + u) * GG, buf[u]);
 #pragma unroll
-            for (int u = 0; u < U; ++u)
+                for (int u = 0; u < U; ++u)
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) argmax_step(buf[u][v], c + u, best[v], besti[v]);
-        }
-        for (; c < p.C; ++c) {
-            float buf[VEC];
-            VecLoad<VEC>::ld(cp + (size_t)c * GG, buf);
+                    for (int v = 0; v < VEC; ++v) argmax_step(buf[u][v], c + u, best[v], besti[v]);
+            }
+            for (; c < p.C; ++c) {
+                float buf[VEC];
+                VecLoad<VEC>::ld(cp + (size_t)c * GG, buf);
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) argmax_step(buf[v], c, best[v], besti[v]);
-        }
+                for (int v = 0; v < VEC; ++v) argmax_step(buf[v], c, best[v], besti[v]);
+            }
 
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const float t5[5] = {t[0][v], t[1][v], t[2][v], t[3][v], t[4][v]};
+                k1_finish<MODE>(p, lvl, a, cell + v, t5, best[v], box[v], conf[v], ccf[v]);
+                cls[v] = besti[v];
+                keep[v] = conf[v] >= p.conf_thres;     // model/YOLOV3.py:310 (NaN conf is dropped, as there)
+            }
+        }
+    } else {
+        // scalar tile: every cell on its own (a 4-cell group may straddle anchors and the end of the level)
+        const float* base[VEC];
+        int av[VEC], cellv[VEC];
+        bool ok[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            const float t5[5] = {t[0][v], t[1][v], t[2][v], t[3][v], t[4][v]};
-            k1_finish<MODE>(p, lvl, a, cell + v, t5, best[v], box[v], conf[v], ccf[v]);
-            cls[v] = besti[v];
-            keep[v] = conf[v] >= p.conf_thres;     // model/YOLOV3.py:310 (NaN conf is dropped, as there)
+            const int rel = rel0 + v;
+            ok[v] = rel < lvl_n;
+            av[v] = ok[v] ? rel / GG : 0;
+            cellv[v] = ok[v] ? rel - av[v] * GG : 0;
+            base[v] = p.head[lvl] + ((size_t)(b * p.A + av[v]) * F) * (size_t)GG + cellv[v];
+        }
+        float t[5][VEC];
+#pragma unroll
+        for (int f = 0; f < 5; ++f)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) t[f][v] = ok[v] ? ldg_stream1(base[v] + (size_t)f * GG) : 0.0f;
+        float best[VEC];
+        int besti[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { best[v] = ok[v] ? ldg_stream1(base[v] + (size_t)5 * GG) : 0.0f; besti[v] = 0; }
+        for (int c = 1; c < p.C; c += 2) {
+            float buf[2][VEC];
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    buf[u][v] = (ok[v] && c + u < p.C) ? ldg_stream1(base[v] + (size_t)(5 + c + u) * GG) : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (c + u < p.C)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) argmax_step(buf[u][v], c + u, best[v], besti[v]);
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            if (ok[v]) {
+                const float t5[5] = {t[0][v], t[1][v], t[2][v], t[3][v], t[4][v]};
+                k1_finish<MODE>(p, lvl, av[v], cellv[v], t5, best[v], box[v], conf[v], ccf[v]);
+                cls[v] = besti[v];
+                keep[v] = conf[v] >= p.conf_thres;
+            }
         }
     }
 
@@ -182,21 +234,21 @@ int yolo_validate(const b200det_yolo_desc* d, const void* ws, size_t ws_bytes) {
     return 0;
 }
 
-template <int VEC>
 static int launch_k1(const b200det_yolo_desc* d, const K1Params& p, cudaStream_t st) {
     dim3 grid(p.n_tiles, d->batch);
     const size_t smem = (size_t)d->num_classes * sizeof(int);
+    constexpr int VEC = 4;
     // U = 8 loads in flight per thread, <= 80 registers (6 CTAs/SM): best of the measured (U, occupancy, cache-hint,
     // 128/256-bit) variants on B200, all of which sit within 4% of each other (see DESIGN.md, K1 tuning).
     switch (d->decode_mode) {
         case B200DET_DECODE_NONE:
-            yolo_decode_filter_kernel<VEC, B200DET_DECODE_NONE, 8, 6><<<grid, kTile / VEC, smem, st>>>(p);
+            yolo_decode_filter_kernel<B200DET_DECODE_NONE, 8, 6><<<grid, kTile / VEC, smem, st>>>(p);
             break;
         case B200DET_DECODE_YOLO_EXP:
-            yolo_decode_filter_kernel<VEC, B200DET_DECODE_YOLO_EXP, 8, 5><<<grid, kTile / VEC, smem, st>>>(p);
+            yolo_decode_filter_kernel<B200DET_DECODE_YOLO_EXP, 8, 5><<<grid, kTile / VEC, smem, st>>>(p);
             break;
         default:
-            yolo_decode_filter_kernel<VEC, B200DET_DECODE_YOLOV5, 8, 5><<<grid, kTile / VEC, smem, st>>>(p);
+            yolo_decode_filter_kernel<B200DET_DECODE_YOLOV5, 8, 5><<<grid, kTile / VEC, smem, st>>>(p);
             break;
     }
     B2_LAUNCH_CHECK("yolo_decode_filter_kernel");
@@ -235,13 +287,15 @@ int yolo_stage_decode(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cud
     K1Params p;
     memset(&p, 0, sizeof(p));
     bool vec4 = true;
-    int off = 0;
+    int off = 0, toff = 0;
     for (int l = 0; l < d->num_levels; ++l) {
         p.head[l] = d->head[l];
         p.G[l] = d->grid[l];
         p.GG[l] = d->grid[l] * d->grid[l];
         p.off[l] = off;
+        p.tile_off[l] = toff;
         off += d->num_anchors * p.GG[l];
+        toff += ceil_div(d->num_anchors * p.GG[l], kTile);
         p.stride[l] = d->stride[l];
         for (int a = 0; a < d->num_anchors; ++a) {
             p.anc[l][a][0] = d->anchors[l][a][0];
@@ -250,6 +304,7 @@ int yolo_stage_decode(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cud
         if (p.GG[l] % 4 != 0 || ((uintptr_t)d->head[l] & 15) != 0) vec4 = false;
     }
     p.off[d->num_levels] = off;
+    p.tile_off[d->num_levels] = toff;
     p.nlevels = d->num_levels; p.A = d->num_anchors; p.C = d->num_classes;
     p.N = w.N; p.n_pad = w.n_pad; p.n_tiles = w.n_tiles;
     p.conf_thres = d->conf_thres;
@@ -262,7 +317,7 @@ int yolo_stage_decode(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cud
     // bit-identical and measured 6% slower on B200 (see yolo_decode_tma.cu)
     const char* k1 = getenv("B200DET_K1");
     if (vec4 && k1 && strcmp(k1, "tma") == 0 && k1_tma_supported(p)) return launch_k1_tma(d, p, st);
-    return vec4 ? launch_k1<4>(d, p, st) : launch_k1<1>(d, p, st);
+    return launch_k1(d, p, st);
 }
 
 // class segment offsets; launched at the head of the sort stage (only the NMS needs them)

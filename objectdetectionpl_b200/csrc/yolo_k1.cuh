@@ -8,7 +8,8 @@ struct K1Params {
     const float* head[B200DET_MAX_LEVELS];
     int G[B200DET_MAX_LEVELS];
     int GG[B200DET_MAX_LEVELS];
-    int off[B200DET_MAX_LEVELS + 1];
+    int off[B200DET_MAX_LEVELS + 1];        // first candidate index of a level
+    int tile_off[B200DET_MAX_LEVELS + 1];   // first tile of a level (levels start on tile boundaries)
     float stride[B200DET_MAX_LEVELS];
     float anc[B200DET_MAX_LEVELS][B200DET_MAX_ANCHORS][2];
     int nlevels, A, C, N, n_pad, n_tiles;

@@ -36,12 +36,19 @@ struct YoloWs {
     int B, C, N, n_pad, n_tiles, n_cls_passes, n_chunks, sort_tiles;
 };
 
+// Candidates per image and the slot count of an image's region.  Every level starts on a tile boundary (so that the
+// cells a decode thread owns are aligned inside their plane whatever the order of the levels — YOLOv3/v4 list the odd
+// 13x13 level first), i.e. n_pad = sum over levels of roundup(A * G^2, tile).
 inline int yolo_counts(const b200det_yolo_desc* d, int* n_out, int* n_pad_out) {
-    long long n = 0;
-    for (int l = 0; l < d->num_levels; ++l) n += (long long)d->num_anchors * d->grid[l] * d->grid[l];
-    if (n <= 0 || n > B200DET_MAX_CANDIDATES) return B200DET_ELIMIT;
+    long long n = 0, pad = 0;
+    for (int l = 0; l < d->num_levels; ++l) {
+        const long long nl = (long long)d->num_anchors * d->grid[l] * d->grid[l];
+        n += nl;
+        pad += (long long)align_up((size_t)nl, kTile);
+    }
+    if (n <= 0 || pad > B200DET_MAX_CANDIDATES) return B200DET_ELIMIT;
     *n_out = (int)n;
-    *n_pad_out = (int)align_up((size_t)n, kTile);
+    *n_pad_out = (int)pad;
     return 0;
 }
 

@@ -176,8 +176,8 @@ def non_max_suppression_host(self, predictions, conf_thres=0.5, nms_thres=0.4, *
         for c in range(nchunks):
             lo, hi = c * chunk, min(B, (c + 1) * chunk)
             if pipe is None:
-                G = sum(num_anchors * t.shape[2] * t.shape[2] for t in predictions)
-                n_pad = (G + L.TILE - 1) // L.TILE * L.TILE
+                # slots per image: every level padded to whole tiles (b200det_yolo_num_candidates)
+                n_pad = sum((num_anchors * t.shape[2] * t.shape[2] + L.TILE - 1) // L.TILE * L.TILE for t in predictions)
                 pipe = _host_pipes[key] = _HostPipe(dev, shapes, chunk, n_pad)
             dst = [t[:hi - lo] for t in pipe.dev_in[c & 1]]
             with torch.cuda.stream(pipe.s_in):

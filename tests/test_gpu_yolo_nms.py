@@ -132,12 +132,13 @@ def test_stage_outputs_sorted_and_segmented():
         return ws[off.value:off.value + nb.value].view(dtype).cpu()
 
     N = sum(A * g * g for g in grids)
-    n_pad = (N + 511) // 512 * 512
+    n_pad = sum((A * g * g + 511) // 512 * 512 for g in grids)      # every level starts on a tile boundary
     count = field("count", torch.int32)
     assert count.tolist() == [N] * B
     pay = field("sorted_pay", torch.int32).view(B, n_pad)
     rank = field("sorted_rank", torch.int32).view(B, n_pad)
     seg = field("seg_off", torch.int32).view(B, C + 1)
+    orig = field("orig", torch.int32).view(B, n_pad)               # slot -> candidate index (levels start on tile boundaries)
     rows = rp.yolo_rows_from_planar([t.cpu() for t in levels], A)
     for b in range(B):
         cls_conf, cls_id = rows[b, :, 5:].max(1)
@@ -147,7 +148,7 @@ def test_stage_outputs_sorted_and_segmented():
         want_pos = torch.argsort(key, stable=True)                 # sorted position -> rank
         slot = pay[b, :N] & 0xFFFFF
         assert torch.equal(rank[b, :N].long(), want_pos), "rank of sorted positions"
-        assert torch.equal(slot.long(), order[want_pos]), "candidate at sorted positions"
+        assert torch.equal(orig[b][slot.long()].long(), order[want_pos]), "candidate at sorted positions"
         assert torch.equal((pay[b, :N] >> 20).long(), cls_id[order[want_pos]])
         hist = torch.bincount(cls_id, minlength=C)
         assert torch.equal(seg[b].long(), torch.cat([torch.zeros(1, dtype=torch.long), hist.cumsum(0)]))
