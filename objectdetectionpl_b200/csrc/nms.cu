@@ -26,9 +26,6 @@ namespace b200det {
 
 constexpr int kNmsT = 384;                 // rows per chunk (384: 6 CTAs/SM; 512 measured 320 vs 295 us at the headline)
 constexpr int kNmsThreads = 256;
-constexpr int kNmsW = kNmsT / 64;          // mask words per full row
-constexpr int kNmsTriWords = 32 * kNmsW * (kNmsW + 1);   // packed lower-triangular rows
-constexpr int kNmsStage = 384;             // earlier keepers staged per phase-A round (fills the aliased mask triangle exactly)
 constexpr int kNmsRounds = 12;             // parallel fixed-point rounds before the serial sweep takes over
 
 struct NmsParams {
@@ -179,37 +176,43 @@ __device__ __forceinline__ void nms_stamp(unsigned long long* tr, int point) {
 // FAST: the pre-filter is sound when "no overlap" implies "not removed", i.e. VARIANT 0 with nms_thres >= 0.
 // NT threads per CTA: 256 for the usual ~300-row segments (6 CTAs/SM); 512 when the average segment is longer than a chunk
 // (few classes, dense crowds): there are then few CTAs and the phase-A / phase-B warp tasks of a segment are the parallelism.
-template <int VARIANT, bool FAST, int NT>
-__global__ void __launch_bounds__(NT, NT == 256 ? 6 : 3) nms_segment_kernel(const NmsParams p) {
-    __shared__ float4 s_box[kNmsT];
-    __shared__ float s_conf[kNmsT];
-    __shared__ uint2 s_q[kNmsT];        // half2 lo, hi   (see box_bounds_h2; split 8 + 4 bytes: one 128-bit word per row
-    __shared__ unsigned s_qt[kNmsT];    // half2 t         measured slower, 308 vs 295 us)
-    __shared__ unsigned long long s_L[kNmsTriWords];
-    __shared__ unsigned long long s_kept[kNmsW];
-    __shared__ __align__(16) uint2 s_state[kNmsT / 32];   // per 32-row group: x = kept rows, y = decided rows
-    __shared__ unsigned long long s_member[kNmsW];
-    __shared__ int s_wpre[kNmsW + 1];
-    __shared__ int s_own[kNmsT];
-    __shared__ int s_pre[kNmsT];
+// CT rows per chunk: 384 (the triangle of 6 mask words per row) — or 192 with 128 threads when the average segment is
+// short (YOLOv3-416: 133 rows): a CTA then needs 14 KB instead of 32 KB of shared memory, 12 of them fit an SM and twice as
+// many segments hide each other's fixed latencies (loads, barriers, global stores).
+template <int VARIANT, bool FAST, int NT, int CT>
+__global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_segment_kernel(const NmsParams p) {
+    constexpr int NW = CT / 64;                       // mask words per full row
+    constexpr int TRI = 32 * NW * (NW + 1);           // packed lower-triangular rows
+    constexpr int STAGE = (TRI * 8 / 28) / 32 * 32;   // earlier keepers staged per phase-A round, in the aliased mask triangle
+    __shared__ float4 s_box[CT];
+    __shared__ float s_conf[CT];
+    __shared__ uint2 s_q[CT];        // half2 lo, hi   (see box_bounds_h2; split 8 + 4 bytes: one 128-bit word per row
+    __shared__ unsigned s_qt[CT];    // half2 t         measured slower, 308 vs 295 us)
+    __shared__ unsigned long long s_L[TRI];
+    __shared__ unsigned long long s_kept[NW];
+    __shared__ __align__(16) uint2 s_state[CT / 32];   // per 32-row group: x = kept rows, y = decided rows
+    __shared__ unsigned long long s_member[NW];
+    __shared__ int s_wpre[NW + 1];
+    __shared__ int s_own[CT];
+    __shared__ int s_pre[CT];
     // phase-A staging (keepers of earlier chunks) lives in the mask triangle: phase A of a chunk is over before phase B
     // writes the triangle, and the triangle of the previous chunk is dead by then.  (Shared memory per CTA decides the
     // carve-out: 5 CTAs x <= 39 KB fit the 196 KB setting and leave 32 KB of L1 for the box gathers; 42 KB per CTA measured
     // 248 vs 238 us.)
-    static_assert(kNmsStage * (16 + 8 + 4) <= kNmsTriWords * 8, "phase-A staging must fit the mask triangle");
+    static_assert(STAGE * (16 + 8 + 4) <= TRI * 8, "phase-A staging must fit the mask triangle");
     float4* const s_kb = reinterpret_cast<float4*>(s_L);
-    uint2* const s_kq = reinterpret_cast<uint2*>(s_L + kNmsStage * 2);
-    unsigned* const s_kqt = reinterpret_cast<unsigned*>(s_L + kNmsStage * 3);
+    uint2* const s_kq = reinterpret_cast<uint2*>(s_L + STAGE * 2);
+    unsigned* const s_kqt = reinterpret_cast<unsigned*>(s_L + STAGE * 3);
     __shared__ int s_last_members;
-    __shared__ uint32_t s_mlist[kNmsT];     // members of in-chunk clusters in ascending row order: owner index << 10 | row
-    __shared__ __align__(4) uint8_t s_nzw[kNmsT];   // per row: which of its mask words are non-zero (most rows: none)
-    static_assert(kNmsW <= 8, "one byte of non-zero-word flags per row");
-    __shared__ uint32_t s_rank[kNmsT];      // score rank of the row, fetched with the boxes so that the owner / merge phases
+    __shared__ uint32_t s_mlist[CT];     // members of in-chunk clusters in ascending row order: owner index << 10 | row
+    __shared__ __align__(4) uint8_t s_nzw[CT];   // per row: which of its mask words are non-zero (most rows: none)
+    static_assert(NW <= 8, "one byte of non-zero-word flags per row");
+    __shared__ uint32_t s_rank[CT];      // score rank of the row, fetched with the boxes so that the owner / merge phases
                                             // do not wait on L2 for it again (VARIANT 0)
-    __shared__ int16_t s_next[kNmsT];       // member list position of the next member of the same cluster, or -1
-    __shared__ int16_t s_first[kNmsT];      // per in-chunk keeper ordinal: list position of its first member, or -1
-    __shared__ int16_t s_last[kNmsT];       // ... of its last member so far (while the chains are built)
-    __shared__ int s_mpre[kNmsT / 32 + 1];  // exclusive prefix of the member bitmap's popcounts
+    __shared__ int16_t s_next[CT];       // member list position of the next member of the same cluster, or -1
+    __shared__ int16_t s_first[CT];      // per in-chunk keeper ordinal: list position of its first member, or -1
+    __shared__ int16_t s_last[CT];       // ... of its last member so far (while the chains are built)
+    __shared__ int s_mpre[CT / 32 + 1];  // exclusive prefix of the member bitmap's popcounts
 
     const int b = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 6 : 3) nms_segment_kernel(cons
     }
     const int n = e - s;
     if (VARIANT == 0 && n <= 0) return;
-    const bool single = n <= kNmsT;
+    const bool single = n <= CT;
     const float thr = p.thr;
 
 #ifdef B200DET_NMS_TRACE
@@ -236,15 +239,15 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 6 : 3) nms_segment_kernel(cons
     int last_k = -1;        // VARIANT 1/2: index of the last keeper so far
     if (tid == 0) s_last_members = 0;
 
-    for (int c0 = s; c0 < e; c0 += kNmsT) {
-        const int nc = min(kNmsT, e - c0);
+    for (int c0 = s; c0 < e; c0 += CT) {
+        const int nc = min(CT, e - c0);
         const int Wc = (nc + 63) >> 6;
 
         // ---- load the chunk ----------------------------------------------------------------
         // both rows of a thread are fetched together: payload -> slot -> box is a chain of two L2 round trips, and a
         // row-at-a-time loop would walk it twice back to back
         {
-            static_assert(kNmsT <= 2 * NT, "a thread loads at most two rows of a chunk");
+            static_assert(CT <= 2 * NT, "a thread loads at most two rows of a chunk");
             const int j0 = tid, j1 = tid + NT;
             uint32_t slot0 = 0, slot1 = 0;
             if (j0 < nc) slot0 = p.spay[img + c0 + j0] & kSlotMask;
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 6 : 3) nms_segment_kernel(cons
                 s_nzw[j] = 0u;
             }
         }
-        if (tid < kNmsW) s_member[tid] = 0ull;      // 32-row groups past nc are never written by the ballots below
+        if (tid < NW) s_member[tid] = 0ull;      // 32-row groups past nc are never written by the ballots below
         __syncthreads();
 
         // ---- phase A: against keepers of earlier chunks ----------------------------------------
@@ -282,8 +285,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 6 : 3) nms_segment_kernel(cons
         if (FAST && Kprev > 0) {
             for (int j = tid; j < nc; j += NT) s_own[j] = INT_MAX;      // s_own doubles as the hit slot until the owners phase
         }
-        for (int kt = 0; kt < Kprev; kt += kNmsStage) {
-            const int nk = min(kNmsStage, Kprev - kt);
+        for (int kt = 0; kt < Kprev; kt += STAGE) {
+            const int nk = min(STAGE, Kprev - kt);
             for (int i = tid; i < nk; i += NT) {
                 const float4 kb = p.kbox[img + s + kt + i];
                 s_kb[i] = kb;
@@ -379,7 +382,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 6 : 3) nms_segment_kernel(cons
         // kept/decided bits of a 32-row group live in one 64-bit word so that a reader sees a consistent pair, and the
         // serial sweep below finishes adversarial chains after kNmsRounds rounds.
         {
-            for (int g = tid >> 5; g < kNmsT / 32; g += NT / 32) {
+            for (int g = tid >> 5; g < CT / 32; g += NT / 32) {
                 const int j = (g << 5) + lane;
                 const bool live = j < nc && s_pre[j] < 0;
                 const bool free_row = live && s_nzw[j] == 0u;                  // overlaps no earlier row: kept
@@ -418,10 +421,10 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 6 : 3) nms_segment_kernel(cons
                 }
                 undecided = __syncthreads_or(left ? 1 : 0);
             }
-            if (tid < kNmsW) s_kept[tid] = ((unsigned long long)s_state[2 * tid + 1].x << 32) | s_state[2 * tid].x;
+            if (tid < NW) s_kept[tid] = ((unsigned long long)s_state[2 * tid + 1].x << 32) | s_state[2 * tid].x;
             __syncthreads();
             if (undecided && tid < 32) {
-                if (lane < kNmsW) s_kept[lane] = 0ull;
+                if (lane < NW) s_kept[lane] = 0ull;
                 __syncwarp();
                 const int ngroups = (nc + 31) >> 5;
                 for (int g = 0; g < ngroups; ++g) {
@@ -458,12 +461,12 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 6 : 3) nms_segment_kernel(cons
             }
             if (tid == 0) {
                 int run = 0;
-                for (int w = 0; w < kNmsW; ++w) { s_wpre[w] = run; run += (w < Wc) ? __popcll(s_kept[w]) : 0; }
-                s_wpre[kNmsW] = run;
+                for (int w = 0; w < NW; ++w) { s_wpre[w] = run; run += (w < Wc) ? __popcll(s_kept[w]) : 0; }
+                s_wpre[NW] = run;
             }
         }
         __syncthreads();
-        const int Kc = s_wpre[kNmsW];
+        const int Kc = s_wpre[NW];
 
         if (c0 == s) nms_stamp(tr, 3);
         // ---- owners (warp-uniform trip count so that the member bitmap can be built with ballots) ------
@@ -526,7 +529,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 6 : 3) nms_segment_kernel(cons
                     const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
                     if (lane >= o) inc += t;
                 }
-                if (lane <= kNmsT / 32) s_mpre[lane] = inc - c;
+                if (lane <= CT / 32) s_mpre[lane] = inc - c;
             }
             __syncthreads();
             auto finish = [&](const int j, const int kidx, const float ax, const float ay, const float az, const float aw,
@@ -597,24 +600,24 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 6 : 3) nms_segment_kernel(cons
                 __syncthreads();                                            // in-chunk merge is done with s_member / s_mpre
                 unsigned long long* s_x = s_L;                              // keys: owner << 32 | row
                 unsigned* xbits = reinterpret_cast<unsigned*>(s_member);
-                for (int g = tid >> 5; g < kNmsT / 32; g += NT / 32) {
+                for (int g = tid >> 5; g < CT / 32; g += NT / 32) {
                     const int j = (g << 5) + lane;
                     const unsigned bal = __ballot_sync(0xFFFFFFFFu, j < nc && s_pre[j] >= 0);
                     if (lane == 0) xbits[g] = bal;
                 }
                 __syncthreads();
                 if (tid < 32) {
-                    const int c = lane < kNmsT / 32 ? __popc(xbits[lane]) : 0;
+                    const int c = lane < CT / 32 ? __popc(xbits[lane]) : 0;
                     int inc = c;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
                         const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
                         if (lane >= o) inc += t;
                     }
-                    if (lane <= kNmsT / 32) s_mpre[lane] = inc - c;
+                    if (lane <= CT / 32) s_mpre[lane] = inc - c;
                 }
                 __syncthreads();
-                const int Mx = s_mpre[kNmsT / 32];
+                const int Mx = s_mpre[CT / 32];
                 int P = 32;
                 while (P < Mx) P <<= 1;                                       // <= 512
                 for (int i = tid; i < P; i += NT) s_x[i] = ~0ull;
@@ -842,13 +845,15 @@ int yolo_stage_nms(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cudaSt
     p.kbox = w.kbox; p.kacc = w.kacc; p.kpos = w.kpos; p.chunk_cnt = w.chunk_cnt; p.n_chunks = w.n_chunks;
     p.n_pad = w.n_pad; p.C = w.C; p.thr = d->nms_thres;
     dim3 grid(d->num_classes, d->batch);
-    // candidates per (image, class) on average, if everything survived: longer than a chunk -> the wide variant
-    const bool wide = w.N / d->num_classes > kNmsT;
+    // candidates per (image, class) on average, if everything survived: longer than a chunk -> the wide variant,
+    // at most 160 -> the small one
+    const int avg = w.N / d->num_classes;
     if (d->nms_thres >= 0.0f) {
-        if (wide) nms_segment_kernel<0, true, 512><<<grid, 512, 0, st>>>(p);
-        else nms_segment_kernel<0, true, kNmsThreads><<<grid, kNmsThreads, 0, st>>>(p);
+        if (avg > kNmsT) nms_segment_kernel<0, true, 512, kNmsT><<<grid, 512, 0, st>>>(p);
+        else if (avg <= 160) nms_segment_kernel<0, true, 128, 192><<<grid, 128, 0, st>>>(p);
+        else nms_segment_kernel<0, true, kNmsThreads, kNmsT><<<grid, kNmsThreads, 0, st>>>(p);
     } else {
-        nms_segment_kernel<0, false, kNmsThreads><<<grid, kNmsThreads, 0, st>>>(p);
+        nms_segment_kernel<0, false, kNmsThreads, kNmsT><<<grid, kNmsThreads, 0, st>>>(p);
     }
     B2_LAUNCH_CHECK("nms_segment_kernel<0>");
     return 0;
@@ -883,8 +888,8 @@ int prior_nms_launch_raw(const uint32_t* count, const uint32_t* spay, const floa
     p.orig = orig; p.dense_box = dense_box; p.dense_label = dense_label; p.P = P;
     p.out_rows = out_rows; p.out_index = out_index; p.out_count = out_count;
     dim3 grid(1, batch);
-    if (mode_min) nms_segment_kernel<2, false, kNmsThreads><<<grid, kNmsThreads, 0, st>>>(p);
-    else nms_segment_kernel<1, false, kNmsThreads><<<grid, kNmsThreads, 0, st>>>(p);
+    if (mode_min) nms_segment_kernel<2, false, kNmsThreads, kNmsT><<<grid, kNmsThreads, 0, st>>>(p);
+    else nms_segment_kernel<1, false, kNmsThreads, kNmsT><<<grid, kNmsThreads, 0, st>>>(p);
     B2_LAUNCH_CHECK("nms_segment_kernel<prior>");
     return 0;
 }
