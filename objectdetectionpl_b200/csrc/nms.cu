@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_
     __shared__ unsigned long long s_kept[NW];
     __shared__ __align__(16) uint2 s_state[CT / 32];   // per 32-row group: x = kept rows, y = decided rows
     __shared__ unsigned long long s_member[NW];
-    __shared__ int s_wpre[NW + 1];
+    __shared__ int s_wpre[NT / 32][NW + 1];              // per warp: exclusive prefix of the kept-row counts per mask word
+    __shared__ unsigned long long s_keptw[NT / 32][NW];  // per warp: its own copy of the kept rows (built without a CTA barrier)
     __shared__ int s_own[CT];
     __shared__ int s_pre[CT];
     // phase-A staging (keepers of earlier chunks) lives in the mask triangle: phase A of a chunk is over before phase B
@@ -211,7 +212,9 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_
                                             // do not wait on L2 for it again (VARIANT 0)
     __shared__ int16_t s_next[CT];       // member list position of the next member of the same cluster, or -1
     __shared__ int16_t s_first[CT];      // per in-chunk keeper ordinal: list position of its first member, or -1
-    __shared__ int16_t s_last[CT];       // ... of its last member so far (while the chains are built)
+    // ... of its last member so far, while the chains are built: lives in s_qt, which is dead after phase B (the
+    // shared-memory budget of 6 CTAs per SM inside the 196 KB carve-out is 32.6 KB per CTA)
+    int16_t* const s_last = reinterpret_cast<int16_t*>(s_qt);
     __shared__ int s_mpre[CT / 32 + 1];  // exclusive prefix of the member bitmap's popcounts
 
     const int b = blockIdx.y;
@@ -270,7 +273,6 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_
                 if (FAST) { const uint4 q = box_bounds_h2(bx, thr); s_q[j] = make_uint2(q.x, q.y); s_qt[j] = q.z; }
                 s_pre[j] = -1;
                 s_first[j] = -1;
-                s_last[j] = -1;
                 s_nzw[j] = 0u;
             }
         }
@@ -421,52 +423,65 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_
                 }
                 undecided = __syncthreads_or(left ? 1 : 0);
             }
-            if (tid < NW) s_kept[tid] = ((unsigned long long)s_state[2 * tid + 1].x << 32) | s_state[2 * tid].x;
-            __syncthreads();
-            if (undecided && tid < 32) {
-                if (lane < NW) s_kept[lane] = 0ull;
-                __syncwarp();
-                const int ngroups = (nc + 31) >> 5;
-                for (int g = 0; g < ngroups; ++g) {
-                    const int j = (g << 5) + lane;
-                    const int wl = g >> 1;                       // word holding this group
-                    const bool valid = j < nc && s_pre[j] < 0;
-                    bool hit = false;
-                    unsigned m = 0;
-                    if (valid) {
-                        const unsigned long long* row = &s_L[tri_off(j)];
-                        for (int w = 0; w < wl; ++w) hit |= (row[w] & s_kept[w]) != 0ull;
-                        const unsigned long long lw = row[wl];
-                        if (g & 1) {
-                            hit |= (lw & s_kept[wl] & 0xFFFFFFFFull) != 0ull;
-                            m = (unsigned)(lw >> 32);
-                        } else {
-                            m = (unsigned)lw;
-                        }
-                    }
-                    const bool pre = valid && !hit;
-                    const unsigned cand = __ballot_sync(0xFFFFFFFFu, pre);
-                    // lanes whose in-group mask is empty are decided already; only the others need the serial steps
-                    const unsigned dep = __ballot_sync(0xFFFFFFFFu, pre && m != 0u);
-                    unsigned kg = cand & ~dep;
-                    for (unsigned dd = dep; dd; dd &= dd - 1u) {
-                        // every lane below the lowest pending one is final in kg -> that lane can be decided now
-                        const bool bit = pre && ((m & kg) == 0u);
-                        const unsigned bal = __ballot_sync(0xFFFFFFFFu, bit);
-                        kg |= bal & (dd & (0u - dd));
-                    }
-                    if (lane == 0 && kg) s_kept[wl] |= (unsigned long long)kg << ((g & 1) * 32);
+            if (undecided) {                              // CTA-uniform: an adversarial chain outlasted the rounds
+                if (tid < 32) {
+                    if (lane < NW) s_kept[lane] = 0ull;
                     __syncwarp();
+                    const int ngroups = (nc + 31) >> 5;
+                    for (int g = 0; g < ngroups; ++g) {
+                        const int j = (g << 5) + lane;
+                        const int wl = g >> 1;                       // word holding this group
+                        const bool valid = j < nc && s_pre[j] < 0;
+                        bool hit = false;
+                        unsigned m = 0;
+                        if (valid) {
+                            const unsigned long long* row = &s_L[tri_off(j)];
+                            for (int w = 0; w < wl; ++w) hit |= (row[w] & s_kept[w]) != 0ull;
+                            const unsigned long long lw = row[wl];
+                            if (g & 1) {
+                                hit |= (lw & s_kept[wl] & 0xFFFFFFFFull) != 0ull;
+                                m = (unsigned)(lw >> 32);
+                            } else {
+                                m = (unsigned)lw;
+                            }
+                        }
+                        const bool pre = valid && !hit;
+                        const unsigned cand = __ballot_sync(0xFFFFFFFFu, pre);
+                        // lanes whose in-group mask is empty are decided already; only the others need the serial steps
+                        const unsigned dep = __ballot_sync(0xFFFFFFFFu, pre && m != 0u);
+                        unsigned kg = cand & ~dep;
+                        for (unsigned dd = dep; dd; dd &= dd - 1u) {
+                            // every lane below the lowest pending one is final in kg -> that lane can be decided now
+                            const bool bit = pre && ((m & kg) == 0u);
+                            const unsigned bal = __ballot_sync(0xFFFFFFFFu, bit);
+                            kg |= bal & (dd & (0u - dd));
+                        }
+                        if (lane == 0 && kg) s_kept[wl] |= (unsigned long long)kg << ((g & 1) * 32);
+                        __syncwarp();
+                    }
                 }
-            }
-            if (tid == 0) {
-                int run = 0;
-                for (int w = 0; w < NW; ++w) { s_wpre[w] = run; run += (w < Wc) ? __popcll(s_kept[w]) : 0; }
-                s_wpre[NW] = run;
+                __syncthreads();
+                if (tid < CT / 32) s_state[tid].x = (unsigned)(s_kept[tid >> 1] >> ((tid & 1) * 32));
+                __syncthreads();
             }
         }
-        __syncthreads();
-        const int Kc = s_wpre[NW];
+        // every warp builds its own copy of the kept words and their prefix from s_state: no CTA barrier, no single thread
+        const int wq = tid >> 5;
+        {
+            unsigned long long kw = 0ull;
+            if (lane < NW) kw = ((unsigned long long)s_state[2 * lane + 1].x << 32) | s_state[2 * lane].x;
+            const int c = lane < Wc ? __popcll(kw) : 0;
+            int inc = c;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (lane < NW) { s_keptw[wq][lane] = kw; s_wpre[wq][lane] = inc - c; }
+            if (lane == NW - 1) s_wpre[wq][NW] = inc;
+            __syncwarp();
+        }
+        const int Kc = s_wpre[wq][NW];
 
         if (c0 == s) nms_stamp(tr, 3);
         // ---- owners (warp-uniform trip count so that the member bitmap can be built with ballots) ------
@@ -482,20 +497,20 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_
                 } else {
                     const int wj = j >> 6;
                     const unsigned long long below = (1ull << (j & 63)) - 1ull;
-                    if ((s_kept[wj] >> (j & 63)) & 1ull) {
-                        own = Kprev + s_wpre[wj] + __popcll(s_kept[wj] & below);
+                    if ((s_keptw[wq][wj] >> (j & 63)) & 1ull) {
+                        own = Kprev + s_wpre[wq][wj] + __popcll(s_keptw[wq][wj] & below);
                         is_keeper = true;
                     } else {
                         const unsigned long long* row = &s_L[tri_off(j)];
                         int i = -1;
                         for (unsigned nz = s_nzw[j]; nz; nz &= nz - 1u) {
                             const int w = __ffs((int)nz) - 1;
-                            const unsigned long long h = row[w] & s_kept[w];
+                            const unsigned long long h = row[w] & s_keptw[wq][w];
                             if (h) { i = (w << 6) + __ffsll((long long)h) - 1; break; }
                         }
                         if (i >= 0) {   // always: a non-kept, non-presuppressed row was hit by a kept row
                             const int wi = i >> 6;
-                            own = Kprev + s_wpre[wi] + __popcll(s_kept[wi] & ((1ull << (i & 63)) - 1ull));
+                            own = Kprev + s_wpre[wq][wi] + __popcll(s_keptw[wq][wi] & ((1ull << (i & 63)) - 1ull));
                             is_member = true;
                         }
                     }
@@ -545,6 +560,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_
                 }
             };
             for (int j = tid; j < nc; j += NT) {
+                s_last[j] = -1;
                 const unsigned mw = mem32[j >> 5];
                 if ((mw >> (j & 31)) & 1u)
                     s_mlist[s_mpre[j >> 5] + __popc(mw & ((1u << (j & 31)) - 1u))] = ((uint32_t)s_own[j] << 10) | (uint32_t)j;
@@ -574,7 +590,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_
             }
             __syncthreads();
             for (int j = tid; j < nc; j += NT) {
-                if (s_pre[j] >= 0 || !((s_kept[j >> 6] >> (j & 63)) & 1ull)) continue;
+                if (s_pre[j] >= 0 || !((s_keptw[wq][j >> 6] >> (j & 63)) & 1ull)) continue;
                 const int kidx = s_own[j];
                 const float4 bj = s_box[j];
                 const float w0 = s_conf[j];
@@ -671,7 +687,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_
             if (last_k >= 0) {
                 int cnt = 0;
                 for (int j = tid; j < nc; j += NT) {
-                    const bool is_keeper = s_pre[j] < 0 && ((s_kept[j >> 6] >> (j & 63)) & 1ull);
+                    const bool is_keeper = s_pre[j] < 0 && ((s_keptw[wq][j >> 6] >> (j & 63)) & 1ull);
                     if (!is_keeper && s_own[j] == last_k) ++cnt;
                 }
                 if (cnt) atomicAdd(&s_last_members, cnt);
