@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(kPriRows) prior_decode_filter_kernel(const K1p
     }
     if (tid == 0) {
         p.tile_count[(size_t)b * p.n_tiles + tile] = (uint32_t)run;
-        if (run) atomicAdd(&p.count[b], (uint32_t)run);
+        if (run && p.count) atomicAdd(&p.count[b], (uint32_t)run);
     }
 }
 
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(256) tile_prefix_kernel(const uint32_t* __rest
 int zero_fill_launch(void* p, size_t bytes, cudaStream_t st);
 bool topk_select_supported(int k);
 int topk_select_launch(const uint32_t* tile_count, const uint32_t* key, const uint32_t* pay, uint32_t* pay_out, int n_pad,
-                       int n_tiles, int k, int batch, cudaStream_t st);
+                       int n_tiles, int k, int batch, cudaStream_t st, uint32_t* count_out, uint32_t* tile_prefix_out);
 int score_sort_launch(const uint32_t* tile_count, const uint32_t* count, uint32_t* digit_hist, uint32_t* ticket,
                       uint32_t* status, uint32_t* key[2], uint32_t* pay[2], int n_pad, int n_tiles, int batch,
                       cudaStream_t st);
@@ -284,7 +284,11 @@ int prior_nms_pipeline(const b200det_prior_desc* d, void* ws, size_t ws_bytes, f
         set_error("workspace too small: %zu < %zu", ws_bytes, w.total_bytes);
         return B200DET_EWORKSPACE;
     }
-    rc = zero_fill_launch(w.count, w.zero_bytes, st);
+    // with the radix select (the default) the select kernel derives the per-image count and the tile prefix itself: three
+    // launches per step (decode+filter, select, NMS); the full-sort path needs the zeroed counters and the prefix kernel
+    const char* tk = getenv("B200DET_TOPK");
+    const bool use_select = topk_select_supported(d->topk) && !(tk && strcmp(tk, "sort") == 0);
+    if (!use_select) rc = zero_fill_launch(w.count, w.zero_bytes, st);
     if (rc) return rc;
 
     K1pParams p;
@@ -293,7 +297,7 @@ int prior_nms_pipeline(const b200det_prior_desc* d, void* ws, size_t ws_bytes, f
     p.P = d->num_priors; p.C = d->num_classes; p.n_pad = w.n_pad; p.n_tiles = w.n_tiles;
     p.class_thresh = d->class_thresh; p.write_dense = d->compat ? 1 : 0;
     p.box4 = w.box4; p.cc2 = w.cc2; p.orig = w.orig; p.key = w.key[0]; p.pay = w.pay[0];
-    p.tile_count = w.tile_count; p.count = w.count; p.dense_box = w.dense_box; p.dense_label = w.dense_label;
+    p.tile_count = w.tile_count; p.count = use_select ? nullptr : w.count; p.dense_box = w.dense_box; p.dense_label = w.dense_label;
     const int cc = d->num_classes < kPriMaxCC ? d->num_classes : kPriMaxCC;
     const size_t smem = (size_t)kPriRows * cc * sizeof(float);
     dim3 grid(w.n_tiles, d->batch);
@@ -311,14 +315,16 @@ int prior_nms_pipeline(const b200det_prior_desc* d, void* ws, size_t ws_bytes, f
         prior_decode_filter_kernel<false, false><<<grid, kPriRows, smem, st>>>(p);
     }
     B2_LAUNCH_CHECK("prior_decode_filter_kernel");
-    tile_prefix_kernel<<<d->batch, 256, 0, st>>>(w.tile_count, w.tile_prefix, w.n_tiles);
-    B2_LAUNCH_CHECK("tile_prefix_kernel");
+    if (!use_select) {
+        tile_prefix_kernel<<<d->batch, 256, 0, st>>>(w.tile_count, w.tile_prefix, w.n_tiles);
+        B2_LAUNCH_CHECK("tile_prefix_kernel");
+    }
 
     // only the topk best-scoring candidates reach the NMS (SSD.py:273): radix select instead of a full sort
     // (B200DET_TOPK=sort keeps the full sort, the A/B reference of the tests)
-    const char* tk = getenv("B200DET_TOPK");
-    if (topk_select_supported(d->topk) && !(tk && strcmp(tk, "sort") == 0))
-        rc = topk_select_launch(w.tile_count, w.key[0], w.pay[0], w.pay[0], w.n_pad, w.n_tiles, d->topk, d->batch, st);
+    if (use_select)
+        rc = topk_select_launch(w.tile_count, w.key[0], w.pay[0], w.pay[0], w.n_pad, w.n_tiles, d->topk, d->batch, st, w.count,
+                                w.tile_prefix);
     else
         rc = score_sort_launch(w.tile_count, w.count, w.digit_hist, w.ticket, w.status, w.key, w.pay, w.n_pad, w.n_tiles, d->batch, st);
     if (rc) return rc;

@@ -20,6 +20,8 @@ struct TopkParams {
     const uint32_t* key;          // [B][n_pad] tile-sparse
     const uint32_t* pay;          // [B][n_pad] tile-sparse  (class << 20 | slot)
     uint32_t* pay_out;            // [B][n_pad] rows 0 .. min(n, k) - 1  (may alias `pay`: written after every read)
+    uint32_t* count_out;          // [B] or null: candidates of the image (= sum of its tile counts)
+    uint32_t* tile_prefix_out;    // [B][n_tiles] or null: exclusive prefix of the tile counts
     int n_pad, n_tiles, k;
 };
 
@@ -36,14 +38,19 @@ __global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const TopkPara
     const size_t img = (size_t)b * p.n_pad;
     const uint32_t* tc = p.tile_count + (size_t)b * p.n_tiles;
     const bool tc_cached = p.n_tiles <= 2048;
-    int part = 0;
-    for (int t = tid; t < p.n_tiles; t += kSelThreads) {
-        const uint32_t c = tc[t];
-        if (tc_cached) s_tc[t] = (uint16_t)c;
-        part += (int)c;
+    // candidates of the image and, when asked for, the exclusive prefix of its tile counts (consumed by the NMS stage for
+    // the reference's filtered-index quirk) — folded in here so that the step needs no counter reset and no prefix launch
+    int n = 0;
+    for (int t0 = 0; t0 < p.n_tiles; t0 += kSelThreads) {
+        const int t = t0 + tid;
+        const int c = t < p.n_tiles ? (int)tc[t] : 0;
+        if (t < p.n_tiles && tc_cached) s_tc[t] = (uint16_t)c;
+        int tot;
+        const int ex = block_exclusive_scan(c, s_scan, &tot);
+        if (p.tile_prefix_out && t < p.n_tiles) p.tile_prefix_out[(size_t)b * p.n_tiles + t] = (uint32_t)(n + ex);
+        n += tot;
     }
-    int n;
-    block_exclusive_scan(part, s_scan, &n);
+    if (p.count_out && tid == 0) p.count_out[b] = (uint32_t)n;
     const int K = min(n, p.k);
     auto valid = [&](int e) -> bool {
         const uint32_t c = tc_cached ? s_tc[e >> kTileShift] : tc[e >> kTileShift];
@@ -219,9 +226,10 @@ __global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const TopkPara
 bool topk_select_supported(int k) { return k >= 1 && k <= kSelMaxK; }
 
 int topk_select_launch(const uint32_t* tile_count, const uint32_t* key, const uint32_t* pay, uint32_t* pay_out, int n_pad,
-                       int n_tiles, int k, int batch, cudaStream_t st) {
+                       int n_tiles, int k, int batch, cudaStream_t st, uint32_t* count_out, uint32_t* tile_prefix_out) {
     TopkParams p;
     p.tile_count = tile_count; p.key = key; p.pay = pay; p.pay_out = pay_out; p.n_pad = n_pad; p.n_tiles = n_tiles; p.k = k;
+    p.count_out = count_out; p.tile_prefix_out = tile_prefix_out;
     topk_select_kernel<<<batch, kSelThreads, 0, st>>>(p);
     B2_LAUNCH_CHECK("topk_select_kernel");
     return 0;
