@@ -122,6 +122,25 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPUs NVML reports as local to its GPU before any pinned host buffer is allocated, so that the
+    H2D / D2H traffic of the `e2e` leg does not cross the socket interconnect (8 ranks share one host)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -214,6 +233,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    local_cpus = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -355,7 +375,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "yolo_decode_filter_kernel<4,0,8,6> (one launch per step, CUDA events around it)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": head_bytes},
-            "stages_us": stage_us, "k1_us_in_timed_region": k1_us, "kept_per_image_mean": kept_total / B, "workspace_mb": ws_bytes / 1e6,
+            "stages_us": stage_us, "k1_us_in_timed_region": k1_us, "rank_cpu_affinity": local_cpus, "kept_per_image_mean": kept_total / B, "workspace_mb": ws_bytes / 1e6,
         }
         if gather_ms is not None:
             line["detection_allgather_ms"] = gather_ms
