@@ -7,12 +7,17 @@
 // the key T of the k-th element; the elements below T plus the first ties at T are collected (<= k of them) and sorted in
 // shared memory.  One 1024-thread CTA per image; the keys are read four times from L2 (480 KB per read at RetinaNet-800).
 // Output: pay_out[r], r < min(n, k), in the order the full sort would have produced — same consumer (nms_segment_kernel<1|2>).
+#include <cooperative_groups.h>
+
 #include "yolo_ws.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace b200det {
 
 constexpr int kSelThreads = 1024;
 constexpr int kSelMaxK = 1024;
+constexpr int kSelCluster = 4;          // CTAs per image: the passes are instruction-bound inside one SM (ncu: 54 us at 59 % issue)
 constexpr int kSelCap = 2048;            // elements the shared-memory list holds
 
 struct TopkParams {
@@ -25,8 +30,19 @@ struct TopkParams {
     int n_pad, n_tiles, k;
 };
 
+template <int CL>
+__device__ __forceinline__ void sel_cluster_sync() {
+    if (CL == 1) __syncthreads();
+    else asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// A cluster of CL CTAs per image (4 for large images, 1 below 16 k slots where the cluster barriers cost more than they save): every CTA histograms / collects its quarter of the image's slots, the histograms
+// are merged over DSMEM (every CTA ends up with the same merged copy and takes the same decisions), rank 0 gathers the
+// collected elements, sorts and writes them.
+template <int CL>
 __global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const TopkParams p) {
-    __shared__ int s_hist[2048];
+    __shared__ int s_hist[2048];                        // this CTA's counts (read by the peers)
+    __shared__ int s_hist_m[2048];                      // merged over the cluster
     __shared__ uint16_t s_tc[B200DET_MAX_CANDIDATES / kTile <= 2048 ? B200DET_MAX_CANDIDATES / kTile : 2048];
     __shared__ unsigned long long s_sel[kSelCap];      // key << 32 | payload  (payload's low 20 bits = slot: the tie order)
     __shared__ int s_cum_le;                            // elements with the known key prefix <= the K-th element's, after a pass
@@ -34,7 +50,9 @@ __global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const TopkPara
     __shared__ uint32_t s_prefix, s_mask;
     __shared__ int s_want, s_nsel, s_tie_take;
 
-    const int b = blockIdx.x, tid = threadIdx.x;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int crank = CL == 1 ? 0 : (int)blockIdx.x;    // cluster dims (CL, 1, 1), gridDim.x == CL
     const size_t img = (size_t)b * p.n_pad;
     const uint32_t* tc = p.tile_count + (size_t)b * p.n_tiles;
     const bool tc_cached = p.n_tiles <= 2048;
@@ -47,10 +65,10 @@ __global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const TopkPara
         if (t < p.n_tiles && tc_cached) s_tc[t] = (uint16_t)c;
         int tot;
         const int ex = block_exclusive_scan(c, s_scan, &tot);
-        if (p.tile_prefix_out && t < p.n_tiles) p.tile_prefix_out[(size_t)b * p.n_tiles + t] = (uint32_t)(n + ex);
+        if (p.tile_prefix_out && crank == 0 && t < p.n_tiles) p.tile_prefix_out[(size_t)b * p.n_tiles + t] = (uint32_t)(n + ex);
         n += tot;
     }
-    if (p.count_out && tid == 0) p.count_out[b] = (uint32_t)n;
+    if (p.count_out && crank == 0 && tid == 0) p.count_out[b] = (uint32_t)n;
     const int K = min(n, p.k);
     auto valid = [&](int e) -> bool {
         const uint32_t c = tc_cached ? s_tc[e >> kTileShift] : tc[e >> kTileShift];
@@ -60,6 +78,8 @@ __global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const TopkPara
     // groups in flight per thread: with one scalar load per iteration the passes were pure L2 latency (~150 us at 120 k slots)
     const uint4* key4 = reinterpret_cast<const uint4*>(p.key + img);
     const int nvec = p.n_pad >> 2;
+    const int vchunk = (nvec + CL - 1) / CL;
+    const int v_lo = crank * vchunk, v_hi = min(nvec, v_lo + vchunk);      // this CTA's share of the image
     auto group_count = [&](int v) -> int {                  // valid keys at the front of group v
         const int e = v << 2;
         const int c = (int)(tc_cached ? s_tc[e >> kTileShift] : tc[e >> kTileShift]) - (e & (kTile - 1));
@@ -67,9 +87,10 @@ __global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const TopkPara
     };
     if (tid == 0) { s_prefix = 0u; s_mask = 0u; s_want = K; s_nsel = 0; s_tie_take = 0; }
     __syncthreads();
-    if (K == 0) return;
+    if (K == 0) return;                                 // cluster-uniform (every CTA computed the same n)
 
     // ---- three MSD passes: find the key T of the K-th smallest element and how many ties at T are taken ----
+    int early_shift = -1;
     const int shifts[3] = {21, 10, 0};
     const int widths[3] = {11, 11, 10};
     for (int ps = 0; ps < 3; ++ps) {
@@ -78,9 +99,9 @@ __global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const TopkPara
         __syncthreads();
         const uint32_t prefix = s_prefix, mask = s_mask;
         const int want = s_want;                             // read before this pass's owner thread updates it
-        for (int v = tid; v < nvec; v += 2 * kSelThreads) {
+        for (int v = v_lo + tid; v < v_hi; v += 2 * kSelThreads) {
             const int v1 = v + kSelThreads;
-            const int c0 = group_count(v), c1 = v1 < nvec ? group_count(v1) : 0;
+            const int c0 = group_count(v), c1 = v1 < v_hi ? group_count(v1) : 0;
             uint4 k0 = make_uint4(0u, 0u, 0u, 0u), k1 = k0;
             if (c0) k0 = key4[v];
             if (c1) k1 = key4[v1];
@@ -91,18 +112,25 @@ __global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const TopkPara
                 if (ok && (ks[q] & mask) == prefix) atomicAdd(&s_hist[(ks[q] >> shift) & (nb - 1)], 1);
             }
         }
-        __syncthreads();
+        sel_cluster_sync<CL>();                              // every CTA's counts are complete
+        for (int i = tid; i < nb; i += kSelThreads) {
+            int m = 0;
+#pragma unroll
+            for (int c = 0; c < CL; ++c) m += CL == 1 ? s_hist[i] : *cluster.map_shared_rank(&s_hist[i], c);
+            s_hist_m[i] = m;
+        }
+        sel_cluster_sync<CL>();                              // the peers are done reading s_hist (it is zeroed again next pass)
         // smallest digit d with cum(d) >= want: two-level scan (each thread owns nb / 1024 <= 2 bins)
         const int per = nb / kSelThreads > 0 ? nb / kSelThreads : 1;
         int mine = 0;
         if (tid * per < nb)
-            for (int q = 0; q < per; ++q) mine += s_hist[tid * per + q];
+            for (int q = 0; q < per; ++q) mine += s_hist_m[tid * per + q];
         int total;
         const int ex = block_exclusive_scan(mine, s_scan, &total);
         if (tid * per < nb && ex < want && ex + mine >= want) {
             int run = ex;
             for (int q = 0; q < per; ++q) {
-                const int h = s_hist[tid * per + q];
+                const int h = s_hist_m[tid * per + q];
                 if (run + h >= want) {
                     s_prefix = prefix | ((uint32_t)(tid * per + q) << shift);
                     s_mask = mask | ((uint32_t)(nb - 1) << shift);
@@ -115,61 +143,24 @@ __global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const TopkPara
             }
         }
         __syncthreads();
-        if (s_cum_le <= kSelCap) {
-            // early finish (the usual case after one or two passes): few enough elements have a key prefix up to the K-th
-            // element's — collect them all in one more read of the keys, sort in shared memory, keep the first K
-            const uint32_t top = s_prefix >> shift;
-            for (int v = tid; v < nvec; v += 2 * kSelThreads) {
-                const int v1 = v + kSelThreads;
-                const int c0 = group_count(v), c1 = v1 < nvec ? group_count(v1) : 0;
-                uint4 k0 = make_uint4(0u, 0u, 0u, 0u), k1 = k0;
-                if (c0) k0 = key4[v];
-                if (c1) k1 = key4[v1];
-                const uint32_t ks[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const bool ok = (q & 3) < (q < 4 ? c0 : c1);
-                    if (ok && (ks[q] >> shift) <= top) {
-                        const int e = ((q < 4 ? v : v1) << 2) + (q & 3);
-                        s_sel[atomicAdd(&s_nsel, 1)] = ((unsigned long long)ks[q] << 32) | p.pay[img + e];
-                    }
-                }
-            }
-            __syncthreads();
-            const int M = s_nsel;                       // == s_cum_le
-            int P = 32;
-            while (P < M) P <<= 1;
-            for (int i = M + tid; i < P; i += kSelThreads) s_sel[i] = ~0ull;
-            __syncthreads();
-            for (int k = 2; k <= P; k <<= 1) {
-                for (int jj = k >> 1; jj > 0; jj >>= 1) {
-                    for (int i = tid; i < P; i += kSelThreads) {
-                        const int l = i ^ jj;
-                        if (l > i) {
-                            const unsigned long long a = s_sel[i], c = s_sel[l];
-                            const unsigned long long ka = (a & 0xFFFFFFFF00000000ull) | (a & kSlotMask);
-                            const unsigned long long kc = (c & 0xFFFFFFFF00000000ull) | (c & kSlotMask);
-                            const bool up = (i & k) == 0;
-                            if ((ka > kc) == up) { s_sel[i] = c; s_sel[l] = a; }
-                        }
-                    }
-                    __syncthreads();
-                }
-            }
-            for (int i = tid; i < K; i += kSelThreads) p.pay_out[img + i] = (uint32_t)s_sel[i];
-            return;
-        }
+        if (s_cum_le <= kSelCap) { early_shift = shift; break; }     // cluster-uniform
     }
+
+    // ---- collect the candidates of this CTA's share into its shared list ----
+    //   early finish (the usual case after one or two passes): few enough elements have a key prefix up to the K-th
+    //     element's — take them all, the sort below keeps the first K;
+    //   after the third pass: everything below T, and the ties at T (all of them when they all belong to the top K;
+    //     otherwise the first `tie_take` in slot order — rank 0 walks the image alone for that rare case).
     const uint32_t T = s_prefix;
     const int tie_take = s_tie_take;
-
-    // ---- collect: everything below T (any order: sorted below), and the first `tie_take` elements equal to T in slot
-    //      order.  When all ties at T are taken (the usual case) no ordering is needed for them either. ----
-    const int ties_total = s_hist[T & 1023u];
-    if (tie_take == ties_total) {
-        for (int v = tid; v < nvec; v += 2 * kSelThreads) {
+    const bool early = early_shift >= 0;
+    const bool ordered_ties = !early && tie_take != s_hist_m[T & 1023u];
+    if (!ordered_ties) {
+        const int cshift = early ? early_shift : 0;
+        const uint32_t top = T >> cshift;
+        for (int v = v_lo + tid; v < v_hi; v += 2 * kSelThreads) {
             const int v1 = v + kSelThreads;
-            const int c0 = group_count(v), c1 = v1 < nvec ? group_count(v1) : 0;
+            const int c0 = group_count(v), c1 = v1 < v_hi ? group_count(v1) : 0;
             uint4 k0 = make_uint4(0u, 0u, 0u, 0u), k1 = k0;
             if (c0) k0 = key4[v];
             if (c1) k1 = key4[v1];
@@ -177,13 +168,13 @@ __global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const TopkPara
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const bool ok = (q & 3) < (q < 4 ? c0 : c1);
-                if (ok && ks[q] <= T) {
+                if (ok && (ks[q] >> cshift) <= top) {
                     const int e = ((q < 4 ? v : v1) << 2) + (q & 3);
                     s_sel[atomicAdd(&s_nsel, 1)] = ((unsigned long long)ks[q] << 32) | p.pay[img + e];
                 }
             }
         }
-    } else {
+    } else if (crank == 0) {
         int tie_base = 0;                                  // ties seen in earlier chunks (position order)
         for (int e0 = 0; e0 < p.n_pad; e0 += kSelThreads) {
             const int e = e0 + tid;
@@ -198,11 +189,26 @@ __global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const TopkPara
             tie_base += tot;
         }
     }
+    sel_cluster_sync<CL>();                                    // every CTA's list is complete
+    if (crank == 0 && !ordered_ties) {                     // rank 0 appends its peers' lists to its own
+        int base = s_nsel;
+        for (int c = 1; c < CL; ++c) {
+            const int nc = *cluster.map_shared_rank(&s_nsel, c);
+            const unsigned long long* src = cluster.map_shared_rank(&s_sel[0], c);
+            for (int i = tid; i < nc; i += kSelThreads) s_sel[base + i] = src[i];
+            base += nc;
+        }
+        __syncthreads();
+        if (tid == 0) s_nsel = base;
+    }
+    sel_cluster_sync<CL>();                                    // the peers' shared memory is no longer needed
+    if (crank != 0) return;
     __syncthreads();
-    // ---- sort the K selected elements by (key, slot) and write them out ----
+    // ---- rank 0: sort the collected elements by (key, slot), write the first K ----
+    const int M = s_nsel;
     int P = 32;
-    while (P < K) P <<= 1;
-    for (int i = K + tid; i < P; i += kSelThreads) s_sel[i] = ~0ull;
+    while (P < M) P <<= 1;
+    for (int i = M + tid; i < P; i += kSelThreads) s_sel[i] = ~0ull;
     __syncthreads();
     for (int k = 2; k <= P; k <<= 1) {
         for (int jj = k >> 1; jj > 0; jj >>= 1) {
@@ -230,8 +236,24 @@ int topk_select_launch(const uint32_t* tile_count, const uint32_t* key, const ui
     TopkParams p;
     p.tile_count = tile_count; p.key = key; p.pay = pay; p.pay_out = pay_out; p.n_pad = n_pad; p.n_tiles = n_tiles; p.k = k;
     p.count_out = count_out; p.tile_prefix_out = tile_prefix_out;
-    topk_select_kernel<<<batch, kSelThreads, 0, st>>>(p);
-    B2_LAUNCH_CHECK("topk_select_kernel");
+    if (n_pad <= 16384) {
+        topk_select_kernel<1><<<dim3(1, batch, 1), kSelThreads, 0, st>>>(p);
+        B2_LAUNCH_CHECK("topk_select_kernel<1>");
+        return 0;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(kSelCluster, batch, 1);
+    cfg.blockDim = dim3(kSelThreads, 1, 1);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kSelCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B2_CUDA(cudaLaunchKernelEx(&cfg, topk_select_kernel<kSelCluster>, p));
     return 0;
 }
 
