@@ -265,8 +265,7 @@ int cluster_sort_capacity() { return kCsCap * kCsMaxCluster; }
 
 template <int CL>
 static int cluster_sort_launch_cl(const ClusterSortParams& p, int batch, cudaStream_t st) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CL, batch, 1);
     cfg.blockDim = dim3(kCsThreads, 1, 1);
     cfg.dynamicSmemBytes = sizeof(CsShared);

@@ -241,8 +241,7 @@ int topk_select_launch(const uint32_t* tile_count, const uint32_t* key, const ui
         B2_LAUNCH_CHECK("topk_select_kernel<1>");
         return 0;
     }
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(kSelCluster, batch, 1);
     cfg.blockDim = dim3(kSelThreads, 1, 1);
     cfg.stream = st;
