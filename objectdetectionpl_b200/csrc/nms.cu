@@ -7,14 +7,16 @@
 //   VARIANT 1/2: SSD / RetinaNet class-agnostic greedy NMS on the top-k rows of an image
 //              (model/SSD.py:270-302), 'union' / 'min' overlap, survive when ovr <= thresh.
 //
-// A segment is processed in chunks of 384 score-ordered rows:
-//   phase A  rows of the chunk vs. the keepers of EARLIER chunks (first hit = owner, early exit);
-//   phase B  lower-triangular 64-bit overlap masks inside the chunk (each (row, word) item = 64 IoUs,
-//            keeper box broadcast from shared memory, row box in registers);
-//   sweep    one warp resolves the chunk serially-exact: 32 rows per step, prior words tested in
-//            parallel per lane, the 32x32 diagonal resolved with 32 ballots;
-//   owners   first kept bit of (mask & kept) -> cluster owner;  merge sums pulled per keeper in row
-//            order (deterministic fp32 order: keeper first, then members by descending score).
+// A segment is processed in chunks of CT (384, or 192 for short segments) score-ordered rows:
+//   phase A  rows of the chunk vs. the keepers of EARLIER chunks, as 32 x 32 warp tasks through the vectorised half2
+//            bound test + exact test; owner = lowest keeper index that removes the row (atomicMin);
+//   phase B  lower-triangular 64-bit overlap masks inside the chunk: warp tasks (mask word x 32-row group), column
+//            bounds broadcast from shared memory, row box in registers, verdict bits accumulated on the FMA pipe;
+//   resolve  greedy keep / remove as a parallel fixed point over all warps (a row is decided once a kept row hits it or
+//            every row in its mask is decided and not kept); a serial 32-ballot sweep finishes adversarial chains;
+//   owners   first kept bit of (mask & kept) -> cluster owner; members compacted in row order and chained per owner;
+//   merge    every keeper walks its chain (deterministic fp32 order: keeper first, then members by descending score);
+//            rows owned by keepers of earlier chunks are bitonic-sorted by (owner, row) and summed per owner run.
 // IoU arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction) and IEEE division so
 // the keep decisions are bit-identical to the reference's fp32 CPU path.
 #include <cuda_fp16.h>

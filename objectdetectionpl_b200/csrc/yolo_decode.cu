@@ -5,9 +5,9 @@
 // (model/YOLOV3.py:289-319, YOLOV5.py:173-202) and the inline decode formulas D1/D2
 // (LightningFunc/accuracy.py:412-435,459-466; utils/YoloV5Utils.py:241-248).
 //
-// HBM-bound streaming kernel: every thread owns VEC consecutive cells of one (image, anchor) slab and
-// walks the 5+C planes at stride G*G, so a warp reads 128*VEC contiguous bytes per plane (fully
-// coalesced, 128-bit loads when G*G % 4 == 0), with 8 independent loads in flight per thread.
+// HBM-bound streaming kernel: every thread owns 4 consecutive cells of one level and walks the 5+C planes at
+// stride G*G, so a warp reads 512 contiguous bytes per plane (128-bit loads in tiles of levels with G*G % 4 == 0,
+// scalar loads otherwise — a per-tile choice), with 8 independent loads in flight per thread.
 // Survivors are compacted IN ORDER inside the CTA's 512-slot tile (ballot-free block scan), so the
 // slot order equals the reference's candidate order and the later stable radix sort breaks score ties
 // by ascending candidate index without any atomically-ordered append.
