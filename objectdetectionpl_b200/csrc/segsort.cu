@@ -13,8 +13,12 @@
 // every tile a CTA waits for belongs to a CTA that has already started — no forward-progress assumption on
 // the block scheduler.  The result is independent of timing (counts are integers), i.e. bit-reproducible.
 // Per-image digit totals of all passes come from one up-front histogram kernel (totals are
-// permutation-invariant).  In-tile ranking is the stable warp-match ranking (match.any + per-warp
+// permutation-invariant).  In-tile ranking is the stable warp-match ranking (8 ballots per digit + per-warp
 // digit counters), 8 bits per pass.
+//
+// This multi-launch sort is the path for images with more slots than one thread-block cluster holds (RetinaNet-sized
+// inputs are handled by the radix select of topk.cu instead) and the A/B reference of the one-launch cluster sort in
+// clustersort.cu, which is what normally runs (B200DET_SORT=global forces this one).
 #include <stdlib.h>
 
 #include "yolo_ws.cuh"
