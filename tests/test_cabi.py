@@ -132,3 +132,17 @@ def test_python_layer_refuses_cpu_tensors_and_bad_shapes():
         od.prior_non_max_suppression(None, (torch.zeros(1, 8, 4), torch.zeros(1, 8, 3)), mode="bogus")
     with pytest.raises(ValueError):
         od.non_max_suppression(None, [])
+
+
+def test_slot_count_formula_of_the_host_pipeline_matches_the_library(lib):
+    """postprocess.non_max_suppression_host sizes its pinned output with the per-level tile padding; the library is the
+    authority (every level starts on a 512-slot tile boundary)."""
+    for A, C, grids in ((3, 80, (80, 40, 20)), (3, 80, (13, 26, 52)), (5, 20, (13,)), (3, 4, (7, 5, 3)), (3, 1, (160, 80, 40))):
+        d = L.YoloDesc()
+        d.batch, d.num_anchors, d.num_classes, d.num_levels = 2, A, C, len(grids)
+        for i, g in enumerate(grids):
+            d.grid[i] = g
+        n, n_pad = ctypes.c_int32(), ctypes.c_int32()
+        assert lib.b200det_yolo_num_candidates(ctypes.byref(d), ctypes.byref(n), ctypes.byref(n_pad)) == 0
+        assert n.value == sum(A * g * g for g in grids)
+        assert n_pad.value == sum((A * g * g + L.TILE - 1) // L.TILE * L.TILE for g in grids)
