@@ -363,6 +363,8 @@ int ap_per_class_launch(const float* tp, const float* conf, const float* pred_cl
 // D1 decode of the planar head, build_targets on the decoded map, six scalar metrics, and the decoded map itself.
 // ------------------------------------------------------------------------------------------------------------------
 int decode_box_launch(const float*, int, int, int, int, int, const float*, float, float*, cudaStream_t);
+int decode_box_aux_launch(const float*, int, int, int, int, const float*, float, float*, float*, cudaStream_t);
+bool decode_box_tileable(int, int, const void*, const void*);
 size_t build_targets_ws_bytes(int, int, int, int);
 int build_targets_launch_ex(const float*, int, const float*, int, const float*, const float*, int, int, int, int, int, float,
                             void*, float*, float*, uint8_t*, uint8_t*, float*, float*, float*, float*, float*, int32_t*,
@@ -375,6 +377,7 @@ struct YsWs {
     float* class_mask;    // [cells]
     uint8_t* obj;         // [cells]
     uint8_t* noobj;       // [cells]
+    float* aux;           // [cells][5] grid-unit box + objectness (tileable planes only)
     void* bt_ws;
     size_t bytes;
 };
@@ -390,6 +393,7 @@ static YsWs ys_layout(void* base, int B, int A, int G, int nt) {
     w.class_mask = (float*)take(cells * 4);
     w.obj = (uint8_t*)take(cells);
     w.noobj = (uint8_t*)take(cells);
+    w.aux = (float*)take(cells * 5 * 4);
     w.bt_ws = take(build_targets_ws_bytes(B, A, G, nt));
     w.bytes = off;
     return w;
@@ -434,6 +438,40 @@ __global__ void __launch_bounds__(256) ys_reduce_kernel(float* __restrict__ rows
     }
 }
 
+// The same sums when the decode left a compact side table (aux[c] = grid box + objectness): nothing wide is touched.
+__global__ void __launch_bounds__(256) ys_reduce_aux_kernel(const float* __restrict__ aux, long long cells,
+                                                            const float* __restrict__ iou_scores, const float* __restrict__ class_mask,
+                                                            const uint8_t* __restrict__ obj, const uint8_t* __restrict__ noobj,
+                                                            double* __restrict__ acc) {
+    __shared__ double s_red[8][8];
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long c = (long long)blockIdx.x * 256 + threadIdx.x; c < cells; c += (long long)gridDim.x * 256) {
+        const float conf = aux[c * 5 + 4];
+        const bool o = obj[c] != 0, no = noobj[c] != 0;
+        const float cm = class_mask[c], iou = iou_scores[c];
+        const float conf50 = conf > 0.5f ? 1.0f : 0.0f;
+        const float det = conf50 * cm * (o ? 1.0f : 0.0f);
+        if (o) { a[0] += 1.0; a[2] += cm; a[3] += conf; }
+        if (no) { a[1] += 1.0; a[4] += conf; }
+        a[5] += conf50;
+        a[6] += (iou > 0.5f ? 1.0f : 0.0f) * det;
+        a[7] += (iou > 0.75f ? 1.0f : 0.0f) * det;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        double v = a[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if ((threadIdx.x & 31) == 0) s_red[k][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += s_red[threadIdx.x][w];
+        atomicAdd(&acc[threadIdx.x], v);
+    }
+}
+
 // metrics[6] = cls_acc, recall50, recall75, precision, conf_obj, conf_noobj  (the order of batch_metrics, :468)
 __global__ void ys_final_kernel(const double* __restrict__ acc, float* __restrict__ metrics) {
     const float n_obj = (float)acc[0];
@@ -451,7 +489,23 @@ int yolo_statistics_launch(const float* head, int B, int A, int C, int G, const 
     YsWs w = ys_layout(ws, B, A, G, nt);
     const int F = 5 + C;
     const long long cells = (long long)B * A * G * G;
-    // decoded map in GRID units first (stride 1): x = sigma + gx, w = exp * anchor  (:412-435)
+    const int grid = (int)((cells + 255) / 256 < 148 * 8 ? (cells + 255) / 256 : 148 * 8);
+    if (decode_box_tileable(G, F, head, out_rows)) {
+        // one pass writes the final rows (pixels) and the grid-unit boxes + objectness build_targets and the sums read
+        int rc = decode_box_aux_launch(head, B, A, C, G, scaled_anchors, stride, out_rows, w.aux, st);
+        if (rc) return rc;
+        rc = build_targets_launch_ex(w.aux, 5, out_rows + 5, F, target, scaled_anchors, B, A, G, C, nt, ignore_thres, w.bt_ws,
+                                     w.iou_scores, w.class_mask, w.obj, w.noobj, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                     w.status, st);
+        if (rc) return rc;
+        B2_CUDA(cudaMemsetAsync(w.acc, 0, 64, st));
+        ys_reduce_aux_kernel<<<grid, 256, 0, st>>>(w.aux, cells, w.iou_scores, w.class_mask, w.obj, w.noobj, w.acc);
+        B2_LAUNCH_CHECK("ys_reduce_aux_kernel");
+        ys_final_kernel<<<1, 1, 0, st>>>(w.acc, metrics);
+        B2_LAUNCH_CHECK("ys_final_kernel");
+        return 0;
+    }
+    // odd planes (13 x 13): decoded map in GRID units first (stride 1): x = sigma + gx, w = exp * anchor  (:412-435)
     int rc = decode_box_launch(head, B, A, C, G, B200DET_DECODE_YOLO_EXP, scaled_anchors, 1.0f, out_rows, st);
     if (rc) return rc;
     rc = build_targets_launch_ex(out_rows, F, out_rows + 5, F, target, scaled_anchors, B, A, G, C, nt, ignore_thres, w.bt_ws,
@@ -459,7 +513,6 @@ int yolo_statistics_launch(const float* head, int B, int A, int C, int G, const 
                                  w.status, st);
     if (rc) return rc;
     B2_CUDA(cudaMemsetAsync(w.acc, 0, 64, st));
-    const int grid = (int)((cells + 255) / 256 < 148 * 8 ? (cells + 255) / 256 : 148 * 8);
     ys_reduce_kernel<<<grid, 256, 0, st>>>(out_rows, F, cells, stride, w.iou_scores, w.class_mask, w.obj, w.noobj, w.acc);
     B2_LAUNCH_CHECK("ys_reduce_kernel");
     ys_final_kernel<<<1, 1, 0, st>>>(w.acc, metrics);

@@ -392,11 +392,13 @@ decode_box_kernel(const float* __restrict__ head, float* __restrict__ out, int A
 constexpr int kDecTileCells = 64;
 constexpr int kDecTileMaxF = 128;
 
-template <int MODE>
+// AUX (the metrics path, M3): also emits a compact [cell][5] side table with the box BEFORE the stride multiply (grid
+// units, what build_targets matches on) and the objectness, so that nobody has to re-read or rescale the wide rows.
+template <int MODE, bool AUX>
 __global__ void __launch_bounds__(256, 6)
 decode_box_tile_kernel(const float* __restrict__ head, float* __restrict__ out, int A, int C, int G, float stride,
-                       const float* __restrict__ anchors) {
-    extern __shared__ __align__(16) float s_tile[];          // [ncell][F]
+                       const float* __restrict__ anchors, float* __restrict__ aux) {
+    extern __shared__ __align__(16) float s_tile[];          // [ncell][F] (+ [ncell][5] with AUX)
     const int GG = G * G, F = 5 + C;
     const int ba = blockIdx.y;
     const int a = ba % A;
@@ -430,18 +432,26 @@ decode_box_tile_kernel(const float* __restrict__ head, float* __restrict__ out, 
                             const int gy = (cell_g + k) / G;
                             const float gxy = f == 0 ? (float)(cell_g + k - gy * G) : (float)gy;
                             const float sg = sigmoidf_acc(x);
-                            if (MODE == B200DET_DECODE_YOLO_EXP) x = __fmul_rn(__fadd_rn(sg, gxy), stride);
-                            else x = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sg, 2.0f), 0.5f), gxy), stride);
+                            if (MODE == B200DET_DECODE_YOLO_EXP) {
+                                const float gu = __fadd_rn(sg, gxy);
+                                if (AUX) s_tile[kDecTileCells * F + ((g << 2) + k) * 5 + f] = gu;
+                                x = __fmul_rn(gu, stride);
+                            } else {
+                                x = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sg, 2.0f), 0.5f), gxy), stride);
+                            }
                         } else if (f < 4) {
                             const float an = f == 2 ? aw : ah;
                             if (MODE == B200DET_DECODE_YOLO_EXP) {
-                                x = __fmul_rn(__fmul_rn(expf(x), an), stride);
+                                const float gu = __fmul_rn(expf(x), an);
+                                if (AUX) s_tile[kDecTileCells * F + ((g << 2) + k) * 5 + f] = gu;
+                                x = __fmul_rn(gu, stride);
                             } else {
                                 const float s2 = __fmul_rn(sigmoidf_acc(x), 2.0f);
                                 x = __fmul_rn(__fmul_rn(s2, s2), an);
                             }
                         } else {
                             x = sigmoidf_acc(x);
+                            if (AUX && f == 4) s_tile[kDecTileCells * F + ((g << 2) + k) * 5 + 4] = x;
                         }
                         v[k] = x;
                     }
@@ -456,17 +466,37 @@ decode_box_tile_kernel(const float* __restrict__ head, float* __restrict__ out, 
     const float4* s4 = reinterpret_cast<const float4*>(s_tile);
     const int n4 = (ncell * F) >> 2;
     for (int i = threadIdx.x; i < n4; i += 256) dst[i] = s4[i];
+    if (AUX) {                                                 // ncell * 5 floats, contiguous and 16-byte aligned (ncell % 4 == 0)
+        float4* adst = reinterpret_cast<float4*>(aux + ((size_t)ba * GG + cell0) * 5);
+        const float4* a4 = reinterpret_cast<const float4*>(s_tile + kDecTileCells * F);
+        for (int i = threadIdx.x; i < (ncell * 5) >> 2; i += 256) adst[i] = a4[i];
+    }
+}
+
+bool decode_box_tileable(int G, int F, const void* head, const void* out) {
+    return ((G * G) & 3) == 0 && F <= kDecTileMaxF && (((uintptr_t)head | (uintptr_t)out) & 15) == 0;
+}
+
+// M3's decode: rows in pixels plus the [cells][5] grid-unit side table; only for tileable planes (the caller checks)
+int decode_box_aux_launch(const float* head, int B, int A, int C, int G, const float* anchors_dev, float stride, float* out,
+                          float* aux, cudaStream_t st) {
+    const int GG = G * G, F = 5 + C;
+    dim3 grid(ceil_div(GG, kDecTileCells), B * A);
+    const size_t smem = (size_t)kDecTileCells * (F + 5) * sizeof(float);
+    decode_box_tile_kernel<B200DET_DECODE_YOLO_EXP, true><<<grid, 256, smem, st>>>(head, out, A, C, G, stride, anchors_dev, aux);
+    B2_LAUNCH_CHECK("decode_box_tile_kernel<aux>");
+    return 0;
 }
 
 int decode_box_launch(const float* head, int B, int A, int C, int G, int mode, const float* anchors_dev, float stride,
                       float* out, cudaStream_t st) {
     const int GG = G * G, F = 5 + C;
-    if ((GG & 3) == 0 && F <= kDecTileMaxF && (((uintptr_t)head | (uintptr_t)out) & 15) == 0) {
+    if (decode_box_tileable(G, F, head, out)) {
         dim3 grid(ceil_div(GG, kDecTileCells), B * A);
         const size_t smem = (size_t)kDecTileCells * F * sizeof(float);
-        if (mode == B200DET_DECODE_NONE) decode_box_tile_kernel<B200DET_DECODE_NONE><<<grid, 256, smem, st>>>(head, out, A, C, G, stride, anchors_dev);
-        else if (mode == B200DET_DECODE_YOLO_EXP) decode_box_tile_kernel<B200DET_DECODE_YOLO_EXP><<<grid, 256, smem, st>>>(head, out, A, C, G, stride, anchors_dev);
-        else decode_box_tile_kernel<B200DET_DECODE_YOLOV5><<<grid, 256, smem, st>>>(head, out, A, C, G, stride, anchors_dev);
+        if (mode == B200DET_DECODE_NONE) decode_box_tile_kernel<B200DET_DECODE_NONE, false><<<grid, 256, smem, st>>>(head, out, A, C, G, stride, anchors_dev, nullptr);
+        else if (mode == B200DET_DECODE_YOLO_EXP) decode_box_tile_kernel<B200DET_DECODE_YOLO_EXP, false><<<grid, 256, smem, st>>>(head, out, A, C, G, stride, anchors_dev, nullptr);
+        else decode_box_tile_kernel<B200DET_DECODE_YOLOV5, false><<<grid, 256, smem, st>>>(head, out, A, C, G, stride, anchors_dev, nullptr);
         B2_LAUNCH_CHECK("decode_box_tile_kernel");
         return 0;
     }
