@@ -405,6 +405,16 @@ __global__ void __launch_bounds__(1024) group_targets_kernel(const float* __rest
     if (threadIdx.x == 0) cnt[b] = base;
 }
 
+// A CTA's 256 consecutive anchors sit in a short run of cells; a target whose box cannot touch the hull of those anchors has
+// IoU exactly 0 with every one of them and (after the image's first target, which seeds the running maximum even at 0) can
+// never win `v > best`.  Each chunk of targets is therefore filtered against the hull first (order kept) and only the
+// survivors — about one in six on the 600-pixel configuration — are walked per anchor.  The hull test repeats the pair
+// test's own rounded operations on bounds (fsub/fadd are monotone), so it never drops a pair the full loop would score
+// above 0; any non-finite or non-positive-area box in the CTA or the image so far switches the filter off.
+__device__ __forceinline__ bool finite4(const float4 v) {
+    return fabsf(v.x) < INFINITY && fabsf(v.y) < INFINITY && fabsf(v.z) < INFINITY && fabsf(v.w) < INFINITY;
+}
+
 __global__ void __launch_bounds__(256) retina_assign_kernel(const float4* __restrict__ anchors, int A,
                                                             const float* __restrict__ targets, int nt,
                                                             const int* __restrict__ list, const int* __restrict__ cnt,
@@ -413,6 +423,9 @@ __global__ void __launch_bounds__(256) retina_assign_kernel(const float4* __rest
     __shared__ float4 s_x[256];     // target cx,cy,w,h (pixels)
     __shared__ float s_a[256];      // target area (+1)
     __shared__ int s_l[256];        // label
+    __shared__ uint8_t s_idx[256];  // surviving targets of the chunk, in order
+    __shared__ float s_hull[8][4];
+    __shared__ int s_scan[33];
     const int b = blockIdx.y;
     const int ai = blockIdx.x * blockDim.x + threadIdx.x;
     const int M = cnt[b];
@@ -420,6 +433,28 @@ __global__ void __launch_bounds__(256) retina_assign_kernel(const float4* __rest
     if (ai < A) an = anchors[ai];
     const float4 ac = cxcywh_to_corners(an);                                     // losses.py:373 ('xywh2xyxy')
     const float aa = __fmul_rn(__fadd_rn(__fsub_rn(ac.z, ac.x), 1.0f), __fadd_rn(__fsub_rn(ac.w, ac.y), 1.0f));
+    // hull of the CTA's anchors, and whether every one of them is an ordinary box
+    float hx0 = INFINITY, hy0 = INFINITY, hx1 = -INFINITY, hy1 = -INFINITY;
+    bool odd = false;
+    if (ai < A) {
+        hx0 = ac.x; hy0 = ac.y; hx1 = ac.z; hy1 = ac.w;
+        odd = !(finite4(ac) && aa > 0.0f && aa < INFINITY);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        hx0 = fminf(hx0, __shfl_xor_sync(0xFFFFFFFFu, hx0, o)); hy0 = fminf(hy0, __shfl_xor_sync(0xFFFFFFFFu, hy0, o));
+        hx1 = fmaxf(hx1, __shfl_xor_sync(0xFFFFFFFFu, hx1, o)); hy1 = fmaxf(hy1, __shfl_xor_sync(0xFFFFFFFFu, hy1, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_hull[threadIdx.x >> 5][0] = hx0; s_hull[threadIdx.x >> 5][1] = hy0;
+        s_hull[threadIdx.x >> 5][2] = hx1; s_hull[threadIdx.x >> 5][3] = hy1;
+    }
+    bool unfiltered = __syncthreads_or(odd) != 0;                                // also publishes s_hull
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        hx0 = fminf(hx0, s_hull[w][0]); hy0 = fminf(hy0, s_hull[w][1]);
+        hx1 = fmaxf(hx1, s_hull[w][2]); hy1 = fmaxf(hy1, s_hull[w][3]);
+    }
     float best = 0.f;
     float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
     int bl = 0;
@@ -427,22 +462,37 @@ __global__ void __launch_bounds__(256) retina_assign_kernel(const float4* __rest
     for (int m0 = 0; m0 < M; m0 += 256) {
         const int mm = min(256, M - m0);
         __syncthreads();
+        bool t_odd = false, keep = false;
         if (threadIdx.x < mm) {
             const float* r = targets + (size_t)list[(size_t)b * nt + m0 + threadIdx.x] * 6;
             const float4 x = make_float4(__fmul_rn(r[2], img_size), __fmul_rn(r[3], img_size), __fmul_rn(r[4], img_size),
                                          __fmul_rn(r[5], img_size));             // losses.py:425
             const float4 c = cxcywh_to_corners(x);
+            const float ta = __fmul_rn(__fadd_rn(__fsub_rn(c.z, c.x), 1.0f), __fadd_rn(__fsub_rn(c.w, c.y), 1.0f));
             s_x[threadIdx.x] = x; s_c[threadIdx.x] = c;
-            s_a[threadIdx.x] = __fmul_rn(__fadd_rn(__fsub_rn(c.z, c.x), 1.0f), __fadd_rn(__fsub_rn(c.w, c.y), 1.0f));
+            s_a[threadIdx.x] = ta;
             s_l[threadIdx.x] = (int)r[1];
+            t_odd = !(finite4(c) && ta > 0.0f && ta < INFINITY);
+            // the pair test on the hull: extents that cannot be positive for any anchor of this CTA
+            const bool apart = __fadd_rn(__fsub_rn(c.z, hx0), 1.0f) <= 0.0f || __fadd_rn(__fsub_rn(hx1, c.x), 1.0f) <= 0.0f ||
+                               __fadd_rn(__fsub_rn(c.w, hy0), 1.0f) <= 0.0f || __fadd_rn(__fsub_rn(hy1, c.y), 1.0f) <= 0.0f;
+            keep = !apart || (m0 + threadIdx.x == 0);                            // the first target seeds best/bx even at IoU 0
         }
+        unfiltered = (__syncthreads_or(t_odd) != 0) || unfiltered;
+        if (unfiltered) keep = threadIdx.x < mm;
+        int n_keep;
+        const int pos = block_exclusive_scan(keep ? 1 : 0, s_scan, &n_keep);
+        if (keep) s_idx[pos] = (uint8_t)threadIdx.x;
         __syncthreads();
-        for (int m = 0; m < mm; ++m) {
+        for (int j = 0; j < n_keep; ++j) {
+            const int m = s_idx[j];
             const float4 c = s_c[m];
             const float iw = fmaxf(__fadd_rn(__fsub_rn(fminf(ac.z, c.z), fmaxf(ac.x, c.x)), 1.0f), 0.0f);   // losses.py:393-397
             const float ih = fmaxf(__fadd_rn(__fsub_rn(fminf(ac.w, c.w), fmaxf(ac.y, c.y)), 1.0f), 0.0f);
             const float inter = __fmul_rn(iw, ih);
-            const float v = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, s_a[m]), inter));                       // losses.py:401
+            const float uni = __fsub_rn(__fadd_rn(aa, s_a[m]), inter);
+            // losses.py:401.  Most (anchor, target) pairs do not touch: 0 / positive is 0 without the IEEE division
+            const float v = (inter == 0.0f && uni > 0.0f) ? 0.0f : __fdiv_rn(inter, uni);
             if (!have || (!(v <= best) && (best == best))) { best = v; bx = s_x[m]; bl = s_l[m]; have = true; }   // :431
         }
     }

@@ -140,6 +140,34 @@ def test_retina_assign_oracle_unsorted_targets():
     torch.testing.assert_close(gl.cpu(), wl, rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("variant", ["small", "many", "degenerate", "nan", "inf", "odd_anchor"])
+def test_retina_assign_hull_filter(variant):
+    """The per-CTA hull filter must be invisible: small targets (most are filtered away), > 256 targets in one image
+    (several chunks), exact duplicates (first maximum wins), and boxes that switch the filter off mid-image."""
+    anchors = synth.retina_priors(256)
+    B = 3
+    n = 300 if variant == "many" else 40
+    tg = synth.labels(B, 9, 91, max_per_image=n, min_per_image=n)
+    tg[:, 4:6] = tg[:, 4:6] * 0.3 + 0.02
+    tg[5] = tg[2]                                        # duplicate inside image 0
+    k = n + n // 2                                       # a row in the middle of image 1
+    if variant == "degenerate":
+        tg[k, 4] = -0.5                                  # negative width -> negative area
+        tg[k + 1, 4:6] = 0.0
+    elif variant == "nan":
+        tg[k, 2] = float("nan")
+    elif variant == "inf":
+        tg[k, 4] = float("inf")
+    elif variant == "odd_anchor":
+        anchors = anchors.clone()
+        anchors[1000, 2] = float("inf")
+        anchors[5000, 3] = -30.0
+    wl, wc = rp.retina_assign(anchors, tg, B, 256.0)
+    gl, gc = od.retina_assign(anchors.to(DEV), tg.to(DEV), B, 256.0)
+    assert torch.equal(gc.cpu(), wc)
+    torch.testing.assert_close(gl.cpu(), wl, rtol=1e-5, atol=1e-6, equal_nan=True)
+
+
 def test_ssd_match_oracle_many_gt():
     pri = synth.ssd_priors()
     g = torch.Generator().manual_seed(9)
