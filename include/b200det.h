@@ -236,8 +236,9 @@ int b200det_retina_assign(const float* anchors, int32_t num_anchors, const float
  * (SURVEY §8f row 2): matched-row gather + D2 decode + GIoU (:105-119), objectness target scatter (:123), class
  * focal-BCE over the matched rows (:127-133) and objectness focal-BCE over every cell (:137; FocalLoss :37-64 around
  * BCEWithLogitsLoss with pos_weight 1).
- *   fwd: giou[m], tobj[B,na,ny,nx] (zero-filled here), sums[3] fp64 (device) = sum(1-giou), sum FL_obj, sum FL_cls;
- *        the means are sums / m, / cells, / (m*C).  with_cls = 0 skips the class term (nc == 1, :127).
+ *   fwd: giou[m], tobj[B,na,ny,nx] (zero-filled here), sums[3] fp64 (device) = the three MEANS on return:
+ *        sum(1-giou) / max(m,1), sum FL_obj / cells, sum FL_cls / max(m*C,1) (accumulated in place, divided by the last
+ *        kernel).  with_cls = 0 skips the class term (nc == 1, :127).
  *   bwd: gpi (zero-filled by the caller) += d/dpi of  g3[0]*inv_nbox*sum(1-giou) + g3[1]*inv_cells*sum FL_obj +
  *        g3[2]*inv_ncls*sum FL_cls, g3 = the three upstream gradients on the DEVICE (no host sync in backward);
  *        tobj is treated as a constant (`giou.detach()`, :123).

@@ -687,6 +687,10 @@ __global__ void __launch_bounds__(256) v5_loss_rows_bwd_kernel(const MatchParams
     }
 }
 
+__global__ void v5_loss_means_kernel(double* __restrict__ sums, double n_box, double n_cells, double n_cls) {
+    if (threadIdx.x < 3) sums[threadIdx.x] = sums[threadIdx.x] / (threadIdx.x == 0 ? n_box : threadIdx.x == 1 ? n_cells : n_cls);
+}
+
 int v5_loss_fwd_launch(const float* pi, int B, int na, int ny, int nx, int F, const int32_t* b, const int32_t* a,
                        const int32_t* gj, const int32_t* gi, const int32_t* tcls, const float* tbox, const float* anch, int m,
                        float cp, float cn, float gamma, float alpha, int with_cls, float* giou, float* tobj, double* sums,
@@ -707,6 +711,10 @@ int v5_loss_fwd_launch(const float* pi, int B, int na, int ny, int nx, int F, co
     const int grid = (int)((cells + 255) / 256 < 148 * 8 ? (cells + 255) / 256 : 148 * 8);
     v5_loss_obj_fwd_kernel<<<grid, 256, 0, st>>>(pi, F, cells, tobj, gamma, alpha, sums);
     B2_LAUNCH_CHECK("v5_loss_obj_fwd_kernel");
+    // sums -> means in place: box / max(m, 1), obj / cells, cls / max(m * C, 1)   (reduction 'mean', losses.py:119-137)
+    v5_loss_means_kernel<<<1, 32, 0, st>>>(sums, (double)(m > 0 ? m : 1), (double)cells,
+                                           (double)((long long)m * (F - 5) > 0 ? (long long)m * (F - 5) : 1));
+    B2_LAUNCH_CHECK("v5_loss_means_kernel");
     return 0;
 }
 

@@ -43,9 +43,9 @@ def build_targets(pred_boxes, pred_cls, target, anchors, ignore_thres):
     return iou_scores, class_mask, obj, noobj, tx, ty, tw, th, tcls, obj.float()
 
 
-def build_targets_v5(p, targets, anchors, nl, na):
-    """Returns `(tcls, tbox, indices, anch)`, four lists of length nl with the reference's dtypes
-    (int64 indices/classes) and row order.  `p[i]` may be a tensor `[B,na,ny,nx,5+C]` or just its shape."""
+def _build_targets_v5_raw(p, targets, anchors, nl, na):
+    """One launch for all levels, one host sync for the row counts.  Per level: `(ib int32 [5, m] = b, a, gj, gi, cls
+    (rows of a wider buffer), tbox [m, 4], anch [m, 2])`."""
     lib = L.load()
     tg = L.require_cuda(targets, "targets").contiguous()
     dev = tg.device
@@ -53,7 +53,6 @@ def build_targets_v5(p, targets, anchors, nl, na):
     anchors_cpu = torch.as_tensor(anchors).detach().float().cpu().reshape(nl, na, 2)
     anchors_dev = torch.as_tensor(anchors, dtype=torch.float32, device=dev).reshape(nl, na, 2)
     cap = max(5 * na * nt, 1)
-    tcls, tbox, indices, anch = [], [], [], []
     counts = torch.empty((nl,), dtype=torch.int32, device=dev)
     bufs = []
     nxs, nys = (ctypes.c_int32 * nl)(), (ctypes.c_int32 * nl)()
@@ -73,14 +72,20 @@ def build_targets_v5(p, targets, anchors, nl, na):
         L.check(lib.b200det_build_targets_v5(tg.data_ptr() if nt else None, nt, nl, arr, na, nxs, nys, *ptrs, counts.data_ptr(),
                                              L.stream_ptr(dev)), "build_targets_v5")     # one launch, one CTA per level
     ms = counts.cpu().tolist()                                            # one host sync for all levels
-    for i, (ib, tb, ac) in enumerate(bufs):
-        m = ms[i]
-        il = ib[:, :m].long()
+    del anchors_dev
+    return [(ib[:, :m], tb[:m], ac[:m]) for (ib, tb, ac), m in zip(bufs, ms)]
+
+
+def build_targets_v5(p, targets, anchors, nl, na):
+    """Returns `(tcls, tbox, indices, anch)`, four lists of length nl with the reference's dtypes
+    (int64 indices/classes) and row order.  `p[i]` may be a tensor `[B,na,ny,nx,5+C]` or just its shape."""
+    tcls, tbox, indices, anch = [], [], [], []
+    for ib, tb, ac in _build_targets_v5_raw(p, targets, anchors, nl, na):
+        il = ib.long()
         indices.append((il[0], il[1], il[2], il[3]))
         tcls.append(il[4])
-        tbox.append(tb[:m])
-        anch.append(ac[:m])
-    del anchors_dev
+        tbox.append(tb)
+        anch.append(ac)
     return tcls, tbox, indices, anch
 
 
@@ -133,15 +138,15 @@ def v5_match_level(pi, tbox, indices, anch):
 
 class _V5LossLevel(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pi, tbox, b, a, gj, gi, anch, tcls, cp, cn, gamma, alpha, with_cls):
+    def forward(ctx, pi, tbox, idx, anch, cp, cn, gamma, alpha, with_cls):
+        # idx: int32 [5, m] = b, a, gj, gi, cls; each row contiguous (rows of a wider buffer are fine)
         lib = L.load()
         pid = L.require_cuda(pi.detach(), "pi")
         if not pid.is_contiguous():
             raise ValueError("pi must be contiguous [B,na,ny,nx,5+C]")
         B, na, ny, nx, F = pid.shape
-        m = int(b.shape[0])
+        m = int(idx.shape[1])
         dev = pid.device
-        idx = torch.stack((b, a, gj, gi, tcls)).to(torch.int32).contiguous() if m else torch.zeros((5, 0), dtype=torch.int32, device=dev)
         tb = tbox.detach().contiguous().float()
         ac = anch.detach().contiguous().float()
         giou = torch.empty((max(m, 1),), dtype=torch.float32, device=dev)
@@ -154,7 +159,7 @@ class _V5LossLevel(torch.autograd.Function):
                                             sums.data_ptr(), L.stream_ptr(dev)), "v5_loss_fwd")
         cells = B * na * ny * nx
         n_box, n_cls = max(m, 1), max(m * (F - 5), 1)
-        means = (sums / torch.tensor([n_box, cells, n_cls], dtype=torch.float64, device=dev)).float()
+        means = sums.float()                                              # the launcher's last kernel divided by the counts
         ctx.save_for_backward(pid, idx, tb, ac, tobj)
         ctx.cfg = (cp, cn, gamma, alpha, int(with_cls), m, cells, n_box, n_cls)
         ctx.mark_non_differentiable(tobj)
@@ -173,7 +178,7 @@ class _V5LossLevel(torch.autograd.Function):
                                             idx[2].data_ptr(), idx[3].data_ptr(), idx[4].data_ptr(), tb.data_ptr(), ac.data_ptr(),
                                             m, cp, cn, gamma, alpha, with_cls, tobj.data_ptr(), g3.data_ptr(), 1.0 / n_box,
                                             1.0 / cells, 1.0 / n_cls, gpi.data_ptr(), L.stream_ptr(pid.device)), "v5_loss_bwd")
-        return (gpi,) + (None,) * 12
+        return (gpi,) + (None,) * 8
 
 
 def v5_loss_level(pi, tbox, indices, anch, tcls, cp=1.0, cn=0.0, gamma=1.5, alpha=0.25, with_cls=True):
@@ -181,7 +186,11 @@ def v5_loss_level(pi, tbox, indices, anch, tcls, cp=1.0, cn=0.0, gamma=1.5, alph
     differentiable w.r.t. `pi`: returns `(mean(1 - giou), mean FL(pi[...,4], tobj), mean FL(ps[:,5:], class targets), tobj)`.
     With no matched rows the first and third are 0 (the reference skips them, :110)."""
     b, a, gj, gi = indices
-    return _V5LossLevel.apply(pi, tbox, b, a, gj, gi, anch, tcls, float(cp), float(cn), float(gamma), float(alpha), bool(with_cls))
+    if b.shape[0]:
+        idx = torch.stack((b, a, gj, gi, tcls)).to(torch.int32)
+    else:
+        idx = torch.zeros((5, 0), dtype=torch.int32, device=pi.device)
+    return _V5LossLevel.apply(pi, tbox, idx, anch, float(cp), float(cn), float(gamma), float(alpha), bool(with_cls))
 
 
 def v5_loss(output, target, anchors, nl, na, nc, cp=1.0, cn=0.0, gamma=1.5, alpha=0.25):
@@ -190,10 +199,11 @@ def v5_loss(output, target, anchors, nl, na, nc, cp=1.0, cn=0.0, gamma=1.5, alph
     Returns the reference's metrics dict of shape-[1] tensors: loss, Localization, Classification, Conf_obj."""
     dev = output[0].device
     lcls = torch.zeros(1, device=dev); lbox = torch.zeros(1, device=dev); lobj = torch.zeros(1, device=dev)
-    tcls, tbox, indices, anch = build_targets_v5(output, target, anchors, nl, na)
+    levels = _build_targets_v5_raw(output, target, anchors, nl, na)         # int32 index rows go straight to the kernels
     for i, pi in enumerate(output):
-        nb = indices[i][0].shape[0]
-        t_box, t_obj, t_cls, _ = v5_loss_level(pi, tbox[i], indices[i], anch[i], tcls[i], cp, cn, gamma, alpha, nc > 1)
+        ib, tb, ac = levels[i]
+        nb = ib.shape[1]
+        t_box, t_obj, t_cls, _ = _V5LossLevel.apply(pi, tb, ib, ac, float(cp), float(cn), float(gamma), float(alpha), nc > 1)
         if nb:
             lbox = lbox + t_box                                           # :119
             if nc > 1:
