@@ -383,107 +383,154 @@ decode_box_kernel(const float* __restrict__ head, float* __restrict__ out, int A
     }
 }
 
-// K0t — the same transpose for planes whose size is a multiple of 4 (every YOLO grid but 13 x 13): a CTA owns 64 consecutive
-// cells of one (image, anchor) slab with ALL their 5+C fields.  The planes are read with 128-bit loads along the cells
-// (16 lanes = 256 contiguous bytes per plane), decoded, and stored into shared memory in the OUTPUT order [cell][field] —
-// which for 64 consecutive cells is one contiguous 64*(5+C)*4-byte block of the result, so the write-out is a linear,
-// 16-byte aligned, fully coalesced copy.  (The 32 x 64 tile kernel above: scalar loads, an integer division per element on
-// the way out, 1.5 TB/s; this one streams the 836 MB of a 640-pixel head level in roughly a third of the time.)
+// K0t — the same transpose, one CTA per 64 consecutive cells of one (image, anchor) slab with ALL their 5+C fields.  The
+// planes are read along the cells — 128-bit loads (16 lanes = 256 contiguous bytes per plane) when the plane size is a
+// multiple of 4 and the head is 16-byte aligned (VEC: every YOLO grid but the odd ones, 13 x 13, 19 x 19), 32-bit loads
+// otherwise — decoded, and stored into shared memory in the OUTPUT order [cell][field], which for 64 consecutive cells is one
+// contiguous 64*(5+C)*4-byte block of the result: the write-out is a linear copy, 128 bits at a time (the tile sits in
+// shared memory at the same offset mod 16 bytes as its destination, so both sides of the copy are aligned whatever the
+// plane size).  (The 32 x 64 tile kernel above: scalar loads, an integer division per element on the way out, 1.5 TB/s;
+// this one streams the 836 MB of a 640-pixel head level at 5.3 TB/s.  The old kernel remains for rows wider than 128.)
 constexpr int kDecTileCells = 64;
 constexpr int kDecTileMaxF = 128;
 
+// one field of one cell; AUX: the box before the stride multiply (grid units) and the objectness go to aux5[0..4]
+template <int MODE, bool AUX>
+__device__ __forceinline__ float decode_field(float x, int f, int cell, int G, float aw, float ah, float stride, float* aux5) {
+    if (MODE == B200DET_DECODE_NONE) return x;
+    if (f < 2) {
+        const int gy = cell / G;
+        const float gxy = f == 0 ? (float)(cell - gy * G) : (float)gy;
+        const float sg = sigmoidf_acc(x);
+        if (MODE == B200DET_DECODE_YOLO_EXP) {
+            const float gu = __fadd_rn(sg, gxy);
+            if (AUX) aux5[f] = gu;
+            return __fmul_rn(gu, stride);
+        }
+        return __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sg, 2.0f), 0.5f), gxy), stride);
+    }
+    if (f < 4) {
+        const float an = f == 2 ? aw : ah;
+        if (MODE == B200DET_DECODE_YOLO_EXP) {
+            const float gu = __fmul_rn(expf(x), an);
+            if (AUX) aux5[f] = gu;
+            return __fmul_rn(gu, stride);
+        }
+        const float s2 = __fmul_rn(sigmoidf_acc(x), 2.0f);
+        return __fmul_rn(__fmul_rn(s2, s2), an);
+    }
+    const float sg = sigmoidf_acc(x);
+    if (AUX && f == 4) aux5[4] = sg;
+    return sg;
+}
+
 // AUX (the metrics path, M3): also emits a compact [cell][5] side table with the box BEFORE the stride multiply (grid
 // units, what build_targets matches on) and the objectness, so that nobody has to re-read or rescale the wide rows.
-template <int MODE, bool AUX>
+template <int MODE, bool AUX, bool VEC>
 __global__ void __launch_bounds__(256, 6)
 decode_box_tile_kernel(const float* __restrict__ head, float* __restrict__ out, int A, int C, int G, float stride,
                        const float* __restrict__ anchors, float* __restrict__ aux) {
-    extern __shared__ __align__(16) float s_tile[];          // [ncell][F] (+ [ncell][5] with AUX)
+    extern __shared__ __align__(16) float s_raw[];            // 4 floats of slack, [ncell][F], then [ncell][5] with AUX
     const int GG = G * G, F = 5 + C;
     const int ba = blockIdx.y;
     const int a = ba % A;
     const int cell0 = blockIdx.x * kDecTileCells;
-    const int ncell = min(kDecTileCells, GG - cell0);          // multiple of 4
+    const int ncell = min(kDecTileCells, GG - cell0);
     const float* src = head + (size_t)ba * F * GG + cell0;
-    const int ngrp = ncell >> 2;                               // float4 groups per plane
+    float* dst = out + ((size_t)ba * GG + cell0) * F;
+    const int mis = (int)((reinterpret_cast<uintptr_t>(dst) >> 2) & 3);       // 0 whenever VEC and `out` is 16-byte aligned
+    float* s_tile = s_raw + mis;
+    float* s_aux = s_raw + 4 + kDecTileCells * F;
     float aw = 0.f, ah = 0.f;
     if (MODE != B200DET_DECODE_NONE) { aw = anchors[a * 2]; ah = anchors[a * 2 + 1]; }
-    // thread -> (cell group g, planes f0, f0 + 16, ...): three independent 128-bit loads in flight before the first is used
-    const int g = threadIdx.x & 15;
-    if (g < ngrp) {
-        const int cell_g = cell0 + (g << 2);
-        for (int f0 = threadIdx.x >> 4; f0 < F; f0 += 48) {
-            float4 ld[3];
+    if (VEC) {
+        // thread -> (cell group g, planes f0, f0 + 16, ...): three independent 128-bit loads in flight before the first is used
+        const int g = threadIdx.x & 15;
+        if (g < (ncell >> 2)) {
+            for (int f0 = threadIdx.x >> 4; f0 < F; f0 += 48) {
+                float4 ld[3];
 #pragma unroll
-            for (int u = 0; u < 3; ++u) {
-                const int f = f0 + 16 * u;
-                if (f < F) ld[u] = ldg_stream4(src + (size_t)f * GG + (g << 2));
-            }
-#pragma unroll
-            for (int u = 0; u < 3; ++u) {
-                const int f = f0 + 16 * u;
-                if (f >= F) continue;
-                float v[4] = {ld[u].x, ld[u].y, ld[u].z, ld[u].w};
-                if (MODE != B200DET_DECODE_NONE) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        float x = v[k];
-                        if (f < 2) {
-                            const int gy = (cell_g + k) / G;
-                            const float gxy = f == 0 ? (float)(cell_g + k - gy * G) : (float)gy;
-                            const float sg = sigmoidf_acc(x);
-                            if (MODE == B200DET_DECODE_YOLO_EXP) {
-                                const float gu = __fadd_rn(sg, gxy);
-                                if (AUX) s_tile[kDecTileCells * F + ((g << 2) + k) * 5 + f] = gu;
-                                x = __fmul_rn(gu, stride);
-                            } else {
-                                x = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sg, 2.0f), 0.5f), gxy), stride);
-                            }
-                        } else if (f < 4) {
-                            const float an = f == 2 ? aw : ah;
-                            if (MODE == B200DET_DECODE_YOLO_EXP) {
-                                const float gu = __fmul_rn(expf(x), an);
-                                if (AUX) s_tile[kDecTileCells * F + ((g << 2) + k) * 5 + f] = gu;
-                                x = __fmul_rn(gu, stride);
-                            } else {
-                                const float s2 = __fmul_rn(sigmoidf_acc(x), 2.0f);
-                                x = __fmul_rn(__fmul_rn(s2, s2), an);
-                            }
-                        } else {
-                            x = sigmoidf_acc(x);
-                            if (AUX && f == 4) s_tile[kDecTileCells * F + ((g << 2) + k) * 5 + 4] = x;
-                        }
-                        v[k] = x;
-                    }
+                for (int u = 0; u < 3; ++u) {
+                    const int f = f0 + 16 * u;
+                    if (f < F) ld[u] = ldg_stream4(src + (size_t)f * GG + (g << 2));
                 }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) s_tile[((g << 2) + k) * F + f] = v[k];
+                for (int u = 0; u < 3; ++u) {
+                    const int f = f0 + 16 * u;
+                    if (f >= F) continue;
+                    const float v[4] = {ld[u].x, ld[u].y, ld[u].z, ld[u].w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int c = (g << 2) + k;
+                        s_tile[c * F + f] = decode_field<MODE, AUX>(v[k], f, cell0 + c, G, aw, ah, stride, s_aux + c * 5);
+                    }
+                }
+            }
+        }
+    } else {
+        // thread -> (cell c, planes f0, f0 + 4, ...): a warp reads 32 consecutive cells of one plane
+        const int c = threadIdx.x & 63;
+        if (c < ncell) {
+            for (int f0 = threadIdx.x >> 6; f0 < F; f0 += 12) {
+                float ld[3];
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int f = f0 + 4 * u;
+                    if (f < F) ld[u] = ldg_stream1(src + (size_t)f * GG + c);
+                }
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int f = f0 + 4 * u;
+                    if (f >= F) continue;
+                    s_tile[c * F + f] = decode_field<MODE, AUX>(ld[u], f, cell0 + c, G, aw, ah, stride, s_aux + c * 5);
+                }
             }
         }
     }
     __syncthreads();
-    float4* dst = reinterpret_cast<float4*>(out + ((size_t)ba * GG + cell0) * F);
-    const float4* s4 = reinterpret_cast<const float4*>(s_tile);
-    const int n4 = (ncell * F) >> 2;
-    for (int i = threadIdx.x; i < n4; i += 256) dst[i] = s4[i];
-    if (AUX) {                                                 // ncell * 5 floats, contiguous and 16-byte aligned (ncell % 4 == 0)
-        float4* adst = reinterpret_cast<float4*>(aux + ((size_t)ba * GG + cell0) * 5);
-        const float4* a4 = reinterpret_cast<const float4*>(s_tile + kDecTileCells * F);
-        for (int i = threadIdx.x; i < (ncell * 5) >> 2; i += 256) adst[i] = a4[i];
+    // linear copy-out: scalars up to the first 16-byte boundary of the destination, 128-bit body, scalar tail
+    const int total = ncell * F;
+    const int first = min((4 - mis) & 3, total);
+    const int n4 = (total - first) >> 2;
+    if ((int)threadIdx.x < first) dst[threadIdx.x] = s_tile[threadIdx.x];
+    {
+        float4* d4 = reinterpret_cast<float4*>(dst + first);
+        const float4* s4 = reinterpret_cast<const float4*>(s_tile + first);
+        for (int i = threadIdx.x; i < n4; i += 256) d4[i] = s4[i];
+        const int done = first + (n4 << 2);
+        if ((int)threadIdx.x < total - done) dst[done + threadIdx.x] = s_tile[done + threadIdx.x];
+    }
+    if (AUX) {                                                 // ncell * 5 floats, contiguous
+        float* adst = aux + ((size_t)ba * GG + cell0) * 5;
+        if (VEC) {                                             // ncell % 4 == 0 and cell0 % 64 == 0: 16-byte aligned
+            const float4* a4 = reinterpret_cast<const float4*>(s_aux);
+            for (int i = threadIdx.x; i < (ncell * 5) >> 2; i += 256) reinterpret_cast<float4*>(adst)[i] = a4[i];
+        } else {
+            for (int i = threadIdx.x; i < ncell * 5; i += 256) adst[i] = s_aux[i];
+        }
     }
 }
 
 bool decode_box_tileable(int G, int F, const void* head, const void* out) {
-    return ((G * G) & 3) == 0 && F <= kDecTileMaxF && (((uintptr_t)head | (uintptr_t)out) & 15) == 0;
+    (void)G; (void)head; (void)out;
+    return F <= kDecTileMaxF;
 }
 
-// M3's decode: rows in pixels plus the [cells][5] grid-unit side table; only for tileable planes (the caller checks)
-int decode_box_aux_launch(const float* head, int B, int A, int C, int G, const float* anchors_dev, float stride, float* out,
-                          float* aux, cudaStream_t st) {
+template <int MODE, bool AUX>
+static void decode_box_tile_launch(const float* head, int B, int A, int C, int G, const float* anchors_dev, float stride,
+                                   float* out, float* aux, cudaStream_t st) {
     const int GG = G * G, F = 5 + C;
     dim3 grid(ceil_div(GG, kDecTileCells), B * A);
-    const size_t smem = (size_t)kDecTileCells * (F + 5) * sizeof(float);
-    decode_box_tile_kernel<B200DET_DECODE_YOLO_EXP, true><<<grid, 256, smem, st>>>(head, out, A, C, G, stride, anchors_dev, aux);
+    const size_t smem = (size_t)(kDecTileCells * (F + (AUX ? 5 : 0)) + 4) * sizeof(float);
+    const bool vec = (GG & 3) == 0 && (((uintptr_t)head | (uintptr_t)out | (uintptr_t)aux) & 15) == 0;
+    if (vec) decode_box_tile_kernel<MODE, AUX, true><<<grid, 256, smem, st>>>(head, out, A, C, G, stride, anchors_dev, aux);
+    else decode_box_tile_kernel<MODE, AUX, false><<<grid, 256, smem, st>>>(head, out, A, C, G, stride, anchors_dev, aux);
+}
+
+// M3's decode: rows in pixels plus the [cells][5] grid-unit side table; rows up to 128 wide (the caller checks)
+int decode_box_aux_launch(const float* head, int B, int A, int C, int G, const float* anchors_dev, float stride, float* out,
+                          float* aux, cudaStream_t st) {
+    decode_box_tile_launch<B200DET_DECODE_YOLO_EXP, true>(head, B, A, C, G, anchors_dev, stride, out, aux, st);
     B2_LAUNCH_CHECK("decode_box_tile_kernel<aux>");
     return 0;
 }
@@ -492,11 +539,9 @@ int decode_box_launch(const float* head, int B, int A, int C, int G, int mode, c
                       float* out, cudaStream_t st) {
     const int GG = G * G, F = 5 + C;
     if (decode_box_tileable(G, F, head, out)) {
-        dim3 grid(ceil_div(GG, kDecTileCells), B * A);
-        const size_t smem = (size_t)kDecTileCells * F * sizeof(float);
-        if (mode == B200DET_DECODE_NONE) decode_box_tile_kernel<B200DET_DECODE_NONE, false><<<grid, 256, smem, st>>>(head, out, A, C, G, stride, anchors_dev, nullptr);
-        else if (mode == B200DET_DECODE_YOLO_EXP) decode_box_tile_kernel<B200DET_DECODE_YOLO_EXP, false><<<grid, 256, smem, st>>>(head, out, A, C, G, stride, anchors_dev, nullptr);
-        else decode_box_tile_kernel<B200DET_DECODE_YOLOV5, false><<<grid, 256, smem, st>>>(head, out, A, C, G, stride, anchors_dev, nullptr);
+        if (mode == B200DET_DECODE_NONE) decode_box_tile_launch<B200DET_DECODE_NONE, false>(head, B, A, C, G, anchors_dev, stride, out, nullptr, st);
+        else if (mode == B200DET_DECODE_YOLO_EXP) decode_box_tile_launch<B200DET_DECODE_YOLO_EXP, false>(head, B, A, C, G, anchors_dev, stride, out, nullptr, st);
+        else decode_box_tile_launch<B200DET_DECODE_YOLOV5, false>(head, B, A, C, G, anchors_dev, stride, out, nullptr, st);
         B2_LAUNCH_CHECK("decode_box_tile_kernel");
         return 0;
     }
