@@ -97,7 +97,8 @@ def main():
         print(f"{t.shape[0]} CTAs; span {(t[:, 5].max() - t0).item() / 1e3:.1f} us; CTA life mean {life.mean():.1f} max {life.max():.1f} us")
         print(" ".join(f"{nm} {d[:, i].mean():5.2f}/{d[:, i].max():5.2f}" for i, nm in enumerate(names)))
     if a.trace_sort:
-        CL = 8
+        per_cta = 6656                                    # clustersort.cu: kCsCap; cluster = 1, 2, 4, 8 or 16 CTAs per image
+        CL = next(c for c in (1, 2, 4, 8, 16) if n_pad.value <= c * per_cta)
         tr = torch.zeros(a.batch * CL * 64, dtype=torch.int64, device=dev)
         lib.b200det_debug_set_trace.argtypes = [ctypes.c_void_p]
         assert lib.b200det_debug_set_trace(tr.data_ptr()) == 0
@@ -109,6 +110,8 @@ def main():
         t0 = t[:, 0, 0].min()
         names = ["load", "rank", "scan+csync", "exchange", "scatter", "csync"]
         print(f"{t.shape[0]} CTAs traced; kernel span {(t[:, :, :7].max() - t0).item() / 1e3:.1f} us")
+        st0 = ((t[:, 0, 0] - t0).double() / 1e3).sort().values
+        print("CTA start times (us), deciles:", " ".join(f"{st0[int(q * (len(st0) - 1) / 10)].item():.1f}" for q in range(11)))
         for ps in range(6):
             if t[:, ps, 0].max() == 0:
                 continue
