@@ -358,17 +358,25 @@ __global__ void ssd_match_kernel(const float4* __restrict__ priors, int P, const
     for (int m = threadIdx.x; m < M; m += blockDim.x) s_gt[m] = center_to_points(gt[m]);
     __syncthreads();
     const int pidx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pidx >= P) return;
-    const float4 d = center_to_points(priors[pidx]);
+    const bool live = pidx < P;
+    const float4 d = center_to_points(priors[live ? pidx : 0]);
     float best = 0.f;
     int bi = 0;
     for (int m = 0; m < M; ++m) {
         const float v = iou_plain(d, s_gt[m]);                                 // losses.py:209
         if (m == 0) { best = v; bi = 0; }
         else if (!(v <= best) && (best == best)) { best = v; bi = m; }        // losses.py:214 (max over GTs)
-        const unsigned long long pk = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)pidx);
-        if (v == v) atomicMax(&gt_best[m], pk);                                // losses.py:211 (max over priors)
+        // losses.py:211 (max over priors, first prior on ties) = max of (iou bits, ~prior index): reduced over the warp
+        // first (two `redux.sync`), one atomic per warp — 175 k atomics on 20 addresses were most of this kernel's time
+        const bool ok = live && v == v;
+        const unsigned vb = ok ? __float_as_uint(v) : 0u;
+        const unsigned vmax = __reduce_max_sync(0xFFFFFFFFu, vb);
+        const unsigned lo = __reduce_max_sync(0xFFFFFFFFu, (ok && vb == vmax) ? 0xFFFFFFFFu - (unsigned)pidx : 0u);
+        const unsigned any_ok = __ballot_sync(0xFFFFFFFFu, ok);
+        if ((threadIdx.x & 31) == 0 && any_ok != 0u)
+            atomicMax(&gt_best[m], ((unsigned long long)vmax << 32) | lo);
     }
+    if (!live) return;
     idx[pidx] = bi;
     matched[pidx] = best >= thresh ? 1 : 0;                                    // losses.py:215
     forced[pidx] = -1;
