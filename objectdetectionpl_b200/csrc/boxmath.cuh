@@ -21,6 +21,22 @@ __device__ __forceinline__ float iou_plus1_eps(const float4 a, const float4 b) {
     return __fdiv_rn(inter, __fadd_rn(__fsub_rn(__fadd_rn(a1, a2), inter), 1e-16f));
 }
 
+// the same value with the two +1-areas supplied by the caller and without the IEEE division when the boxes do not touch
+// (0 / den is +-0 for any non-zero, non-NaN den; the sign of a zero is invisible to the comparisons that consume IoUs)
+__device__ __forceinline__ float box_area_plus1(const float4 a) {
+    return __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.0f), __fadd_rn(__fsub_rn(a.w, a.y), 1.0f));
+}
+__device__ __forceinline__ float iou_plus1_eps_pre(const float4 a, const float4 b, const float a1, const float a2) {
+    const float ix1 = fmaxf(a.x, b.x), iy1 = fmaxf(a.y, b.y);
+    const float ix2 = fminf(a.z, b.z), iy2 = fminf(a.w, b.w);
+    const float iw = fmaxf(__fadd_rn(__fsub_rn(ix2, ix1), 1.0f), 0.0f);
+    const float ih = fmaxf(__fadd_rn(__fsub_rn(iy2, iy1), 1.0f), 0.0f);
+    const float inter = __fmul_rn(iw, ih);
+    const float den = __fadd_rn(__fsub_rn(__fadd_rn(a1, a2), inter), 1e-16f);
+    if (inter == 0.0f && (den > 0.0f || den < 0.0f)) return 0.0f;
+    return __fdiv_rn(inter, den);
+}
+
 // accuracy.py:19-32 on corner boxes
 __device__ __forceinline__ float iou_plain(const float4 a, const float4 b) {
     const float dx = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);

@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(256) bs_aim_kernel(const float* __restrict__ r
                                                      int* __restrict__ first, float thr, float* __restrict__ tp) {
     __shared__ float4 s_box[256];
     __shared__ float s_lab[256];
+    __shared__ float s_area[256];
     const int b = blockIdx.y;
     const int k = blockIdx.x * 256 + threadIdx.x;
     const int K = count[b];
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(256) bs_aim_kernel(const float* __restrict__ r
         pb = make_float4(r[0], r[1], r[2], r[3]);
         pl = r[6];                                                          // output[:, -1]  (accuracy.py:128)
     }
+    const float pa = box_area_plus1(pb);
     bool label_ok = false, have = false;
     float best = 0.f;
     int bi = -1;
@@ -94,11 +96,12 @@ __global__ void __launch_bounds__(256) bs_aim_kernel(const float* __restrict__ r
             const float* t = targets + (size_t)list[(size_t)b * nt + m0 + threadIdx.x] * 6;
             s_lab[threadIdx.x] = t[1];
             s_box[threadIdx.x] = make_float4(t[2], t[3], t[4], t[5]);      // corners, as bbox_iou's default reads them
+            s_area[threadIdx.x] = box_area_plus1(s_box[threadIdx.x]);
         }
         __syncthreads();
         for (int m = 0; m < mm; ++m) {
             label_ok |= s_lab[m] == pl;                                     // `pred_label not in target_labels` (:146)
-            const float v = iou_plus1_eps(pb, s_box[m]);
+            const float v = iou_plus1_eps_pre(pb, s_box[m], pa, s_area[m]);  // most pairs do not touch: no division
             if (!have || (!(v <= best) && (best == best))) { best = v; bi = m0 + m; have = true; }   // torch.max(0)
         }
     }
