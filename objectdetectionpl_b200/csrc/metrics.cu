@@ -142,6 +142,10 @@ int batch_statistics_launch(const float* rows, const long long* row_start, const
 int score_sort_launch(const uint32_t* tile_count, const uint32_t* count, uint32_t* digit_hist, uint32_t* ticket,
                       uint32_t* status, uint32_t* key[2], uint32_t* pay[2], int n_pad, int n_tiles, int batch,
                       cudaStream_t st);
+bool score_sort_is_lookback(int n_pad);
+int partition_pass_launch(const uint32_t* count, uint32_t* digit_hist, uint32_t* ticket, uint32_t* status,
+                          const uint32_t* pay_in, uint32_t* pay_out, int n_pad, int n_tiles, int pass, int shift,
+                          cudaStream_t st);
 
 struct ApWs {
     uint32_t* count;        // [1]
@@ -201,6 +205,35 @@ __global__ void __launch_bounds__(256) ap_gather_kernel(const uint32_t* __restri
     packed[s] = v;
 }
 
+// The same gather for the partitioned route (<= 255 evaluated classes): the word is (u << 8 | true positive) with u the
+// FIRST index of the detection's class in `classes` (255: not evaluated), and the bin totals of u are counted on the way —
+// one more stable radix pass on u then leaves every evaluated class as one contiguous, confidence-ordered run.
+__global__ void __launch_bounds__(256) ap_gather_bins_kernel(const uint32_t* __restrict__ spay, const float* __restrict__ tp,
+                                                             const float* __restrict__ pred_cls, int n,
+                                                             const int* __restrict__ classes, int num_classes,
+                                                             uint32_t* __restrict__ binned, uint32_t* __restrict__ bin_hist) {
+    __shared__ int s_cls[256];
+    __shared__ int s_hist[256];
+    s_hist[threadIdx.x] = 0;
+    if ((int)threadIdx.x < num_classes) s_cls[threadIdx.x] = classes[threadIdx.x];
+    __syncthreads();
+    const int s = blockIdx.x * 256 + threadIdx.x;
+    if (s < n) {
+        const uint32_t i = spay[s];
+        const float c = pred_cls[i];
+        int u = 255;
+        if (c >= 0.0f && c < 1073741824.0f && c == floorf(c)) {
+            const int ci = (int)c;
+            for (int j = 0; j < num_classes; ++j)
+                if (s_cls[j] == ci) { u = j; break; }
+        }
+        binned[s] = ((uint32_t)u << 8) | (tp[i] != 0.0f ? 1u : 0u);
+        atomicAdd(&s_hist[u], 1);
+    }
+    __syncthreads();
+    if (s_hist[threadIdx.x]) atomicAdd(&bin_hist[threadIdx.x], (uint32_t)s_hist[threadIdx.x]);
+}
+
 constexpr int kApThreads = 1024;
 constexpr int kApRows = 8;               // rows per thread and chunk in the backward pass
 
@@ -240,15 +273,29 @@ __device__ __forceinline__ double block_suffix_max_excl(double v, double* s_warp
 // whole rank-ordered array twice: forward for the totals (rows of the class n_p, true positives), backward for the
 // precision envelope from the right (accuracy.py:277-278) and the sum of recall steps times it (:282-285).  In the
 // backward pass the running counts follow from the totals, so nothing is stored per row.
+// SEG: the array is partitioned by class (ap_gather_bins_kernel + one radix pass): the CTA walks only its own run, found
+// from the bin totals; rows are (u << 8 | tp) and all belong to the class.
+template <bool SEG>
 __global__ void __launch_bounds__(kApThreads) ap_class_kernel(const int32_t* __restrict__ packed, int n,
                                                               const int* __restrict__ classes, const int* __restrict__ n_gt,
+                                                              const uint32_t* __restrict__ bin_hist,
                                                               double* __restrict__ out_p, double* __restrict__ out_r,
                                                               double* __restrict__ out_ap, double* __restrict__ out_f1) {
     __shared__ unsigned long long s_w[33];
     __shared__ double s_d[32];
     __shared__ double s_red[32];
     const int u = blockIdx.x, tid = threadIdx.x;
-    const int c = classes[u];
+    int c = classes[u];
+    if (SEG) {
+        int u0 = u;                                       // a repeated class shares the run of its first occurrence
+        for (int j = u - 1; j >= 0; --j)
+            if (classes[j] == c) u0 = j;
+        int start = 0;
+        for (int j = 0; j < u0; ++j) start += (int)bin_hist[j];
+        packed += start;
+        n = (int)bin_hist[u0];
+        c = u0 << 7;                                      // (row >> 1) of (u0 << 8 | tp)
+    }
     const double denom = (double)n_gt[u] + 1e-16;                                  // accuracy.py:247
     // forward: totals
     unsigned long long tot = 0ull;
@@ -350,12 +397,24 @@ int ap_per_class_launch(const float* tp, const float* conf, const float* pred_cl
     B2_LAUNCH_CHECK("ap_prepare_kernel");
     rc = score_sort_launch(w.tile_count, w.count, w.digit_hist, w.ticket, w.status, w.key, w.pay, w.n_pad, w.n_tiles, 1, st);
     if (rc) return rc;
+    if (n > 0 && num_classes > 0 && num_classes <= 255 && score_sort_is_lookback(w.n_pad)) {
+        // large inputs: partition the confidence-ordered rows by class so that a class CTA walks ~n / classes rows, not n
+        uint32_t* bin_hist = w.digit_hist + (size_t)kScorePasses * 256;            // zeroed above, unused by the score passes
+        ap_gather_bins_kernel<<<ceil_div(n, 256), 256, 0, st>>>(w.pay[0], tp, pred_cls, n, classes, num_classes, w.pay[1], bin_hist);
+        B2_LAUNCH_CHECK("ap_gather_bins_kernel");
+        rc = partition_pass_launch(w.count, w.digit_hist, w.ticket, w.status, w.pay[1], (uint32_t*)w.packed, w.n_pad, w.n_tiles,
+                                   kScorePasses, 8, st);
+        if (rc) return rc;
+        ap_class_kernel<true><<<num_classes, kApThreads, 0, st>>>(w.packed, n, classes, n_gt, bin_hist, out_p, out_r, out_ap, out_f1);
+        B2_LAUNCH_CHECK("ap_class_kernel<seg>");
+        return 0;
+    }
     if (n > 0) {
         ap_gather_kernel<<<ceil_div(n, 256), 256, 0, st>>>(w.pay[0], tp, pred_cls, n, w.packed);
         B2_LAUNCH_CHECK("ap_gather_kernel");
     }
     if (num_classes > 0) {
-        ap_class_kernel<<<num_classes, kApThreads, 0, st>>>(w.packed, n, classes, n_gt, out_p, out_r, out_ap, out_f1);
+        ap_class_kernel<false><<<num_classes, kApThreads, 0, st>>>(w.packed, n, classes, n_gt, nullptr, out_p, out_r, out_ap, out_f1);
         B2_LAUNCH_CHECK("ap_class_kernel");
     }
     return 0;

@@ -253,6 +253,26 @@ int score_sort_launch(const uint32_t* tile_count, const uint32_t* count, uint32_
     return 0;
 }
 
+// True when score_sort_launch takes the multi-launch route for this size (its histogram kernel then leaves zeroed look-back
+// words and tickets for all kMaxPasses passes, which partition_pass_launch below relies on).
+bool score_sort_is_lookback(int n_pad) { return !use_cluster_sort(n_pad); }
+
+// One more stable 8-bit pass over the payloads of a SINGLE sequence sorted by score_sort_launch (look-back route): a stable
+// partition into <= 256 bins by (pay >> shift) & 255.  `digit_hist[pass]` must hold the bin totals (the caller counts them).
+int partition_pass_launch(const uint32_t* count, uint32_t* digit_hist, uint32_t* ticket, uint32_t* status,
+                          const uint32_t* pay_in, uint32_t* pay_out, int n_pad, int n_tiles, int pass, int shift,
+                          cudaStream_t st) {
+    SortParams p;
+    memset(&p, 0, sizeof(p));
+    p.count = count; p.digit_hist = digit_hist; p.ticket = ticket; p.status = status;
+    p.sort_tiles = ceil_div(n_pad, kSortTile); p.B = 1; p.n_pad = n_pad; p.n_tiles = n_tiles;
+    p.pay_in = pay_in; p.pay_out = pay_out; p.pass = pass; p.shift = shift;
+    dim3 grid(ceil_div(n_pad, kSortTile), 1);
+    sort_pass_kernel<false, 1, 0, false><<<grid, kSortThreads, 0, st>>>(p);
+    B2_LAUNCH_CHECK("sort_pass_kernel(partition)");
+    return 0;
+}
+
 int yolo_stage_sort(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cudaStream_t st) {
     int rc = yolo_validate(d, ws, ws_bytes);
     if (rc) return rc;

@@ -83,8 +83,10 @@ def test_batch_statistics_raw_on_padded_nms_output():
         assert np.array_equal(tp[b, :k].double().cpu().numpy(), want[b][0])
 
 
+# > 53 248 detections and <= 255 evaluated classes take the class-partitioned route (254 + the absent class = 255 is its
+# widest case), 300 classes the streaming one on the same sort; the last has more detections than a headline batch keeps
 @pytest.mark.parametrize("n,C,seed", [(1, 1, 1), (300, 3, 2), (5000, 20, 3), (70000, 80, 4), (1500, 300, 5),
-                                      (1300000, 80, 6)])      # the last: more detections than one headline batch keeps
+                                      (60000, 254, 7), (60000, 300, 8), (1300000, 80, 6)])
 def test_ap_per_class_against_oracle(n, C, seed):
     g = torch.Generator().manual_seed(seed)
     conf = ((torch.randperm(n, generator=g).double() + 0.5) / n).float()     # distinct values: numpy's argsort is unstable on ties
@@ -98,6 +100,23 @@ def test_ap_per_class_against_oracle(n, C, seed):
     for a, b in zip(got[:4], want[:4]):
         np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-300)
     assert (got[2] >= 0).all()        # (random tp flags may exceed the label count, so recall / AP can pass 1 here)
+
+
+def test_ap_per_class_device_repeated_class():
+    """A class listed twice (not what np.unique produces, but legal at the C ABI) gets the same numbers twice."""
+    n = 80000
+    g = torch.Generator().manual_seed(11)
+    conf = ((torch.randperm(n, generator=g).double() + 0.5) / n).float().to(DEV)
+    cls = torch.randint(0, 6, (n,), generator=g).float().to(DEV)
+    tp = (torch.rand(n, generator=g) < 0.4).float().to(DEV)
+    classes = torch.tensor([0, 3, 5, 3, 9], dtype=torch.int32, device=DEV)
+    n_gt = torch.tensor([50, 70, 20, 70, 4], dtype=torch.int32, device=DEV)
+    p, r, ap, f1 = (x.cpu() for x in od.ap_per_class_device(tp, conf, cls, classes, n_gt))
+    assert p[1] == p[3] and r[1] == r[3] and ap[1] == ap[3] and f1[1] == f1[3] and ap[1] > 0
+    assert p[4] == 0 and ap[4] == 0                                        # class 9 has no detections
+    uniq = torch.tensor([0, 3, 5], dtype=torch.int32, device=DEV)
+    p2, r2, ap2, f12 = (x.cpu() for x in od.ap_per_class_device(tp, conf, cls, uniq, n_gt[:3].contiguous()))
+    assert torch.equal(p[:3], p2) and torch.equal(ap[:3], ap2) and torch.equal(r[:3], r2)
 
 
 def test_ap_per_class_perfect_and_empty():
