@@ -10,7 +10,7 @@ from objectdetectionpl_b200 import synth
 DEV = torch.device("cuda:0")
 
 
-def timed(fn, iters=20, warm=3):
+def timed(fn, iters=int(os.environ.get("B200DET_CFG_ITERS", "20")), warm=3):
     for _ in range(warm):
         fn()
     ts = []
