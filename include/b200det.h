@@ -252,6 +252,13 @@ int b200det_v5_loss_bwd(const float* pi, int32_t batch, int32_t na, int32_t ny, 
                         const float* tbox, const float* anch, int32_t m, float cp, float cn, float gamma, float alpha,
                         int32_t with_cls, const float* tobj, const float* g3, float inv_nbox, float inv_cells,
                         float inv_ncls, float* gpi, void* stream);
+/* The tail of the same forward (losses.py:139-152): means[nl][3] (fp64, what b200det_v5_loss_fwd left per level) are added
+ * in level order in fp32, scaled by the three gains and summed: out4 = (loss, Localization, Classification, Conf_obj).
+ * _bwd: g3[3] for b200det_v5_loss_bwd (the same for every level) from the upstream gradients of those four outputs
+ * (device scalars, NULL = no gradient). */
+int b200det_v5_loss_combine(const double* means, int32_t nl, float wbox, float wobj, float wcls, float* out4, void* stream);
+int b200det_v5_loss_combine_bwd(const float* g_loss, const float* g_box, const float* g_cls, const float* g_obj, float wbox,
+                                float wobj, float wcls, float* g3, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * M1 — true-positive matching of detections against labels.  Replaces `get_batch_statistics(outputs,

@@ -48,6 +48,8 @@ int v5_loss_fwd_launch(const float*, int, int, int, int, int, const int32_t*, co
 int v5_loss_bwd_launch(const float*, int, int, int, int, int, const int32_t*, const int32_t*, const int32_t*, const int32_t*,
                        const int32_t*, const float*, const float*, int, float, float, float, float, int, const float*,
                        const float*, float, float, float, float*, cudaStream_t);
+int v5_loss_combine_launch(const double*, int, float, float, float, float*, cudaStream_t);
+int v5_loss_combine_bwd_launch(const float*, const float*, const float*, const float*, float, float, float, float*, cudaStream_t);
 size_t build_targets_ws_bytes(int, int, int, int);
 int build_targets_launch(const float*, const float*, const float*, const float*, int, int, int, int, int, float, void*,
                          float*, float*, uint8_t*, uint8_t*, float*, float*, float*, float*, float*, int32_t*, cudaStream_t);
@@ -257,6 +259,16 @@ int b200det_v5_loss_bwd(const float* pi, int32_t B, int32_t na, int32_t ny, int3
     B2_CHECK_ARG(((uintptr_t)tbox & 15) == 0, "tbox must be 16-byte aligned");
     return v5_loss_bwd_launch(pi, B, na, ny, nx, F, b, a, gj, gi, tcls, tbox, anch, m, cp, cn, gamma, alpha, with_cls, tobj,
                               g3, inv_nbox, inv_cells, inv_ncls, gpi, (cudaStream_t)st);
+}
+
+int b200det_v5_loss_combine(const double* means, int32_t nl, float wbox, float wobj, float wcls, float* out4, void* st) {
+    B2_CHECK_ARG(means && out4 && nl > 0, "null argument / bad level count");
+    return v5_loss_combine_launch(means, nl, wbox, wobj, wcls, out4, (cudaStream_t)st);
+}
+int b200det_v5_loss_combine_bwd(const float* g_loss, const float* g_box, const float* g_cls, const float* g_obj, float wbox,
+                                float wobj, float wcls, float* g3, void* st) {
+    B2_CHECK_ARG(g3 != nullptr, "null argument");
+    return v5_loss_combine_bwd_launch(g_loss, g_box, g_cls, g_obj, wbox, wobj, wcls, g3, (cudaStream_t)st);
 }
 
 size_t b200det_build_targets_workspace_bytes(int32_t B, int32_t A, int32_t G, int32_t nt) {

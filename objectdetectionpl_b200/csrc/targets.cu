@@ -726,6 +726,43 @@ int v5_loss_fwd_launch(const float* pi, int B, int na, int ny, int nx, int F, co
     return 0;
 }
 
+// losses.py:139-152 on the device: the per-level means (fp64 -> fp32) are added in level order to fp32 zeros, scaled by the
+// three gains, summed: out = (loss, Localization, Classification, Conf_obj).  Levels without matched rows contribute 0.
+__global__ void v5_loss_combine_kernel(const double* __restrict__ means, int nl, float wbox, float wobj, float wcls,
+                                       float* __restrict__ out) {
+    if (threadIdx.x != 0) return;
+    float lbox = 0.f, lobj = 0.f, lcls = 0.f;
+    for (int i = 0; i < nl; ++i) {
+        lbox = __fadd_rn(lbox, (float)means[i * 3 + 0]);
+        lobj = __fadd_rn(lobj, (float)means[i * 3 + 1]);
+        lcls = __fadd_rn(lcls, (float)means[i * 3 + 2]);
+    }
+    lbox = __fmul_rn(lbox, wbox); lobj = __fmul_rn(lobj, wobj); lcls = __fmul_rn(lcls, wcls);
+    out[0] = __fadd_rn(__fadd_rn(lbox, lobj), lcls);
+    out[1] = lbox; out[2] = lcls; out[3] = lobj;
+}
+// backward of the combination: g3 = (d/d mean_box, d/d mean_obj, d/d mean_cls), the same for every level
+__global__ void v5_loss_combine_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict__ g_box,
+                                           const float* __restrict__ g_cls, const float* __restrict__ g_obj, float wbox,
+                                           float wobj, float wcls, float* __restrict__ g3) {
+    if (threadIdx.x != 0) return;
+    const float gl = g_loss ? g_loss[0] : 0.f;
+    g3[0] = __fmul_rn(__fadd_rn(gl, g_box ? g_box[0] : 0.f), wbox);
+    g3[1] = __fmul_rn(__fadd_rn(gl, g_obj ? g_obj[0] : 0.f), wobj);
+    g3[2] = __fmul_rn(__fadd_rn(gl, g_cls ? g_cls[0] : 0.f), wcls);
+}
+int v5_loss_combine_launch(const double* means, int nl, float wbox, float wobj, float wcls, float* out, cudaStream_t st) {
+    v5_loss_combine_kernel<<<1, 32, 0, st>>>(means, nl, wbox, wobj, wcls, out);
+    B2_LAUNCH_CHECK("v5_loss_combine_kernel");
+    return 0;
+}
+int v5_loss_combine_bwd_launch(const float* g_loss, const float* g_box, const float* g_cls, const float* g_obj, float wbox,
+                               float wobj, float wcls, float* g3, cudaStream_t st) {
+    v5_loss_combine_bwd_kernel<<<1, 32, 0, st>>>(g_loss, g_box, g_cls, g_obj, wbox, wobj, wcls, g3);
+    B2_LAUNCH_CHECK("v5_loss_combine_bwd_kernel");
+    return 0;
+}
+
 // gpi must be zero-filled by the caller; g3 (device) = upstream gradients of the three means, inv_* = 1 / their counts
 int v5_loss_bwd_launch(const float* pi, int B, int na, int ny, int nx, int F, const int32_t* b, const int32_t* a,
                        const int32_t* gj, const int32_t* gi, const int32_t* tcls, const float* tbox, const float* anch, int m,

@@ -193,26 +193,85 @@ def v5_loss_level(pi, tbox, indices, anch, tcls, cp=1.0, cn=0.0, gamma=1.5, alph
     return _V5LossLevel.apply(pi, tbox, idx, anch, float(cp), float(cn), float(gamma), float(alpha), bool(with_cls))
 
 
+_V5_GAINS = (0.05, 1.0, 0.58)          # box, obj, cls  (losses.py:139-141)
+
+
+class _V5LossAll(torch.autograd.Function):
+    """All levels and the combination of `MultiScaleRegionLoss_v5.forward` as ONE autograd node: the per-level Python and
+    the ~15 tiny autograd nodes of the level-by-level form were two thirds of its wall time."""
+
+    @staticmethod
+    def forward(ctx, levels, cfg, *pis):
+        lib = L.load()
+        cp, cn, gamma, alpha, with_cls = cfg
+        nl = len(pis)
+        pids = []
+        for pi in pis:
+            pid = L.require_cuda(pi.detach(), "pi")
+            if not pid.is_contiguous():
+                raise ValueError("pi must be contiguous [B,na,ny,nx,5+C]")
+            pids.append(pid)
+        dev = pids[0].device
+        cells = [pid.numel() // pid.shape[-1] for pid in pids]
+        ms = [int(ib.shape[1]) for ib, _, _ in levels]
+        tobj = torch.empty((sum(cells),), dtype=torch.float32, device=dev)            # all levels, back to back
+        giou = torch.empty((max(sum(ms), 1),), dtype=torch.float32, device=dev)
+        means = torch.empty((nl, 3), dtype=torch.float64, device=dev)
+        out = torch.empty((4,), dtype=torch.float32, device=dev)
+        st = L.stream_ptr(dev)
+        with torch.cuda.device(dev):
+            t_off = g_off = 0
+            for i, (pid, (ib, tb, ac)) in enumerate(zip(pids, levels)):
+                B, na, ny, nx, F = pid.shape
+                L.check(lib.b200det_v5_loss_fwd(pid.data_ptr(), B, na, ny, nx, F, ib[0].data_ptr(), ib[1].data_ptr(),
+                                                ib[2].data_ptr(), ib[3].data_ptr(), ib[4].data_ptr(), tb.data_ptr(), ac.data_ptr(),
+                                                ms[i], cp, cn, gamma, alpha, int(with_cls), giou.data_ptr() + 4 * g_off,
+                                                tobj.data_ptr() + 4 * t_off, means.data_ptr() + 24 * i, st), "v5_loss_fwd")
+                t_off += cells[i]
+                g_off += ms[i]
+            L.check(lib.b200det_v5_loss_combine(means.data_ptr(), nl, *_V5_GAINS, out.data_ptr(), st), "v5_loss_combine")
+        ctx.save_for_backward(tobj, *pids)
+        ctx.levels, ctx.cfg, ctx.cells, ctx.ms = levels, cfg, cells, ms
+        return out[0:1], out[1:2], out[2:3], out[3:4]
+
+    @staticmethod
+    def backward(ctx, g_loss, g_box, g_cls, g_obj):
+        lib = L.load()
+        tobj, *pids = ctx.saved_tensors
+        cp, cn, gamma, alpha, with_cls = ctx.cfg
+        dev = tobj.device
+        gs = [None if g is None else g.contiguous().float() for g in (g_loss, g_box, g_cls, g_obj)]
+        g3 = torch.empty((3,), dtype=torch.float32, device=dev)
+        st = L.stream_ptr(dev)
+        grads = []
+        with torch.cuda.device(dev):
+            L.check(lib.b200det_v5_loss_combine_bwd(*(None if g is None else g.data_ptr() for g in gs), *_V5_GAINS, g3.data_ptr(),
+                                                    st), "v5_loss_combine_bwd")
+            t_off = 0
+            for i, (pid, (ib, tb, ac)) in enumerate(zip(pids, ctx.levels)):
+                B, na, ny, nx, F = pid.shape
+                m, cells = ctx.ms[i], ctx.cells[i]
+                gpi = torch.zeros_like(pid)
+                L.check(lib.b200det_v5_loss_bwd(pid.data_ptr(), B, na, ny, nx, F, ib[0].data_ptr(), ib[1].data_ptr(),
+                                                ib[2].data_ptr(), ib[3].data_ptr(), ib[4].data_ptr(), tb.data_ptr(), ac.data_ptr(),
+                                                m, cp, cn, gamma, alpha, int(with_cls), tobj.data_ptr() + 4 * t_off, g3.data_ptr(),
+                                                1.0 / max(m, 1), 1.0 / cells, 1.0 / max(m * (F - 5), 1), gpi.data_ptr(), st),
+                        "v5_loss_bwd")
+                grads.append(gpi)
+                t_off += cells
+        return (None, None, *grads)
+
+
 def v5_loss(output, target, anchors, nl, na, nc, cp=1.0, cn=0.0, gamma=1.5, alpha=0.25):
-    """`MultiScaleRegionLoss_v5.forward` (losses.py:98-152, reduction 'mean', label smoothing 0, focal gamma 1.5) on top of
-    `build_targets_v5` + `v5_loss_level`.  `anchors` are the criterion's scaled anchors `[nl, na, 2]` (:95-96).
+    """`MultiScaleRegionLoss_v5.forward` (losses.py:98-152, reduction 'mean', label smoothing 0, focal gamma 1.5):
+    `build_targets_v5` (one launch, one host sync), the fused per-level loss kernels and the gain-weighted combination, as
+    one autograd node.  `anchors` are the criterion's scaled anchors `[nl, na, 2]` (:95-96).
     Returns the reference's metrics dict of shape-[1] tensors: loss, Localization, Classification, Conf_obj."""
-    dev = output[0].device
-    lcls = torch.zeros(1, device=dev); lbox = torch.zeros(1, device=dev); lobj = torch.zeros(1, device=dev)
     levels = _build_targets_v5_raw(output, target, anchors, nl, na)         # int32 index rows go straight to the kernels
-    for i, pi in enumerate(output):
-        ib, tb, ac = levels[i]
-        nb = ib.shape[1]
-        t_box, t_obj, t_cls, _ = _V5LossLevel.apply(pi, tb, ib, ac, float(cp), float(cn), float(gamma), float(alpha), nc > 1)
-        if nb:
-            lbox = lbox + t_box                                           # :119
-            if nc > 1:
-                lcls = lcls + t_cls                                       # :131
-        lobj = lobj + t_obj                                               # :137
-    lbox = lbox * 0.05
-    lobj = lobj * 1.0
-    lcls = lcls * 0.58
-    return {"loss": lbox + lobj + lcls, "Localization": lbox, "Classification": lcls, "Conf_obj": lobj}
+    levels = [(ib, tb.contiguous(), ac.contiguous()) for ib, tb, ac in levels]
+    cfg = (float(cp), float(cn), float(gamma), float(alpha), nc > 1)
+    loss, lbox, lcls, lobj = _V5LossAll.apply(levels, cfg, *output)
+    return {"loss": loss, "Localization": lbox, "Classification": lcls, "Conf_obj": lobj}
 
 
 def ssd_match(default_boxes, annotations_boxes, match_thresh=0.5):

@@ -224,3 +224,33 @@ def test_v5_loss_without_targets():
     got = od.v5_loss([t.to(DEV) for t in p_cpu], tg.to(DEV), anchors.to(DEV), 2, 3, 4)
     for k in want:
         torch.testing.assert_close(got[k].cpu(), want[k], rtol=1e-5, atol=1e-7)
+
+
+def test_v5_loss_level_by_level_equals_fused_node():
+    """`v5_loss_level` (one autograd node per level, reference-typed int64 indices) and `v5_loss` (one node for all levels)
+    run the same kernels: same terms, and gradients through a mix of the four outputs agree."""
+    B, C = 4, 12
+    g = torch.Generator().manual_seed(31)
+    p_cpu = [torch.randn(B, 3, 160 // s, 160 // s, 5 + C, generator=g) for s in (8, 16, 32)]
+    tg = synth.labels(B, C, 5, max_per_image=12).to(DEV)
+    stride = torch.tensor([8., 16., 32.])
+    anchors = (torch.tensor(synth.YOLOV5_ANCHORS).float().view(3, -1, 2) / stride.view(-1, 1, 1)).to(DEV)
+    pa = [t.to(DEV).requires_grad_(True) for t in p_cpu]
+    pb = [t.to(DEV).requires_grad_(True) for t in p_cpu]
+    fused = od.v5_loss(pa, tg, anchors, 3, 3, C)
+    (fused["loss"] * 2.0 + fused["Localization"] * 3.0 - fused["Conf_obj"] + fused["Classification"] * 0.5).sum().backward()
+    tcls, tbox, indices, anch = od.build_targets_v5(pb, tg, anchors, 3, 3)
+    lbox = torch.zeros(1, device=DEV); lobj = torch.zeros(1, device=DEV); lcls = torch.zeros(1, device=DEV)
+    for i in range(3):
+        t_box, t_obj, t_cls, _ = od.v5_loss_level(pb[i], tbox[i], indices[i], anch[i], tcls[i])
+        if indices[i][0].shape[0]:
+            lbox = lbox + t_box
+            lcls = lcls + t_cls
+        lobj = lobj + t_obj
+    lbox, lobj, lcls = lbox * 0.05, lobj * 1.0, lcls * 0.58
+    loss = lbox + lobj + lcls
+    (loss * 2.0 + lbox * 3.0 - lobj + lcls * 0.5).sum().backward()
+    assert torch.equal(fused["loss"], loss) and torch.equal(fused["Localization"], lbox)
+    assert torch.equal(fused["Classification"], lcls) and torch.equal(fused["Conf_obj"], lobj)
+    for a, b in zip(pa, pb):
+        torch.testing.assert_close(a.grad, b.grad, rtol=1e-6, atol=1e-12)
