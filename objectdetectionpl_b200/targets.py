@@ -10,6 +10,7 @@
 from __future__ import annotations
 
 import ctypes
+import weakref
 
 import torch
 
@@ -43,6 +44,26 @@ def build_targets(pred_boxes, pred_cls, target, anchors, ignore_thres):
     return iou_scores, class_mask, obj, noobj, tx, ty, tw, th, tcls, obj.float()
 
 
+_ANCHOR_CACHE = {}          # id(tensor) -> (weakref to the tensor, its version, host array)
+
+
+def _host_anchors(anchors, nl, na):
+    """The criterion's scaled anchors as a host float array for the launch parameters.  They are constants of the model:
+    a device tensor is copied to the host once per tensor object and version (the copy is a host sync), not every step."""
+    if isinstance(anchors, torch.Tensor) and anchors.is_cuda:
+        hit = _ANCHOR_CACHE.get(id(anchors))
+        if hit is not None and hit[0]() is anchors and hit[1] == anchors._version:
+            return hit[2]
+        if len(_ANCHOR_CACHE) > 64:
+            _ANCHOR_CACHE.clear()
+        vals = anchors.detach().float().cpu().reshape(nl, na, 2).reshape(-1).tolist()
+        arr = (ctypes.c_float * (2 * na * nl))(*vals)
+        _ANCHOR_CACHE[id(anchors)] = (weakref.ref(anchors), anchors._version, arr)
+        return arr
+    vals = torch.as_tensor(anchors).detach().float().reshape(nl, na, 2).reshape(-1).tolist()
+    return (ctypes.c_float * (2 * na * nl))(*vals)
+
+
 def _build_targets_v5_raw(p, targets, anchors, nl, na):
     """One launch for all levels, one host sync for the row counts.  Per level: `(ib int32 [5, m] = b, a, gj, gi, cls
     (rows of a wider buffer), tbox [m, 4], anch [m, 2])`."""
@@ -50,8 +71,7 @@ def _build_targets_v5_raw(p, targets, anchors, nl, na):
     tg = L.require_cuda(targets, "targets").contiguous()
     dev = tg.device
     nt = tg.shape[0]
-    anchors_cpu = torch.as_tensor(anchors).detach().float().cpu().reshape(nl, na, 2)
-    anchors_dev = torch.as_tensor(anchors, dtype=torch.float32, device=dev).reshape(nl, na, 2)
+    arr = _host_anchors(anchors, nl, na)
     cap = max(5 * na * nt, 1)
     counts = torch.empty((nl,), dtype=torch.int32, device=dev)
     bufs = []
@@ -67,12 +87,10 @@ def _build_targets_v5_raw(p, targets, anchors, nl, na):
             ptrs[k][i] = ib[k].data_ptr()
         ptrs[5][i], ptrs[6][i] = tb.data_ptr(), ac.data_ptr()
         bufs.append((ib, tb, ac))
-    arr = (ctypes.c_float * (2 * na * nl))(*anchors_cpu.reshape(-1).tolist())
     with torch.cuda.device(dev):
         L.check(lib.b200det_build_targets_v5(tg.data_ptr() if nt else None, nt, nl, arr, na, nxs, nys, *ptrs, counts.data_ptr(),
                                              L.stream_ptr(dev)), "build_targets_v5")     # one launch, one CTA per level
     ms = counts.cpu().tolist()                                            # one host sync for all levels
-    del anchors_dev
     return [(ib[:, :m], tb[:m], ac[:m]) for (ib, tb, ac), m in zip(bufs, ms)]
 
 

@@ -254,3 +254,25 @@ def test_v5_loss_level_by_level_equals_fused_node():
     assert torch.equal(fused["Classification"], lcls) and torch.equal(fused["Conf_obj"], lobj)
     for a, b in zip(pa, pb):
         torch.testing.assert_close(a.grad, b.grad, rtol=1e-6, atol=1e-12)
+
+
+def test_build_targets_v5_device_anchors_cache_sees_updates():
+    """Device-resident anchors are copied to the host once per tensor and version: an in-place change must be seen, and a
+    different tensor that happens to reuse the storage must not hit the old entry."""
+    tg = synth.labels(2, 5, 3, max_per_image=10).to(DEV)
+    shapes = [(2, 3, 20, 20, 10)]
+    a1 = torch.tensor([[[1.25, 1.6], [2.0, 3.75], [4.1, 2.9]]], device=DEV)
+    want1 = od.build_targets_v5(shapes, tg, a1.cpu(), 1, 3)
+    got1 = od.build_targets_v5(shapes, tg, a1, 1, 3)
+    got1b = od.build_targets_v5(shapes, tg, a1, 1, 3)               # cached
+    a1.mul_(3.0)                                                      # same object, new version
+    want2 = od.build_targets_v5(shapes, tg, a1.cpu(), 1, 3)
+    got2 = od.build_targets_v5(shapes, tg, a1, 1, 3)
+    del a1
+    a3 = torch.tensor([[[9.0, 9.0], [0.5, 0.5], [2.0, 2.0]]], device=DEV)   # may reuse a1's storage
+    want3 = od.build_targets_v5(shapes, tg, a3.cpu(), 1, 3)
+    got3 = od.build_targets_v5(shapes, tg, a3, 1, 3)
+    for got, want in ((got1, want1), (got1b, want1), (got2, want2), (got3, want3)):
+        assert torch.equal(got[0][0], want[0][0]) and torch.equal(got[1][0], want[1][0]) and torch.equal(got[3][0], want[3][0])
+        assert all(torch.equal(x, y) for x, y in zip(got[2][0], want[2][0]))
+    assert got1[0][0].shape != got2[0][0].shape or not torch.equal(got1[3][0], got2[3][0])

@@ -66,10 +66,12 @@ def main():
                     rows=[int(t.shape[0]) for t in tcls]))
     out.append(dict(cfg="4: v5 matched-row GIoU fwd+bwd (3 levels, through autograd)", us=us_m))
 
+    anchors_dev = anchors.to(DEV)                  # the criterion keeps its scaled anchors on the device (losses.py:95-96)
+
     def loss_fwd_bwd():
         for t in p:
             t.grad = None
-        od.v5_loss(p, tg, anchors.to(DEV), 3, 3, C)["loss"].backward()
+        od.v5_loss(p, tg, anchors_dev, 3, 3, C)["loss"].backward()
     us_l = timed(loss_fwd_bwd)
     out.append(dict(cfg="4: fused v5 loss (build_targets_v5 + box/obj/cls terms) fwd+bwd, 3 levels, B=64 C=80", us=us_l,
                     head_MB=sum(t.numel() for t in p) * 4 / 1e6))
