@@ -101,3 +101,28 @@ def test_fused_decode_nms_matches_decode_then_nms():
     for b in range(B):
         assert torch.equal(gidx[b].cpu(), widx[b])
         torch.testing.assert_close(got[b].cpu(), want[b], rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("G,C,off_out,off_head", [(20, 80, 1, 0), (20, 7, 2, 1), (13, 4, 3, 0), (6, 123, 1, 3), (7, 130, 1, 1)])
+def test_decode_box_c_abi_unaligned_pointers_and_canaries(G, C, off_out, off_head):
+    """The C entry takes any 4-byte aligned pointers: the tile kernel drops to 32-bit loads and matches its shared-memory
+    tile to the destination's 16-byte phase.  Same values as the aligned call, nothing written outside [out, out + n)."""
+    from objectdetectionpl_b200 import _lib as L
+    lib = L.load()
+    B, A, F = 2, 3, 5 + C
+    head = synth.raw_logits(B, A, C, G, 5).to(DEV)
+    anc = torch.tensor([[3.625, 2.8125], [4.875, 6.1875], [11.65625, 10.1875]], device=DEV)
+    want = od.decode_box(head, anc, 16.0, "yolo_exp", num_anchors=A)
+    n = want.numel()
+    pad = 64
+    buf = torch.full((n + 2 * pad,), 12345.0, device=DEV)
+    hbuf = torch.zeros(head.numel() + 8, device=DEV)
+    hbuf[off_head:off_head + head.numel()] = head.reshape(-1)
+    out_ptr = buf.data_ptr() + 4 * (pad + off_out)
+    rc = lib.b200det_decode_box(hbuf.data_ptr() + 4 * off_head, B, A, C, G, L.DECODE_YOLO_EXP, anc.data_ptr(), 16.0, out_ptr,
+                                L.stream_ptr(head.device))
+    assert rc == 0, lib.b200det_last_error()
+    torch.cuda.synchronize()
+    got = buf[pad + off_out: pad + off_out + n]
+    assert torch.equal(got, want.reshape(-1))
+    assert bool((buf[:pad + off_out] == 12345.0).all()) and bool((buf[pad + off_out + n:] == 12345.0).all())
