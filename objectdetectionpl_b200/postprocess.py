@@ -135,24 +135,43 @@ class _HostPipe:
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
         self.dev_in = [[torch.empty((chunk,) + tuple(sh[1:]), dtype=torch.float32, device=dev) for sh in shapes]
                        for _ in range(2)]
+        self.buf_free = [None, None]      # event: the pipeline has consumed what dev_in[i] last held
+        self.chunk_seq = 0                # chunks submitted so far (across calls): dev_in alternates on it
+        self.calls = 0                    # calls submitted so far: the two pinned result sets alternate on it
         B = shapes[0][0]
-        self.host_rows = torch.empty((B, n_pad, 7), dtype=torch.float32).pin_memory()
-        self.host_index = torch.empty((B, n_pad), dtype=torch.int32).pin_memory()
-        self.host_count = torch.empty((B,), dtype=torch.int32).pin_memory()
+        self.host = [(torch.empty((B, n_pad, 7), dtype=torch.float32).pin_memory(),
+                      torch.empty((B, n_pad), dtype=torch.int32).pin_memory(),
+                      torch.empty((B,), dtype=torch.int32).pin_memory()) for _ in range(2)]
 
 
 _host_pipes = {}
 
 
-def non_max_suppression_host(self, predictions, conf_thres=0.5, nms_thres=0.4, *, compat=True, num_anchors=3,
-                             device=None, chunk_images=8, decode=None, anchors=None, strides=None, return_index=False):
-    """`non_max_suppression` for predictions that live in HOST memory (pinned memory for full PCIe speed).
+class HostNmsHandle:
+    """A submitted `non_max_suppression_host_async` call; `result()` waits for its last device->host copy."""
 
-    Same arguments and the same rows as `non_max_suppression` (model/YOLOV5.py:157); the batch is cut into chunks of
-    `chunk_images` images and the three legs run on separate streams, so the host->device copy of chunk k+1 overlaps
-    the CUDA pipeline of chunk k and the device->host copy of chunk k-1 (every image is independent, SURVEY.md §8e).
-    Returns a list of `None` / fp32 `[K,7]` HOST tensors: views into a pinned buffer that is reused by the next call
-    with the same shapes (clone them to keep them)."""
+    def __init__(self, done, host, return_index, keep):
+        self._done, self._host, self._return_index, self._keep = done, host, return_index, keep
+        self._out = None
+
+    def result(self):
+        if self._out is None:
+            self._done.synchronize()
+            self._keep = None
+            rows, index, count = self._host
+            counts = count.tolist()
+            out: List[Optional[torch.Tensor]] = [rows[b, :k] if k else None for b, k in enumerate(counts)]
+            self._out = (out, [index[b, :k].long() if k else None for b, k in enumerate(counts)]) if self._return_index else out
+        return self._out
+
+
+def non_max_suppression_host_async(self, predictions, conf_thres=0.5, nms_thres=0.4, *, compat=True, num_anchors=3,
+                                   device=None, chunk_images=8, decode=None, anchors=None, strides=None, return_index=False):
+    """Submit `non_max_suppression_host` without waiting: returns a `HostNmsHandle` whose `result()` is that function's
+    return value.  Submitting batch i+1 before collecting batch i keeps the host->device link busy across batches (the
+    tail of a batch — the pipeline and the device->host copy of its last chunk — otherwise leaves it idle).  Two calls
+    may be in flight per (device, shapes) configuration: the rows of a call live in one of two pinned buffers and stay
+    valid until the second submission after it.  `predictions` must not be modified before `result()` returns."""
     if not isinstance(predictions, (list, tuple)):
         predictions = [predictions]
     for i, t in enumerate(predictions):
@@ -164,45 +183,63 @@ def non_max_suppression_host(self, predictions, conf_thres=0.5, nms_thres=0.4, *
     B = predictions[0].shape[0]
     chunk = max(1, min(int(chunk_images), B))
     thr = YOLO_FORCED_CONF_THRES if compat else conf_thres
-    n_pad = None
     shapes = tuple(tuple(t.shape) for t in predictions)
     key = (dev.index, shapes, chunk, num_anchors)
     pipe = _host_pipes.get(key)
+    if pipe is None:
+        # slots per image: every level padded to whole tiles (b200det_yolo_num_candidates)
+        n_pad = sum((num_anchors * t.shape[2] * t.shape[2] + L.TILE - 1) // L.TILE * L.TILE for t in predictions)
+        with torch.cuda.device(dev):
+            pipe = _host_pipes[key] = _HostPipe(dev, shapes, chunk, n_pad)
     nchunks = (B + chunk - 1) // chunk
-    ev_in = [torch.cuda.Event() for _ in range(nchunks)]
-    ev_done = [torch.cuda.Event() for _ in range(nchunks)]
+    host = pipe.host[pipe.calls & 1]
+    pipe.calls += 1
     keep = []
     with torch.cuda.device(dev):
         for c in range(nchunks):
             lo, hi = c * chunk, min(B, (c + 1) * chunk)
-            if pipe is None:
-                # slots per image: every level padded to whole tiles (b200det_yolo_num_candidates)
-                n_pad = sum((num_anchors * t.shape[2] * t.shape[2] + L.TILE - 1) // L.TILE * L.TILE for t in predictions)
-                pipe = _host_pipes[key] = _HostPipe(dev, shapes, chunk, n_pad)
-            dst = [t[:hi - lo] for t in pipe.dev_in[c & 1]]
+            slot = pipe.chunk_seq & 1
+            pipe.chunk_seq += 1
+            dst = [t[:hi - lo] for t in pipe.dev_in[slot]]
+            ev_in, ev_done = torch.cuda.Event(), torch.cuda.Event()
             with torch.cuda.stream(pipe.s_in):
-                if c >= 2:
-                    pipe.s_in.wait_event(ev_done[c - 2])            # the pipeline is done with this input buffer
+                if pipe.buf_free[slot] is not None:
+                    pipe.s_in.wait_event(pipe.buf_free[slot])        # the pipeline is done with this input buffer
                 for d_, t in zip(dst, predictions):
                     d_.copy_(t[lo:hi], non_blocking=True)
-                ev_in[c].record(pipe.s_in)
+                ev_in.record(pipe.s_in)
             with torch.cuda.stream(pipe.s_cmp):
-                pipe.s_cmp.wait_event(ev_in[c])
+                pipe.s_cmp.wait_event(ev_in)
                 rows, index, count = yolo_nms_raw(dst, num_anchors, thr, nms_thres, decode, anchors, strides, return_index)
-                ev_done[c].record(pipe.s_cmp)
+                ev_done.record(pipe.s_cmp)
+            pipe.buf_free[slot] = ev_done
             with torch.cuda.stream(pipe.s_out):
-                pipe.s_out.wait_event(ev_done[c])
-                pipe.host_rows[lo:hi].copy_(rows, non_blocking=True)
-                pipe.host_count[lo:hi].copy_(count, non_blocking=True)
+                pipe.s_out.wait_event(ev_done)
+                host[0][lo:hi].copy_(rows, non_blocking=True)
+                host[2][lo:hi].copy_(count, non_blocking=True)
                 if return_index:
-                    pipe.host_index[lo:hi].copy_(index, non_blocking=True)
+                    host[1][lo:hi].copy_(index, non_blocking=True)
+            for t in (rows, index, count):
+                if t is not None:
+                    t.record_stream(pipe.s_out)
             keep.append((rows, index, count))                        # alive until the copies have run
-        pipe.s_out.synchronize()
-    counts = pipe.host_count.tolist()
-    out: List[Optional[torch.Tensor]] = [pipe.host_rows[b, :k] if k else None for b, k in enumerate(counts)]
-    if return_index:
-        return out, [pipe.host_index[b, :k].long() if k else None for b, k in enumerate(counts)]
-    return out
+        done = torch.cuda.Event()
+        done.record(pipe.s_out)
+    return HostNmsHandle(done, host, return_index, keep)
+
+
+def non_max_suppression_host(self, predictions, conf_thres=0.5, nms_thres=0.4, *, compat=True, num_anchors=3,
+                             device=None, chunk_images=8, decode=None, anchors=None, strides=None, return_index=False):
+    """`non_max_suppression` for predictions that live in HOST memory (pinned memory for full PCIe speed).
+
+    Same arguments and the same rows as `non_max_suppression` (model/YOLOV5.py:157); the batch is cut into chunks of
+    `chunk_images` images and the three legs run on separate streams, so the host->device copy of chunk k+1 overlaps
+    the CUDA pipeline of chunk k and the device->host copy of chunk k-1 (every image is independent, SURVEY.md §8e).
+    Returns a list of `None` / fp32 `[K,7]` HOST tensors: views into one of two pinned buffers that alternate between
+    calls with the same shapes (clone them to keep them beyond the next call but one)."""
+    return non_max_suppression_host_async(self, predictions, conf_thres, nms_thres, compat=compat, num_anchors=num_anchors,
+                                          device=device, chunk_images=chunk_images, decode=decode, anchors=anchors,
+                                          strides=strides, return_index=return_index).result()
 
 
 def non_max_suppression_v2(self, predictions, conf_thres=0.5, nms_thres=0.4, *, compat=True, decode=None, anchors=None,

@@ -41,3 +41,26 @@ def test_host_pipeline_sparse_none_entries():
     assert got[1] is None and want[1] is None
     for b in (0, 2, 3):
         assert torch.equal(got[b], want[b].cpu())
+
+
+def test_host_pipeline_async_two_batches_in_flight():
+    """Batch i+1 submitted before batch i is collected: different inputs, same shapes (same cached buffers and streams);
+    the rows of a call stay valid until the second submission after it."""
+    batches = [[t.pin_memory() for t in synth.yolo_planar(B=6, A=3, C=20, grids=[20, 10, 5], img=160, seed=70 + i, v5_view=True)]
+               for i in range(5)]
+    wants = [od.non_max_suppression(None, [t.to(DEV) for t in lv], return_index=True) for lv in batches]
+    handles, results = [], []
+    for i, lv in enumerate(batches):
+        handles.append(od.non_max_suppression_host_async(None, lv, device=DEV, chunk_images=4, return_index=True))
+        if i >= 1:
+            got, gidx = handles[i - 1].result()
+            # compare right away: these rows live in a pinned buffer that the submission after next will overwrite
+            for b in range(6):
+                assert torch.equal(got[b], wants[i - 1][0][b].cpu()), f"batch {i - 1} image {b}"
+                assert torch.equal(gidx[b], wants[i - 1][1][b].cpu())
+            results.append(i - 1)
+    got, gidx = handles[-1].result()
+    assert handles[-1].result() is handles[-1].result()          # idempotent
+    for b in range(6):
+        assert torch.equal(got[b], wants[-1][0][b].cpu())
+    assert results == [0, 1, 2, 3]
