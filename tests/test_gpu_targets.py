@@ -72,8 +72,9 @@ def test_build_targets_v5_golden(name):
             assert torch.equal(idx[i][k].cpu(), T(d[f"{nm}_{i}"])), (i, nm)
 
 
-def test_build_targets_v5_full_batch_and_empty():
-    B, C, img = 64, 80, 640
+@pytest.mark.parametrize("B", [64, 160])        # 3 x nt = 9.4 k pairs (one compaction round) / ~24 k (two rounds, ragged tail)
+def test_build_targets_v5_full_batch_and_empty(B):
+    C, img = 80, 640
     tg = synth.labels(B, C, 4, max_per_image=100)
     stride = torch.tensor([8., 16., 32.])
     anchors = torch.tensor(synth.YOLOV5_ANCHORS).float().view(3, -1, 2) / stride.view(-1, 1, 1)
