@@ -106,7 +106,7 @@ def _yolo_nms(predictions, num_anchors, conf_thres, nms_thres, compat, decode, a
     thr = YOLO_FORCED_CONF_THRES if compat else conf_thres
     rows, index, count = yolo_nms_raw(predictions, num_anchors, thr, nms_thres, decode, anchors, strides, return_index, layout)
     counts = count.cpu().tolist()                        # the one host sync of the call
-    out: List[Optional[torch.Tensor]] = [rows[b, :k] if k else None for b, k in enumerate(counts)]   # YOLOV3.py:306,333
+    out: List[Optional[torch.Tensor]] = [r[:k] if k else None for r, k in zip(rows.unbind(0), counts)]   # YOLOV3.py:306,333
     if return_index:
         return out, [index[b, :k].long() if k else None for b, k in enumerate(counts)]
     return out
@@ -160,7 +160,7 @@ class HostNmsHandle:
             self._keep = None
             rows, index, count = self._host
             counts = count.tolist()
-            out: List[Optional[torch.Tensor]] = [rows[b, :k] if k else None for b, k in enumerate(counts)]
+            out: List[Optional[torch.Tensor]] = [r[:k] if k else None for r, k in zip(rows.unbind(0), counts)]
             self._out = (out, [index[b, :k].long() if k else None for b, k in enumerate(counts)]) if self._return_index else out
         return self._out
 
@@ -292,7 +292,7 @@ def prior_non_max_suppression(self, predictions, topk=100, nms_thresh=0.5, class
     if compat and bool((c[1] == 1).any()):
         raise IndexError("too many indices for tensor of dimension 1")   # model/SSD.py:262,266 (0-dim index)
     kept = c[0].tolist()
-    out = [rows[b, :k] for b, k in enumerate(kept)]
+    out = [r[:k] for r, k in zip(rows.unbind(0), kept)]
     if return_index:
         return out, [index[b, :k].long() for b, k in enumerate(kept)]
     return out
