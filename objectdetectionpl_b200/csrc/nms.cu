@@ -101,45 +101,43 @@ __device__ __forceinline__ bool removes(const float4 a, const float4 b, const fl
     return !(ratio <= thr);
 }
 
-// Conservative half2 summary of a corner box for the pair pre-filter (one 16-byte shared-memory word per row):
-//   lo = (x1, y1) rounded DOWN,  hi = (x2 + 1, y2 + 1) rounded UP,  t = thr' * (w + 1, h + 1) rounded DOWN,
-//   thr' = thr * (1 - 2^-7)  (covers the half-precision rounding of the subtraction below and of the product).
-// With d = hmin2(hi_a, hi_b) - hmax2(lo_a, lo_b) >= (iw, ih) of the exact arithmetic (monotone rounding), a pair can
-// only reach IoU_+1 > thr if  d > max(t_a, t_b)  in BOTH axes, because
-//   IoU <= inter / max(area_a, area_b) <= iw / max(w_a + 1, w_b + 1)   (and likewise for ih).
-// The test never rejects a pair the reference would remove (for thr >= 0: degenerate boxes with w + 1 <= 0 only ADD
-// candidates, which the exact test then rejects); it costs 5 half2 instructions + one 128-bit shared load instead of
-// ~30 fp32 instructions and passes ~1% of random pairs (a plain "do they overlap" test passes ~7%).
-__device__ __forceinline__ uint4 box_bounds_h2(const float4 b, const float thr) {
+// Conservative half2 summary of a corner box for the pair pre-filter (one 8-byte shared-memory word per row):
+//   lo = (x1, y1) rounded DOWN,  u = (x2 + 1, y2 + 1) - thr' * (w + 1, h + 1) rounded UP,  thr' = thr * (1 - 2^-7).
+// A pair can only reach IoU_+1 > thr if  min(u_a, u_b) > max(lo_a, lo_b)  in BOTH axes, because
+//   IoU <= inter / max(area_a, area_b) <= iw / max(w_a + 1, w_b + 1)   (and likewise for ih), i.e.
+//   iw = min(x2_a, x2_b) + 1 - max(x1_a, x1_b) > thr * (w_a + 1)  and  > thr * (w_b + 1), which gives
+//   (x2_a + 1) - thr (w_a + 1) > max(x1)  and the same for b.   (All roundings go the passing way; the 2^-7 covers the fp32
+//   rounding of the reference's own ratio.)  The test never rejects a pair the reference would remove (for thr >= 0:
+//   degenerate boxes with w + 1 <= 0 only ADD candidates, which the exact test then rejects).  It is weaker than testing
+//   min(hi) - max(lo) against max(t_a, t_b) — it lets a small box inside a large one through — but costs 3 half2
+//   instructions + the mask accumulate instead of 5, and one 64-bit shared load instead of 64 + 32: on the headline data
+//   it passes 2.3 % of the pairs instead of 0.9 % (2.8 instead of 1.8 exact tests per lane and 32 x 32 task).
+__device__ __forceinline__ uint2 box_bounds_h2(const float4 b, const float thr) {
     const __half2 lo = __halves2half2(__float2half_rd(b.x), __float2half_rd(b.y));
-    const __half2 hi = __halves2half2(__float2half_ru(__fadd_ru(b.z, 1.0f)), __float2half_ru(__fadd_ru(b.w, 1.0f)));
     const float thr_lo = __fmul_rd(thr, 1.0f - 0.0078125f);
-    const __half2 t = __halves2half2(__float2half_rd(__fmul_rd(thr_lo, __fadd_rd(__fsub_rd(b.z, b.x), 1.0f))),
-                                     __float2half_rd(__fmul_rd(thr_lo, __fadd_rd(__fsub_rd(b.w, b.y), 1.0f))));
-    uint4 r;
+    const float tx = __fmul_rd(thr_lo, __fadd_rd(__fsub_rd(b.z, b.x), 1.0f));
+    const float ty = __fmul_rd(thr_lo, __fadd_rd(__fsub_rd(b.w, b.y), 1.0f));
+    const __half2 u = __halves2half2(__float2half_ru(__fsub_ru(__fadd_ru(b.z, 1.0f), tx)),
+                                     __float2half_ru(__fsub_ru(__fadd_ru(b.w, 1.0f), ty)));
+    uint2 r;
     r.x = *reinterpret_cast<const unsigned*>(&lo);
-    r.y = *reinterpret_cast<const unsigned*>(&hi);
-    r.z = *reinterpret_cast<const unsigned*>(&t);
-    r.w = 0u;
+    r.y = *reinterpret_cast<const unsigned*>(&u);
     return r;
 }
-__device__ __forceinline__ bool may_remove(const uint4 qa, const uint4 qb) {
+__device__ __forceinline__ bool may_remove(const uint2 qa, const uint2 qb) {
     const __half2 lo = __hmax2(*reinterpret_cast<const __half2*>(&qa.x), *reinterpret_cast<const __half2*>(&qb.x));
-    const __half2 hi = __hmin2(*reinterpret_cast<const __half2*>(&qa.y), *reinterpret_cast<const __half2*>(&qb.y));
-    const __half2 t = __hmax2(*reinterpret_cast<const __half2*>(&qa.z), *reinterpret_cast<const __half2*>(&qb.z));
-    return __hbgt2(__hsub2(hi, lo), t);
+    const __half2 u = __hmin2(*reinterpret_cast<const __half2*>(&qa.y), *reinterpret_cast<const __half2*>(&qb.y));
+    return __hbgt2(u, lo);
 }
 
 // The same test for 32 consecutive rows of shared memory against one box, as a 32-bit mask.  The ALU pipe is the
 // bottleneck of this kernel (ncu: alu 70 %, fma 16 %), so the per-pair verdicts are not turned into predicates and
 // bit-inserted (HSET2 + ISETP + SEL + IADD3 on the ALU pipe) but accumulated on the FMA pipe: HSET2.BF yields 1.0 / 0.0
 // per axis, `acc = verdict * 2^k + acc` (HFMA2) collects 8 pairs per half in the mantissa of 1024 + v (exact, v < 256),
-// and three byte permutes + one AND per 32 pairs combine the two axes.  Per pair: 3 HMNMX2 + HSET2 (ALU), 2 on the FMA pipe.
-__device__ __forceinline__ unsigned may_remove_mask32(const uint2* __restrict__ q, const unsigned* __restrict__ qt,
-                                                      const uint4 qj) {
+// and three byte permutes + one AND per 32 pairs combine the two axes.  Per pair: 2 HMNMX2 + HSET2 (ALU), HFMA2 (FMA).
+__device__ __forceinline__ unsigned may_remove_mask32(const uint2* __restrict__ q, const uint2 qj) {
     const __half2 lo_j = *reinterpret_cast<const __half2*>(&qj.x);
-    const __half2 hi_j = *reinterpret_cast<const __half2*>(&qj.y);
-    const __half2 t_j = *reinterpret_cast<const __half2*>(&qj.z);
+    const __half2 u_j = *reinterpret_cast<const __half2*>(&qj.y);
     unsigned u[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -147,11 +145,9 @@ __device__ __forceinline__ unsigned may_remove_mask32(const uint2* __restrict__ 
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const uint2 qa = q[g * 8 + k];
-            const unsigned ta = qt[g * 8 + k];
             const __half2 lo = __hmax2(*reinterpret_cast<const __half2*>(&qa.x), lo_j);
-            const __half2 hi = __hmin2(*reinterpret_cast<const __half2*>(&qa.y), hi_j);
-            const __half2 t = __hmax2(*reinterpret_cast<const __half2*>(&ta), t_j);
-            const __half2 verdict = __hgt2(__hsub2(hi, lo), t);                 // 1.0 where the axis passes
+            const __half2 up = __hmin2(*reinterpret_cast<const __half2*>(&qa.y), u_j);
+            const __half2 verdict = __hgt2(up, lo);                              // 1.0 where the axis passes
             const float w = (float)(1 << k);
             acc = __hfma2(verdict, __floats2half2_rn(w, w), acc);
         }
@@ -188,8 +184,8 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_
     constexpr int STAGE = (TRI * 8 / 28) / 32 * 32;   // earlier keepers staged per phase-A round, in the aliased mask triangle
     __shared__ float4 s_box[CT];
     __shared__ float s_conf[CT];
-    __shared__ uint2 s_q[CT];        // half2 lo, hi   (see box_bounds_h2; split 8 + 4 bytes: one 128-bit word per row
-    __shared__ unsigned s_qt[CT];    // half2 t         measured slower, 308 vs 295 us)
+    __shared__ uint2 s_q[CT];        // half2 lo, u   (see box_bounds_h2)
+    __shared__ unsigned s_qt[CT];    // (storage of s_last below)
     __shared__ unsigned long long s_L[TRI];
     __shared__ unsigned long long s_kept[NW];
     __shared__ __align__(16) uint2 s_state[CT / 32];   // per 32-row group: x = kept rows, y = decided rows
@@ -205,7 +201,6 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_
     static_assert(STAGE * (16 + 8 + 4) <= TRI * 8, "phase-A staging must fit the mask triangle");
     float4* const s_kb = reinterpret_cast<float4*>(s_L);
     uint2* const s_kq = reinterpret_cast<uint2*>(s_L + STAGE * 2);
-    unsigned* const s_kqt = reinterpret_cast<unsigned*>(s_L + STAGE * 3);
     __shared__ int s_last_members;
     __shared__ uint32_t s_mlist[CT];     // members of in-chunk clusters in ascending row order: owner index << 10 | row
     __shared__ __align__(4) uint8_t s_nzw[CT];   // per row: which of its mask words are non-zero (most rows: none)
@@ -214,8 +209,8 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_
                                             // do not wait on L2 for it again (VARIANT 0)
     __shared__ int16_t s_next[CT];       // member list position of the next member of the same cluster, or -1
     __shared__ int16_t s_first[CT];      // per in-chunk keeper ordinal: list position of its first member, or -1
-    // ... of its last member so far, while the chains are built: lives in s_qt, which is dead after phase B (the
-    // shared-memory budget of 6 CTAs per SM inside the 196 KB carve-out is 32.6 KB per CTA)
+    // ... of its last member so far, while the chains are built (the shared-memory budget of 6 CTAs per SM inside the
+    // 196 KB carve-out is 32.6 KB per CTA)
     int16_t* const s_last = reinterpret_cast<int16_t*>(s_qt);
     __shared__ int s_mpre[CT / 32 + 1];  // exclusive prefix of the member bitmap's popcounts
 
@@ -272,7 +267,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_
                 const float4 bx = h ? b1 : b0;
                 s_box[j] = bx;
                 s_conf[j] = h ? f1 : f0;
-                if (FAST) { const uint4 q = box_bounds_h2(bx, thr); s_q[j] = make_uint2(q.x, q.y); s_qt[j] = q.z; }
+                if (FAST) s_q[j] = box_bounds_h2(bx, thr);
                 s_pre[j] = -1;
                 s_first[j] = -1;
                 s_nzw[j] = 0u;
@@ -294,7 +289,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_
             for (int i = tid; i < nk; i += NT) {
                 const float4 kb = p.kbox[img + s + kt + i];
                 s_kb[i] = kb;
-                if (FAST) { const uint4 q = box_bounds_h2(kb, thr); s_kq[i] = make_uint2(q.x, q.y); s_kqt[i] = q.z; }
+                if (FAST) s_kq[i] = box_bounds_h2(kb, thr);
             }
             __syncthreads();
             if (FAST) {
@@ -306,8 +301,8 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_
                     if (!__any_sync(0xFFFFFFFFu, active)) continue;
                     if (!active) continue;
                     const float4 bj = s_box[j];
-                    const uint4 qj = make_uint4(s_q[j].x, s_q[j].y, s_qt[j], 0u);
-                    unsigned cand = may_remove_mask32(s_kq + kb0, s_kqt + kb0, qj);
+                    const uint2 qj = s_q[j];
+                    unsigned cand = may_remove_mask32(s_kq + kb0, qj);
                     if (nk - kb0 < 32) cand &= (1u << (nk - kb0)) - 1u;                   // stale entries past the stage
                     while (cand) {
                         const int k = __ffs((int)cand) - 1;
@@ -351,12 +346,12 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_
                         const int ni = min(64, j - i0);
                     if (FAST) {
                         // pass 1: half2 bounding test, branch-free; pass 2: exact test on the few candidates
-                        const uint4 qj = make_uint4(s_q[j].x, s_q[j].y, s_qt[j], 0u);
+                        const uint2 qj = s_q[j];
                         unsigned c_lo = 0u, c_hi = 0u;
                         // all 64 columns of the word are tested (rows >= j hold valid or stale-but-harmless bounds)
                         // and the columns >= ni are masked off afterwards: no variable-trip-count loop on the diagonal
-                        c_lo = may_remove_mask32(s_q + i0, s_qt + i0, qj);
-                        if (ni > 32) c_hi = may_remove_mask32(s_q + i0 + 32, s_qt + i0 + 32, qj);
+                        c_lo = may_remove_mask32(s_q + i0, qj);
+                        if (ni > 32) c_hi = may_remove_mask32(s_q + i0 + 32, qj);
                         if (ni < 32) c_lo &= (1u << ni) - 1u;
                         else if (ni < 64) c_hi &= (1u << (ni - 32)) - 1u;
                         unsigned long long cand = ((unsigned long long)c_hi << 32) | c_lo;
