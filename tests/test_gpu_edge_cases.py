@@ -153,3 +153,16 @@ def test_arbitrary_bit_patterns_terminate(layout):
                 assert torch.equal(rows[b, :k].view(torch.int32), rows_p[b, :k].view(torch.int32))     # bit patterns (NaN-safe)
         torch.cuda.synchronize()
         assert int(count_p.min()) >= 0
+
+
+@pytest.mark.parametrize("nms_thres", [0.0, 0.05, 0.2, 0.45, 0.7, 0.95])
+@pytest.mark.parametrize("C,seed", [(1, 3), (4, 4), (20, 5)])
+def test_threshold_sweep_dense_overlaps(nms_thres, C, seed):
+    """The half2 pre-filter folds the threshold into its per-row summary: sweep it from 0 to 0.95 on boxes that overlap
+    heavily (few classes, boxes a third of the image wide, nested small-in-large pairs) and on ordinary heads."""
+    lv = synth.yolo_planar(B=2, A=3, C=C, grids=[12, 6], img=96, seed=seed, v5_view=False)
+    g = torch.Generator().manual_seed(seed)
+    for t in lv:                                         # widths / heights from tiny to image-sized: nested pairs
+        v = t.view(2, 3, 5 + C, t.shape[-1], t.shape[-1])
+        v[:, :, 2:4] = 2.0 + torch.rand(v[:, :, 2:4].shape, generator=g) ** 3 * 94.0
+    _run(lv, nms_thres=nms_thres)
