@@ -181,11 +181,10 @@ template <int VARIANT, bool FAST, int NT, int CT>
 __global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_segment_kernel(const NmsParams p) {
     constexpr int NW = CT / 64;                       // mask words per full row
     constexpr int TRI = 32 * NW * (NW + 1);           // packed lower-triangular rows
-    constexpr int STAGE = (TRI * 8 / 28) / 32 * 32;   // earlier keepers staged per phase-A round, in the aliased mask triangle
+    constexpr int STAGE = (TRI * 8 / 24) / 32 * 32;   // earlier keepers staged per phase-A round, in the aliased mask triangle
     __shared__ float4 s_box[CT];
     __shared__ float s_conf[CT];
     __shared__ uint2 s_q[CT];        // half2 lo, u   (see box_bounds_h2)
-    __shared__ unsigned s_qt[CT];    // (storage of s_last below)
     __shared__ unsigned long long s_L[TRI];
     __shared__ unsigned long long s_kept[NW];
     __shared__ __align__(16) uint2 s_state[CT / 32];   // per 32-row group: x = kept rows, y = decided rows
@@ -198,7 +197,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_
     // writes the triangle, and the triangle of the previous chunk is dead by then.  (Shared memory per CTA decides the
     // carve-out: 5 CTAs x <= 39 KB fit the 196 KB setting and leave 32 KB of L1 for the box gathers; 42 KB per CTA measured
     // 248 vs 238 us.)
-    static_assert(STAGE * (16 + 8 + 4) <= TRI * 8, "phase-A staging must fit the mask triangle");
+    static_assert(STAGE * (16 + 8) <= TRI * 8, "phase-A staging (box + half2 summary) must fit the mask triangle");
     float4* const s_kb = reinterpret_cast<float4*>(s_L);
     uint2* const s_kq = reinterpret_cast<uint2*>(s_L + STAGE * 2);
     __shared__ int s_last_members;
@@ -211,7 +210,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_
     __shared__ int16_t s_first[CT];      // per in-chunk keeper ordinal: list position of its first member, or -1
     // ... of its last member so far, while the chains are built (the shared-memory budget of 6 CTAs per SM inside the
     // 196 KB carve-out is 32.6 KB per CTA)
-    int16_t* const s_last = reinterpret_cast<int16_t*>(s_qt);
+    __shared__ int16_t s_last[CT];
     __shared__ int s_mpre[CT / 32 + 1];  // exclusive prefix of the member bitmap's popcounts
 
     const int b = blockIdx.y;
