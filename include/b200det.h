@@ -48,6 +48,8 @@ extern "C" {
 #define B200DET_DECODE_NONE 0      /* values used as-is: what every reference NMS does (model/YOLOV3.py:289-305) */
 #define B200DET_DECODE_YOLO_EXP 1  /* D1: sigmoid xy + grid, exp wh * anchor, * stride (accuracy.py:412-435,461) */
 #define B200DET_DECODE_YOLOV5 2    /* D2: (2s-0.5+grid)*stride, (2s)^2*anchor (utils/YoloV5Utils.py:244-248)    */
+#define B200DET_DECODE_YOLOV4_NORM 3 /* D3: ((s*sxy - 0.5(sxy-1)) + grid)/G, exp*anchor/G -> normalised corners
+                                        x1 = bx - bw/2, x2 = x1 + bw (utils/YoloV4Utils.py:84-159); anchors in grid units */
 
 /* memory layout of the head levels */
 #define B200DET_LAYOUT_PLANAR 0         /* [B, A, 5+C, G, G]: what every reference NMS reads (model/YOLOV3.py:294-300)  */
@@ -77,9 +79,12 @@ typedef struct b200det_yolo_desc {
     float conf_thres;                                /* keep rows with conf >= conf_thres              */
     float nms_thres;                                 /* suppress when IoU_+1 > nms_thres               */
     int32_t layout;                                  /* B200DET_LAYOUT_* (0 = planar)                  */
+    float scale_x_y;                                 /* B200DET_DECODE_YOLOV4_NORM only (YoloV4Utils.py:84); 0 = 1.0 */
 } b200det_yolo_desc;
 
-/* candidates per image N = sum_l A*G_l^2; per-image regions are padded to n_pad = roundup(N, TILE) */
+/* candidates per image N = sum_l A*G_l^2.  Every level starts on a tile boundary, so the per-image region holds
+ * n_pad = sum_l roundup(A*G_l^2, TILE) slots (>= roundup(N, TILE): YOLOv3-416 has N = 10647, n_pad = 11264).
+ * out_rows / out_index of the calls below MUST be sized from the n_pad this query returns. */
 int b200det_yolo_num_candidates(const b200det_yolo_desc* d, int32_t* n, int32_t* n_pad);
 size_t b200det_yolo_workspace_bytes(const b200det_yolo_desc* d);
 
@@ -117,6 +122,18 @@ int b200det_yolo_workspace_field(const b200det_yolo_desc* d, const char* name, s
 int b200det_decode_box(const float* head, int32_t batch, int32_t num_anchors, int32_t num_classes,
                        int32_t grid, int32_t decode_mode, const float* anchors /*[A,2] device; NULL for DECODE_NONE*/, float stride,
                        float* out /*[B, A*G*G, 5+C]*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * D3 — `yolo_forward_dynamic(output, conf_thresh, num_classes, anchors, num_anchors, scale_x_y, ...)` of
+ * LightningFunc/utils/YoloV4Utils.py:36-176 for one head level (planar [B, A*(5+C), H, W]):
+ *   boxes  normalised corner boxes, row r = (b, a*H*W + cell) at boxes[r*ld_boxes + 0..3]   (reference: [B,N,1,4], ld 4)
+ *   confs  sigmoid(cls) * sigmoid(obj) at confs[r*ld_confs + 0..C-1]                         (reference: [B,N,C],   ld C)
+ *   det    optional (may be NULL): sigmoid(obj) at det[r*ld_det]
+ * anchors [A,2] on the device, in grid units (what the reference's callers pass, YoloV4Utils.py:99-102).
+ * ---------------------------------------------------------------------------------------------- */
+int b200det_yolo_forward_dynamic(const float* head, int32_t batch, int32_t num_anchors, int32_t num_classes, int32_t height,
+                                 int32_t width, const float* anchors, float scale_x_y, float* boxes, int64_t ld_boxes,
+                                 float* confs, int64_t ld_confs, float* det, int64_t ld_det, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * D4 + N2 — SSD / RetinaNet prior decode, sigmoid-argmax, score filter, top-k, class-agnostic greedy
@@ -205,7 +222,9 @@ int b200det_v5_match_bwd(const float* pi, int32_t batch, int32_t num_anchors, in
  * Outputs (caller-allocated, any content): iou_scores, class_mask, tx,ty,tw,th fp32 [B,A,G,G];
  * obj_mask, noobj_mask uint8 [B,A,G,G]; tcls fp32 [B,A,G,G,C].  Duplicate cells: highest target row
  * wins (the reference's CPU index_put_ order); tcls is multi-hot.  status[0] (int32, device) is set
- * to a bit mask: bit0 = index guard of accuracy.py:340-344 tripped, bit1 = label guard of :361-367. */
+ * to a bit mask: bit0 = index guard of accuracy.py:340-344 tripped, bit1 = label guard of :361-367,
+ * bit2 = a negative image / cell / label index below -size (the reference's indexing raises IndexError
+ * there; here every scatter is skipped and the Python layer raises from the bit). */
 size_t b200det_build_targets_workspace_bytes(int32_t batch, int32_t num_anchors, int32_t grid, int32_t num_targets);
 int b200det_build_targets(const float* pred_boxes, const float* pred_cls, const float* target,
                           const float* anchors, int32_t batch, int32_t num_anchors, int32_t grid,

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200det.so")
 
 MAX_LEVELS, MAX_ANCHORS, MAX_CLASSES, MAX_CANDIDATES, TILE = 8, 16, 4095, 1 << 20, 512
-DECODE_NONE, DECODE_YOLO_EXP, DECODE_YOLOV5 = 0, 1, 2
+DECODE_NONE, DECODE_YOLO_EXP, DECODE_YOLOV5, DECODE_YOLOV4_NORM = 0, 1, 2, 3
 LAYOUT_PLANAR, LAYOUT_CHANNELS_LAST = 0, 1
 IOU, GIOU, DIOU, CIOU = 0, 1, 2, 3
 
@@ -22,7 +22,7 @@ class YoloDesc(Structure):
     _fields_ = [("batch", c_int32), ("num_anchors", c_int32), ("num_classes", c_int32), ("num_levels", c_int32),
                 ("head", c_void_p * MAX_LEVELS), ("grid", c_int32 * MAX_LEVELS), ("decode_mode", c_int32),
                 ("stride", c_float * MAX_LEVELS), ("anchors", ((c_float * 2) * MAX_ANCHORS) * MAX_LEVELS),
-                ("conf_thres", c_float), ("nms_thres", c_float), ("layout", c_int32)]
+                ("conf_thres", c_float), ("nms_thres", c_float), ("layout", c_int32), ("scale_x_y", c_float)]
 
 
 class PriorDesc(Structure):
@@ -49,6 +49,7 @@ SIGNATURES = {
     "b200det_yolo_stage_emit": (_i32, [_PY, _vp, _sz, _vp, _vp, _vp, _vp]),
     "b200det_yolo_workspace_field": (_i32, [_PY, c_char_p, POINTER(_sz), POINTER(_sz)]),
     "b200det_decode_box": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _f, _vp, _vp]),
+    "b200det_yolo_forward_dynamic": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _f, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
     "b200det_prior_workspace_bytes": (_sz, [_PP]),
     "b200det_prior_nms": (_i32, [_PP, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
     "b200det_xywh2xyxy": (_i32, [_vp, _vp, _i64, _vp]),

@@ -24,6 +24,8 @@ int yolo_stage_sort(const b200det_yolo_desc*, void*, size_t, cudaStream_t);
 int yolo_stage_nms(const b200det_yolo_desc*, void*, size_t, cudaStream_t);
 int yolo_stage_emit(const b200det_yolo_desc*, void*, size_t, float*, int32_t*, int32_t*, cudaStream_t);
 int decode_box_launch(const float*, int, int, int, int, int, const float*, float, float*, cudaStream_t);
+int yolo_forward_dynamic_launch(const float*, int, int, int, int, int, const float*, float, float*, long long, float*, long long,
+                                float*, long long, cudaStream_t);
 size_t prior_workspace_bytes(const b200det_prior_desc*);
 int prior_nms_pipeline(const b200det_prior_desc*, void*, size_t, float*, int32_t*, int32_t*, int32_t*, cudaStream_t);
 int xywh2xyxy_launch(const float*, float*, long long, cudaStream_t);
@@ -158,6 +160,19 @@ int b200det_decode_box(const float* head, int32_t B, int32_t A, int32_t C, int32
     B2_CHECK_ARG(mode == B200DET_DECODE_NONE || anchors_dev, "anchors required for decode modes");
     B2_CHECK_LIMIT((long long)B * A <= 65535, "B*A %lld > 65535", (long long)B * A);
     return decode_box_launch(head, B, A, C, G, mode, anchors_dev, stride, out, (cudaStream_t)st);
+}
+
+int b200det_yolo_forward_dynamic(const float* head, int32_t B, int32_t A, int32_t C, int32_t H, int32_t W, const float* anchors_dev,
+                                 float scale_x_y, float* boxes, int64_t ld_boxes, float* confs, int64_t ld_confs, float* det,
+                                 int64_t ld_det, void* st) {
+    B2_CHECK_ARG(head && anchors_dev && boxes && confs, "head / anchors / boxes / confs is null");
+    B2_CHECK_ARG(B > 0 && A > 0 && C > 0 && H > 0 && W > 0, "B, A, C, H, W must be > 0");
+    B2_CHECK_ARG(ld_boxes >= 4 && ld_confs >= C && (!det || ld_det >= 1), "row pitches too small");
+    B2_CHECK_LIMIT((long long)B * A <= 65535, "B*A %lld > 65535", (long long)B * A);
+    B2_CHECK_LIMIT(C <= B200DET_MAX_CLASSES, "num_classes %d > %d", C, B200DET_MAX_CLASSES);
+    B2_CHECK_LIMIT((long long)H * W < (1ll << 30), "plane too large");
+    return yolo_forward_dynamic_launch(head, B, A, C, H, W, anchors_dev, scale_x_y, boxes, (long long)ld_boxes, confs,
+                                       (long long)ld_confs, det, (long long)ld_det, (cudaStream_t)st);
 }
 
 size_t b200det_prior_workspace_bytes(const b200det_prior_desc* d) {

@@ -269,10 +269,14 @@ static int cluster_sort_launch_cl(const ClusterSortParams& p, int batch, cudaStr
     cfg.gridDim = dim3(CL, batch, 1);
     cfg.blockDim = dim3(kCsThreads, 1, 1);
     cfg.dynamicSmemBytes = sizeof(CsShared);
-    static bool attr_set = false;       // per instantiation; the attribute is idempotent, a race only repeats the call
-    if (!attr_set) {
+    // The opt-in above the 48 KB default is a per-DEVICE function attribute: cache it per device ordinal (one process may
+    // drive several GPUs).  The attribute is idempotent, so a race between threads only repeats the call.
+    static bool attr_set[64] = {};
+    int dev = 0;
+    B2_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         B2_CUDA(cudaFuncSetAttribute(cluster_sort_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CsShared)));
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     cfg.stream = st;
     cudaLaunchAttribute attr[1];

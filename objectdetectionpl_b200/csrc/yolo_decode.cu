@@ -219,7 +219,7 @@ int yolo_validate(const b200det_yolo_desc* d, const void* ws, size_t ws_bytes) {
         B2_CHECK_ARG(d->head[l] != nullptr, "head[%d] is null", l);
         B2_CHECK_ARG(d->grid[l] > 0, "grid[%d] must be > 0", l);
     }
-    B2_CHECK_ARG(d->decode_mode >= B200DET_DECODE_NONE && d->decode_mode <= B200DET_DECODE_YOLOV5, "bad decode_mode %d",
+    B2_CHECK_ARG(d->decode_mode >= B200DET_DECODE_NONE && d->decode_mode <= B200DET_DECODE_YOLOV4_NORM, "bad decode_mode %d",
                  d->decode_mode);
     int N, n_pad;
     B2_CHECK_LIMIT(yolo_counts(d, &N, &n_pad) == 0, "candidates per image out of (0, %d]", B200DET_MAX_CANDIDATES);
@@ -246,6 +246,9 @@ static int launch_k1(const b200det_yolo_desc* d, const K1Params& p, cudaStream_t
             break;
         case B200DET_DECODE_YOLO_EXP:
             yolo_decode_filter_kernel<B200DET_DECODE_YOLO_EXP, 8, 5><<<grid, kTile / VEC, smem, st>>>(p);
+            break;
+        case B200DET_DECODE_YOLOV4_NORM:
+            yolo_decode_filter_kernel<B200DET_DECODE_YOLOV4_NORM, 8, 5><<<grid, kTile / VEC, smem, st>>>(p);
             break;
         default:
             yolo_decode_filter_kernel<B200DET_DECODE_YOLOV5, 8, 5><<<grid, kTile / VEC, smem, st>>>(p);
@@ -308,6 +311,8 @@ int yolo_stage_decode(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cud
     p.nlevels = d->num_levels; p.A = d->num_anchors; p.C = d->num_classes;
     p.N = w.N; p.n_pad = w.n_pad; p.n_tiles = w.n_tiles;
     p.conf_thres = d->conf_thres;
+    p.sxy = d->scale_x_y != 0.0f ? d->scale_x_y : 1.0f;
+    p.soff = (float)(0.5 * ((double)p.sxy - 1.0));
     p.box4 = w.box4; p.cc2 = w.cc2; p.orig = w.orig; p.key = w.key[0]; p.pay = w.pay[0];
     p.tile_count = w.tile_count; p.count = w.count; p.cls_hist = w.cls_hist;
     if (yolo_fast_path(w)) { p.count = nullptr; p.cls_hist = nullptr; }      // see yolo_stage_reset
@@ -316,7 +321,8 @@ int yolo_stage_decode(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cud
     // default: the register-staged LDG kernel; B200DET_K1=tma selects the bulk-async (TMA) pipeline, which is
     // bit-identical and measured 6% slower on B200 (see yolo_decode_tma.cu)
     const char* k1 = getenv("B200DET_K1");
-    if (vec4 && k1 && strcmp(k1, "tma") == 0 && k1_tma_supported(p)) return launch_k1_tma(d, p, st);
+    if (vec4 && k1 && strcmp(k1, "tma") == 0 && k1_tma_supported(p) && d->decode_mode != B200DET_DECODE_YOLOV4_NORM)
+        return launch_k1_tma(d, p, st);
     return launch_k1(d, p, st);
 }
 

@@ -186,6 +186,7 @@ int launch_k1_rows(const b200det_yolo_desc* d, const K1Params& p, cudaStream_t s
     switch (d->decode_mode) {
         case B200DET_DECODE_NONE: return launch(yolo_decode_filter_rows_kernel<B200DET_DECODE_NONE>);
         case B200DET_DECODE_YOLO_EXP: return launch(yolo_decode_filter_rows_kernel<B200DET_DECODE_YOLO_EXP>);
+        case B200DET_DECODE_YOLOV4_NORM: return launch(yolo_decode_filter_rows_kernel<B200DET_DECODE_YOLOV4_NORM>);
         default: return launch(yolo_decode_filter_rows_kernel<B200DET_DECODE_YOLOV5>);
     }
 }

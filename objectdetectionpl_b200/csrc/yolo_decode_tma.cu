@@ -284,11 +284,13 @@ static int launch_mode(const K1Params& p, int total_tiles, int sm_count, cudaStr
 
 int launch_k1_tma(const b200det_yolo_desc* d, const K1Params& p, cudaStream_t st) {
     const int total_tiles = p.n_tiles * d->batch;
-    static int sm_count = 0;
+    static int sm_counts[64] = {};      // per device ordinal
+    int dev = 0;
+    B2_CUDA(cudaGetDevice(&dev));
+    int sm_count = (dev >= 0 && dev < 64) ? sm_counts[dev] : 0;
     if (sm_count == 0) {
-        int dev = 0;
-        B2_CUDA(cudaGetDevice(&dev));
         B2_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        if (dev >= 0 && dev < 64) sm_counts[dev] = sm_count;
     }
     switch (d->decode_mode) {
         case B200DET_DECODE_NONE: return launch_mode<B200DET_DECODE_NONE>(p, total_tiles, sm_count, st);

@@ -14,6 +14,7 @@ struct K1Params {
     float anc[B200DET_MAX_LEVELS][B200DET_MAX_ANCHORS][2];
     int nlevels, A, C, N, n_pad, n_tiles;
     float conf_thres;
+    float sxy, soff;                        // DECODE_YOLOV4_NORM: scale_x_y and 0.5 * (scale_x_y - 1)
     // outputs
     float4* box4;
     float2* cc2;
@@ -44,6 +45,21 @@ __device__ __forceinline__ void k1_finish(const K1Params& p, int lvl, int a, int
         const float gx = (float)(cell - gy * G);
         const float st = p.stride[lvl];
         const float aw = p.anc[lvl][a][0], ah = p.anc[lvl][a][1];
+        if (MODE == B200DET_DECODE_YOLOV4_NORM) {
+            // utils/YoloV4Utils.py:84-85,117-121,147-148,156-159: normalised corners, x2 = x1 + bw
+            const float Gf = (float)G;
+            const float bx = __fdiv_rn(__fadd_rn(__fsub_rn(__fmul_rn(sigmoidf_acc(t[0]), p.sxy), p.soff), gx), Gf);
+            const float by = __fdiv_rn(__fadd_rn(__fsub_rn(__fmul_rn(sigmoidf_acc(t[1]), p.sxy), p.soff), (float)gy), Gf);
+            const float bw = __fdiv_rn(__fmul_rn(expf(t[2]), aw), Gf);
+            const float bh = __fdiv_rn(__fmul_rn(expf(t[3]), ah), Gf);
+            box[0] = __fsub_rn(bx, __fmul_rn(bw, 0.5f));
+            box[1] = __fsub_rn(by, __fmul_rn(bh, 0.5f));
+            box[2] = __fadd_rn(box[0], bw);
+            box[3] = __fadd_rn(box[1], bh);
+            conf = sigmoidf_acc(t[4]);
+            ccf = sigmoidf_acc(best);
+            return;
+        }
         if (MODE == B200DET_DECODE_YOLO_EXP) {
             // accuracy.py:432-435 then *stride (:461)
             cx = __fmul_rn(__fadd_rn(sigmoidf_acc(t[0]), gx), st);

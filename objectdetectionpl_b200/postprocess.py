@@ -12,6 +12,7 @@ Everything runs on the GPU through libb200det.so; CPU tensors raise.
 """
 from __future__ import annotations
 
+import collections
 import ctypes
 from typing import List, Optional, Sequence
 
@@ -21,14 +22,15 @@ from . import _lib as L
 
 YOLO_FORCED_CONF_THRES = -0.0151   # model/YOLOV5.py:164 — the reference overwrites its conf_thres argument
 
-_DECODE = {None: L.DECODE_NONE, "none": L.DECODE_NONE, "yolo_exp": L.DECODE_YOLO_EXP, "yolov5": L.DECODE_YOLOV5}
+_DECODE = {None: L.DECODE_NONE, "none": L.DECODE_NONE, "yolo_exp": L.DECODE_YOLO_EXP, "yolov5": L.DECODE_YOLOV5,
+           "yolov4_norm": L.DECODE_YOLOV4_NORM}
 
 
 _LAYOUT = {None: L.LAYOUT_PLANAR, "planar": L.LAYOUT_PLANAR, "channels_last": L.LAYOUT_CHANNELS_LAST}
 
 
 def _yolo_desc(levels: Sequence[torch.Tensor], num_anchors: int, conf_thres: float, nms_thres: float,
-               decode, anchors, strides, layout=None) -> L.YoloDesc:
+               decode, anchors, strides, layout=None, scale_x_y: float = 1.0) -> L.YoloDesc:
     if len(levels) == 0 or len(levels) > L.MAX_LEVELS:
         raise ValueError(f"need 1..{L.MAX_LEVELS} prediction levels, got {len(levels)}")
     d = L.YoloDesc()
@@ -56,7 +58,10 @@ def _yolo_desc(levels: Sequence[torch.Tensor], num_anchors: int, conf_thres: flo
         d.grid[i] = G
     d.batch, d.num_anchors, d.num_classes, d.num_levels = B, num_anchors, C, len(levels)
     d.decode_mode = _DECODE[decode]
+    d.scale_x_y = float(scale_x_y)
     if d.decode_mode != L.DECODE_NONE:
+        if d.decode_mode == L.DECODE_YOLOV4_NORM and strides is None:
+            strides = [1.0] * len(levels)                    # D3 normalises by the grid size; no stride
         if anchors is None or strides is None or len(anchors) != len(levels) or len(strides) != len(levels):
             raise ValueError("decode modes need per-level `anchors` ([A,2] each) and `strides`")
         for i in range(len(levels)):
@@ -80,11 +85,12 @@ def _yolo_desc(levels: Sequence[torch.Tensor], num_anchors: int, conf_thres: flo
 
 
 def yolo_nms_raw(levels: Sequence[torch.Tensor], num_anchors: int = 3, conf_thres: float = YOLO_FORCED_CONF_THRES,
-                 nms_thres: float = 0.4, decode=None, anchors=None, strides=None, want_index: bool = False, layout=None):
+                 nms_thres: float = 0.4, decode=None, anchors=None, strides=None, want_index: bool = False, layout=None,
+                 scale_x_y: float = 1.0):
     """Enqueue the whole pipeline; returns device tensors (rows [B,n_pad,7], index [B,n_pad]|None, count [B])
     without synchronising — the building block for benchmarks and CUDA-graph capture."""
     lib = L.load()
-    d = _yolo_desc(levels, num_anchors, conf_thres, nms_thres, decode, anchors, strides, layout)
+    d = _yolo_desc(levels, num_anchors, conf_thres, nms_thres, decode, anchors, strides, layout, scale_x_y)
     dev = levels[0].device
     n, n_pad = ctypes.c_int32(), ctypes.c_int32()
     L.check(lib.b200det_yolo_num_candidates(ctypes.byref(d), ctypes.byref(n), ctypes.byref(n_pad)), "yolo_num_candidates")
@@ -100,11 +106,13 @@ def yolo_nms_raw(levels: Sequence[torch.Tensor], num_anchors: int = 3, conf_thre
     return rows, index, count
 
 
-def _yolo_nms(predictions, num_anchors, conf_thres, nms_thres, compat, decode, anchors, strides, return_index, layout=None):
+def _yolo_nms(predictions, num_anchors, conf_thres, nms_thres, compat, decode, anchors, strides, return_index, layout=None,
+              scale_x_y=1.0):
     if not isinstance(predictions, (list, tuple)):
         predictions = [predictions]                      # model/YOLOV3.py:281-282
     thr = YOLO_FORCED_CONF_THRES if compat else conf_thres
-    rows, index, count = yolo_nms_raw(predictions, num_anchors, thr, nms_thres, decode, anchors, strides, return_index, layout)
+    rows, index, count = yolo_nms_raw(predictions, num_anchors, thr, nms_thres, decode, anchors, strides, return_index, layout,
+                                      scale_x_y)
     counts = count.cpu().tolist()                        # the one host sync of the call
     out: List[Optional[torch.Tensor]] = [r[:k] if k else None for r, k in zip(rows.unbind(0), counts)]   # YOLOV3.py:306,333
     if return_index:
@@ -113,19 +121,20 @@ def _yolo_nms(predictions, num_anchors, conf_thres, nms_thres, compat, decode, a
 
 
 def non_max_suppression(self, predictions, conf_thres=0.5, nms_thres=0.4, *, compat=True, decode=None, anchors=None,
-                        strides=None, return_index=False, layout=None):
+                        strides=None, return_index=False, layout=None, scale_x_y=1.0):
     """Drop-in for YOLOv3/v4/v5 `non_max_suppression` (3 anchors per level).
 
     Returns a list (one entry per image) of `None` or fp32 `[K,7]` rows
     `(x1, y1, x2, y2, object_conf, class_score, class_pred)` in descending score order.
     compat=True (default) reproduces the reference bit-for-bit, including its forced
     `conf_thres = -0.0151`; compat=False honours `conf_thres`.  Extensions (keyword-only):
-    `decode` in {None,'yolo_exp','yolov5'} with per-level `anchors`/`strides`, `return_index`, and
+    `decode` in {None,'yolo_exp','yolov5','yolov4_norm'} with per-level `anchors`/`strides` (`yolov4_norm`: grid-unit
+    anchors, `scale_x_y`, boxes come out as normalised corners — utils/YoloV4Utils.py:36-176), `return_index`, and
     `layout='channels_last'`: the levels are read as what their `[B, A, G, G, 5+C]` shape says (the layout YOLOv5's
     head really writes, model/YOLOV5.py:96) instead of the reference's planar re-interpretation of the same bytes
     (YOLOV5.py:178-183) — same result as the default on the permuted tensor, without the permute copy.
     """
-    return _yolo_nms(predictions, 3, conf_thres, nms_thres, compat, decode, anchors, strides, return_index, layout)
+    return _yolo_nms(predictions, 3, conf_thres, nms_thres, compat, decode, anchors, strides, return_index, layout, scale_x_y)
 
 
 class _HostPipe:
@@ -139,26 +148,42 @@ class _HostPipe:
         self.chunk_seq = 0                # chunks submitted so far (across calls): dev_in alternates on it
         self.calls = 0                    # calls submitted so far: the two pinned result sets alternate on it
         B = shapes[0][0]
+        self.batch, self.chunk, self.last_done = B, chunk, None
         self.host = [(torch.empty((B, n_pad, 7), dtype=torch.float32).pin_memory(),
                       torch.empty((B, n_pad), dtype=torch.int32).pin_memory(),
                       torch.empty((B,), dtype=torch.int32).pin_memory()) for _ in range(2)]
 
+    def in_flight(self):
+        return self.last_done is not None and not self.last_done.query()
 
-_host_pipes = {}
+
+_host_pipes = collections.OrderedDict()      # LRU over (device, per-image head shapes, chunk, anchors)
+_HOST_PIPES_MAX = 4
+
+
+def clear_host_pipes():
+    """Release the pinned result buffers, device input buffers and streams of the host-input pipelines."""
+    _host_pipes.clear()
 
 
 class HostNmsHandle:
     """A submitted `non_max_suppression_host_async` call; `result()` waits for its last device->host copy."""
 
-    def __init__(self, done, host, return_index, keep):
+    def __init__(self, done, host, return_index, keep, pipe, generation, batch):
         self._done, self._host, self._return_index, self._keep = done, host, return_index, keep
+        self._pipe, self._generation, self._batch = pipe, generation, batch
         self._out = None
 
     def result(self):
         if self._out is None:
+            # the rows live in one of the pipe's two pinned sets: a third submission before this call was collected has
+            # re-used the set — fail loudly instead of returning another batch's rows
+            if self._pipe.calls - self._generation > 2:
+                raise RuntimeError("non_max_suppression_host_async: this call's pinned result buffer was overwritten by a "
+                                   "later submission (at most two calls may be in flight per configuration)")
             self._done.synchronize()
             self._keep = None
-            rows, index, count = self._host
+            rows, index, count = (t[:self._batch] for t in self._host)
             counts = count.tolist()
             out: List[Optional[torch.Tensor]] = [r[:k] if k else None for r, k in zip(rows.unbind(0), counts)]
             self._out = (out, [index[b, :k].long() if k else None for b, k in enumerate(counts)]) if self._return_index else out
@@ -184,16 +209,29 @@ def non_max_suppression_host_async(self, predictions, conf_thres=0.5, nms_thres=
     chunk = max(1, min(int(chunk_images), B))
     thr = YOLO_FORCED_CONF_THRES if compat else conf_thres
     shapes = tuple(tuple(t.shape) for t in predictions)
-    key = (dev.index, shapes, chunk, num_anchors)
+    # keyed on the PER-IMAGE shapes: a smaller batch (the last one of an epoch) re-uses the buffers of the largest seen
+    key = (dev.index, tuple(sh[1:] for sh in shapes), int(chunk_images), num_anchors)
     pipe = _host_pipes.get(key)
+    if pipe is not None and pipe.batch < B:
+        if pipe.in_flight():
+            torch.cuda.synchronize(dev)
+        del _host_pipes[key]
+        pipe = None
     if pipe is None:
         # slots per image: every level padded to whole tiles (b200det_yolo_num_candidates)
         n_pad = sum((num_anchors * t.shape[2] * t.shape[2] + L.TILE - 1) // L.TILE * L.TILE for t in predictions)
         with torch.cuda.device(dev):
-            pipe = _host_pipes[key] = _HostPipe(dev, shapes, chunk, n_pad)
+            pipe = _HostPipe(dev, shapes, max(1, min(int(chunk_images), B)), n_pad)
+        _host_pipes[key] = pipe
+        while len(_host_pipes) > _HOST_PIPES_MAX:
+            _host_pipes.popitem(last=False)
+    else:
+        _host_pipes.move_to_end(key)
+    chunk = min(chunk, pipe.chunk)
     nchunks = (B + chunk - 1) // chunk
     host = pipe.host[pipe.calls & 1]
     pipe.calls += 1
+    generation = pipe.calls
     keep = []
     with torch.cuda.device(dev):
         for c in range(nchunks):
@@ -225,7 +263,8 @@ def non_max_suppression_host_async(self, predictions, conf_thres=0.5, nms_thres=
             keep.append((rows, index, count))                        # alive until the copies have run
         done = torch.cuda.Event()
         done.record(pipe.s_out)
-    return HostNmsHandle(done, host, return_index, keep)
+    pipe.last_done = done
+    return HostNmsHandle(done, host, return_index, keep, pipe, generation, B)
 
 
 def non_max_suppression_host(self, predictions, conf_thres=0.5, nms_thres=0.4, *, compat=True, num_anchors=3,
@@ -298,13 +337,17 @@ def prior_non_max_suppression(self, predictions, topk=100, nms_thresh=0.5, class
     return out
 
 
-def decode_box(head: torch.Tensor, anchors, stride: float, mode: str = "yolo_exp", num_anchors: Optional[int] = None):
+def decode_box(head: torch.Tensor, anchors, stride: float, mode: str = "yolo_exp", num_anchors: Optional[int] = None,
+               scale_x_y: float = 1.0):
     """Full decoded map of one level: planar `[B, A*(5+C), G, G]` -> `[B, A*G*G, 5+C]`.
 
     mode 'yolo_exp' (D1, accuracy.py:412-435,459-466): x=(σ+gx)·stride, w=exp·anchor·stride, σ(conf), σ(cls);
          `anchors` are the SCALED anchors (grid units) exactly as the reference's callers pass them.
     mode 'yolov5'  (D2, utils/YoloV5Utils.py:244-248): xy=(2σ-0.5+g)·stride, wh=(2σ)²·anchor (pixel anchors).
     mode 'none': the planar->rows permute of model/YOLOV3.py:294-300 only.
+    mode 'yolov4_norm' (D3, utils/YoloV4Utils.py:36-176): rows `(x1, y1, x2, y2, σ(obj), σ(cls)·σ(obj) ...)` with
+         normalised corner boxes; `anchors` in grid units, `scale_x_y` as there, `stride` unused
+         (`yolo_forward_dynamic` is the same kernel with the reference's two-tensor return).
     """
     lib = L.load()
     L.require_cuda(head, "head")
@@ -326,7 +369,47 @@ def decode_box(head: torch.Tensor, anchors, stride: float, mode: str = "yolo_exp
         raise ValueError(f"head of shape {tuple(head.shape)} is not [B, {A}, 5+C, {G}, {G}] storage")
     F = head.numel() // (B * A * G * G)
     out = torch.empty((B, A * G * G, F), dtype=torch.float32, device=head.device)
+    if m == L.DECODE_YOLOV4_NORM:
+        with torch.cuda.device(head.device):
+            L.check(lib.b200det_yolo_forward_dynamic(head.data_ptr(), B, A, F - 5, G, G, anc.data_ptr(), float(scale_x_y),
+                                                     out.data_ptr(), F, out.data_ptr() + 20, F, out.data_ptr() + 16, F,
+                                                     L.stream_ptr(head.device)), "yolo_forward_dynamic")
+        return out
     with torch.cuda.device(head.device):
         L.check(lib.b200det_decode_box(head.data_ptr(), B, A, F - 5, G, m, anc.data_ptr() if anc is not None else None,
                                        float(stride), out.data_ptr(), L.stream_ptr(head.device)), "decode_box")
     return out
+
+
+def yolo_forward_dynamic(output, conf_thresh, num_classes, anchors, num_anchors, scale_x_y, only_objectness=1,
+                         validation=False, *, return_det_confs=False):
+    """Drop-in for `yolo_forward_dynamic` (LightningFunc/utils/YoloV4Utils.py:36-176), decode D3 of one YOLOv4 head level.
+
+    `output` planar `[B, num_anchors*(5+num_classes), H, W]`; `anchors` the flat list `[w0, h0, w1, h1, ...]` in grid
+    units the reference's callers pass (or an `[A,2]` tensor).  Returns `(boxes [B, A*H*W, 1, 4], confs [B, A*H*W, C])`:
+    normalised corner boxes and `sigmoid(cls) * sigmoid(obj)`.  `conf_thresh`, `only_objectness` and `validation` are
+    accepted and unused, as in the reference."""
+    lib = L.load()
+    L.require_cuda(output, "output")
+    if output.dim() != 4 or output.shape[1] != num_anchors * (5 + num_classes):
+        raise ValueError(f"output must be [B, {num_anchors}*(5+{num_classes}), H, W], got {tuple(output.shape)}")
+    head = output.contiguous()
+    B, H, W = head.shape[0], head.shape[2], head.shape[3]
+    anc = torch.as_tensor(anchors, dtype=torch.float32).reshape(-1)[:2 * num_anchors].reshape(num_anchors, 2)
+    anc = anc.to(head.device).contiguous()
+    N = num_anchors * H * W
+    boxes = torch.empty((B, N, 1, 4), dtype=torch.float32, device=head.device)
+    confs = torch.empty((B, N, num_classes), dtype=torch.float32, device=head.device)
+    det = torch.empty((B, N), dtype=torch.float32, device=head.device) if return_det_confs else None
+    with torch.cuda.device(head.device):
+        L.check(lib.b200det_yolo_forward_dynamic(head.data_ptr(), B, num_anchors, num_classes, H, W, anc.data_ptr(),
+                                                 float(scale_x_y), boxes.data_ptr(), 4, confs.data_ptr(), num_classes,
+                                                 det.data_ptr() if det is not None else None, 1, L.stream_ptr(head.device)),
+                "yolo_forward_dynamic")
+    return (boxes, confs, det) if return_det_confs else (boxes, confs)
+
+
+def get_region_boxes(boxes_and_confs):
+    """Drop-in for `get_region_boxes` (LightningFunc/utils/YoloV4Utils.py:18-34): concatenates the per-level results of
+    `yolo_forward_dynamic` along the candidate axis."""
+    return [torch.cat([item[0] for item in boxes_and_confs], dim=1), torch.cat([item[1] for item in boxes_and_confs], dim=1)]

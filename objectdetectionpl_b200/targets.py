@@ -17,9 +17,16 @@ import torch
 from . import _lib as L
 
 
+# build_targets reads the kernel's status word (one 4-byte device->host copy, i.e. a stream sync) to raise the reference's
+# IndexError on target rows whose negative indices cannot wrap into range.  Set to False to keep the call asynchronous:
+# such rows then make every scatter be skipped (all-zero targets) without an exception.
+CHECK_INDEX_STATUS = True
+
+
 def build_targets(pred_boxes, pred_cls, target, anchors, ignore_thres):
     """Returns the reference's 10-tuple `(iou_scores, class_mask, obj_mask, noobj_mask, tx, ty, tw, th, tcls,
-    tconf)` with identical dtypes (masks uint8).  Duplicate cells: the highest target row wins."""
+    tconf)` with identical dtypes (masks uint8).  Duplicate cells: the highest target row wins.  Index errors: see
+    `CHECK_INDEX_STATUS`."""
     lib = L.load()
     pb = L.require_cuda(pred_boxes, "pred_boxes").contiguous()
     pc = L.require_cuda(pred_cls, "pred_cls").contiguous()
@@ -41,6 +48,10 @@ def build_targets(pred_boxes, pred_cls, target, anchors, ignore_thres):
                                           class_mask.data_ptr(), obj.data_ptr(), noobj.data_ptr(), tx.data_ptr(), ty.data_ptr(),
                                           tw.data_ptr(), th.data_ptr(), tcls.data_ptr(), status.data_ptr(), L.stream_ptr(dev)),
                 "build_targets")
+    if CHECK_INDEX_STATUS and (int(status.item()) & 4):
+        # a negative image / cell / label index below -size: the reference's advanced indexing raises here
+        # (accuracy.py:345-374) instead of returning targets
+        raise IndexError("build_targets: a target row indexes outside [-size, size) of the [B, A, G, G(, C)] maps")
     return iou_scores, class_mask, obj, noobj, tx, ty, tw, th, tcls, obj.float()
 
 

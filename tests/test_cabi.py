@@ -55,9 +55,10 @@ def test_struct_layout_matches_c(tmp_path):
 #include <stddef.h>
 #include "b200det.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(b200det_yolo_desc), offsetof(b200det_yolo_desc, head),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(b200det_yolo_desc), offsetof(b200det_yolo_desc, head),
          offsetof(b200det_yolo_desc, grid), offsetof(b200det_yolo_desc, decode_mode), offsetof(b200det_yolo_desc, stride),
-         offsetof(b200det_yolo_desc, anchors), offsetof(b200det_yolo_desc, conf_thres), offsetof(b200det_yolo_desc, nms_thres));
+         offsetof(b200det_yolo_desc, anchors), offsetof(b200det_yolo_desc, conf_thres), offsetof(b200det_yolo_desc, nms_thres),
+         offsetof(b200det_yolo_desc, layout), offsetof(b200det_yolo_desc, scale_x_y));
   printf("%zu %zu %zu %zu %zu %zu\n", sizeof(b200det_prior_desc), offsetof(b200det_prior_desc, loc),
          offsetof(b200det_prior_desc, priors), offsetof(b200det_prior_desc, topk), offsetof(b200det_prior_desc, mode_min),
          offsetof(b200det_prior_desc, compat));
@@ -69,7 +70,18 @@ int main(void) {
     y = [int(v) for v in out[0].split()]
     Y = L.YoloDesc
     assert y == [ctypes.sizeof(Y), Y.head.offset, Y.grid.offset, Y.decode_mode.offset, Y.stride.offset, Y.anchors.offset,
-                 Y.conf_thres.offset, Y.nms_thres.offset]
+                 Y.conf_thres.offset, Y.nms_thres.offset, Y.layout.offset, Y.scale_x_y.offset]
+    # the binding INTEGRATION.md shows a maintainer: execute its class statement and compare it with the C layout
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"^class YoloDesc\(ctypes\.Structure\):.*?\n((?:[ \t]+.*\n)+)", doc, flags=re.M)
+    assert m, "INTEGRATION.md no longer shows the YoloDesc binding"
+    ns = {"ctypes": ctypes}
+    exec(m.group(0), ns)
+    D = ns["YoloDesc"]
+    assert [f[0] for f in D._fields_] == [f[0] for f in Y._fields_], "INTEGRATION.md's YoloDesc fields differ from _lib.YoloDesc"
+    assert ctypes.sizeof(D) == y[0]
+    for name, _ in Y._fields_:
+        assert getattr(D, name).offset == getattr(Y, name).offset and getattr(D, name).size == getattr(Y, name).size, name
     p = [int(v) for v in out[1].split()]
     P = L.PriorDesc
     assert p == [ctypes.sizeof(P), P.loc.offset, P.priors.offset, P.topk.offset, P.mode_min.offset, P.compat.offset]

@@ -126,3 +126,59 @@ def test_decode_box_c_abi_unaligned_pointers_and_canaries(G, C, off_out, off_hea
     got = buf[pad + off_out: pad + off_out + n]
     assert torch.equal(got, want.reshape(-1))
     assert bool((buf[:pad + off_out] == 12345.0).all()) and bool((buf[pad + off_out + n:] == 12345.0).all())
+
+
+def test_yolo_forward_dynamic_golden_d3():
+    """D3: `yolo_forward_dynamic` of the unmodified reference (LightningFunc/utils/YoloV4Utils.py:36-176, scale_x_y 1.05)
+    on the golden head; boxes [B,N,1,4] normalised corners, confs [B,N,C] = sigmoid(cls) * sigmoid(obj); 1e-5 relative."""
+    d = load("decode")
+    head = T(d["head"])
+    A = 3
+    C = head.shape[1] // A - 5
+    flat = [float(v) for v in d["anchors"].reshape(-1)]
+    boxes, confs = od.yolo_forward_dynamic(head.to(DEV), 0.5, C, flat, A, 1.05)
+    assert tuple(boxes.shape) == tuple(d["d3_boxes"].shape) and tuple(confs.shape) == tuple(d["d3_confs"].shape)
+    assert boxes.is_contiguous() and confs.is_contiguous()
+    torch.testing.assert_close(boxes.cpu(), T(d["d3_boxes"]), rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(confs.cpu(), T(d["d3_confs"]), rtol=1e-5, atol=1e-9)
+    rb, rc = od.get_region_boxes([(boxes, confs), (boxes, confs)])
+    assert tuple(rb.shape) == (boxes.shape[0], 2 * boxes.shape[1], 1, 4) and tuple(rc.shape) == (confs.shape[0], 2 * confs.shape[1], C)
+    # rows form of the same kernel
+    rows = od.decode_box(head.to(DEV), T(d["anchors"]), 1.0, "yolov4_norm", scale_x_y=1.05)
+    assert torch.equal(rows[..., :4], boxes.squeeze(2)) and torch.equal(rows[..., 5:], confs)
+
+
+@pytest.mark.parametrize("G,C,sxy", [(13, 4, 1.2), (20, 80, 1.05), (19, 7, 1.0), (8, 200, 1.1), (6, 1100, 1.05)])
+def test_yolo_forward_dynamic_vs_oracle(G, C, sxy):
+    B, A = 2, 3
+    head = synth.raw_logits(B, A, C, G, 300 + G)
+    anc = torch.tensor([[1.5, 2.0], [3.625, 2.8125], [4.875, 6.1875]])
+    wb, wc = rp.decode_yolov4_norm(head, anc, scale_x_y=sxy)
+    boxes, confs, det = od.yolo_forward_dynamic(head.to(DEV), 0.4, C, anc, A, sxy, return_det_confs=True)
+    torch.testing.assert_close(boxes.cpu().squeeze(2), wb, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(confs.cpu(), wc, rtol=1e-5, atol=1e-9)
+    want_det = torch.sigmoid(head.view(B, A, 5 + C, G * G)[:, :, 4]).reshape(B, -1)
+    torch.testing.assert_close(det.cpu(), want_det, rtol=1e-5, atol=1e-9)
+
+
+def test_fused_yolov4_norm_decode_nms_matches_decode_then_nms():
+    """K1 mode DECODE_YOLOV4_NORM: non_max_suppression(decode='yolov4_norm') == oracle NMS on rows whose box is the D3
+    corner box (as cx, cy, w, h), conf = sigmoid(obj), class scores = sigmoid(cls)."""
+    B, A, C, G = 2, 3, 5, 16
+    head = synth.raw_logits(B, A, C, G, 91)
+    head.view(B, A, 5 + C, G, G)[:, :, 4] += 3.0
+    anc = torch.tensor([[1.25, 1.625], [2.0, 3.75], [4.125, 2.875]])
+    dev_head = head.to(DEV)
+    got, gidx = od.non_max_suppression(None, [dev_head], conf_thres=0.25, compat=False, decode="yolov4_norm", anchors=[anc],
+                                       return_index=True, scale_x_y=1.05)
+    boxes, confs, det = od.yolo_forward_dynamic(dev_head, 0.4, C, anc, A, 1.05, return_det_confs=True)
+    xyxy = boxes.squeeze(2).cpu()
+    cls = torch.sigmoid(head.view(B, A, 5 + C, G * G)[:, :, 5:]).permute(0, 1, 3, 2).reshape(B, -1, C)
+    # the oracle NMS wants cx, cy, w, h rows; the corner box of the fused path is (x1, y1, x1 + w, y1 + h)
+    w, h = xyxy[..., 2] - xyxy[..., 0], xyxy[..., 3] - xyxy[..., 1]
+    rows = torch.cat([torch.stack([xyxy[..., 0] + w / 2, xyxy[..., 1] + h / 2, w, h, det.cpu()], -1), cls], -1)
+    want, widx = rp.yolo_nms_fast(rows, conf_thres=0.25)
+    for b in range(B):
+        assert torch.equal(gidx[b].cpu(), widx[b])
+        assert torch.equal(got[b][:, 6].cpu(), want[b][:, 6])
+        torch.testing.assert_close(got[b][:, :6].cpu(), want[b][:, :6], rtol=1e-4, atol=1e-5)
