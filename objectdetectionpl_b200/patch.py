@@ -3,6 +3,8 @@ functions (model/YOLOV5.py:134-150) and the module-global lookups of LightningFu
 `LightningFunc/step.py` stays untouched."""
 from __future__ import annotations
 
+import sys
+
 from . import boxes, metrics, postprocess, targets
 
 
@@ -17,7 +19,13 @@ def install_model(model_cls):
         fn = postprocess.non_max_suppression
     setattr(model_cls, "non_max_suppression", fn)
     if name in ("yolov2", "yolov3", "yolov4"):
-        setattr(model_cls, "get_yolo_statistics", metrics.get_yolo_statistics)     # step.py:99 (model/YOLOV3.py:252)
+        setattr(model_cls, "get_yolo_statistics", metrics.get_yolo_statistics)     # step.py:99
+        # the model's constructor re-binds the attribute from ITS module's global (`__build_func`, model/YOLOV3.py:252:
+        # `setattr(obj, "get_yolo_statistics", get_yolo_statistics)`), so that global is patched too — otherwise building
+        # the model after install() would silently restore the stock function
+        mod = sys.modules.get(getattr(model_cls, "__module__", None))
+        if mod is not None and hasattr(mod, "get_yolo_statistics"):
+            mod.get_yolo_statistics = metrics.get_yolo_statistics
     return model_cls
 
 

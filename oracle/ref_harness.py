@@ -1,11 +1,14 @@
-"""TEST INFRASTRUCTURE ONLY — loader for the *unmodified* reference, used in this container to pin the oracle.
+"""TEST INFRASTRUCTURE ONLY — loader for the *unmodified* reference (Leyan529/ObjectDetectionPL, pure Python).
 
-`/root/reference` (Leyan529/ObjectDetectionPL) is pure Python, so it cannot be compiled into
-`oracle/_ref`; instead it is imported here, in the build container, to
+In the build container it is imported from `/root/reference` to
   (1) validate the restatement in `oracle/ref_port.py`, and
   (2) generate the golden vectors committed under `tests/golden/` (see `oracle/gen_golden.py`).
-It does NOT travel to the GPU box (`/root/reference` does not exist there): nothing under `-m gpu`,
-`smoke()` or `bench.py` imports this module.
+On the GPU box `/root/reference` does not exist; there the byte-identical copy staged by `oracle/stage_ref.py` into the
+git-ignored `oracle/_ref/` is imported instead (checked against `oracle/ref_manifest.json`), so that
+  (3) the `-m gpu` drop-in tests can run the reference's own criterion / NMS / test_step stock and with
+      `objectdetectionpl_b200.install()` applied, and
+  (4) `bench.py --impl reference` and the `cpu_baseline` leg time the reference's own CPU code.
+Nothing under `objectdetectionpl_b200/` imports this module: the product path never touches the reference.
 
 The shims below only make the reference importable/runnable on a CPU-only, Lightning-less box
 (SURVEY.md §8c); no reference source is copied or modified:
@@ -25,11 +28,26 @@ import types
 import torch
 import torch.nn as nn
 
-REF_ROOT = os.environ.get("B200DET_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _find_root():
+    env = os.environ.get("B200DET_REFERENCE_ROOT")
+    for cand in ([env] if env else []) + ["/root/reference", _STAGED]:
+        if cand and os.path.isdir(os.path.join(cand, "LightningFunc")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REF_ROOT, "LightningFunc"))
+
+
+def is_staged_copy() -> bool:
+    return os.path.abspath(REF_ROOT) == os.path.abspath(_STAGED)
 
 
 def _stub(name, **attrs):
@@ -59,15 +77,32 @@ def install_shims():
     mpl.pyplot = plt
     if not hasattr(collections, "Iterable"):
         collections.Iterable = collections.abc.Iterable
-    # CPU aliases for the .cuda()-hard-coded bits of the reference.
+    # CPU aliases for the .cuda()-hard-coded bits of the reference (on a GPU box: only inside `cpu_only()`).
     if not torch.cuda.is_available():
-        torch.Tensor.cuda = lambda self, *a, **k: self
-        torch.cuda.FloatTensor = torch.FloatTensor
-        torch.cuda.LongTensor = torch.LongTensor
-        torch.cuda.ByteTensor = torch.ByteTensor
+        _alias_cuda_to_cpu()
     if REF_ROOT not in sys.path:
         sys.path.insert(0, REF_ROOT)
     _installed = True
+
+
+def _alias_cuda_to_cpu():
+    saved = (torch.Tensor.cuda, torch.cuda.FloatTensor, torch.cuda.LongTensor, torch.cuda.ByteTensor)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.cuda.FloatTensor = torch.FloatTensor
+    torch.cuda.LongTensor = torch.LongTensor
+    torch.cuda.ByteTensor = torch.ByteTensor
+    return saved
+
+
+@contextlib.contextmanager
+def cpu_only():
+    """Run the reference's CPU path on a box that HAS a GPU: while active, `.cuda()` and the `torch.cuda.*Tensor`
+    constructors the reference hard-codes (SSD.py:305, accuracy.py:421, losses.py:73-99) resolve to their CPU forms."""
+    saved = _alias_cuda_to_cpu()
+    try:
+        yield
+    finally:
+        torch.Tensor.cuda, torch.cuda.FloatTensor, torch.cuda.LongTensor, torch.cuda.ByteTensor = saved
 
 
 @contextlib.contextmanager
