@@ -98,6 +98,13 @@ size_t b200det_yolo_workspace_bytes(const b200det_yolo_desc* d);
 int b200det_yolo_nms(const b200det_yolo_desc* d, void* workspace, size_t workspace_bytes,
                      float* out_rows, int32_t* out_index, int32_t* out_count, void* stream);
 
+/* The same pipeline with a PACKED result: the rows of all images back to back, image b at rows
+ * [out_offsets[b], out_offsets[b+1]) of out_rows [>= sum of counts, 7] (capacity B*n_pad always suffices) and likewise
+ * out_index (may be NULL); out_offsets [B+1] int32 (device).  One tiny extra launch (the prefix over the images); the
+ * host splits the result with ONE slicing call and copies only the kept rows when it needs them on the host. */
+int b200det_yolo_nms_packed(const b200det_yolo_desc* d, void* workspace, size_t workspace_bytes, float* out_rows,
+                            int32_t* out_index, int32_t* out_count, int32_t* out_offsets, void* stream);
+
 /* Stage entry points (the pipeline above is exactly these five calls in order); used by the tests
  * and by profiling.  All operate on the workspace laid out by b200det_yolo_workspace_bytes().
  * reset = one cudaMemsetAsync of the counter header; decode = the fused decode+filter kernel alone. */
@@ -107,6 +114,8 @@ int b200det_yolo_stage_sort(const b200det_yolo_desc* d, void* workspace, size_t 
 int b200det_yolo_stage_nms(const b200det_yolo_desc* d, void* workspace, size_t workspace_bytes, void* stream);
 int b200det_yolo_stage_emit(const b200det_yolo_desc* d, void* workspace, size_t workspace_bytes,
                             float* out_rows, int32_t* out_index, int32_t* out_count, void* stream);
+int b200det_yolo_stage_emit_packed(const b200det_yolo_desc* d, void* workspace, size_t workspace_bytes, float* out_rows,
+                                   int32_t* out_index, int32_t* out_count, int32_t* out_offsets, void* stream);
 
 /* Workspace introspection for tests: byte offset and element count of a named internal array
  * ("box4","cc2","orig","key","pay","rank","count","tile_count","cls_hist","seg_off","sorted_pay",
@@ -292,6 +301,17 @@ size_t b200det_batch_statistics_workspace_bytes(int32_t batch, int32_t num_targe
 int b200det_batch_statistics(const float* rows, const int64_t* row_start, const int32_t* count, int32_t batch,
                              int32_t max_count, const float* targets, int32_t num_targets, float iou_threshold,
                              void* ws, size_t ws_bytes, float* tp, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Detection packing for the multi-GPU exchange step (the detections of all images are consumed together by the test
+ * epoch, LightningFunc/step.py:95,102-130): rows [B, row_pitch, 7] + count [B] (the padded output of b200det_yolo_nms,
+ * row_pitch = n_pad; or b200det_prior_nms, row_pitch = topk) -> out [cap, 8] dense rows = 7 detection columns + the
+ * GLOBAL image id (image_offset + b), image b at [offsets[b], offsets[b+1]) in its score order.  offsets [B+1] int32
+ * (device, may be NULL).  max_rows >= max(count) sizes the grid (row_pitch is always enough); rows beyond `cap` are
+ * dropped (offsets[B] still reports the full total, so the caller can detect it).
+ * ---------------------------------------------------------------------------------------------- */
+int b200det_pack_detections(const float* rows, const int32_t* count, int32_t batch, int64_t row_pitch, int32_t max_rows,
+                            int32_t image_offset, float* out, int64_t cap, int32_t* offsets, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * M2 — per-class precision / recall / AP / F1.  Replaces `ap_per_class(tp, conf, pred_cls, target_cls)`

@@ -42,6 +42,8 @@ SIGNATURES = {
     "b200det_yolo_num_candidates": (_i32, [_PY, POINTER(_i32), POINTER(_i32)]),
     "b200det_yolo_workspace_bytes": (_sz, [_PY]),
     "b200det_yolo_nms": (_i32, [_PY, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "b200det_yolo_nms_packed": (_i32, [_PY, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "b200det_yolo_stage_emit_packed": (_i32, [_PY, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
     "b200det_yolo_stage_reset": (_i32, [_PY, _vp, _sz, _vp]),
     "b200det_yolo_stage_decode": (_i32, [_PY, _vp, _sz, _vp]),
     "b200det_yolo_stage_sort": (_i32, [_PY, _vp, _sz, _vp]),
@@ -75,6 +77,7 @@ SIGNATURES = {
     "b200det_ssd_match": (_i32, [_vp, _i32, _vp, _i32, _f, _vp, _sz, _vp, _vp, _vp]),
     "b200det_retina_assign_workspace_bytes": (_sz, [_i32, _i32]),
     "b200det_retina_assign": (_i32, [_vp, _i32, _vp, _i32, _i32, _f, _vp, _sz, _vp, _vp, _vp]),
+    "b200det_pack_detections": (_i32, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _i64, _vp, _vp]),
     "b200det_batch_statistics_workspace_bytes": (_sz, [_i32, _i32]),
     "b200det_batch_statistics": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _i32, _f, _vp, _sz, _vp, _vp]),
     "b200det_yolo_statistics_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),

@@ -22,7 +22,7 @@ int yolo_stage_reset(const b200det_yolo_desc*, void*, size_t, cudaStream_t);
 int yolo_stage_decode(const b200det_yolo_desc*, void*, size_t, cudaStream_t);
 int yolo_stage_sort(const b200det_yolo_desc*, void*, size_t, cudaStream_t);
 int yolo_stage_nms(const b200det_yolo_desc*, void*, size_t, cudaStream_t);
-int yolo_stage_emit(const b200det_yolo_desc*, void*, size_t, float*, int32_t*, int32_t*, cudaStream_t);
+int yolo_stage_emit(const b200det_yolo_desc*, void*, size_t, float*, int32_t*, int32_t*, int32_t*, cudaStream_t);
 int decode_box_launch(const float*, int, int, int, int, int, const float*, float, float*, cudaStream_t);
 int yolo_forward_dynamic_launch(const float*, int, int, int, int, int, const float*, float, float*, long long, float*, long long,
                                 float*, long long, cudaStream_t);
@@ -60,6 +60,7 @@ int ssd_match_launch(const float*, int, const float*, int, float, void*, int32_t
 size_t retina_assign_ws_bytes(int, int);
 int retina_assign_launch(const float*, int, const float*, int, int, float, void*, float*, int32_t*, cudaStream_t);
 
+int pack_detections_launch(const float*, const int32_t*, int, long long, int, int, float*, long long, int32_t*, cudaStream_t);
 size_t batch_statistics_ws_bytes(int, int);
 int batch_statistics_launch(const float*, const long long*, const int*, int, int, const float*, int, float, void*, float*,
                             cudaStream_t);
@@ -110,11 +111,16 @@ int b200det_yolo_stage_nms(const b200det_yolo_desc* d, void* ws, size_t n, void*
 }
 int b200det_yolo_stage_emit(const b200det_yolo_desc* d, void* ws, size_t n, float* out_rows, int32_t* out_index,
                             int32_t* out_count, void* st) {
-    return yolo_stage_emit(d, ws, n, out_rows, out_index, out_count, (cudaStream_t)st);
+    return yolo_stage_emit(d, ws, n, out_rows, out_index, out_count, nullptr, (cudaStream_t)st);
+}
+int b200det_yolo_stage_emit_packed(const b200det_yolo_desc* d, void* ws, size_t n, float* out_rows, int32_t* out_index,
+                                   int32_t* out_count, int32_t* out_offsets, void* st) {
+    B2_CHECK_ARG(out_offsets != nullptr, "out_offsets is null");
+    return yolo_stage_emit(d, ws, n, out_rows, out_index, out_count, out_offsets, (cudaStream_t)st);
 }
 
-int b200det_yolo_nms(const b200det_yolo_desc* d, void* ws, size_t n, float* out_rows, int32_t* out_index,
-                     int32_t* out_count, void* st) {
+static int yolo_pipeline(const b200det_yolo_desc* d, void* ws, size_t n, float* out_rows, int32_t* out_index, int32_t* out_count,
+                         int32_t* out_offsets, void* st) {
     int rc = yolo_stage_reset(d, ws, n, (cudaStream_t)st);
     if (rc) return rc;
     rc = yolo_stage_decode(d, ws, n, (cudaStream_t)st);
@@ -123,7 +129,18 @@ int b200det_yolo_nms(const b200det_yolo_desc* d, void* ws, size_t n, float* out_
     if (rc) return rc;
     rc = yolo_stage_nms(d, ws, n, (cudaStream_t)st);
     if (rc) return rc;
-    return yolo_stage_emit(d, ws, n, out_rows, out_index, out_count, (cudaStream_t)st);
+    return yolo_stage_emit(d, ws, n, out_rows, out_index, out_count, out_offsets, (cudaStream_t)st);
+}
+
+int b200det_yolo_nms_packed(const b200det_yolo_desc* d, void* ws, size_t n, float* out_rows, int32_t* out_index,
+                            int32_t* out_count, int32_t* out_offsets, void* st) {
+    B2_CHECK_ARG(out_offsets != nullptr, "out_offsets is null");
+    return yolo_pipeline(d, ws, n, out_rows, out_index, out_count, out_offsets, st);
+}
+
+int b200det_yolo_nms(const b200det_yolo_desc* d, void* ws, size_t n, float* out_rows, int32_t* out_index,
+                     int32_t* out_count, void* st) {
+    return yolo_pipeline(d, ws, n, out_rows, out_index, out_count, nullptr, st);
 }
 
 int b200det_yolo_workspace_field(const b200det_yolo_desc* d, const char* name, size_t* offset, size_t* bytes) {
@@ -335,6 +352,16 @@ int b200det_retina_assign(const float* anchors, int32_t A, const float* targets,
         return B200DET_EWORKSPACE;
     }
     return retina_assign_launch(anchors, A, targets, nt, B, img_size, ws, loc, cls, (cudaStream_t)st);
+}
+
+int b200det_pack_detections(const float* rows, const int32_t* count, int32_t B, int64_t row_pitch, int32_t max_rows,
+                            int32_t image_offset, float* out, int64_t cap, int32_t* offsets, void* st) {
+    B2_CHECK_ARG(B > 0 && row_pitch >= 0 && max_rows >= 0 && cap >= 0, "bad sizes");
+    B2_CHECK_LIMIT(B <= 65535, "batch %d > 65535", B);
+    B2_CHECK_ARG(count && (max_rows == 0 || (rows && out)), "null argument");
+    B2_CHECK_ARG(((uintptr_t)out & 15) == 0, "out must be 16-byte aligned");
+    return pack_detections_launch(rows, count, B, (long long)row_pitch, max_rows, image_offset, out, (long long)cap, offsets,
+                                  (cudaStream_t)st);
 }
 
 size_t b200det_batch_statistics_workspace_bytes(int32_t B, int32_t nt) {

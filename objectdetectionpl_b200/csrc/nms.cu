@@ -748,7 +748,31 @@ struct EmitParams {
     int32_t* out_index;    // [B][n_pad] or null
     int32_t* out_count;    // [B]
     int n_pad, n_chunks;
+    const int32_t* out_base;   // packed output: first output row of every image ([B+1], from yolo_emit_prefix_kernel), or null
 };
+
+// Packed output only: per-image kept-row totals (sum of the chunk counters the NMS kernel accumulated) and their exclusive
+// prefix = the first output row of every image.  One CTA; a thread per image.
+__global__ void __launch_bounds__(1024) yolo_emit_prefix_kernel(const uint32_t* __restrict__ count,
+                                                                const uint32_t* __restrict__ chunk_cnt, int B, int n_chunks,
+                                                                int32_t* __restrict__ out_base) {
+    __shared__ int s_scan[33];
+    int carry = 0;
+    for (int b0 = 0; b0 < B; b0 += 1024) {
+        const int b = b0 + (int)threadIdx.x;
+        int tot = 0;
+        if (b < B) {
+            const int used = min(n_chunks, ((int)count[b] + kEmitChunk - 1) >> kEmitShift);
+            const uint32_t* cc = chunk_cnt + (size_t)b * n_chunks;
+            for (int c = 0; c < used; ++c) tot += (int)cc[c];
+        }
+        int total;
+        const int ex = block_exclusive_scan(tot, s_scan, &total);
+        if (b < B) out_base[b] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) out_base[B] = carry;
+}
 
 constexpr int kEmitThreads = kEmitChunk / 4;   // 4 consecutive ranks per thread
 constexpr int kEmitPerCta = 1;                 // chunks per CTA (4 per CTA measured slower: 49 vs 39 us - the kernel is
@@ -761,6 +785,7 @@ __global__ void __launch_bounds__(kEmitThreads) yolo_emit_kernel(const EmitParam
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     const int c_first = blockIdx.x * kEmitPerCta;
     const size_t img = (size_t)b * p.n_pad;
+    const size_t oimg = p.out_base ? (size_t)p.out_base[b] : img;          // first output row of the image
     const int n = (int)p.count[b];
     if (c_first > 0 && (c_first << kEmitShift) >= n) return;
     const uint32_t* cc = p.chunk_cnt + (size_t)b * p.n_chunks;
@@ -804,7 +829,7 @@ __global__ void __launch_bounds__(kEmitThreads) yolo_emit_kernel(const EmitParam
         int ex = block_exclusive_scan(cnt, s_scan, &total);     // trailing barrier also protects s_rows reuse
         // rows are staged with the same alignment (mod 4 floats) as their place in the output, so the copy below
         // moves whole aligned float4 words
-        const size_t gfloat = (img + (size_t)base) * 7;
+        const size_t gfloat = (oimg + (size_t)base) * 7;
         const int sh = (int)(gfloat & 3);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -837,7 +862,7 @@ __global__ void __launch_bounds__(kEmitThreads) yolo_emit_kernel(const EmitParam
             }
         }
         if (p.out_index) {
-            int32_t* di = p.out_index + img + base;
+            int32_t* di = p.out_index + oimg + base;
             for (int i = tid; i < total; i += kEmitThreads) di[i] = s_idx[i];
         }
         base += total;
@@ -872,14 +897,19 @@ int yolo_stage_nms(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cudaSt
 }
 
 int yolo_stage_emit(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, float* out_rows, int32_t* out_index,
-                    int32_t* out_count, cudaStream_t st) {
+                    int32_t* out_count, int32_t* out_offsets, cudaStream_t st) {
     int rc = yolo_validate(d, ws, ws_bytes);
     if (rc) return rc;
     B2_CHECK_ARG(out_rows && out_count, "out_rows / out_count is null");
     B2_CHECK_ARG(((uintptr_t)out_rows & 15) == 0, "out_rows must be 16-byte aligned");
     YoloWs w;
     yolo_ws_layout(d, ws, &w);
+    if (out_offsets) {
+        yolo_emit_prefix_kernel<<<1, 1024, 0, st>>>(w.count, w.chunk_cnt, d->batch, w.n_chunks, out_offsets);
+        B2_LAUNCH_CHECK("yolo_emit_prefix_kernel");
+    }
     EmitParams p;
+    p.out_base = out_offsets;
     p.count = w.count; p.kpay = w.kpay; p.mbox = w.mbox; p.cc2 = w.cc2; p.orig = w.orig; p.chunk_cnt = w.chunk_cnt;
     p.out_rows = out_rows; p.out_index = out_index; p.out_count = out_count; p.n_pad = w.n_pad; p.n_chunks = w.n_chunks;
     dim3 grid(ceil_div(w.n_chunks, kEmitPerCta), d->batch);

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import collections
 import ctypes
+import threading
 from typing import List, Optional, Sequence
 
 import torch
@@ -106,17 +107,87 @@ def yolo_nms_raw(levels: Sequence[torch.Tensor], num_anchors: int = 3, conf_thre
     return rows, index, count
 
 
+class _YoloPlan:
+    """Everything about a `non_max_suppression` call that only depends on the head SHAPES (and the scalar options): the
+    filled-in descriptor, slot count, workspace size, a pinned host buffer for the counts and the event that guards it.
+    A call with known shapes then costs: patch the level pointers, allocate the two result tensors, ONE ctypes call,
+    one pinned device->host copy of the counts, one `split`."""
+
+    def __init__(self, levels, num_anchors, thr, nms_thres, decode, anchors, strides, layout, scale_x_y):
+        lib = L.load()
+        self.d = _yolo_desc(levels, num_anchors, thr, nms_thres, decode, anchors, strides, layout, scale_x_y)
+        n, n_pad = ctypes.c_int32(), ctypes.c_int32()
+        L.check(lib.b200det_yolo_num_candidates(ctypes.byref(self.d), ctypes.byref(n), ctypes.byref(n_pad)), "yolo_num_candidates")
+        self.n_pad, self.B = n_pad.value, self.d.batch
+        self.ws_bytes = lib.b200det_yolo_workspace_bytes(ctypes.byref(self.d))
+        self.dref = ctypes.byref(self.d)
+        self.host = torch.empty((2 * self.B + 1,), dtype=torch.int32).pin_memory()     # count [B] | offsets [B+1]
+        self.event = torch.cuda.Event()
+        self.fn = lib.b200det_yolo_nms_packed
+        self.lock = threading.Lock()                     # the descriptor and the pinned counts are per plan, not per call
+
+
+_yolo_plans = collections.OrderedDict()
+_YOLO_PLANS_MAX = 16
+
+
+def _plan_key(levels, num_anchors, thr, nms_thres, decode, anchors, strides, layout, scale_x_y):
+    def freeze(x):
+        if x is None:
+            return None
+        return tuple(tuple(float(v) for v in torch.as_tensor(a, dtype=torch.float32).reshape(-1).tolist()) if not isinstance(a, (int, float))
+                     else float(a) for a in x)
+    t0 = levels[0]
+    return (t0.device.index, tuple(tuple(t.shape) for t in levels), num_anchors, float(thr), float(nms_thres), decode,
+            freeze(anchors), freeze(strides), layout, float(scale_x_y))
+
+
 def _yolo_nms(predictions, num_anchors, conf_thres, nms_thres, compat, decode, anchors, strides, return_index, layout=None,
               scale_x_y=1.0):
     if not isinstance(predictions, (list, tuple)):
         predictions = [predictions]                      # model/YOLOV3.py:281-282
     thr = YOLO_FORCED_CONF_THRES if compat else conf_thres
-    rows, index, count = yolo_nms_raw(predictions, num_anchors, thr, nms_thres, decode, anchors, strides, return_index, layout,
-                                      scale_x_y)
-    counts = count.cpu().tolist()                        # the one host sync of the call
-    out: List[Optional[torch.Tensor]] = [r[:k] if k else None for r, k in zip(rows.unbind(0), counts)]   # YOLOV3.py:306,333
+    if len(predictions) == 0 or len(predictions) > L.MAX_LEVELS:
+        raise ValueError(f"need 1..{L.MAX_LEVELS} prediction levels, got {len(predictions)}")
+    for i, t in enumerate(predictions):
+        L.require_cuda(t, f"predictions[{i}]")
+    key = _plan_key(predictions, num_anchors, thr, nms_thres, decode, anchors, strides, layout, scale_x_y)
+    plan = _yolo_plans.get(key)
+    if plan is None:
+        plan = _yolo_plans[key] = _YoloPlan(predictions, num_anchors, thr, nms_thres, decode, anchors, strides, layout, scale_x_y)
+        while len(_yolo_plans) > _YOLO_PLANS_MAX:
+            _yolo_plans.popitem(last=False)
+    d, B, n_pad = plan.d, plan.B, plan.n_pad
+    dev = predictions[0].device
+    with plan.lock:
+        return _yolo_nms_planned(plan, predictions, d, B, n_pad, dev, return_index)
+
+
+def _yolo_nms_planned(plan, predictions, d, B, n_pad, dev, return_index):
+    for i, t in enumerate(predictions):                  # same shapes as the planned call (part of the key): only pointers move
+        if t.device != dev:
+            raise ValueError("all prediction levels must live on one device")
+        if not t.is_contiguous():
+            raise ValueError(f"predictions[{i}] must be contiguous (the reference .view()s it, model/YOLOV3.py:296)")
+        d.head[i] = t.data_ptr()
+    with torch.cuda.device(dev):
+        ws = L.workspace(plan.ws_bytes, dev)
+        rows = torch.empty((B * n_pad, 7), dtype=torch.float32, device=dev)
+        index = torch.empty((B * n_pad,), dtype=torch.int32, device=dev) if return_index else None
+        meta = torch.empty((2 * B + 1,), dtype=torch.int32, device=dev)               # count [B] | offsets [B+1]
+        mp = meta.data_ptr()
+        L.check(plan.fn(plan.dref, ws.data_ptr(), ws.numel(), rows.data_ptr(), index.data_ptr() if return_index else None,
+                        mp, mp + 4 * B, L.stream_ptr(dev)), "yolo_nms_packed")
+        plan.host.copy_(meta, non_blocking=True)
+        plan.event.record()
+        plan.event.synchronize()                          # the one host sync of the call
+    counts = plan.host[:B].tolist()
+    total = int(plan.host[2 * B])
+    parts = rows[:total].split(counts)                   # one call: B views of the packed rows
+    out: List[Optional[torch.Tensor]] = [p if k else None for p, k in zip(parts, counts)]            # YOLOV3.py:306,333
     if return_index:
-        return out, [index[b, :k].long() if k else None for b, k in enumerate(counts)]
+        iparts = index[:total].long().split(counts)
+        return out, [p if k else None for p, k in zip(iparts, counts)]
     return out
 
 

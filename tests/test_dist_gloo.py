@@ -34,12 +34,15 @@ def _worker(rank, world, port, out_dir):
         shard = [t[lo:hi] for t in levels]
         dets = rp.yolo_nms(shard, num_anchors=A)
         gathered = odist.gather_detections(dets, image_offset=lo)
+        local, counts = odist._pack_list(dets, lo)
+        g = odist.exchange(local, counts, batch_max=3)           # the device path's host logic: counts -> offsets -> slices
+        per_image = [None if t is None else t.clone() for t in g.per_image()]
         tg = synth.labels(B, C, seed=5, max_per_image=4)
         local_t = odist.shard_targets(tg, lo, hi)
         counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
         dist.all_gather(counts, torch.tensor([local_t.shape[0]]))
-        torch.save({"gathered": gathered, "nt": [int(c) for c in counts], "lo": lo, "hi": hi,
-                    "local_t": local_t}, os.path.join(out_dir, f"rank{rank}.pt"))
+        torch.save({"gathered": gathered, "nt": [int(c) for c in counts], "lo": lo, "hi": hi, "per_image": per_image,
+                    "batches": g.batches, "totals": g.totals, "local_t": local_t}, os.path.join(out_dir, f"rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -62,6 +65,10 @@ def test_pack_unpack_roundtrip():
     back = odist.unpack_detections(packed, 14)
     assert torch.equal(back[10], dets[0]) and torch.equal(back[12], dets[2]) and back[11] is None and back[13] is None
     assert odist.pack_detections([None, None], 0).shape == (0, 8)
+    # rows that are not grouped by image are ordered first (stable: the score order inside an image survives)
+    shuffled = torch.cat([packed[3:], packed[:3]])
+    back2 = odist.unpack_detections(shuffled, 14)
+    assert torch.equal(back2[10], dets[0]) and torch.equal(back2[12], dets[2])
 
 
 def test_two_rank_gather_equals_single_process():
@@ -78,6 +85,10 @@ def test_two_rank_gather_equals_single_process():
     back = odist.unpack_detections(res[0]["gathered"], B)
     for i in range(B):
         assert torch.equal(back[i], whole[i])
+    for r in res:                                   # GatheredDetections.per_image(): offset slicing, uneven shards (3 + 2)
+        assert r["batches"] == [3, 2] and sum(r["totals"]) == want.shape[0] and len(r["per_image"]) == B
+        for i in range(B):
+            assert torch.equal(r["per_image"][i], whole[i])
     tg = synth.labels(B, C, seed=5, max_per_image=4)
     assert sum(res[0]["nt"]) == tg.shape[0]
     for r in res:                                   # targets re-based to the shard
