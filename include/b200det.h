@@ -101,9 +101,14 @@ int b200det_yolo_nms(const b200det_yolo_desc* d, void* workspace, size_t workspa
 /* The same pipeline with a PACKED result: the rows of all images back to back, image b at rows
  * [out_offsets[b], out_offsets[b+1]) of out_rows [>= sum of counts, 7] (capacity B*n_pad always suffices) and likewise
  * out_index (may be NULL); out_offsets [B+1] int32 (device).  One tiny extra launch (the prefix over the images); the
- * host splits the result with ONE slicing call and copies only the kept rows when it needs them on the host. */
+ * host splits the result with ONE slicing call and copies only the kept rows when it needs them on the host.
+ * The counts are final once the NMS stage is done, one stage before the rows are: `counts_early` (may be NULL) receives
+ * count [B] | offsets [B+1] as 2B+1 int32 at that point — it may be MAPPED PINNED HOST memory, the kernel writes it directly —
+ * and `counts_ready_event` (a cudaEvent_t, may be NULL) is recorded right after, before the emit stage is enqueued.  A host
+ * that waits on that event can size and slice the result while the emit kernel is still writing the rows. */
 int b200det_yolo_nms_packed(const b200det_yolo_desc* d, void* workspace, size_t workspace_bytes, float* out_rows,
-                            int32_t* out_index, int32_t* out_count, int32_t* out_offsets, void* stream);
+                            int32_t* out_index, int32_t* out_count, int32_t* out_offsets, int32_t* counts_early,
+                            void* counts_ready_event, void* stream);
 
 /* Stage entry points (the pipeline above is exactly these five calls in order); used by the tests
  * and by profiling.  All operate on the workspace laid out by b200det_yolo_workspace_bytes().
@@ -169,6 +174,12 @@ size_t b200det_prior_workspace_bytes(const b200det_prior_desc* d);
  *   number of candidates that passed class_thresh (the Python layer raises IndexError on 1, SSD.py:266) */
 int b200det_prior_nms(const b200det_prior_desc* d, void* workspace, size_t workspace_bytes,
                       float* out_rows, int32_t* out_index, int32_t* out_count, int32_t* cand_count, void* stream);
+/* Stage entry points (b200det_prior_nms is exactly these two calls in order); used by profiling and by bench.py to put
+ * CUDA events around the streaming kernel alone.  decode = prior decode + sigmoid-argmax + score filter (reads loc/cls
+ * once: the HBM-bound part); select_nms = top-k selection + greedy NMS + output. */
+int b200det_prior_stage_decode(const b200det_prior_desc* d, void* workspace, size_t workspace_bytes, void* stream);
+int b200det_prior_stage_select_nms(const b200det_prior_desc* d, void* workspace, size_t workspace_bytes, float* out_rows,
+                                   int32_t* out_index, int32_t* out_count, int32_t* cand_count, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * N3 / N4 / T3 / T5 — elementwise box maths.

@@ -42,7 +42,7 @@ SIGNATURES = {
     "b200det_yolo_num_candidates": (_i32, [_PY, POINTER(_i32), POINTER(_i32)]),
     "b200det_yolo_workspace_bytes": (_sz, [_PY]),
     "b200det_yolo_nms": (_i32, [_PY, _vp, _sz, _vp, _vp, _vp, _vp]),
-    "b200det_yolo_nms_packed": (_i32, [_PY, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "b200det_yolo_nms_packed": (_i32, [_PY, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200det_yolo_stage_emit_packed": (_i32, [_PY, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
     "b200det_yolo_stage_reset": (_i32, [_PY, _vp, _sz, _vp]),
     "b200det_yolo_stage_decode": (_i32, [_PY, _vp, _sz, _vp]),
@@ -54,6 +54,8 @@ SIGNATURES = {
     "b200det_yolo_forward_dynamic": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _f, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
     "b200det_prior_workspace_bytes": (_sz, [_PP]),
     "b200det_prior_nms": (_i32, [_PP, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "b200det_prior_stage_decode": (_i32, [_PP, _vp, _sz, _vp]),
+    "b200det_prior_stage_select_nms": (_i32, [_PP, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
     "b200det_xywh2xyxy": (_i32, [_vp, _vp, _i64, _vp]),
     "b200det_bbox_iou_plus1": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _vp]),
     "b200det_pair_iou": (_i32, [_vp, _vp, _i64, _vp, _vp]),

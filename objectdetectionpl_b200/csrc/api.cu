@@ -22,12 +22,15 @@ int yolo_stage_reset(const b200det_yolo_desc*, void*, size_t, cudaStream_t);
 int yolo_stage_decode(const b200det_yolo_desc*, void*, size_t, cudaStream_t);
 int yolo_stage_sort(const b200det_yolo_desc*, void*, size_t, cudaStream_t);
 int yolo_stage_nms(const b200det_yolo_desc*, void*, size_t, cudaStream_t);
-int yolo_stage_emit(const b200det_yolo_desc*, void*, size_t, float*, int32_t*, int32_t*, int32_t*, cudaStream_t);
+int yolo_stage_emit(const b200det_yolo_desc*, void*, size_t, float*, int32_t*, int32_t*, int32_t*, int32_t*, cudaEvent_t,
+                    cudaStream_t);
 int decode_box_launch(const float*, int, int, int, int, int, const float*, float, float*, cudaStream_t);
 int yolo_forward_dynamic_launch(const float*, int, int, int, int, int, const float*, float, float*, long long, float*, long long,
                                 float*, long long, cudaStream_t);
 size_t prior_workspace_bytes(const b200det_prior_desc*);
 int prior_nms_pipeline(const b200det_prior_desc*, void*, size_t, float*, int32_t*, int32_t*, int32_t*, cudaStream_t);
+int prior_stage_decode(const b200det_prior_desc*, void*, size_t, cudaStream_t);
+int prior_stage_select_nms(const b200det_prior_desc*, void*, size_t, float*, int32_t*, int32_t*, int32_t*, cudaStream_t);
 int xywh2xyxy_launch(const float*, float*, long long, cudaStream_t);
 int bbox_iou_plus1_launch(const float*, long long, const float*, long long, int, float*, cudaStream_t);
 int pair_iou_launch(const float*, const float*, long long, float*, cudaStream_t);
@@ -111,16 +114,16 @@ int b200det_yolo_stage_nms(const b200det_yolo_desc* d, void* ws, size_t n, void*
 }
 int b200det_yolo_stage_emit(const b200det_yolo_desc* d, void* ws, size_t n, float* out_rows, int32_t* out_index,
                             int32_t* out_count, void* st) {
-    return yolo_stage_emit(d, ws, n, out_rows, out_index, out_count, nullptr, (cudaStream_t)st);
+    return yolo_stage_emit(d, ws, n, out_rows, out_index, out_count, nullptr, nullptr, nullptr, (cudaStream_t)st);
 }
 int b200det_yolo_stage_emit_packed(const b200det_yolo_desc* d, void* ws, size_t n, float* out_rows, int32_t* out_index,
                                    int32_t* out_count, int32_t* out_offsets, void* st) {
     B2_CHECK_ARG(out_offsets != nullptr, "out_offsets is null");
-    return yolo_stage_emit(d, ws, n, out_rows, out_index, out_count, out_offsets, (cudaStream_t)st);
+    return yolo_stage_emit(d, ws, n, out_rows, out_index, out_count, out_offsets, nullptr, nullptr, (cudaStream_t)st);
 }
 
 static int yolo_pipeline(const b200det_yolo_desc* d, void* ws, size_t n, float* out_rows, int32_t* out_index, int32_t* out_count,
-                         int32_t* out_offsets, void* st) {
+                         int32_t* out_offsets, int32_t* counts_early, void* counts_ready, void* st) {
     int rc = yolo_stage_reset(d, ws, n, (cudaStream_t)st);
     if (rc) return rc;
     rc = yolo_stage_decode(d, ws, n, (cudaStream_t)st);
@@ -129,18 +132,19 @@ static int yolo_pipeline(const b200det_yolo_desc* d, void* ws, size_t n, float* 
     if (rc) return rc;
     rc = yolo_stage_nms(d, ws, n, (cudaStream_t)st);
     if (rc) return rc;
-    return yolo_stage_emit(d, ws, n, out_rows, out_index, out_count, out_offsets, (cudaStream_t)st);
+    return yolo_stage_emit(d, ws, n, out_rows, out_index, out_count, out_offsets, counts_early, (cudaEvent_t)counts_ready,
+                           (cudaStream_t)st);
 }
 
 int b200det_yolo_nms_packed(const b200det_yolo_desc* d, void* ws, size_t n, float* out_rows, int32_t* out_index,
-                            int32_t* out_count, int32_t* out_offsets, void* st) {
+                            int32_t* out_count, int32_t* out_offsets, int32_t* counts_early, void* counts_ready_event, void* st) {
     B2_CHECK_ARG(out_offsets != nullptr, "out_offsets is null");
-    return yolo_pipeline(d, ws, n, out_rows, out_index, out_count, out_offsets, st);
+    return yolo_pipeline(d, ws, n, out_rows, out_index, out_count, out_offsets, counts_early, counts_ready_event, st);
 }
 
 int b200det_yolo_nms(const b200det_yolo_desc* d, void* ws, size_t n, float* out_rows, int32_t* out_index,
                      int32_t* out_count, void* st) {
-    return yolo_pipeline(d, ws, n, out_rows, out_index, out_count, nullptr, st);
+    return yolo_pipeline(d, ws, n, out_rows, out_index, out_count, nullptr, nullptr, nullptr, st);
 }
 
 int b200det_yolo_workspace_field(const b200det_yolo_desc* d, const char* name, size_t* offset, size_t* bytes) {
@@ -199,6 +203,14 @@ size_t b200det_prior_workspace_bytes(const b200det_prior_desc* d) {
 int b200det_prior_nms(const b200det_prior_desc* d, void* ws, size_t n, float* out_rows, int32_t* out_index,
                       int32_t* out_count, int32_t* cand_count, void* st) {
     return prior_nms_pipeline(d, ws, n, out_rows, out_index, out_count, cand_count, (cudaStream_t)st);
+}
+
+int b200det_prior_stage_decode(const b200det_prior_desc* d, void* ws, size_t n, void* st) {
+    return prior_stage_decode(d, ws, n, (cudaStream_t)st);
+}
+int b200det_prior_stage_select_nms(const b200det_prior_desc* d, void* ws, size_t n, float* out_rows, int32_t* out_index,
+                                   int32_t* out_count, int32_t* cand_count, void* st) {
+    return prior_stage_select_nms(d, ws, n, out_rows, out_index, out_count, cand_count, (cudaStream_t)st);
 }
 
 int b200det_xywh2xyxy(const float* x, float* y, int64_t n, void* st) {

@@ -755,7 +755,8 @@ struct EmitParams {
 // prefix = the first output row of every image.  One CTA; a thread per image.
 __global__ void __launch_bounds__(1024) yolo_emit_prefix_kernel(const uint32_t* __restrict__ count,
                                                                 const uint32_t* __restrict__ chunk_cnt, int B, int n_chunks,
-                                                                int32_t* __restrict__ out_base) {
+                                                                int32_t* __restrict__ out_base,
+                                                                int32_t* __restrict__ early /* [2B+1] or null */) {
     __shared__ int s_scan[33];
     int carry = 0;
     for (int b0 = 0; b0 < B; b0 += 1024) {
@@ -768,10 +769,16 @@ __global__ void __launch_bounds__(1024) yolo_emit_prefix_kernel(const uint32_t* 
         }
         int total;
         const int ex = block_exclusive_scan(tot, s_scan, &total);
-        if (b < B) out_base[b] = carry + ex;
+        if (b < B) {
+            out_base[b] = carry + ex;
+            if (early) { early[b] = tot; early[B + b] = carry + ex; }
+        }
         carry += total;
     }
-    if (threadIdx.x == 0) out_base[B] = carry;
+    if (threadIdx.x == 0) {
+        out_base[B] = carry;
+        if (early) early[2 * B] = carry;
+    }
 }
 
 constexpr int kEmitThreads = kEmitChunk / 4;   // 4 consecutive ranks per thread
@@ -897,7 +904,7 @@ int yolo_stage_nms(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cudaSt
 }
 
 int yolo_stage_emit(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, float* out_rows, int32_t* out_index,
-                    int32_t* out_count, int32_t* out_offsets, cudaStream_t st) {
+                    int32_t* out_count, int32_t* out_offsets, int32_t* counts_early, cudaEvent_t counts_ready, cudaStream_t st) {
     int rc = yolo_validate(d, ws, ws_bytes);
     if (rc) return rc;
     B2_CHECK_ARG(out_rows && out_count, "out_rows / out_count is null");
@@ -905,8 +912,9 @@ int yolo_stage_emit(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, float
     YoloWs w;
     yolo_ws_layout(d, ws, &w);
     if (out_offsets) {
-        yolo_emit_prefix_kernel<<<1, 1024, 0, st>>>(w.count, w.chunk_cnt, d->batch, w.n_chunks, out_offsets);
+        yolo_emit_prefix_kernel<<<1, 1024, 0, st>>>(w.count, w.chunk_cnt, d->batch, w.n_chunks, out_offsets, counts_early);
         B2_LAUNCH_CHECK("yolo_emit_prefix_kernel");
+        if (counts_ready) B2_CUDA(cudaEventRecord(counts_ready, st));
     }
     EmitParams p;
     p.out_base = out_offsets;

@@ -272,22 +272,31 @@ size_t prior_workspace_bytes(const b200det_prior_desc* d) {
     return w.total_bytes;
 }
 
-int prior_nms_pipeline(const b200det_prior_desc* d, void* ws, size_t ws_bytes, float* out_rows, int32_t* out_index,
-                       int32_t* out_count, int32_t* cand_count, cudaStream_t st) {
+static bool prior_use_select(const b200det_prior_desc* d) {
+    const char* tk = getenv("B200DET_TOPK");
+    return topk_select_supported(d->topk) && !(tk && strcmp(tk, "sort") == 0);
+}
+
+static int prior_check_ws(const b200det_prior_desc* d, void* ws, size_t ws_bytes, PriorWs* w) {
     int rc = prior_validate(d);
     if (rc) return rc;
     B2_CHECK_ARG(ws != nullptr && ((uintptr_t)ws & 255) == 0, "workspace must be non-null and 256-byte aligned");
-    B2_CHECK_ARG(out_rows && out_count, "out_rows / out_count is null");
-    PriorWs w;
-    prior_ws_layout(d, ws, &w);
-    if (ws_bytes < w.total_bytes) {
-        set_error("workspace too small: %zu < %zu", ws_bytes, w.total_bytes);
+    prior_ws_layout(d, ws, w);
+    if (ws_bytes < w->total_bytes) {
+        set_error("workspace too small: %zu < %zu", ws_bytes, w->total_bytes);
         return B200DET_EWORKSPACE;
     }
+    return 0;
+}
+
+// stage 1 of the pipeline: K1' (prior decode + sigmoid-argmax + score filter + ordered tile compaction)
+int prior_stage_decode(const b200det_prior_desc* d, void* ws, size_t ws_bytes, cudaStream_t st) {
+    PriorWs w;
+    int rc = prior_check_ws(d, ws, ws_bytes, &w);
+    if (rc) return rc;
     // with the radix select (the default) the select kernel derives the per-image count and the tile prefix itself: three
     // launches per step (decode+filter, select, NMS); the full-sort path needs the zeroed counters and the prefix kernel
-    const char* tk = getenv("B200DET_TOPK");
-    const bool use_select = topk_select_supported(d->topk) && !(tk && strcmp(tk, "sort") == 0);
+    const bool use_select = prior_use_select(d);
     if (!use_select) rc = zero_fill_launch(w.count, w.zero_bytes, st);
     if (rc) return rc;
 
@@ -319,7 +328,17 @@ int prior_nms_pipeline(const b200det_prior_desc* d, void* ws, size_t ws_bytes, f
         tile_prefix_kernel<<<d->batch, 256, 0, st>>>(w.tile_count, w.tile_prefix, w.n_tiles);
         B2_LAUNCH_CHECK("tile_prefix_kernel");
     }
+    return 0;
+}
 
+// stages 2 + 3: top-k selection and the class-agnostic greedy NMS on the selected rows
+int prior_stage_select_nms(const b200det_prior_desc* d, void* ws, size_t ws_bytes, float* out_rows, int32_t* out_index,
+                           int32_t* out_count, int32_t* cand_count, cudaStream_t st) {
+    PriorWs w;
+    int rc = prior_check_ws(d, ws, ws_bytes, &w);
+    if (rc) return rc;
+    B2_CHECK_ARG(out_rows && out_count, "out_rows / out_count is null");
+    const bool use_select = prior_use_select(d);
     // only the topk best-scoring candidates reach the NMS (SSD.py:273): radix select instead of a full sort
     // (B200DET_TOPK=sort keeps the full sort, the A/B reference of the tests)
     if (use_select)
@@ -335,6 +354,14 @@ int prior_nms_pipeline(const b200det_prior_desc* d, void* ws, size_t ws_bytes, f
     if (cand_count)
         B2_CUDA(cudaMemcpyAsync(cand_count, w.count, (size_t)d->batch * 4, cudaMemcpyDeviceToDevice, st));
     return 0;
+}
+
+int prior_nms_pipeline(const b200det_prior_desc* d, void* ws, size_t ws_bytes, float* out_rows, int32_t* out_index,
+                       int32_t* out_count, int32_t* cand_count, cudaStream_t st) {
+    B2_CHECK_ARG(out_rows && out_count, "out_rows / out_count is null");
+    int rc = prior_stage_decode(d, ws, ws_bytes, st);
+    if (rc) return rc;
+    return prior_stage_select_nms(d, ws, ws_bytes, out_rows, out_index, out_count, cand_count, st);
 }
 
 }  // namespace b200det

@@ -121,8 +121,11 @@ class _YoloPlan:
         self.n_pad, self.B = n_pad.value, self.d.batch
         self.ws_bytes = lib.b200det_yolo_workspace_bytes(ctypes.byref(self.d))
         self.dref = ctypes.byref(self.d)
-        self.host = torch.empty((2 * self.B + 1,), dtype=torch.int32).pin_memory()     # count [B] | offsets [B+1]
+        # count [B] | offsets [B+1], written by the device straight into this pinned (mapped, UVA) host buffer as soon as
+        # the NMS stage is done; `event` is recorded by the library at that point, before the emit stage
+        self.host = torch.empty((2 * self.B + 1,), dtype=torch.int32).pin_memory()
         self.event = torch.cuda.Event()
+        self.event.record()                               # creates the underlying cudaEvent_t
         self.fn = lib.b200det_yolo_nms_packed
         self.lock = threading.Lock()                     # the descriptor and the pinned counts are per plan, not per call
 
@@ -177,13 +180,13 @@ def _yolo_nms_planned(plan, predictions, d, B, n_pad, dev, return_index):
         meta = torch.empty((2 * B + 1,), dtype=torch.int32, device=dev)               # count [B] | offsets [B+1]
         mp = meta.data_ptr()
         L.check(plan.fn(plan.dref, ws.data_ptr(), ws.numel(), rows.data_ptr(), index.data_ptr() if return_index else None,
-                        mp, mp + 4 * B, L.stream_ptr(dev)), "yolo_nms_packed")
-        plan.host.copy_(meta, non_blocking=True)
-        plan.event.record()
-        plan.event.synchronize()                          # the one host sync of the call
-    counts = plan.host[:B].tolist()
-    total = int(plan.host[2 * B])
-    parts = rows[:total].split(counts)                   # one call: B views of the packed rows
+                        mp, mp + 4 * B, plan.host.data_ptr(), plan.event.cuda_event, L.stream_ptr(dev)), "yolo_nms_packed")
+        # the one host sync of the call: it waits for the NMS stage only.  The list below is sliced while the emit kernel
+        # still writes the rows; whatever the caller does with them next is stream-ordered behind it, as with any torch op.
+        plan.event.synchronize()
+    meta_h = plan.host.tolist()
+    counts, total = meta_h[:B], meta_h[2 * B]
+    parts = torch.ops.aten.unsafe_split_with_sizes.default(rows[:total], counts)      # one call: B slices of the packed rows
     out: List[Optional[torch.Tensor]] = [p if k else None for p, k in zip(parts, counts)]            # YOLOV3.py:306,333
     if return_index:
         iparts = index[:total].long().split(counts)

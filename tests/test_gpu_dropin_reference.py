@@ -143,7 +143,8 @@ def test_v5_criterion_forward_backward_stock_vs_installed(ref):
     for k in want_m:
         torch.testing.assert_close(got_m[k], want_m[k], rtol=1e-5, atol=1e-7, msg=lambda s, k=k: f"{k}: {s}")
     for a, b in zip(got_g, want_g):
-        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-8)
+        # gradients of a mean over ~1e5 cells are ~1e-7 per element: the absolute floor is relative to the largest one
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5 * float(b.abs().max()))
 
 
 @pytest.mark.gpu
@@ -169,7 +170,7 @@ def test_region_loss_v3_forward_stock_vs_installed(ref):
         got, got_g = run(crit)
     for i, (a, b) in enumerate(zip(got, want)):
         torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-7, msg=lambda s, i=i: f"output {i}: {s}")
-    torch.testing.assert_close(got_g, want_g, rtol=1e-4, atol=1e-8)
+    torch.testing.assert_close(got_g, want_g, rtol=1e-4, atol=1e-5 * float(want_g.abs().max()))
 
 
 def _fake_module(ref, checkname, heads, nms, img):

@@ -55,11 +55,17 @@ def test_packed_c_abi_offsets_and_canaries():
     cnt = torch.empty(B, dtype=torch.int32, device=DEV)
     off = torch.empty(B + 1, dtype=torch.int32, device=DEV)
     st = L.stream_ptr(torch.device(DEV))
+    early = torch.full((2 * B + 1,), -1, dtype=torch.int32).pin_memory()       # written by the device (mapped pinned memory)
+    ev = torch.cuda.Event()
+    ev.record()
     L.check(lib.b200det_yolo_nms_packed(ctypes.byref(d), ws.data_ptr(), wsb, rows.data_ptr(), idx.data_ptr(), cnt.data_ptr(),
-                                        off.data_ptr(), st))
+                                        off.data_ptr(), early.data_ptr(), ev.cuda_event, st))
+    ev.synchronize()                                                            # counts are final before the rows are
+    early_now = early.clone()
     prow, pidx, pcnt = od.yolo_nms_raw(lv, A, 0.3, want_index=True)
     torch.cuda.synchronize()
     c, o = cnt.cpu(), off.cpu()
+    assert torch.equal(early_now[:B], c) and torch.equal(early_now[B:], o)
     assert torch.equal(c, pcnt.cpu()) and o[0] == 0 and torch.equal(o[1:], torch.cumsum(c, 0).int())
     total = int(o[B])
     assert 0 < total < cap
