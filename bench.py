@@ -1,28 +1,47 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the detection post-processing hot path.
+"""bench.py — benchmark of the detection post-processing / target-assignment hot path.
 
-Metric (BASELINE.json): decode+NMS images/sec at batch 64, 640x640, YOLOv5s COCO (C=80) heads.
-A "step" is one pass of the hot path (fused decode+filter -> per-image sort -> class-aware merge-NMS
--> ordered emit) over one batch of 64 synthetic images per GPU (weak scaling: 64 images per rank).
+Headline metric (BASELINE.json): decode+NMS images/sec at batch 64, 640x640, YOLOv5s COCO (C=80) heads.
+A "step" is one pass of the hot path over one batch of synthetic input per GPU (weak scaling: the per-rank batch is
+fixed, ranks own disjoint image blocks, no data-path collective).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]                  this repo's CUDA path
-  python bench.py --impl reference [--steps K] [--warmup W]            the reference algorithm on host cores
-  torchrun --nproc-per-node N ... bench.py --gpus N ...                one rank per GPU, no data-path collective
+  python bench.py [--config NAME] [--gpus N] [--steps K] [--warmup W]        this repo's CUDA path
+  python bench.py --impl reference [--config NAME] [--steps K] [--warmup W]  the UNMODIFIED reference on the host cores
+  torchrun --nproc-per-node N ... bench.py --gpus N ...                      one rank per GPU
 
-Prints ONE JSON line (rank 0).  `value` = whole-job images/s with inputs resident in HBM; `e2e` = the same
-metric through the public API from pinned HOST buffers (H2D of the heads and D2H of the detections inside
-the timed region); `roofline` = achieved HBM GB/s of the dominant streaming kernel (fused decode+filter)
-against the measured copy peak; `cpu_baseline` = the oracle port of the reference timed on this host.
+--config (default `headline`; every BASELINE.json configuration is a bench line):
+  headline   YOLOv5s 640x640 COCO heads, batch 64, decode + filter + sort + class-aware merge-NMS      (the BASELINE metric)
+  cfg1       YOLOv5s 640x640 VOC (20 classes), batch 1                                                 (BASELINE configs[0])
+  cfg2       YOLOv3 416x416 COCO, batch 64                                                             (configs[1])
+  ssd300     SSD300 (8 732 priors) prior decode + top-100 greedy NMS, batch 32                         (configs[2])
+  retina800  RetinaNet 800x800 (120 087 anchors), batch 32                                             (configs[2])
+  cfg4       YOLOv5s training-step build_targets_v5 + fused GIoU / objectness / class loss fwd+bwd, batch 64   (configs[3])
+  crowd512   dense-crowd YOLOv5l 1280x1280, 5 classes, conf_thres 0.001, 64 images per GPU (512 over 8 GPUs) followed by the
+             NCCL all-gather of the detections, timed as its own leg (`detection_allgather_ms`)        (configs[4])
+
+Prints ONE JSON line (rank 0):
+  value            whole-job images/s through the PUBLIC API (`od.non_max_suppression(None, levels)` etc. on device-resident
+                   inputs; CUDA events around the wrapper call, its host sync on the counts and the list build included —
+                   SURVEY 8d)
+  pipeline_value   the same work enqueued through the C-ABI stage entry points without any host sync (round 1's `value`)
+  e2e              the same metric through the public host-input API: pinned HOST buffers in, H2D and D2H inside the timed
+                   region
+  roofline         achieved HBM GB/s of the dominant streaming kernel (CUDA events around that launch, inside the timed
+                   region) against the measured copy peak
+  cpu_baseline     the reference's own CPU code (oracle/_ref, the unmodified reference staged by oracle/stage_ref.py) timed on
+                   this host on a bounded sample
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import statistics
 import sys
 import threading
 import time
+import types
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -30,37 +49,49 @@ if ROOT not in sys.path:
 
 import torch
 
-WORKLOAD = dict(name="yolov5s_640_coco_bs64", model="yolov5", img=640, classes=80, anchors=3, batch=64, seed=1234)
-METRIC = "decode+NMS images/sec (bs64, 640x640, YOLOv5s COCO heads)"
+L2_BYTES = 126e6
+
+CONFIGS = {
+    "headline": dict(kind="yolo", name="yolov5s_640_coco_bs64", model="yolov5", img=640, classes=80, anchors=3, batch=64, seed=1234,
+                     metric="decode+NMS images/sec (bs64, 640x640, YOLOv5s COCO heads)"),
+    "cfg1": dict(kind="yolo", name="yolov5s_640_voc_bs1", model="yolov5", img=640, classes=20, anchors=3, batch=1, seed=1,
+                 metric="decode+NMS images/sec (bs1, 640x640, YOLOv5s VOC heads)"),
+    "cfg2": dict(kind="yolo", name="yolov3_416_coco_bs64", model="yolov3", img=416, classes=80, anchors=3, batch=64, seed=2,
+                 metric="decode+NMS images/sec (bs64, 416x416, YOLOv3 COCO heads)"),
+    "ssd300": dict(kind="prior", name="ssd300_coco_bs32", which="SSD", classes=80, batch=32, seed=3,
+                   metric="prior decode + top-100 NMS images/sec (bs32, SSD300, 8732 priors, 80 classes)"),
+    "retina800": dict(kind="prior", name="retinanet800_coco_bs32", which="RetinaNet", classes=80, batch=32, seed=3,
+                      metric="prior decode + top-100 NMS images/sec (bs32, RetinaNet 800x800, 120087 anchors, 80 classes)"),
+    "cfg4": dict(kind="targets", name="yolov5s_640_targets_bs64", img=640, classes=80, batch=64, seed=4,
+                 metric="build_targets_v5 + GIoU/obj/cls loss fwd+bwd images/sec (bs64, 640x640, YOLOv5s COCO heads, <=100 boxes/image)"),
+    "crowd512": dict(kind="yolo", name="yolov5l_1280_crowd_64_per_gpu", model="yolov5", img=1280, classes=5, anchors=3, batch=64,
+                     seed=5, crowd=True, conf_thres=0.001,
+                     metric="decode+NMS images/sec (dense crowd, 1280x1280 YOLOv5l heads, 5 classes, conf_thres 0.001, 64 images/GPU)"),
+}
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 500; fewer for the slow configs)")
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=WORKLOAD["batch"], help="images per GPU (default 64)")
-    ap.add_argument("--e2e-steps", type=int, default=50)
+    ap.add_argument("--config", default="headline", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (default: the configuration's)")
+    ap.add_argument("--e2e-steps", type=int, default=40)
+    ap.add_argument("--gather-iters", type=int, default=20)
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="wall budget of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
 def dist_env():
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return rank, world, local
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
-def make_inputs(batch, seed):
-    from objectdetectionpl_b200 import synth
-    w = WORKLOAD
-    grids = synth.grids_for(w["model"], w["img"])
-    return synth.yolo_planar(batch, w["anchors"], w["classes"], grids, w["img"], seed, v5_view=True), grids
-
-
+# ------------------------------------------------------------------------------------------------------------------
+# plumbing: clocks, affinity, stdout
+# ------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
@@ -151,50 +182,6 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_reference_run(levels_cpu, steps, warmup, budget_s):
-    """The reference algorithm (oracle port of model/YOLOV5.py:157-218, torch eager on the host cores), one image
-    per step.  O(K*N) per image (~10-20 s), so the number of steps is capped by a wall budget."""
-    from oracle import ref_port as rp  # checker / baseline only
-    torch.set_num_threads(os.cpu_count() or 1)
-    B = levels_cpu[0].shape[0]
-    times = []
-    done = 0
-    t_start = time.perf_counter()
-    w_eff = min(warmup, 1)
-    for i in range(w_eff + steps):
-        img = [t[i % B:i % B + 1] for t in levels_cpu]
-        t0 = time.perf_counter()
-        rp.yolo_nms(img, num_anchors=WORKLOAD["anchors"])
-        dt = time.perf_counter() - t0
-        if i >= w_eff:
-            times.append(dt)
-            done += 1
-        elapsed = time.perf_counter() - t_start
-        if elapsed + dt > budget_s and done >= 1:
-            break
-    per_img = sum(times) / len(times)
-    return 1.0 / per_img, done, w_eff
-
-
-def run_reference(args, rank):
-    if rank != 0:
-        return
-    levels, _ = make_inputs(min(args.batch, 8), WORKLOAD["seed"])
-    ips, done, w_eff = cpu_reference_run(levels, args.steps, args.warmup, args.cpu_budget_s)
-    cores = os.cpu_count() or 1
-    sample = (f"{done} timed step(s) of 1 image each (25200 candidates, all survive) after {w_eff} warm-up; steps capped by a "
-              f"{args.cpu_budget_s:.0f}s wall budget because the reference loop is O(K*N) per image")
-    line = {
-        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": done,
-        "warmup": w_eff, "ms_per_step": 1e3 / ips, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD["name"], "images_per_step": 1, "candidates_per_image": 25200, "classes": 80},
-        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    emit_json(line)
-
-
 _JSON_FD = None
 
 
@@ -215,19 +202,376 @@ def emit_json(line):
         os.write(_JSON_FD, data)
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# synthetic inputs (CPU, seeded)
+# ------------------------------------------------------------------------------------------------------------------
+def yolo_inputs(cfg, batch, seed):
+    from objectdetectionpl_b200 import synth
+    if cfg.get("crowd"):
+        grids = [cfg["img"] // 8, cfg["img"] // 16, cfg["img"] // 32]
+        return synth.yolo_crowd(batch, cfg["anchors"], cfg["classes"], grids, cfg["img"], seed=seed), grids
+    grids = synth.grids_for(cfg["model"], cfg["img"])
+    return synth.yolo_planar(batch, cfg["anchors"], cfg["classes"], grids, cfg["img"], seed, v5_view=(cfg["model"] == "yolov5")), grids
+
+
+def prior_inputs(cfg, batch, seed):
+    from objectdetectionpl_b200 import synth
+    pri = synth.ssd_priors() if cfg["which"] == "SSD" else synth.retina_priors(800)
+    loc, cls = synth.prior_heads(batch, pri.shape[0], cfg["classes"], seed)
+    return pri, loc, cls
+
+
+def targets_inputs(cfg, batch, seed):
+    from objectdetectionpl_b200 import synth
+    C, img = cfg["classes"], cfg["img"]
+    g = torch.Generator().manual_seed(seed + 100)
+    heads = [torch.randn(batch, 3, img // s, img // s, 5 + C, generator=g) for s in (8, 16, 32)]
+    tg = synth.labels(batch, C, seed)
+    return heads, tg
+
+
+def base_config(cfg, batch, world):
+    c = {"workload": cfg["name"], "images_per_gpu": batch, "global_batch": batch * world, "classes": cfg["classes"]}
+    if cfg["kind"] == "yolo":
+        from objectdetectionpl_b200 import synth
+        grids = [cfg["img"] // 8, cfg["img"] // 16, cfg["img"] // 32] if cfg.get("crowd") else synth.grids_for(cfg["model"], cfg["img"])
+        c["candidates_per_image"] = sum(cfg["anchors"] * g * g for g in grids)
+        c["conf_thres"] = cfg.get("conf_thres", "reference-forced -0.0151 (all candidates survive)")
+        c["nms_thres"] = 0.4
+    elif cfg["kind"] == "prior":
+        c["priors_per_image"] = 8732 if cfg["which"] == "SSD" else 120087
+        c["topk"], c["class_thresh"], c["nms_thresh"] = 100, 0.45, 0.5
+    else:
+        c["max_boxes_per_image"] = 100
+    return c
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the reference arm / CPU baseline: the reference's OWN code on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def reference_runner(cfg, batch, seed):
+    """Returns (step_fn, images_per_step, kind, what): one call of step_fn(i) runs a bounded sample of the workload through the
+    reference's own CPU implementation (unmodified source from oracle/_ref resp. /root/reference)."""
+    from oracle import ref_harness as rh           # checker / baseline only — never on the product path
+    torch.set_num_threads(os.cpu_count() or 1)
+    staged = "oracle/_ref (unmodified reference, staged by oracle/stage_ref.py)" if rh.is_staged_copy() else rh.REF_ROOT
+    if cfg["kind"] == "yolo":
+        nimg = min(batch, 8)
+        levels, _ = yolo_inputs(cfg, nimg, seed)
+        N = base_config(cfg, batch, 1)["candidates_per_image"]
+        if cfg.get("crowd"):
+            # the unmodified reference overwrites its conf_thres argument (model/YOLOV5.py:164: conf_thres = -0.0151), so it cannot
+            # run this configuration (conf_thres 0.001) at all; the line-by-line port honours the argument
+            from oracle import ref_port as rp
+
+            def step(i):
+                rp.yolo_nms([t[i % nimg:i % nimg + 1] for t in levels], num_anchors=cfg["anchors"], conf_thres=cfg["conf_thres"],
+                            compat=False)
+            return step, 1, "port", (f"1 image per step ({N} candidates, ~10 % above conf_thres 0.001); oracle/ref_port.py::yolo_nms — the "
+                                     "unmodified reference forces conf_thres = -0.0151 and cannot run this configuration")
+        fn = rh.yolo_nms({"yolov5": 5, "yolov3": 3}[cfg["model"]])
+
+        def step(i):
+            with rh.cpu_only():
+                fn(None, [t[i % nimg:i % nimg + 1].clone() for t in levels])
+        return step, 1, "reference", (f"1 image per step ({N} candidates, all survive the forced conf_thres); "
+                                      f"{fn.__qualname__} from {staged}; the loop is O(K*N) per image")
+    if cfg["kind"] == "prior":
+        pri, loc, cls = prior_inputs(cfg, batch, seed)
+        fn = rh.ssd_nms(cfg["which"])
+        me = types.SimpleNamespace(iou_boxes=pri)
+
+        def step(i):
+            with rh.cpu_only():
+                fn(me, (loc, cls))
+        return step, batch, "reference", f"the full batch of {batch} images per step; {fn.__qualname__} from {staged}"
+    from objectdetectionpl_b200 import synth
+    heads, tg = targets_inputs(cfg, batch, seed)
+    with rh.cpu_only():
+        crit = rh.losses().MultiScaleRegionLoss_v5(synth.YOLOV5_ANCHORS, None, None, None, None, cfg["classes"], cfg["img"])
+
+    def step(i):
+        with rh.cpu_only():
+            p = [h.detach().requires_grad_(True) for h in heads]
+            crit(p, tg.clone())["loss"].sum().backward()
+    return step, batch, "reference", (f"the full batch of {batch} images per step; MultiScaleRegionLoss_v5 forward + backward "
+                                      f"(LightningFunc/losses.py:98-152) from {staged}")
+
+
+def run_cpu(cfg, batch, seed, steps, warmup, budget_s):
+    """-> dict(value images/s, steps done, warmup, cores, kind, sample)"""
+    step, per_step, kind, what = reference_runner(cfg, batch, seed)
+    t_start = time.perf_counter()
+    times = []
+    w_eff = 0
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        step(i)
+        dt = time.perf_counter() - t0
+        if i < warmup and (time.perf_counter() - t_start) + 2 * dt < 0.3 * budget_s:
+            w_eff += 1
+            continue
+        times.append(dt)
+        if (time.perf_counter() - t_start) + dt > budget_s:
+            break
+    per = sum(times) / len(times)
+    return dict(value=per_step / per, done=len(times), warmup=w_eff, cores=os.cpu_count() or 1, kind=kind,
+                sample=f"{len(times)} timed step(s) after {w_eff} warm-up, {what}; all host threads "
+                       f"(torch.set_num_threads({os.cpu_count()})); bounded by a {budget_s:.0f}s wall budget")
+
+
+def run_reference(args, cfg, rank):
+    if rank != 0:
+        return
+    batch = args.batch or cfg["batch"]
+    r = run_cpu(cfg, batch, cfg["seed"], args.steps or 3, min(args.warmup, 1), args.cpu_budget_s)
+    line = {
+        "impl": "reference", "metric": cfg["metric"], "value": r["value"], "unit": "images/s", "n_gpus": args.gpus, "steps": r["done"],
+        "warmup": r["warmup"], "ms_per_step": 1e3 / r["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": base_config(cfg, batch, 1),
+        "cpu_baseline": {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    emit_json(line)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# workloads on the GPU
+# ------------------------------------------------------------------------------------------------------------------
+def rotation(nbytes):
+    """Input sets to rotate through so that consecutive steps never find their input in L2 (126 MB)."""
+    if nbytes > 1.5 * L2_BYTES:
+        return 1
+    return max(2, min(128, int(2.5 * L2_BYTES // max(nbytes, 1)) + 1))
+
+
+class YoloWorkload:
+    def __init__(self, cfg, batch, seed, dev):
+        import objectdetectionpl_b200 as od
+        from objectdetectionpl_b200 import _lib as L
+        from objectdetectionpl_b200.postprocess import _yolo_desc
+        self.od, self.L, self.lib, self.cfg, self.dev, self.B = od, L, L.load(), cfg, dev, batch
+        self.levels_cpu, self.grids = yolo_inputs(cfg, batch, seed)
+        self.pinned = [t.pin_memory() for t in self.levels_cpu]
+        self.A, self.C = cfg["anchors"], cfg["classes"]
+        self.N = sum(self.A * g * g for g in self.grids)
+        self.head_bytes = batch * self.N * (5 + self.C) * 4
+        self.R = rotation(self.head_bytes)
+        self.sets = [[t.to(dev) for t in self.pinned]]
+        for r in range(1, self.R):                 # identical bytes at different addresses: results identical, L2 never warm
+            self.sets.append([t.clone() for t in self.sets[0]])
+        self.compat = "conf_thres" not in cfg
+        self.thr = od.YOLO_FORCED_CONF_THRES if self.compat else cfg["conf_thres"]
+        self.kw = {} if self.compat else dict(compat=False, conf_thres=cfg["conf_thres"])
+        lib = self.lib
+        self.descs = [_yolo_desc(s, self.A, self.thr, 0.4, None, None, None) for s in self.sets]
+        n, n_pad = ctypes.c_int32(), ctypes.c_int32()
+        L.check(lib.b200det_yolo_num_candidates(ctypes.byref(self.descs[0]), ctypes.byref(n), ctypes.byref(n_pad)))
+        self.n_pad = n_pad.value
+        self.ws_bytes = lib.b200det_yolo_workspace_bytes(ctypes.byref(self.descs[0]))
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.rows = torch.empty((batch, self.n_pad, 7), dtype=torch.float32, device=dev)
+        self.count = torch.empty((batch,), dtype=torch.int32, device=dev)
+        self.st = torch.cuda.current_stream(dev).cuda_stream
+        self.kernel = "yolo_decode_filter_kernel<MODE=0, U=8, MINB=6> (fused decode + filter + class argmax + ordered compaction)"
+        self.stage_names = ["decode", "sort", "nms", "emit"]
+        # our kernels per step: K1, sort, NMS, emit (+ the emit prefix in the packed public-API form).  The sort is ONE cluster
+        # launch up to 53 248 slots per image; larger images take the look-back sort: counter zero-fill, histogram, 4 score passes,
+        # class pass, segment scan
+        sort_launches = 1 if self.n_pad <= 53248 else 8
+        self.launches_pipe = 3 + sort_launches
+        self.launches_api = 4 + sort_launches
+        self.alg_bytes = self.head_bytes
+        self.l2 = (f"inputs {self.head_bytes / 1e6:.1f} MB per GPU and step > 126 MB L2 (no flush needed)" if self.R == 1 else
+                   f"{self.R} input sets of {self.head_bytes / 1e6:.1f} MB rotated ({self.R * self.head_bytes / 1e6:.0f} MB > 2x the 126 MB L2)")
+
+    def api_step(self, i):
+        out = self.od.non_max_suppression(None, self.sets[i % self.R], **self.kw)
+        return out
+
+    def pipe_step(self, i, ev=None, split=False):
+        L, lib, st = self.L, self.lib, self.st
+        dref, wp, wb = ctypes.byref(self.descs[i % self.R]), self.ws.data_ptr(), self.ws_bytes
+        L.check(lib.b200det_yolo_stage_reset(dref, wp, wb, st))
+        if ev is not None:
+            ev[0].record()
+        L.check(lib.b200det_yolo_stage_decode(dref, wp, wb, st))                 # K1 alone between ev[0] and ev[1]
+        if ev is not None:
+            ev[1].record()
+        L.check(lib.b200det_yolo_stage_sort(dref, wp, wb, st))
+        if split:
+            ev[2].record()
+        L.check(lib.b200det_yolo_stage_nms(dref, wp, wb, st))
+        if split:
+            ev[3].record()
+        L.check(lib.b200det_yolo_stage_emit(dref, wp, wb, self.rows.data_ptr(), None, self.count.data_ptr(), st))
+        if split:
+            ev[4].record()
+
+    def kept(self):
+        return int(self.count.sum().item())
+
+    def e2e_run(self, n):
+        """`non_max_suppression_host_async`: 8-image chunks, H2D of chunk k+1 / pipeline of chunk k / D2H of chunk k-1 overlap;
+        batch i+1 is submitted before batch i is collected.  A step is collected when its detections are in pinned host
+        memory and the host has read the row counts."""
+        od, prev, nrows = self.od, None, 0
+        for _ in range(n):
+            h = od.non_max_suppression_host_async(None, self.pinned, device=self.dev, **self.kw)
+            if prev is not None:
+                nrows = sum(x.shape[0] for x in prev.result() if x is not None)
+            prev = h
+        return sum(x.shape[0] for x in prev.result() if x is not None)
+
+    def e2e_bytes(self):
+        return sum(t.numel() * 4 for t in self.pinned), self.B * self.n_pad * 7 * 4 + self.B * 4
+
+    e2e_api = ("objectdetectionpl_b200.non_max_suppression_host_async (pinned host in/out, 8-image chunks on 3 streams, "
+               "batch i+1 submitted before batch i is collected)")
+
+
+class PriorWorkload:
+    def __init__(self, cfg, batch, seed, dev):
+        import objectdetectionpl_b200 as od
+        from objectdetectionpl_b200 import _lib as L
+        self.od, self.L, self.lib, self.cfg, self.dev, self.B = od, L, L.load(), cfg, dev, batch
+        pri, loc, cls = prior_inputs(cfg, batch, seed)
+        self.P, self.C = pri.shape[0], cfg["classes"]
+        self.pri = pri.to(dev)
+        self.pinned = [loc.pin_memory(), cls.pin_memory()]
+        self.head_bytes = (loc.numel() + cls.numel()) * 4
+        self.R = rotation(self.head_bytes)
+        self.sets = [[t.to(dev) for t in self.pinned]]
+        for r in range(1, self.R):
+            self.sets.append([t.clone() for t in self.sets[0]])
+        self.me = types.SimpleNamespace(iou_boxes=self.pri)
+        self.descs = []
+        for loc_d, cls_d in self.sets:
+            d = L.PriorDesc()
+            d.batch, d.num_priors, d.num_classes = batch, self.P, self.C
+            d.loc, d.cls, d.priors = loc_d.data_ptr(), cls_d.data_ptr(), self.pri.data_ptr()
+            d.topk, d.nms_thresh, d.class_thresh, d.mode_min, d.compat = 100, 0.5, 0.45, 0, 1
+            self.descs.append(d)
+        self.ws_bytes = self.lib.b200det_prior_workspace_bytes(ctypes.byref(self.descs[0]))
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.rows = torch.empty((batch, 100, 7), dtype=torch.float32, device=dev)
+        self.count = torch.empty((2, batch), dtype=torch.int32, device=dev)
+        self.st = torch.cuda.current_stream(dev).cuda_stream
+        self.kernel = "prior_decode_filter_kernel<true,true> (prior decode + sigmoid-argmax + score filter + ordered compaction)"
+        self.stage_names = ["decode", "select+nms"]
+        self.launches_pipe = self.launches_api = 3            # K1', radix select, NMS (the counts copy is a cudaMemcpyAsync)
+        self.alg_bytes = self.head_bytes
+        self.l2 = (f"inputs {self.head_bytes / 1e6:.1f} MB per GPU and step > 126 MB L2 (no flush needed)" if self.R == 1 else
+                   f"{self.R} input sets of {self.head_bytes / 1e6:.1f} MB rotated ({self.R * self.head_bytes / 1e6:.0f} MB > 2x the 126 MB L2)")
+
+    def api_step(self, i):
+        loc, cls = self.sets[i % self.R]
+        return self.od.prior_non_max_suppression(self.me, (loc, cls))
+
+    def pipe_step(self, i, ev=None, split=False):
+        L, lib, st = self.L, self.lib, self.st
+        dref, wp, wb = ctypes.byref(self.descs[i % self.R]), self.ws.data_ptr(), self.ws_bytes
+        if ev is not None:
+            ev[0].record()
+        L.check(lib.b200det_prior_stage_decode(dref, wp, wb, st))                # K1' alone between ev[0] and ev[1]
+        if ev is not None:
+            ev[1].record()
+        L.check(lib.b200det_prior_stage_select_nms(dref, wp, wb, self.rows.data_ptr(), None, self.count[0].data_ptr(),
+                                                   self.count[1].data_ptr(), st))
+        if split:
+            ev[2].record()
+
+    def kept(self):
+        return int(self.count[0].sum().item())
+
+    def e2e_run(self, n):
+        nrows = 0
+        for _ in range(n):
+            out = self.od.prior_non_max_suppression_host(self.me, tuple(self.pinned), device=self.dev)
+            nrows = sum(x.shape[0] for x in out)
+        return nrows
+
+    def e2e_bytes(self):
+        return sum(t.numel() * 4 for t in self.pinned), self.B * 100 * 7 * 4 + 2 * self.B * 4
+
+    e2e_api = "objectdetectionpl_b200.prior_non_max_suppression_host (pinned host loc/cls in, pinned host rows out)"
+
+
+class TargetsWorkload:
+    def __init__(self, cfg, batch, seed, dev):
+        import objectdetectionpl_b200 as od
+        from objectdetectionpl_b200 import synth
+        self.od, self.cfg, self.dev, self.B, self.C = od, cfg, dev, batch, cfg["classes"]
+        heads, tg = targets_inputs(cfg, batch, seed)
+        self.pinned = [h.pin_memory() for h in heads]
+        self.tg_pinned = tg.pin_memory()
+        self.tg = tg.to(dev)
+        self.nt = int(tg.shape[0])
+        self.p = [h.to(dev).requires_grad_(True) for h in self.pinned]
+        stride = torch.tensor([8., 16., 32.])
+        self.anchors = (torch.tensor(synth.YOLOV5_ANCHORS).float().view(3, -1, 2) / stride.view(-1, 1, 1)).to(dev)
+        self.head_bytes = sum(h.numel() * 4 for h in heads)
+        self.R = 1
+        tcls, _, _, _ = od.build_targets_v5([tuple(h.shape) for h in heads], self.tg, self.anchors, 3, 3)
+        self.m = [int(t.shape[0]) for t in tcls]
+        M, F = sum(self.m), 5 + self.C
+        cells = sum(h.numel() // F for h in heads)
+        # SURVEY 8d: nt*24 in + sum m_i (4*8 + 16 + 8 + 8) out + gathered sum m_i (5+C)*4; plus what the fused loss tail must touch:
+        # the objectness logit of every cell (read, and its gradient written) and the gradient rows of the matched cells
+        self.alg_bytes = self.nt * 24 + M * (32 + 16 + 8 + 8) + 2 * M * F * 4 + 2 * cells * 4
+        self.kernel = ("whole step: build_targets_v5_kernel + v5_loss_rows/obj fwd + bwd kernels (latency-bound; the objectness column "
+                       "is one 4-byte field per 340-byte row)")
+        self.stage_names = []
+        # build_targets_v5 (1); forward per level: rows + objectness kernels (2 x 3) and the combine (1); backward: combine (1) and
+        # per level rows + objectness kernels (2 x 3).  (torch's own zero-fill kernels of tobj / the gradient buffers are not ours.)
+        self.launches_pipe = self.launches_api = 1 + 6 + 1 + 1 + 6
+        self.l2 = f"heads {self.head_bytes / 1e6:.1f} MB per GPU > 126 MB L2 (no flush needed)"
+
+    def api_step(self, i):
+        for t in self.p:
+            t.grad = None
+        m = self.od.v5_loss(self.p, self.tg, self.anchors, 3, 3, self.C)
+        m["loss"].backward()
+        return m
+
+    def pipe_step(self, i, ev=None, split=False):
+        if ev is not None:
+            ev[0].record()
+        self.api_step(i)
+        if ev is not None:
+            ev[1].record()
+
+    def kept(self):
+        return sum(self.m)
+
+    def e2e_run(self, n):
+        dev, val = self.dev, 0.0
+        for _ in range(n):
+            p = [h.to(dev, non_blocking=True).requires_grad_(True) for h in self.pinned]
+            tg = self.tg_pinned.to(dev, non_blocking=True)
+            m = self.od.v5_loss(p, tg, self.anchors, 3, 3, self.C)
+            m["loss"].backward()
+            val = float(torch.cat([m["loss"], m["Localization"], m["Classification"], m["Conf_obj"]]).cpu()[0])
+        return val
+
+    def e2e_bytes(self):
+        return sum(t.numel() * 4 for t in self.pinned) + self.tg_pinned.numel() * 4, 16
+
+    e2e_api = ("pinned host heads + labels -> device, objectdetectionpl_b200.v5_loss(...)['loss'].backward(), the four loss scalars "
+               "read back (the head gradients stay on the device, where the backbone's backward consumes them)")
+
+
 def main():
     args = parse()
+    cfg = CONFIGS[args.config]
     rank, world, local = dist_env()
     claim_stdout()
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, cfg, rank)
         return
 
-    import ctypes
     import torch.distributed as dist
     import objectdetectionpl_b200 as od
-    from objectdetectionpl_b200 import _lib as L
-    from objectdetectionpl_b200.postprocess import _yolo_desc
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
@@ -238,157 +582,144 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    lib = L.load()
-    w = WORKLOAD
-    B = args.batch
-    levels_cpu, grids = make_inputs(B, w["seed"] + rank)          # per-rank shard of the global batch (by image)
-    pinned = [t.pin_memory() for t in levels_cpu]
-    levels = [t.to(dev) for t in pinned]
-    N = sum(w["anchors"] * g * g for g in grids)
-    head_bytes = B * N * (5 + w["classes"]) * 4
-
-    # ---- stage-wise descriptors (the pipeline call is exactly these four stage calls) -----------------------------
-    d = _yolo_desc(levels, w["anchors"], od.YOLO_FORCED_CONF_THRES, 0.4, None, None, None)
-    n, n_pad = ctypes.c_int32(), ctypes.c_int32()
-    L.check(lib.b200det_yolo_num_candidates(ctypes.byref(d), ctypes.byref(n), ctypes.byref(n_pad)))
-    ws_bytes = lib.b200det_yolo_workspace_bytes(ctypes.byref(d))
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    rows = torch.empty((B, n_pad.value, 7), dtype=torch.float32, device=dev)
-    count = torch.empty((B,), dtype=torch.int32, device=dev)
-    st = torch.cuda.current_stream(dev).cuda_stream
-    dref, wp, rp_, cp = ctypes.byref(d), ws.data_ptr(), rows.data_ptr(), count.data_ptr()
-
-    def step(ev=None, split=False):
-        L.check(lib.b200det_yolo_stage_reset(dref, wp, ws_bytes, st))       # zero-fill of the counter header
-        if ev is not None:
-            ev[0].record()
-        L.check(lib.b200det_yolo_stage_decode(dref, wp, ws_bytes, st))      # K1 alone between ev[0] and ev[1]
-        if ev is not None:
-            ev[1].record()
-        L.check(lib.b200det_yolo_stage_sort(dref, wp, ws_bytes, st))
-        if split:
-            ev[2].record()
-        L.check(lib.b200det_yolo_stage_nms(dref, wp, ws_bytes, st))
-        if split:
-            ev[3].record()
-        L.check(lib.b200det_yolo_stage_emit(dref, wp, ws_bytes, rp_, None, cp, st))
-        if split:
-            ev[4].record()
+    B = args.batch or cfg["batch"]
+    K = args.steps or (500 if cfg["kind"] != "targets" else 200)
+    W = max(args.warmup, 3)
+    wl = {"yolo": YoloWorkload, "prior": PriorWorkload, "targets": TargetsWorkload}[cfg["kind"]](cfg, B, cfg["seed"] + rank, dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    K = args.steps
-    # Inside the timed region only K1 is bracketed by events (roofline.achieved must be measured there); the split of
-    # the other stages comes from a short extra pass afterwards so that its events do not sit in the headline loop.
-    stage_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
-    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for i in range(W):
+        wl.api_step(i)
+        wl.pipe_step(i)
+    torch.cuda.synchronize(dev)
+
+    # ---- timed region: (A) the public API, (B) the stage entry points with CUDA events around the streaming kernel -----
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k1_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
     barrier()
     with ClockSampler(local) as clk:
-        t_begin.record()
+        a0.record()
         for i in range(K):
-            step(stage_ev[i])
-        t_end.record()
+            wl.api_step(i)
+        a1.record()
         barrier()
-    total_ms = t_begin.elapsed_time(t_end)
-    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    total_ms_max = float(tmax.item())
-    ms_per_step = total_ms_max / K
-    value = world * B * K / (total_ms_max * 1e-3)
-    k1_us = statistics.mean(stage_ev[i][0].elapsed_time(stage_ev[i][1]) for i in range(K)) * 1e3
-    Ks = min(K, 50)
-    split_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(Ks)]
-    for i in range(Ks):
-        step(split_ev[i], split=True)
-    torch.cuda.synchronize(dev)
-    names = ["decode", "sort", "nms", "emit"]
-    stage_us = {nm: statistics.mean(split_ev[i][k].elapsed_time(split_ev[i][k + 1]) for i in range(Ks)) * 1e3
-                for k, nm in enumerate(names)}
-    kept = count.cpu()
-    kept_total = int(kept.sum())
+        b0.record()
+        for i in range(K):
+            wl.pipe_step(i, k1_ev[i])
+        b1.record()
+        barrier()
+    api_ms = max_over_ranks(a0.elapsed_time(a1))
+    pipe_ms = max_over_ranks(b0.elapsed_time(b1))
+    value = world * B * K / (api_ms * 1e-3)
+    pipeline_value = world * B * K / (pipe_ms * 1e-3)
+    k1_us = statistics.mean(k1_ev[i][0].elapsed_time(k1_ev[i][1]) for i in range(K)) * 1e3
+    kept_total = wl.kept()
 
-    # ---- end-to-end through the public API from pinned host buffers -------------------------------------------------
-    # non_max_suppression_host_async: chunks of 8 images, H2D of chunk k+1 / CUDA pipeline of chunk k / D2H of chunk k-1
-    # overlap; batch i+1 is submitted before batch i is collected (two pinned result sets), so the host->device link stays
-    # busy across steps.  A step is collected when its detections (padded rows + counts) are in pinned host memory and
-    # the host has read them (row count per image).  Every step's H2D and D2H lie inside the timed region.
-    def e2e_run(n):
-        prev, nrows = None, 0
-        for _ in range(n):
-            h = od.non_max_suppression_host_async(None, pinned, device=dev)
-            if prev is not None:
-                nrows = sum(x.shape[0] for x in prev.result() if x is not None)
-            prev = h
-        return sum(x.shape[0] for x in prev.result() if x is not None)
+    stage_us = {}
+    if wl.stage_names:
+        Ks, ns = min(K, 50), len(wl.stage_names)
+        sev = [[torch.cuda.Event(enable_timing=True) for _ in range(ns + 1)] for _ in range(Ks)]
+        for i in range(Ks):
+            wl.pipe_step(i, sev[i], split=True)
+        torch.cuda.synchronize(dev)
+        stage_us = {nm: statistics.mean(sev[i][k].elapsed_time(sev[i][k + 1]) for i in range(Ks)) * 1e3
+                    for k, nm in enumerate(wl.stage_names)}
 
-    e2e_run(3)
+    # ---- end to end from pinned host buffers ---------------------------------------------------------------------------
+    wl.e2e_run(3)
     Ke = max(1, min(args.e2e_steps, K))
     barrier()
-    t0 = time.perf_counter()
-    e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e_begin.record()
-    nrows = e2e_run(Ke)
-    e_end.record()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    wl.e2e_run(Ke)
+    e1.record()
     barrier()
-    e_ms = torch.tensor([e_begin.elapsed_time(e_end)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * Ke / (float(e_ms.item()) * 1e-3)
-    h2d = sum(t.numel() * 4 for t in pinned)
-    d2h = B * n_pad.value * 7 * 4 + B * 4          # padded rows [B, n_pad, 7] + counts (no host sync before the copy)
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * B * Ke / (e2e_ms * 1e-3)
+    h2d, d2h = wl.e2e_bytes()
 
-    # ---- the one exchange step of the path: all-gather of detections for mAP (outside the timed region) --------------
-    gather_ms = None
-    if world > 1:
-        dets = od.non_max_suppression(None, levels)
-        torch.cuda.synchronize(dev)
-        g0 = time.perf_counter()
-        allp = od.dist.gather_detections(dets, image_offset=rank * B, device=dev)
-        torch.cuda.synchronize(dev)
-        gather_ms = (time.perf_counter() - g0) * 1e3
-        assert int(allp[:, 7].max().item()) == world * B - 1
+    # ---- the one exchange step of the path: all-gather of the detections for mAP, timed as its own leg ---------------------
+    gather = None
+    if cfg["kind"] == "yolo" and (world > 1 or args.config == "crowd512"):
+        rows, _, count = od.yolo_nms_raw(wl.sets[0], wl.A, wl.thr)
+        send = torch.empty((B * rows.shape[1], 8), dtype=torch.float32, device=dev)
+        for _ in range(3):
+            g = od.dist.gather_detections_raw(rows, count, rank * B, send=send)
+        barrier()
+        gt = []
+        for _ in range(max(1, args.gather_iters)):
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if world > 1:
+                dist.barrier()
+            g0.record()
+            g = od.dist.gather_detections_raw(rows, count, rank * B, send=send)
+            g1.record()
+            torch.cuda.synchronize(dev)
+            gt.append(g0.elapsed_time(g1))
+        g_ms = max_over_ranks(statistics.median(gt))
+        per = g.per_image()
+        assert len(per) == world * B and sum(g.totals) == sum(0 if p is None else p.shape[0] for p in per)
+        ids = g.rows[world - 1, :g.totals[world - 1], 7]
+        assert int(ids.max().item()) == world * B - 1 and int(g.rows[0, 0, 7].item()) == 0
+        payload = sum(g.totals) * 32
+        gather = {"ms": g_ms, "rows_total": sum(g.totals), "payload_MB": payload / 1e6, "algbw_GBps": payload / (g_ms * 1e-3) / 1e9,
+                  "how": "device-side pack kernel + all_gather_into_tensor(counts) + one host read + all_gather_into_tensor(rows) into a "
+                         "persistent buffer; median of %d warm iterations, CUDA events, max over ranks" % max(1, args.gather_iters)}
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        achieved = head_bytes / (k1_us * 1e-6) / 1e9
-        launches = 1 + 1 + 1 + 1                               # K1; cluster sort; NMS; emit (the reset stage launches nothing)
+        achieved = wl.alg_bytes / (k1_us * 1e-6) / 1e9
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "k1_traffic.json")   # dram__bytes_read+write of one K1 launch (ncu --set full)
+        tp = os.path.join(ROOT, "profiles", "k1_traffic.json")   # dram__bytes_read+write of one launch (ncu --set full), per config
         if os.path.exists(tp):
             try:
-                traffic = float(json.load(open(tp))["dram_bytes_per_launch"])
+                tj = json.load(open(tp))
+                traffic = float(tj.get(args.config, {}).get("dram_bytes_per_launch")) if args.config in tj else None
             except Exception:
                 traffic = None
+        c = base_config(cfg, B, world)
+        c["parallelism"] = f"image-sharded x{world}, no data-path collective"
+        c["l2"] = wl.l2
         line = {
-            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": w["name"], "images_per_gpu": B, "global_batch": B * world, "candidates_per_image": N,
-                       "classes": w["classes"], "conf_thres": "reference-forced -0.0151 (all candidates survive)",
-                       "nms_thres": 0.4, "parallelism": f"image-sharded x{world}, no data-path collective",
-                       "l2": f"inputs {head_bytes / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)"},
-            "clocks": clk.summary(),
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "api": "objectdetectionpl_b200.non_max_suppression_host_async (pinned host in/out, 8-image chunks on 3 streams, batch i+1 submitted before batch i is collected)"},
-            "gpu_launches": launches * K,
-            "roofline": {"bound": "hbm", "kernel": "yolo_decode_filter_kernel<4,0,8,6> (one launch per step, CUDA events around it)",
+            "metric": cfg["metric"], "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": api_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": c, "clocks": clk.summary(),
+            "value_api": "public API on device-resident inputs, CUDA events around the wrapper calls (host sync on the counts and "
+                         "the list build included)",
+            "pipeline_value": pipeline_value, "pipeline_ms_per_step": pipe_ms / K,
+            "api_over_pipeline": (api_ms / pipe_ms),
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+                    "ms_per_step": e2e_ms / Ke, "h2d_GBps": h2d / (e2e_ms / Ke * 1e-3) / 1e9, "api": wl.e2e_api},
+            "gpu_launches": (wl.launches_api + wl.launches_pipe) * K,
+            "gpu_launches_note": f"{wl.launches_api} of this repo's kernels per public-API step + {wl.launches_pipe} per stage-entry step, {K} steps each",
+            "roofline": {"bound": "hbm", "kernel": wl.kernel + " — one launch per step, CUDA events around it in the timed region",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": head_bytes},
-            "stages_us": stage_us, "k1_us_in_timed_region": k1_us, "rank_cpu_affinity": local_cpus, "kept_per_image_mean": kept_total / B, "workspace_mb": ws_bytes / 1e6,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": wl.alg_bytes,
+                         "pipeline_frac": (wl.alg_bytes + (kept_total * 28 if cfg["kind"] != "targets" else 0)) / (pipe_ms / K * 1e-3) / 1e9 / peak},
+            "stages_us": stage_us, "k1_us_in_timed_region": k1_us, "rank_cpu_affinity": local_cpus,
+            "kept_per_image_mean": kept_total / B, "us_per_image": api_ms / K * 1e3 / B,
         }
-        if gather_ms is not None:
-            line["detection_allgather_ms"] = gather_ms
+        if cfg["kind"] == "targets":
+            line["targets_per_s"] = wl.nt * K / (api_ms * 1e-3) * world
+            line["us_per_step"] = api_ms / K * 1e3
+            line["matched_rows_per_level"] = wl.m
+        if gather is not None:
+            line["detection_allgather_ms"] = gather["ms"]
+            line["detection_allgather"] = gather
         if world == 1 and not args.no_cpu_baseline:
-            ips, done, w_eff = cpu_reference_run([t[:2] for t in levels_cpu], 1, 0, 60.0)
-            line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": f"{done} image of the same batch (25200 candidates, all survive), no warm-up, "
-                                              "torch-CPU port of the reference loop with all host threads"}
+            r = run_cpu(cfg, B, cfg["seed"], 2, 0, 25.0)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
         emit_json(line)
     if world > 1:
         dist.destroy_process_group()
