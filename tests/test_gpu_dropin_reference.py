@@ -130,8 +130,8 @@ def test_v5_criterion_forward_backward_stock_vs_installed(ref):
     tg = synth.labels(B, C, 6, max_per_image=8)
 
     def run(c, dev):
-        p = [h.to(dev).requires_grad_(True) for h in heads]
-        m = c(p, tg.to(dev))
+        p = [h.detach().clone().to(dev).requires_grad_(True) for h in heads]
+        m = c(p, tg.clone().to(dev))
         m["loss"].sum().backward()
         return {k: v.detach().float().cpu() for k, v in m.items()}, [t.grad.cpu() for t in p]
 
