@@ -21,6 +21,7 @@
 // the keep decisions are bit-identical to the reference's fp32 CPU path.
 #include <cuda_fp16.h>
 #include <limits.h>
+#include <stdlib.h>
 
 #include "yolo_ws.cuh"
 
@@ -29,6 +30,8 @@ namespace b200det {
 constexpr int kNmsT = 384;                 // rows per chunk (384: 6 CTAs/SM; 512 measured 320 vs 295 us at the headline)
 constexpr int kNmsThreads = 256;
 constexpr int kNmsRounds = 12;             // parallel fixed-point rounds before the serial sweep takes over
+constexpr int kNmsLevels = 32;             // TAB: quantisation levels of the per-axis bound tables (one lane per level in the scans)
+constexpr int kNmsQCap = 128;              // TAB: candidate-pair queue entries per warp
 
 struct NmsParams {
     const uint32_t* seg_off;    // [B][C+1]     VARIANT 0
@@ -159,6 +162,38 @@ __device__ __forceinline__ unsigned may_remove_mask32(const uint2* __restrict__ 
     return __byte_perm(ra, rb, 0x5410) & __byte_perm(ra, rb, 0x7632);
 }
 
+// ---- TAB pre-filter -------------------------------------------------------------------------------------------------
+// The same necessary condition as box_bounds_h2 / may_remove (per axis: u_a > lo_b and u_b > lo_a with lo = x1,
+// u = x2 + 1 - thr' (w + 1)), but evaluated for 64 columns at once by table lookup instead of pair by pair:
+// every bound is quantised to one of kNmsLevels levels with a MONOTONE map (level(v) = clamp(floor((v - base) * inv)); base / inv
+// from the min lo and max u of the chunk), so lo_i < u_j implies level(lo_i) <= level(u_j).  Per axis two tables of
+// column bitmaps:  A[q] = { columns i : level(lo_i) <= q }  and  B[q] = { i : level(u_i) >= q };  the columns that can
+// remove / be removed by row j are  A_x[level(u_x_j)] & B_x[level(lo_x_j)] & A_y[level(u_y_j)] & B_y[level(lo_y_j)]:
+// four 64-bit shared loads and three ANDs per (row, 64 columns) instead of 64 x (load + 4 half2 instructions).  It lets
+// about twice as many pairs through as the half2 test (quantisation slack); those pairs are not tested lane by lane in a
+// divergent loop but pushed into a per-warp queue and tested 32 at a time with every lane busy.  Rows with a non-finite
+// bound never remove anything and are never removed (their IoU is 0 or NaN), so whatever level they land on is fine.
+__device__ __forceinline__ void box_bounds_f32(const float4 b, const float thr, float& lox, float& loy, float& ux, float& uy) {
+    const float thr_lo = __fmul_rd(thr, 1.0f - 0.0078125f);
+    lox = b.x;
+    loy = b.y;
+    ux = __fsub_ru(__fadd_ru(b.z, 1.0f), __fmul_rd(thr_lo, __fadd_rd(__fsub_rd(b.z, b.x), 1.0f)));
+    uy = __fsub_ru(__fadd_ru(b.w, 1.0f), __fmul_rd(thr_lo, __fadd_rd(__fsub_rd(b.w, b.y), 1.0f)));
+}
+__device__ __forceinline__ int ordered_int(float f) {            // signed-int order == float order (finite values)
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+__device__ __forceinline__ float ordered_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+__device__ __forceinline__ bool finite_f(float f) { return (__float_as_uint(f) & 0x7F800000u) != 0x7F800000u; }
+__device__ __forceinline__ unsigned bound_level(float v, float base, float inv) {
+    const int l = __float2int_rd(__fmul_rn(__fsub_rn(v, base), inv));           // NaN -> 0, +-inf -> saturates
+    return (unsigned)min(kNmsLevels - 1, max(0, l));
+}
+
+#ifdef B200DET_NMS_DEBUG
+__device__ unsigned long long g_nms_dbg[8];
+#endif
 // Development aid: phase timestamps of the first chunk of every segment CTA (see tools/stage_timing.py --trace-nms).
 __device__ unsigned long long* g_nms_trace = nullptr;
 __device__ __forceinline__ void nms_stamp(unsigned long long* tr, int point) {
@@ -177,8 +212,10 @@ __device__ __forceinline__ void nms_stamp(unsigned long long* tr, int point) {
 // CT rows per chunk: 384 (the triangle of 6 mask words per row) — or 192 with 128 threads when the average segment is
 // short (YOLOv3-416: 133 rows): a CTA then needs 14 KB instead of 32 KB of shared memory, 12 of them fit an SM and twice as
 // many segments hide each other's fixed latencies (loads, barriers, global stores).
-template <int VARIANT, bool FAST, int NT, int CT>
-__global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_segment_kernel(const NmsParams p) {
+template <int VARIANT, bool FAST, int NT, int CT, bool TAB = false>
+__global__ void __launch_bounds__(NT, TAB ? (NT == 128 ? 10 : (NT == 256 ? 5 : 2)) : (NT == 128 ? 12 : (NT == 256 ? 6 : 3)))
+nms_segment_kernel(const NmsParams p) {
+    static_assert(!TAB || (VARIANT == 0 && FAST), "the table pre-filter is built for the YOLO class-aware NMS with nms_thres >= 0");
     constexpr int NW = CT / 64;                       // mask words per full row
     constexpr int TRI = 32 * NW * (NW + 1);           // packed lower-triangular rows
     constexpr int STAGE = (TRI * 8 / 24) / 32 * 32;   // earlier keepers staged per phase-A round, in the aliased mask triangle
@@ -212,6 +249,11 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_
     // 196 KB carve-out is 32.6 KB per CTA)
     __shared__ int16_t s_last[CT];
     __shared__ int s_mpre[CT / 32 + 1];  // exclusive prefix of the member bitmap's popcounts
+    // TAB pre-filter (see box_bounds_f32): bound tables, per-row levels, per-warp candidate queues, chunk range
+    __shared__ __align__(16) unsigned long long s_tab[TAB ? 4 : 1][TAB ? kNmsLevels : 1][TAB ? NW : 1];
+    __shared__ uchar4 s_lvl[TAB ? CT : 1];           // level(u_x), level(lo_x), level(u_y), level(lo_y) of the row
+    __shared__ uint32_t s_queue[TAB ? NT / 32 : 1][TAB ? kNmsQCap : 1];
+    __shared__ int s_rng[4];                         // ordered-int min lo_x, max u_x, min lo_y, max u_y of the chunk
 
     const int b = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -237,10 +279,18 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_
     int Kprev = 0;          // keepers found in earlier chunks
     int last_k = -1;        // VARIANT 1/2: index of the last keeper so far
     if (tid == 0) s_last_members = 0;
+    if (TAB) {
+        if (tid < 4) s_rng[tid] = (tid & 1) ? INT_MIN : INT_MAX;
+        __syncthreads();
+    }
 
     for (int c0 = s; c0 < e; c0 += CT) {
         const int nc = min(CT, e - c0);
         const int Wc = (nc + 63) >> 6;
+        if (TAB) {
+            uint4* z = reinterpret_cast<uint4*>(&s_tab[0][0][0]);
+            for (int i = tid; i < 4 * kNmsLevels * NW / 2; i += NT) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
 
         // ---- load the chunk ----------------------------------------------------------------
         // both rows of a thread are fetched together: payload -> slot -> box is a chain of two L2 round trips, and a
@@ -270,6 +320,24 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_
                 s_pre[j] = -1;
                 s_first[j] = -1;
                 s_nzw[j] = 0u;
+            }
+            if (TAB) {
+                // range of the chunk's bounds (finite ones): per-warp redux, one shared atomic per warp and value
+                int mn_x = INT_MAX, mx_x = INT_MIN, mn_y = INT_MAX, mx_y = INT_MIN;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if ((h ? j1 : j0) >= nc) continue;
+                    float lox, loy, ux, uy;
+                    box_bounds_f32(h ? b1 : b0, thr, lox, loy, ux, uy);
+                    if (finite_f(lox) && finite_f(ux)) { mn_x = min(mn_x, ordered_int(lox)); mx_x = max(mx_x, ordered_int(ux)); }
+                    if (finite_f(loy) && finite_f(uy)) { mn_y = min(mn_y, ordered_int(loy)); mx_y = max(mx_y, ordered_int(uy)); }
+                }
+                mn_x = __reduce_min_sync(0xFFFFFFFFu, mn_x); mx_x = __reduce_max_sync(0xFFFFFFFFu, mx_x);
+                mn_y = __reduce_min_sync(0xFFFFFFFFu, mn_y); mx_y = __reduce_max_sync(0xFFFFFFFFu, mx_y);
+                if (lane == 0) {
+                    atomicMin(&s_rng[0], mn_x); atomicMax(&s_rng[1], mx_x);
+                    atomicMin(&s_rng[2], mn_y); atomicMax(&s_rng[3], mx_y);
+                }
             }
         }
         if (tid < NW) s_member[tid] = 0ull;      // 32-row groups past nc are never written by the ballots below
@@ -325,6 +393,54 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_
         }
 
         if (c0 == s) nms_stamp(tr, 1);
+        if (TAB) {
+            // ---- bound tables of the chunk's live rows (see box_bounds_f32) ----------------------------------------
+            unsigned* const tab32 = reinterpret_cast<unsigned*>(&s_tab[0][0][0]);       // [4][levels][2 * NW] 32-bit halves
+            const float base_x = ordered_float(s_rng[0]), top_x = ordered_float(s_rng[1]);
+            const float base_y = ordered_float(s_rng[2]), top_y = ordered_float(s_rng[3]);
+            float inv_x = top_x > base_x ? __fdiv_rn((float)kNmsLevels, __fsub_rn(top_x, base_x)) : 0.0f;
+            float inv_y = top_y > base_y ? __fdiv_rn((float)kNmsLevels, __fsub_rn(top_y, base_y)) : 0.0f;
+            if (!finite_f(inv_x)) inv_x = 0.0f;
+            if (!finite_f(inv_y)) inv_y = 0.0f;
+            for (int j = tid; j < nc; j += NT) {
+                if (s_pre[j] >= 0) continue;                                 // removed by an earlier chunk: not a column
+                float lox, loy, ux, uy;
+                box_bounds_f32(s_box[j], thr, lox, loy, ux, uy);
+                const unsigned l_ux = bound_level(ux, base_x, inv_x), l_lox = bound_level(lox, base_x, inv_x);
+                const unsigned l_uy = bound_level(uy, base_y, inv_y), l_loy = bound_level(loy, base_y, inv_y);
+                s_lvl[j] = make_uchar4((unsigned char)l_ux, (unsigned char)l_lox, (unsigned char)l_uy, (unsigned char)l_loy);
+                const unsigned bit = 1u << (j & 31);
+                const int h = j >> 5;
+                atomicOr(&tab32[((0 * kNmsLevels + l_lox) * 2 * NW) + h], bit);           // A_x: exact level of lo_x
+                atomicOr(&tab32[((1 * kNmsLevels + l_ux) * 2 * NW) + h], bit);            // B_x: exact level of u_x
+                atomicOr(&tab32[((2 * kNmsLevels + l_loy) * 2 * NW) + h], bit);
+                atomicOr(&tab32[((3 * kNmsLevels + l_uy) * 2 * NW) + h], bit);
+            }
+            __syncthreads();
+            if (tid < 4) s_rng[tid] = (tid & 1) ? INT_MIN : INT_MAX;          // everybody has read the range: reset for the next chunk
+            // A[q] = OR of the exact levels <= q (prefix over the lanes = levels), B[q] = OR of the levels >= q (suffix)
+            static_assert(kNmsLevels == 32, "one lane per level");
+            for (int c = tid >> 5; c < 4 * 2 * NW; c += NT / 32) {
+                const int t = c / (2 * NW), h = c - t * 2 * NW;
+                unsigned* cell = &tab32[((t * kNmsLevels + lane) * 2 * NW) + h];
+                unsigned v = *cell;
+                if (t & 1) {
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned u = __shfl_down_sync(0xFFFFFFFFu, v, o);
+                        if (lane + o < 32) v |= u;
+                    }
+                } else {
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned u = __shfl_up_sync(0xFFFFFFFFu, v, o);
+                        if (lane >= o) v |= u;
+                    }
+                }
+                *cell = v;
+            }
+            __syncthreads();
+        }
         // ---- phase B: lower-triangular overlap masks inside the chunk --------------------------
         // One task = (mask word w, 32-row group g >= 2w).  The tasks are dealt round-robin to the warps: looping over
         // the words with rows striped over the CTA leaves the high warps idle for the later words (6 task slots for
@@ -332,7 +448,76 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 12 : (NT == 256 ? 6 : 3)) nms_
         const int ngroups_b = (nc + 31) >> 5;
         int n_tasks = 0;
         for (int w = 0; w < Wc; ++w) n_tasks += ngroups_b - 2 * w;
-        for (int t = tid >> 5; t < n_tasks; t += NT / 32) {
+        if (TAB) {
+            // candidate columns by table lookup; candidate pairs go through the warp's queue and are tested 32 at a time
+            uint32_t* const qw = s_queue[tid >> 5];
+            int fill = 0;
+            auto test_pair = [&](const uint32_t ent) {
+                const int j = (int)(ent >> 10), i = (int)(ent & 1023u);
+                if (removes<VARIANT>(s_box[i], s_box[j], thr)) {
+                    atomicOr(reinterpret_cast<unsigned*>(&s_L[tri_off(j) + (i >> 6)]) + ((i >> 5) & 1), 1u << (i & 31));
+                    atomicOr(reinterpret_cast<unsigned*>(s_nzw) + (j >> 2), (1u << (i >> 6)) << (8 * (j & 3)));
+                }
+            };
+            for (int t = tid >> 5; t < n_tasks; t += NT / 32) {
+                int w = 0, rem = t;
+                while (rem >= ngroups_b - 2 * w) { rem -= ngroups_b - 2 * w; ++w; }
+                const int i0 = w << 6;
+                const int j = ((2 * w + rem) << 5) + lane;
+                unsigned long long cand = 0ull;
+                if (j < nc) {
+                    if (s_pre[j] < 0) {
+                        const uchar4 lv = s_lvl[j];
+                        cand = s_tab[0][lv.x][w] & s_tab[1][lv.y][w] & s_tab[2][lv.z][w] & s_tab[3][lv.w][w];
+                        const int ni = j - i0;                                     // >= 0: columns of the word before row j
+                        if (ni < 64) cand &= (1ull << ni) - 1ull;
+#ifdef B200DET_NMS_DEBUG
+                        {
+                            const unsigned long long tri = ni < 64 ? (1ull << ni) - 1ull : ~0ull;
+                            atomicAdd(&g_nms_dbg[0], (unsigned long long)__popcll(tri));
+                            atomicAdd(&g_nms_dbg[1], (unsigned long long)__popcll(tri & s_tab[0][lv.x][w]));
+                            atomicAdd(&g_nms_dbg[2], (unsigned long long)__popcll(tri & s_tab[1][lv.y][w]));
+                            atomicAdd(&g_nms_dbg[3], (unsigned long long)__popcll(tri & s_tab[2][lv.z][w]));
+                            atomicAdd(&g_nms_dbg[4], (unsigned long long)__popcll(tri & s_tab[3][lv.w][w]));
+                            atomicAdd(&g_nms_dbg[5], (unsigned long long)__popcll(cand));
+                            atomicAdd(&g_nms_dbg[6], (unsigned long long)(lv.x + 256 * lv.y));
+                            atomicAdd(&g_nms_dbg[7], (unsigned long long)(lv.z + 256 * lv.w));
+                        }
+#endif
+                    }
+                    s_L[tri_off(j) + w] = 0ull;                                    // hits are OR-ed in by test_pair
+                }
+                for (;;) {
+                    const int cnt = __popcll(cand);
+                    int inc = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int u = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                        if (lane >= o) inc += u;
+                    }
+                    const int total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+                    if (total == 0) break;
+                    int pos = fill + inc - cnt;
+                    while (cand && pos < kNmsQCap) {
+                        const int k = __ffsll((long long)cand) - 1;
+                        cand &= cand - 1ull;
+                        qw[pos++] = ((uint32_t)j << 10) | (uint32_t)(i0 + k);
+                    }
+                    fill = min(kNmsQCap, fill + total);
+                    __syncwarp();
+                    int done = 0;
+                    for (; fill - done >= 32; done += 32) test_pair(qw[done + lane]);
+                    const int r = fill - done;                                     // < 32 entries carried to the next round
+                    const uint32_t carry = lane < r ? qw[done + lane] : 0u;
+                    __syncwarp();
+                    if (lane < r) qw[lane] = carry;
+                    __syncwarp();
+                    fill = r;
+                }
+            }
+            if (lane < fill) test_pair(qw[lane]);
+        }
+        for (int t = tid >> 5; !TAB && t < n_tasks; t += NT / 32) {
             int w = 0, rem = t;
             while (rem >= ngroups_b - 2 * w) { rem -= ngroups_b - 2 * w; ++w; }
             const int i0 = w << 6;
@@ -892,7 +1077,13 @@ int yolo_stage_nms(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cudaSt
     // candidates per (image, class) on average, if everything survived: longer than a chunk -> the wide variant,
     // at most 160 -> the small one
     const int avg = w.N / d->num_classes;
-    if (d->nms_thres >= 0.0f) {
+    const char* pf = getenv("B200DET_NMS");           // "tab": table pre-filter + queued exact tests; "half2": pair-wise half2 test
+    const bool tab = pf && strcmp(pf, "tab") == 0;
+    if (d->nms_thres >= 0.0f && tab) {
+        if (avg > kNmsT) nms_segment_kernel<0, true, 512, kNmsT, true><<<grid, 512, 0, st>>>(p);
+        else if (avg <= 160) nms_segment_kernel<0, true, 128, 192, true><<<grid, 128, 0, st>>>(p);
+        else nms_segment_kernel<0, true, kNmsThreads, kNmsT, true><<<grid, kNmsThreads, 0, st>>>(p);
+    } else if (d->nms_thres >= 0.0f) {
         if (avg > kNmsT) nms_segment_kernel<0, true, 512, kNmsT><<<grid, 512, 0, st>>>(p);
         else if (avg <= 160) nms_segment_kernel<0, true, 128, 192><<<grid, 128, 0, st>>>(p);
         else nms_segment_kernel<0, true, kNmsThreads, kNmsT><<<grid, kNmsThreads, 0, st>>>(p);
@@ -950,3 +1141,14 @@ extern "C" int b200det_debug_set_nms_trace(void* dev_ptr) {
     unsigned long long* p = (unsigned long long*)dev_ptr;
     return (int)cudaMemcpyToSymbol(b200det::g_nms_trace, &p, sizeof(p));
 }
+
+#ifdef B200DET_NMS_DEBUG
+extern "C" int b200det_debug_nms_counters(unsigned long long* out8_host, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out8_host, b200det::g_nms_dbg, 64);
+    if (e == cudaSuccess && reset) {
+        unsigned long long z[8] = {0};
+        e = cudaMemcpyToSymbol(b200det::g_nms_dbg, z, 64);
+    }
+    return (int)e;
+}
+#endif
