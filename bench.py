@@ -679,6 +679,15 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak()
+        # plain pinned-copy ceiling of this kind of box at this many ranks (tools/h2d_bandwidth.py under torchrun, all ranks copying
+        # at once; profiles/h2d_ceiling.json), what the e2e leg is judged against
+        ceiling = None
+        hp = os.path.join(ROOT, "profiles", "h2d_ceiling.json")
+        if os.path.exists(hp):
+            try:
+                ceiling = json.load(open(hp)).get(str(world))
+            except Exception:
+                ceiling = None
         achieved = wl.alg_bytes / (k1_us * 1e-6) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "k1_traffic.json")   # dram__bytes_read+write of one launch (ncu --set full), per config
@@ -700,7 +709,10 @@ def main():
             "pipeline_value": pipeline_value, "pipeline_ms_per_step": pipe_ms / K,
             "api_over_pipeline": (api_ms / pipe_ms),
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "ms_per_step": e2e_ms / Ke, "h2d_GBps": h2d / (e2e_ms / Ke * 1e-3) / 1e9, "api": wl.e2e_api},
+                    "ms_per_step": e2e_ms / Ke, "h2d_GBps": world * h2d / (e2e_ms / Ke * 1e-3) / 1e9,
+                    "h2d_ceiling_gbs": ceiling["aggregate_GBps"] if ceiling else None,
+                    "frac_of_h2d_ceiling": (world * h2d / (e2e_ms / Ke * 1e-3) / 1e9) / ceiling["aggregate_GBps"] if ceiling else None,
+                    "api": wl.e2e_api},
             "gpu_launches": (wl.launches_api + wl.launches_pipe) * K,
             "gpu_launches_note": f"{wl.launches_api} of this repo's kernels per public-API step + {wl.launches_pipe} per stage-entry step, {K} steps each",
             "roofline": {"bound": "hbm", "kernel": wl.kernel + " — one launch per step, CUDA events around it in the timed region",
