@@ -40,6 +40,12 @@ struct ClusterSortParams {
     uint32_t* rank[2];
     int n_pad, n_tiles, C;
     int n_cls_passes;             // 0 (score only), 1 or 2
+    // dense-first mode (large, sparsely surviving images — see yolo_compact_kernel in segsort.cu): the survivors were
+    // compacted to positions [0, count) of (dense_key, dense_pay); pass 0 reads those instead of the tile-sparse key[0] / pay[0].
+    // An image with more survivors than the cluster holds is left to the multi-launch sort (its `overflow` word is set).
+    const uint32_t* dense_key;
+    const uint32_t* dense_pay;
+    const uint32_t* overflow;     // [B] or null
 };
 
 __device__ __forceinline__ bool sparse_valid_cs(const uint32_t* tile_count_img, int e) {
@@ -221,7 +227,7 @@ __device__ __forceinline__ void cs_pass(CsShared& sm, const ClusterSortParams& p
     cs_stamp(tr, 6);
 }
 
-template <int CL>
+template <int CL, bool DENSE = false>
 __global__ void __launch_bounds__(kCsThreads, 2) cluster_sort_kernel(const ClusterSortParams p) {
     extern __shared__ __align__(16) unsigned char cs_smem_raw[];
     CsShared& sm = *reinterpret_cast<CsShared*>(cs_smem_raw);
@@ -243,12 +249,16 @@ __global__ void __launch_bounds__(kCsThreads, 2) cluster_sort_kernel(const Clust
         n = (int)p.count[b];
     }
     unsigned long long* tr = g_cs_trace ? g_cs_trace + ((size_t)(b * CL + crank) * 8) * 8 : nullptr;
+    if (DENSE && p.overflow[b]) return;                 // cluster-uniform: too many survivors, the multi-launch sort takes it
 
     for (int i = tid; i < kCsWarps * 256; i += kCsThreads) (&sm.tab[0][0])[i] = make_uint2(0u, 0u);
     __syncthreads();
 
     // score passes: key/pay ping-pong 0 -> 1 -> 0 -> 1 -> 0 (the last one moves the payload only)
-    cs_pass<CL, true, true, true, 0>(sm, p, tc, img, n, crank, 0, p.key[0], p.pay[0], nullptr, p.key[1], p.pay[1], nullptr, nullptr, tr);
+    if (DENSE)
+        cs_pass<CL, false, true, true, 0>(sm, p, tc, img, n, crank, 0, p.dense_key, p.dense_pay, nullptr, p.key[1], p.pay[1], nullptr, nullptr, tr);
+    else
+        cs_pass<CL, true, true, true, 0>(sm, p, tc, img, n, crank, 0, p.key[0], p.pay[0], nullptr, p.key[1], p.pay[1], nullptr, nullptr, tr);
     cs_pass<CL, false, true, true, 0>(sm, p, tc, img, n, crank, 8, p.key[1], p.pay[1], nullptr, p.key[0], p.pay[0], nullptr, nullptr, tr ? tr + 8 : tr);
     cs_pass<CL, false, true, true, 0>(sm, p, tc, img, n, crank, 16, p.key[0], p.pay[0], nullptr, p.key[1], p.pay[1], nullptr, nullptr, tr ? tr + 16 : tr);
     cs_pass<CL, false, true, false, 0>(sm, p, tc, img, n, crank, 24, p.key[1], p.pay[1], nullptr, nullptr, p.pay[0], nullptr, nullptr, tr ? tr + 24 : tr);
@@ -263,7 +273,7 @@ __global__ void __launch_bounds__(kCsThreads, 2) cluster_sort_kernel(const Clust
 // Largest candidate-slot count per image the cluster sort handles (8 CTAs x 6 656 keys).
 int cluster_sort_capacity() { return kCsCap * kCsMaxCluster; }
 
-template <int CL>
+template <int CL, bool DENSE = false>
 static int cluster_sort_launch_cl(const ClusterSortParams& p, int batch, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CL, batch, 1);
@@ -275,7 +285,7 @@ static int cluster_sort_launch_cl(const ClusterSortParams& p, int batch, cudaStr
     int dev = 0;
     B2_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        B2_CUDA(cudaFuncSetAttribute(cluster_sort_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CsShared)));
+        B2_CUDA(cudaFuncSetAttribute(cluster_sort_kernel<CL, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CsShared)));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     cfg.stream = st;
@@ -286,12 +296,28 @@ static int cluster_sort_launch_cl(const ClusterSortParams& p, int batch, cudaStr
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    B2_CUDA(cudaLaunchKernelEx(&cfg, cluster_sort_kernel<CL>, p));
+    B2_CUDA(cudaLaunchKernelEx(&cfg, cluster_sort_kernel<CL, DENSE>, p));
     return 0;
 }
 
 // One-launch sort of every image's candidates.  n_cls_passes = 0: score order only, result in pay[0];
 // otherwise (class, score) order in yolo_sorted_pay / yolo_sorted_rank and, when seg_off != null, the class offsets.
+// Dense-first variant for images with more slots than a cluster holds: survivors already compacted into (dense_key, dense_pay),
+// count[b] final, overflow[b] set for images with more than cluster_sort_dense_capacity() survivors (those are skipped here).
+int cluster_sort_dense_capacity() { return kCsCap * 4; }          // cluster of 4: 64 images = 256 CTAs = one wave on 148 SMs
+
+int cluster_sort_dense_launch(const uint32_t* tile_count, uint32_t* count, uint32_t* seg_off, const uint32_t* dense_key,
+                              const uint32_t* dense_pay, const uint32_t* overflow, uint32_t* key[2], uint32_t* pay[2],
+                              uint32_t* rank[2], int n_pad, int n_tiles, int C, int n_cls_passes, int batch, cudaStream_t st) {
+    ClusterSortParams p;
+    memset(&p, 0, sizeof(p));
+    p.tile_count = tile_count; p.count = count; p.seg_off = seg_off;
+    for (int i = 0; i < 2; ++i) { p.key[i] = key[i]; p.pay[i] = pay[i]; p.rank[i] = rank[i]; }
+    p.n_pad = n_pad; p.n_tiles = n_tiles; p.C = C; p.n_cls_passes = n_cls_passes;
+    p.dense_key = dense_key; p.dense_pay = dense_pay; p.overflow = overflow;
+    return cluster_sort_launch_cl<4, true>(p, batch, st);
+}
+
 int cluster_sort_launch(const uint32_t* tile_count, uint32_t* count, bool count_from_tiles, uint32_t* chunk_cnt,
                         int n_chunks, uint32_t* seg_off, uint32_t* key[2], uint32_t* pay[2], uint32_t* rank[2], int n_pad,
                         int n_tiles, int C, int n_cls_passes, int batch, cudaStream_t st) {

@@ -39,7 +39,27 @@ static bool use_cluster_sort(int n_pad) {
     return n_pad <= cluster_sort_capacity();
 }
 
-bool yolo_fast_path(const YoloWs& w) { return use_cluster_sort(w.n_pad) && w.n_cls_passes == 1; }
+int cluster_sort_dense_capacity();
+int cluster_sort_dense_launch(const uint32_t* tile_count, uint32_t* count, uint32_t* seg_off, const uint32_t* dense_key,
+                              const uint32_t* dense_pay, const uint32_t* overflow, uint32_t* key[2], uint32_t* pay[2],
+                              uint32_t* rank[2], int n_pad, int n_tiles, int C, int n_cls_passes, int batch, cudaStream_t st);
+
+// Images with more slots than one cluster sorts (1280-pixel heads: 101 376 slots) usually keep a small fraction of them
+// (conf_thres 0.001: ~10 k).  Those take the DENSE route: a compaction kernel moves the survivors to [0, count) (stable, via the
+// prefix of the tile counts), a cluster of 4 sorts them in one launch, and the multi-launch sort below only runs — gated by a
+// per-image flag, its kernels return at once otherwise — for images with more survivors than the cluster holds.
+// B200DET_SORT=global forces the plain multi-launch sort (the A/B reference).
+static bool use_dense_sort(int n_pad, int n_cls_passes) {
+    const char* e = getenv("B200DET_SORT");
+    if (e && strcmp(e, "global") == 0) return false;
+    return n_pad > cluster_sort_capacity() && n_cls_passes == 1;
+}
+
+// True when the sort stage derives count / class offsets / zeroed counters itself, so that the reset stage launches nothing and
+// the decode kernel skips its global counter atomics.
+bool yolo_fast_path(const YoloWs& w) {
+    return (use_cluster_sort(w.n_pad) && w.n_cls_passes == 1) || use_dense_sort(w.n_pad, w.n_cls_passes);
+}
 
 struct SortParams {
     const uint32_t* tile_count;  // [B][n_tiles] (first pass: tile-sparse input), else unused
@@ -58,6 +78,8 @@ struct SortParams {
     int pass;                    // index into digit_hist
     int shift;                   // bit offset of the digit
     int n_cls_passes;
+    const uint32_t* only_flagged; // [B] or null: when set, images whose word is 0 are skipped (dense route, see use_dense_sort)
+    int dense_hist;              // the histogram kernel reads dense [0, count) input instead of the tile-sparse layout
 };
 
 __device__ __forceinline__ bool sparse_valid(const uint32_t* tile_count_img, int e) {
@@ -84,6 +106,8 @@ __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const SortParam
     const int b = blockIdx.y;
     const int e0 = blockIdx.x * kSortTile;
     if (e0 >= p.n_pad) return;
+    if (p.only_flagged && p.only_flagged[b] == 0u) return;
+    const int dense_n = p.dense_hist ? (int)p.count[b] : 0;
     const uint32_t* tc = p.tile_count + (size_t)b * p.n_tiles;
     for (int i = threadIdx.x; i < kMaxPasses * 256; i += kSortThreads) (&h[0][0])[i] = 0;
     for (int ps = 0; ps < kMaxPasses; ++ps)      // look-back words of this (image, tile), all passes
@@ -94,7 +118,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const SortParam
 #pragma unroll 4
     for (int k = 0; k < kSortItems; ++k) {
         const int e = e0 + k * kSortThreads + threadIdx.x;
-        const bool valid = e < p.n_pad && sparse_valid(tc, e);
+        const bool valid = p.dense_hist ? e < dense_n : (e < p.n_pad && sparse_valid(tc, e));
         uint32_t key = 0, pay = 0;
         if (valid) { key = p.key_in[img + e]; pay = p.pay_in[img + e]; }
         // plain shared-memory atomics: measured 14 us vs 51 us for ballot-aggregated increments on B200
@@ -136,6 +160,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_pass_kernel(const SortParam
 
     const int b = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (p.only_flagged && p.only_flagged[b] == 0u) return;
     if (tid == 0) s_tile = (int)atomicAdd(&p.ticket[(size_t)p.pass * p.B + b], 1u);
 #pragma unroll
     for (int w = 0; w < NW; ++w) s_warp[w][tid] = 0;
@@ -224,6 +249,73 @@ __global__ void __launch_bounds__(kSortThreads) sort_pass_kernel(const SortParam
 }
 
 
+// Dense route, step 1: move the survivors of every image from the tile-sparse K1 layout to positions [0, count) of
+// (dkey, dpay), in slot order (= candidate order: the later passes are stable).  One CTA per 8 candidate tiles; the first CTA of
+// an image also writes the image's count, zeroes what the later stages expect zeroed (emit chunk counters; digit histogram and
+// tickets of the gated multi-launch sort) and raises the overflow flag when the survivors do not fit the cluster.
+constexpr int kCompactTiles = 8;
+__global__ void __launch_bounds__(256) yolo_compact_kernel(const uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ key,
+                                                           const uint32_t* __restrict__ pay, uint32_t* __restrict__ dkey,
+                                                           uint32_t* __restrict__ dpay, uint32_t* __restrict__ count,
+                                                           uint32_t* __restrict__ chunk_cnt, int n_chunks,
+                                                           uint32_t* __restrict__ digit_hist, uint32_t* __restrict__ ticket,
+                                                           uint32_t* __restrict__ overflow, int capacity, int n_pad, int n_tiles, int B) {
+    __shared__ int s_scan[33];
+    __shared__ int s_base[kCompactTiles + 1];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int t0 = blockIdx.x * kCompactTiles;
+    const uint32_t* tc = tile_count + (size_t)b * n_tiles;
+    // survivors in the tiles before this CTA's (and, for the first CTA, in the whole image)
+    const int upto = blockIdx.x == 0 ? n_tiles : t0;
+    int part = 0;
+    for (int t = tid; t < upto; t += 256) part += (int)tc[t];
+    int before;
+    block_exclusive_scan(part, s_scan, &before);
+    if (blockIdx.x == 0) {
+        const int total = before;
+        before = 0;
+        if (tid == 0) {
+            count[b] = (uint32_t)total;
+            overflow[b] = total > capacity ? 1u : 0u;
+        }
+        for (int i = tid; i < n_chunks; i += 256) chunk_cnt[(size_t)b * n_chunks + i] = 0u;
+        for (int i = tid; i < kMaxPasses * 256; i += 256) digit_hist[(size_t)b * kMaxPasses * 256 + i] = 0u;
+        if (tid < kMaxPasses) ticket[(size_t)tid * B + b] = 0u;
+    }
+    if (tid == 0) {
+        int run = before;
+        for (int k = 0; k < kCompactTiles; ++k) {
+            s_base[k] = run;
+            run += (t0 + k < n_tiles) ? (int)tc[t0 + k] : 0;
+        }
+        s_base[kCompactTiles] = run;
+    }
+    __syncthreads();
+    const size_t img = (size_t)b * n_pad;
+    for (int k = 0; k < kCompactTiles; ++k) {
+        const int cnt = s_base[k + 1] - s_base[k];
+        const size_t src = img + (size_t)(t0 + k) * kTile, dst = img + (size_t)s_base[k];
+        for (int i = tid; i < cnt; i += 256) {
+            dkey[dst + i] = key[src + i];
+            dpay[dst + i] = pay[src + i];
+        }
+    }
+}
+
+// class segment offsets of the flagged images from the class digit totals of the multi-launch sort's histogram
+__global__ void __launch_bounds__(256) seg_from_hist_kernel(const uint32_t* __restrict__ digit_hist, const uint32_t* __restrict__ flagged,
+                                                            const uint32_t* __restrict__ count, uint32_t* __restrict__ seg_off, int C) {
+    __shared__ int s_scan[33];
+    const int b = blockIdx.x;
+    if (flagged[b] == 0u) return;
+    const uint32_t* h = digit_hist + ((size_t)b * kMaxPasses + kScorePasses) * 256;
+    const int c = threadIdx.x;
+    int total;
+    const int ex = block_exclusive_scan(c < C ? (int)h[c] : 0, s_scan, &total);
+    if (c < C) seg_off[(size_t)b * (C + 1) + c] = (uint32_t)ex;
+    if (c == 0) seg_off[(size_t)b * (C + 1) + C] = count[b];
+}
+
 // Score-only sort (4 passes) for the prior pipeline; the sorted payload ends in pay[0].
 int score_sort_launch(const uint32_t* tile_count, const uint32_t* count, uint32_t* digit_hist, uint32_t* ticket,
                       uint32_t* status, uint32_t* key[2], uint32_t* pay[2], int n_pad, int n_tiles, int batch,
@@ -306,19 +398,44 @@ int class_score_sort(const YoloWs& w, bool fast, cudaStream_t st) {
     p.n_pad = w.n_pad; p.n_tiles = w.n_tiles; p.n_cls_passes = w.n_cls_passes;
     dim3 grid(ceil_div(w.n_pad, kSortTile), d->batch);
 
-    rc = seg_scan_launch(w.cls_hist, w.seg_off, d->num_classes, d->batch, st);
-    if (rc) return rc;
-    p.key_in = w.key[0]; p.pay_in = w.pay[0];
+    const bool dense = fast && use_dense_sort(w.n_pad, w.n_cls_passes);
+    uint32_t* const overflow = w.cls_hist;         // [B] words of the (otherwise unused on this route) class histogram
+    if (dense) {
+        // survivors -> (rank[0], rank[1]) (free until the class pass), cluster of 4 per image, then the gated multi-launch sort
+        dim3 cgrid(ceil_div(w.n_tiles, kCompactTiles), d->batch);
+        yolo_compact_kernel<<<cgrid, 256, 0, st>>>(w.tile_count, w.key[0], w.pay[0], w.rank[0], w.rank[1], w.count, w.chunk_cnt,
+                                                   w.n_chunks, w.digit_hist, w.ticket, overflow, cluster_sort_dense_capacity(),
+                                                   w.n_pad, w.n_tiles, w.B);
+        B2_LAUNCH_CHECK("yolo_compact_kernel");
+        uint32_t* key[2] = {w.key[0], w.key[1]};
+        uint32_t* pay[2] = {w.pay[0], w.pay[1]};
+        uint32_t* rank[2] = {w.rank[0], w.rank[1]};
+        rc = cluster_sort_dense_launch(w.tile_count, w.count, w.seg_off, w.rank[0], w.rank[1], overflow, key, pay, rank, w.n_pad,
+                                       w.n_tiles, d->num_classes, w.n_cls_passes, d->batch, st);
+        if (rc) return rc;
+        p.only_flagged = overflow;
+        p.dense_hist = 1;
+    } else {
+        rc = seg_scan_launch(w.cls_hist, w.seg_off, d->num_classes, d->batch, st);
+        if (rc) return rc;
+    }
+    p.key_in = dense ? w.rank[0] : w.key[0]; p.pay_in = dense ? w.rank[1] : w.pay[0];
     sort_hist_kernel<<<grid, kSortThreads, 0, st>>>(p);
     B2_LAUNCH_CHECK("sort_hist_kernel");
+    if (dense) {
+        seg_from_hist_kernel<<<d->batch, 256, 0, st>>>(w.digit_hist, overflow, w.count, w.seg_off, d->num_classes);
+        B2_LAUNCH_CHECK("seg_from_hist_kernel");
+    }
 
     for (int pass = 0; pass < kScorePasses; ++pass) {
         const int src = pass & 1, dst = src ^ 1;
         p.key_in = w.key[src]; p.pay_in = w.pay[src];
         p.key_out = w.key[dst]; p.pay_out = w.pay[dst];
+        if (dense && pass == 0) { p.key_in = w.rank[0]; p.pay_in = w.rank[1]; }
         p.pass = pass; p.shift = 8 * pass;
         const bool last_score = pass == kScorePasses - 1;
-        if (pass == 0) sort_pass_kernel<true, 0, 0, true><<<grid, kSortThreads, 0, st>>>(p);
+        if (pass == 0 && dense) sort_pass_kernel<false, 0, 0, true><<<grid, kSortThreads, 0, st>>>(p);
+        else if (pass == 0) sort_pass_kernel<true, 0, 0, true><<<grid, kSortThreads, 0, st>>>(p);
         else if (!last_score) sort_pass_kernel<false, 0, 0, true><<<grid, kSortThreads, 0, st>>>(p);
         else sort_pass_kernel<false, 0, 0, false><<<grid, kSortThreads, 0, st>>>(p);
         B2_LAUNCH_CHECK("sort_pass_kernel(score)");

@@ -80,3 +80,31 @@ def test_cluster_sort_prior_path(P, C, B):
     for b in range(B):
         assert torch.equal(outs[0][0][b, :k[b]], outs[1][0][b, :k[b]])
         assert torch.equal(outs[0][1][b, :k[b]], outs[1][1][b, :k[b]])
+
+
+@pytest.mark.parametrize("case", ["sparse", "all_survive", "mixed", "just_over_capacity"])
+def test_dense_route_for_large_images_equals_lookback_sort(case):
+    """Images with more slots than one cluster sorts (> 53 248) take the dense route: compaction + cluster of 4, with the
+    multi-launch sort gated per image for those whose survivors exceed the cluster (26 624).  All three situations —
+    nobody overflows, everybody overflows, some do — must match the plain multi-launch sort bit for bit."""
+    B, A, C, grids, img = 3, 3, 5, [160, 80, 40], 1280                      # N = 100 800, 101 376 slots
+    if case == "sparse":
+        lv, thr = synth.yolo_crowd(B, A, C, grids, img, seed=5), 0.001      # ~10 k survivors per image
+    elif case == "all_survive":
+        lv, thr = synth.yolo_crowd(B, A, C, grids, img, seed=6), -0.0151    # 100 800 survivors: every image overflows
+    elif case == "mixed":
+        lv, thr = synth.yolo_crowd(B, A, C, grids, img, seed=7), 0.001
+        p = lv[0].view(B, A, 5 + C, 160, 160)
+        p[1, :, 4] = p[1, :, 4].clamp_min(0.002)                            # image 1: all 76 800 cells of the first level survive
+        synth.make_tie_free(lv, A)
+    else:
+        lv, thr = synth.yolo_crowd(B, A, C, grids, img, seed=8, keep_frac=0.27), 0.001   # ~27.2 k: around the capacity
+    levels = [t.to(DEV) for t in lv]
+    got = _run_yolo(levels, A, thr, None)
+    want = _run_yolo(levels, A, thr, "global")
+    ks = [r.shape[0] for r, _ in want]
+    assert min(ks) > 0
+    for b in range(B):
+        assert got[b][0].shape == want[b][0].shape, f"{case} image {b}: kept {got[b][0].shape[0]} vs {want[b][0].shape[0]}"
+        assert torch.equal(got[b][1], want[b][1]), f"{case} image {b}: kept candidate indices differ"
+        assert torch.equal(got[b][0], want[b][0]), f"{case} image {b}: rows differ"
