@@ -92,9 +92,11 @@ __device__ __forceinline__ void cs_pass(CsShared& sm, const ClusterSortParams& p
                                         const size_t img, const int n, const int crank, const int shift,
                                         const uint32_t* in_key, const uint32_t* in_pay, const uint32_t* in_rank,
                                         uint32_t* out_key, uint32_t* out_pay, uint32_t* out_rank, uint32_t* seg_off_img,
-                                        unsigned long long* tr) {
+                                        unsigned long long* tr, const int per_warp = 32 * kCsItems) {
+    // per_warp: positions owned by a warp (multiple of 32, <= 32 * kCsItems).  The dense route spreads a small image evenly over
+    // the cluster's CTAs (fewer serial ranking steps per warp); everywhere else a warp owns its full 13 x 32 positions.
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wbase = crank * kCsCap + warp * (32 * kCsItems);
+    const int wbase = crank * (per_warp * kCsWarps) + warp * per_warp;
     const int limit = FIRST ? p.n_pad : n;
     const uint32_t* in_digit = SCORE ? in_key : in_pay;
     const unsigned lt = lanemask_lt();
@@ -106,7 +108,7 @@ __device__ __forceinline__ void cs_pass(CsShared& sm, const ClusterSortParams& p
 #pragma unroll
     for (int k = 0; k < kCsItems; ++k) {
         const int e = wbase + k * 32 + lane;
-        bool valid = e < limit;
+        bool valid = e < limit && k * 32 < per_warp;
         if (FIRST) valid = valid && (uint32_t)(e & (kTile - 1)) < tc[e >> kTileShift];
         srcw[k] = valid ? __ldcg(in_digit + img + e) : 0u;
         packed[k] = valid ? 0u : kNone;
@@ -117,7 +119,7 @@ __device__ __forceinline__ void cs_pass(CsShared& sm, const ClusterSortParams& p
     // clears the mask again, so the table is self-cleaning.
 #pragma unroll
     for (int k = 0; k < kCsItems; ++k) {
-        if (wbase + k * 32 >= limit) continue;               // warp-uniform
+        if (wbase + k * 32 >= limit || k * 32 >= per_warp) continue;               // warp-uniform
         const bool valid = packed[k] != kNone;
         const uint32_t dig = (srcw[k] >> shift) & 0xFFu;
         uint2* slot = &sm.tab[warp][dig];
@@ -254,20 +256,26 @@ __global__ void __launch_bounds__(kCsThreads, 2) cluster_sort_kernel(const Clust
     for (int i = tid; i < kCsWarps * 256; i += kCsThreads) (&sm.tab[0][0])[i] = make_uint2(0u, 0u);
     __syncthreads();
 
+    // positions per warp: the full 13 x 32 except on the dense route, where the image's n keys are dealt evenly to the CL CTAs
+    int pw = 32 * kCsItems;
+    if (DENSE) {
+        const int per_cta = ((n + CL - 1) / CL + kCsThreads - 1) / kCsThreads * kCsThreads;      // multiple of 512, <= kCsCap
+        pw = min(32 * kCsItems, max(32, per_cta / kCsWarps));
+    }
     // score passes: key/pay ping-pong 0 -> 1 -> 0 -> 1 -> 0 (the last one moves the payload only)
     if (DENSE)
-        cs_pass<CL, false, true, true, 0>(sm, p, tc, img, n, crank, 0, p.dense_key, p.dense_pay, nullptr, p.key[1], p.pay[1], nullptr, nullptr, tr);
+        cs_pass<CL, false, true, true, 0>(sm, p, tc, img, n, crank, 0, p.dense_key, p.dense_pay, nullptr, p.key[1], p.pay[1], nullptr, nullptr, tr, pw);
     else
-        cs_pass<CL, true, true, true, 0>(sm, p, tc, img, n, crank, 0, p.key[0], p.pay[0], nullptr, p.key[1], p.pay[1], nullptr, nullptr, tr);
-    cs_pass<CL, false, true, true, 0>(sm, p, tc, img, n, crank, 8, p.key[1], p.pay[1], nullptr, p.key[0], p.pay[0], nullptr, nullptr, tr ? tr + 8 : tr);
-    cs_pass<CL, false, true, true, 0>(sm, p, tc, img, n, crank, 16, p.key[0], p.pay[0], nullptr, p.key[1], p.pay[1], nullptr, nullptr, tr ? tr + 16 : tr);
-    cs_pass<CL, false, true, false, 0>(sm, p, tc, img, n, crank, 24, p.key[1], p.pay[1], nullptr, nullptr, p.pay[0], nullptr, nullptr, tr ? tr + 24 : tr);
+        cs_pass<CL, true, true, true, 0>(sm, p, tc, img, n, crank, 0, p.key[0], p.pay[0], nullptr, p.key[1], p.pay[1], nullptr, nullptr, tr, pw);
+    cs_pass<CL, false, true, true, 0>(sm, p, tc, img, n, crank, 8, p.key[1], p.pay[1], nullptr, p.key[0], p.pay[0], nullptr, nullptr, tr ? tr + 8 : tr, pw);
+    cs_pass<CL, false, true, true, 0>(sm, p, tc, img, n, crank, 16, p.key[0], p.pay[0], nullptr, p.key[1], p.pay[1], nullptr, nullptr, tr ? tr + 16 : tr, pw);
+    cs_pass<CL, false, true, false, 0>(sm, p, tc, img, n, crank, 24, p.key[1], p.pay[1], nullptr, nullptr, p.pay[0], nullptr, nullptr, tr ? tr + 24 : tr, pw);
     if (p.n_cls_passes >= 1) {
         uint32_t* so = p.seg_off ? p.seg_off + (size_t)b * (p.C + 1) : nullptr;
-        cs_pass<CL, false, false, false, 1>(sm, p, tc, img, n, crank, (int)kSlotBits, nullptr, p.pay[0], nullptr, nullptr, p.pay[1], p.rank[0], so, tr ? tr + 32 : tr);
+        cs_pass<CL, false, false, false, 1>(sm, p, tc, img, n, crank, (int)kSlotBits, nullptr, p.pay[0], nullptr, nullptr, p.pay[1], p.rank[0], so, tr ? tr + 32 : tr, pw);
     }
     if (p.n_cls_passes >= 2)
-        cs_pass<CL, false, false, false, 2>(sm, p, tc, img, n, crank, (int)kSlotBits + 8, nullptr, p.pay[1], p.rank[0], nullptr, p.pay[0], p.rank[1], nullptr, tr ? tr + 40 : tr);
+        cs_pass<CL, false, false, false, 2>(sm, p, tc, img, n, crank, (int)kSlotBits + 8, nullptr, p.pay[1], p.rank[0], nullptr, p.pay[0], p.rank[1], nullptr, tr ? tr + 40 : tr, pw);
 }
 
 // Largest candidate-slot count per image the cluster sort handles (8 CTAs x 6 656 keys).

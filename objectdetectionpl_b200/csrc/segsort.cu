@@ -292,10 +292,12 @@ __global__ void __launch_bounds__(256) yolo_compact_kernel(const uint32_t* __res
     }
     __syncthreads();
     const size_t img = (size_t)b * n_pad;
-    for (int k = 0; k < kCompactTiles; ++k) {
+    static_assert(kCompactTiles == 256 / 32, "one warp per tile");
+    {
+        const int k = tid >> 5, lane = tid & 31;
         const int cnt = s_base[k + 1] - s_base[k];
         const size_t src = img + (size_t)(t0 + k) * kTile, dst = img + (size_t)s_base[k];
-        for (int i = tid; i < cnt; i += 256) {
+        for (int i = lane; i < cnt; i += 32) {
             dkey[dst + i] = key[src + i];
             dpay[dst + i] = pay[src + i];
         }
