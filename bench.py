@@ -376,9 +376,9 @@ class YoloWorkload:
         self.kernel = "yolo_decode_filter_kernel<MODE=0, U=8, MINB=6> (fused decode + filter + class argmax + ordered compaction)"
         self.stage_names = ["decode", "sort", "nms", "emit"]
         # our kernels per step: K1, sort, NMS, emit (+ the emit prefix in the packed public-API form).  The sort is ONE cluster
-        # launch up to 53 248 slots per image; larger images take the look-back sort: counter zero-fill, histogram, 4 score passes,
-        # class pass, segment scan
-        sort_launches = 1 if self.n_pad <= 53248 else 8
+        # launch up to 53 248 slots per image; larger images take the dense route: compaction, cluster of 4, and the gated
+        # multi-launch sort (histogram, class offsets, 4 score passes, class pass — empty launches unless an image overflows)
+        sort_launches = 1 if self.n_pad <= 53248 else 9
         self.launches_pipe = 3 + sort_launches
         self.launches_api = 4 + sort_launches
         self.alg_bytes = self.head_bytes

@@ -361,8 +361,11 @@ nms_segment_kernel(const NmsParams p) {
             __syncthreads();
             if (FAST) {
                 const int nkb = (nk + 31) >> 5, ngr = (nc + 31) >> 5;
+                // task index -> (row group, keeper block) without an integer division (nkb <= 14, t < 2^11: the float
+                // reciprocal with the +0.5 nudge is exact; the division was 6 % of the kernel on the dense-crowd shard)
+                const float inv_nkb = __frcp_rn((float)nkb);
                 for (int t = tid >> 5; t < ngr * nkb; t += NT / 32) {
-                    const int g = t / nkb, kb0 = (t - g * nkb) << 5;
+                    const int g = __float2int_rz(__fmul_rn((float)t + 0.5f, inv_nkb)), kb0 = (t - g * nkb) << 5;
                     const int j = (g << 5) + lane;
                     const bool active = j < nc && s_pre[j] < 0;
                     if (!__any_sync(0xFFFFFFFFu, active)) continue;
