@@ -110,6 +110,13 @@ int b200det_yolo_nms_packed(const b200det_yolo_desc* d, void* workspace, size_t 
                             int32_t* out_index, int32_t* out_count, int32_t* out_offsets, int32_t* counts_early,
                             void* counts_ready_event, void* stream);
 
+/* The PADDED pipeline (b200det_yolo_nms) with the early counts of the packed form: `counts_early` (may be NULL; device or
+ * mapped pinned host memory) receives count [B] | exclusive offsets [B+1] as soon as the NMS stage is done, and
+ * `counts_ready_event` (cudaEvent_t, may be NULL) is recorded right after, before the emit stage is enqueued. */
+int b200det_yolo_nms_early(const b200det_yolo_desc* d, void* workspace, size_t workspace_bytes, float* out_rows,
+                           int32_t* out_index, int32_t* out_count, int32_t* counts_early, void* counts_ready_event,
+                           void* stream);
+
 /* Stage entry points (the pipeline above is exactly these five calls in order); used by the tests
  * and by profiling.  All operate on the workspace laid out by b200det_yolo_workspace_bytes().
  * reset = one cudaMemsetAsync of the counter header; decode = the fused decode+filter kernel alone. */

@@ -42,6 +42,7 @@ SIGNATURES = {
     "b200det_yolo_num_candidates": (_i32, [_PY, POINTER(_i32), POINTER(_i32)]),
     "b200det_yolo_workspace_bytes": (_sz, [_PY]),
     "b200det_yolo_nms": (_i32, [_PY, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "b200det_yolo_nms_early": (_i32, [_PY, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200det_yolo_nms_packed": (_i32, [_PY, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200det_yolo_stage_emit_packed": (_i32, [_PY, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
     "b200det_yolo_stage_reset": (_i32, [_PY, _vp, _sz, _vp]),

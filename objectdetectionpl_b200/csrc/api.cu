@@ -142,6 +142,11 @@ int b200det_yolo_nms_packed(const b200det_yolo_desc* d, void* ws, size_t n, floa
     return yolo_pipeline(d, ws, n, out_rows, out_index, out_count, out_offsets, counts_early, counts_ready_event, st);
 }
 
+int b200det_yolo_nms_early(const b200det_yolo_desc* d, void* ws, size_t n, float* out_rows, int32_t* out_index,
+                           int32_t* out_count, int32_t* counts_early, void* counts_ready_event, void* st) {
+    return yolo_pipeline(d, ws, n, out_rows, out_index, out_count, nullptr, counts_early, counts_ready_event, st);
+}
+
 int b200det_yolo_nms(const b200det_yolo_desc* d, void* ws, size_t n, float* out_rows, int32_t* out_index,
                      int32_t* out_count, void* st) {
     return yolo_pipeline(d, ws, n, out_rows, out_index, out_count, nullptr, nullptr, nullptr, st);

@@ -958,13 +958,13 @@ __global__ void __launch_bounds__(1024) yolo_emit_prefix_kernel(const uint32_t* 
         int total;
         const int ex = block_exclusive_scan(tot, s_scan, &total);
         if (b < B) {
-            out_base[b] = carry + ex;
+            if (out_base) out_base[b] = carry + ex;
             if (early) { early[b] = tot; early[B + b] = carry + ex; }
         }
         carry += total;
     }
     if (threadIdx.x == 0) {
-        out_base[B] = carry;
+        if (out_base) out_base[B] = carry;
         if (early) early[2 * B] = carry;
     }
 }
@@ -1105,11 +1105,11 @@ int yolo_stage_emit(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, float
     B2_CHECK_ARG(((uintptr_t)out_rows & 15) == 0, "out_rows must be 16-byte aligned");
     YoloWs w;
     yolo_ws_layout(d, ws, &w);
-    if (out_offsets) {
+    if (out_offsets || counts_early) {
         yolo_emit_prefix_kernel<<<1, 1024, 0, st>>>(w.count, w.chunk_cnt, d->batch, w.n_chunks, out_offsets, counts_early);
         B2_LAUNCH_CHECK("yolo_emit_prefix_kernel");
-        if (counts_ready) B2_CUDA(cudaEventRecord(counts_ready, st));
     }
+    if (counts_ready) B2_CUDA(cudaEventRecord(counts_ready, st));
     EmitParams p;
     p.out_base = out_offsets;
     p.count = w.count; p.kpay = w.kpay; p.mbox = w.mbox; p.cc2 = w.cc2; p.orig = w.orig; p.chunk_cnt = w.chunk_cnt;

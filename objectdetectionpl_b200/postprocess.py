@@ -126,8 +126,9 @@ class _YoloPlan:
         self.host = torch.empty((2 * self.B + 1,), dtype=torch.int32).pin_memory()
         self.event = torch.cuda.Event()
         self.event.record()                               # creates the underlying cudaEvent_t
-        self.fn = lib.b200det_yolo_nms_packed
+        self.fn = lib.b200det_yolo_nms_early
         self.lock = threading.Lock()                     # the descriptor and the pinned counts are per plan, not per call
+        self.spare = None                                # result buffers allocated ahead for the next call (while the GPU was busy)
 
 
 _yolo_plans = collections.OrderedDict()
@@ -175,22 +176,28 @@ def _yolo_nms_planned(plan, predictions, d, B, n_pad, dev, return_index):
         d.head[i] = t.data_ptr()
     with torch.cuda.device(dev):
         ws = L.workspace(plan.ws_bytes, dev)
-        rows = torch.empty((B * n_pad, 7), dtype=torch.float32, device=dev)
-        index = torch.empty((B * n_pad,), dtype=torch.int32, device=dev) if return_index else None
-        meta = torch.empty((2 * B + 1,), dtype=torch.int32, device=dev)               # count [B] | offsets [B+1]
-        mp = meta.data_ptr()
+        spare, plan.spare = plan.spare, None
+        if spare is not None and spare[0].device == dev:
+            rows, count = spare
+        else:
+            rows = torch.empty((B, n_pad, 7), dtype=torch.float32, device=dev)
+            count = torch.empty((B,), dtype=torch.int32, device=dev)
+        index = torch.empty((B, n_pad), dtype=torch.int32, device=dev) if return_index else None
         L.check(plan.fn(plan.dref, ws.data_ptr(), ws.numel(), rows.data_ptr(), index.data_ptr() if return_index else None,
-                        mp, mp + 4 * B, plan.host.data_ptr(), plan.event.cuda_event, L.stream_ptr(dev)), "yolo_nms_packed")
-        # the one host sync of the call: it waits for the NMS stage only.  The list below is sliced while the emit kernel
-        # still writes the rows; whatever the caller does with them next is stream-ordered behind it, as with any torch op.
+                        count.data_ptr(), plan.host.data_ptr(), plan.event.cuda_event, L.stream_ptr(dev)), "yolo_nms_early")
+        # ---- the GPU is busy for the next few hundred microseconds: everything that does not need the counts happens now ----
+        views = list(rows.unbind(0))                     # B views [n_pad, 7]; shrunk in place once the counts are known
+        iviews = list(index.long().unbind(0)) if return_index else None
+        plan.spare = (torch.empty((B, n_pad, 7), dtype=torch.float32, device=dev),       # the next call's result buffers
+                      torch.empty((B,), dtype=torch.int32, device=dev))
+        # the one host sync of the call: it waits for the NMS stage only (the counts are final there and were written straight
+        # into pinned host memory).  The emit kernel may still be writing the rows when this function returns; whatever the
+        # caller does with them next is stream-ordered behind it, as with any torch op.
         plan.event.synchronize()
-    meta_h = plan.host.tolist()
-    counts, total = meta_h[:B], meta_h[2 * B]
-    parts = torch.ops.aten.unsafe_split_with_sizes.default(rows[:total], counts)      # one call: B slices of the packed rows
-    out: List[Optional[torch.Tensor]] = [p if k else None for p, k in zip(parts, counts)]            # YOLOV3.py:306,333
+    counts = plan.host.tolist()[:B]
+    out: List[Optional[torch.Tensor]] = [v.resize_(k, 7) if k else None for v, k in zip(views, counts)]   # YOLOV3.py:306,333
     if return_index:
-        iparts = index[:total].long().split(counts)
-        return out, [p if k else None for p, k in zip(iparts, counts)]
+        return out, [v.resize_(k) if k else None for v, k in zip(iviews, counts)]
     return out
 
 
