@@ -397,6 +397,9 @@ def prior_nms_raw(loc: torch.Tensor, cls: torch.Tensor, priors: torch.Tensor, to
     return rows, index, count
 
 
+_prior_count_bufs = {}      # (device, batch) -> (pinned [2, B] int32, event)
+
+
 def prior_non_max_suppression(self, predictions, topk=100, nms_thresh=0.5, class_thresh=0.45, mode="union", *,
                               compat=True, return_index=False):
     """Drop-in for SSD / RetinaNet `non_max_suppression` (model/SSD.py:249, model/RetinaNet.py:117).
@@ -408,13 +411,26 @@ def prior_non_max_suppression(self, predictions, topk=100, nms_thresh=0.5, class
         raise TypeError("Unknown nms mode: %s." % mode)  # model/SSD.py:298-299
     loc, cls = predictions
     rows, index, count = prior_nms_raw(loc, cls, self.iou_boxes, topk, nms_thresh, class_thresh, mode, compat, return_index)
-    c = count.cpu()
-    if compat and bool((c[1] == 1).any()):
+    dev, B = rows.device, rows.shape[0]
+    key = (dev.index, B)
+    slot = _prior_count_bufs.get(key)
+    if slot is None:
+        if len(_prior_count_bufs) >= 16:
+            _prior_count_bufs.clear()
+        slot = _prior_count_bufs[key] = (torch.empty((2, B), dtype=torch.int32).pin_memory(), torch.cuda.Event())
+    host, ev = slot
+    with torch.cuda.device(dev):
+        host.copy_(count, non_blocking=True)             # kept rows [0] and candidates above the score threshold [1]
+        ev.record()
+        views = list(rows.unbind(0))                     # built while the GPU works; shrunk in place after the one sync
+        iviews = list(index.long().unbind(0)) if return_index else None
+        ev.synchronize()
+    kept, cand = host.tolist()
+    if compat and 1 in cand:
         raise IndexError("too many indices for tensor of dimension 1")   # model/SSD.py:262,266 (0-dim index)
-    kept = c[0].tolist()
-    out = [r[:k] for r, k in zip(rows.unbind(0), kept)]
+    out = [v.resize_(k, 7) for v, k in zip(views, kept)]
     if return_index:
-        return out, [index[b, :k].long() for b, k in enumerate(kept)]
+        return out, [v.resize_(k) for v, k in zip(iviews, kept)]
     return out
 
 

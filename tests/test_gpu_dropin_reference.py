@@ -127,7 +127,19 @@ def test_v5_criterion_forward_backward_stock_vs_installed(ref):
     crit = ref.losses.MultiScaleRegionLoss_v5(synth.YOLOV5_ANCHORS, None, None, None, None, C, img)
     g = torch.Generator().manual_seed(5)
     heads = [torch.randn(B, 3, img // s, img // s, 5 + C, generator=g) for s in (8, 16, 32)]
-    tg = synth.labels(B, C, 6, max_per_image=8)
+    # two well separated boxes per image: build_targets_v5 then yields no duplicate (image, anchor, cell) rows, so the
+    # reference's own `tobj[b, a, gj, gi] = ...` scatter (losses.py:123) has one writer per cell.  (With duplicates the winner of
+    # torch's CUDA index_put_ is not defined — the stock criterion on the CPU and the same criterion on CUDA then differ in
+    # `Conf_obj` by ~1e-4 whatever build_targets_v5 is used.)
+    tg = torch.tensor([[b, (b + k) % C, 0.27 + 0.46 * k, 0.31 + 0.4 * ((b + k) % 2), 0.11 + 0.02 * b, 0.17 + 0.03 * k]
+                       for b in range(B) for k in range(2)], dtype=torch.float32)
+    chk = od.build_targets_v5([(B, 3, img // s, img // s, 5 + C) for s in (8, 16, 32)], tg.to(DEV), crit.anchors, 3, 3)[2]
+    rows = 0
+    for bb, aa, gj, gi in chk:
+        cell = ((bb * 3 + aa) * 64 + gj) * 64 + gi
+        assert cell.unique().numel() == cell.numel(), "the test labels must not produce duplicate cells"
+        rows += cell.numel()
+    assert rows >= 20
 
     def run(c, dev):
         p = [h.detach().clone().to(dev).requires_grad_(True) for h in heads]

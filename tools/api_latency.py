@@ -5,7 +5,10 @@ import torch
 import objectdetectionpl_b200 as od
 from objectdetectionpl_b200 import synth
 dev = torch.device("cuda:0")
-for B, C, mode, thr in ((1, 20, "uniform", 0.5), (1, 80, "sparse", 0.25), (8, 80, "sparse", 0.25), (64, 80, "uniform", 0.5)):
+CASES = ((1, 20, "uniform", 0.5), (1, 80, "sparse", 0.25), (8, 80, "sparse", 0.25), (64, 80, "uniform", 0.5))
+if os.environ.get("API_LATENCY_ONLY"):
+    CASES = tuple(c for c in CASES if str(c[0]) in os.environ["API_LATENCY_ONLY"].split(","))
+for B, C, mode, thr in CASES:
     lv = [t.to(dev) for t in synth.yolo_planar(B, 3, C, [80, 40, 20], 640, 3, conf_mode=mode, v5_view=True, tie_free=False)]
     kw = dict(compat=(mode == "uniform"), conf_thres=thr)
     for _ in range(5):
