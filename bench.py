@@ -577,7 +577,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    local_cpus = bind_to_gpu_numa_node(local) if world > 1 else None
+    local_cpus = bind_to_gpu_numa_node(local)      # before any pinned allocation: keeps the host buffers on the GPU's NUMA node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
