@@ -255,6 +255,8 @@ def reference_runner(cfg, batch, seed):
     from oracle import ref_harness as rh           # checker / baseline only — never on the product path
     torch.set_num_threads(os.cpu_count() or 1)
     staged = "oracle/_ref (unmodified reference, staged by oracle/stage_ref.py)" if rh.is_staged_copy() else rh.REF_ROOT
+    if not rh.available():
+        return port_runner(cfg, batch, seed)
     if cfg["kind"] == "yolo":
         nimg = min(batch, 8)
         levels, _ = yolo_inputs(cfg, nimg, seed)
@@ -296,6 +298,36 @@ def reference_runner(cfg, batch, seed):
             crit(p, tg.clone())["loss"].sum().backward()
     return step, batch, "reference", (f"the full batch of {batch} images per step; MultiScaleRegionLoss_v5 forward + backward "
                                       f"(LightningFunc/losses.py:98-152) from {staged}")
+
+
+def port_runner(cfg, batch, seed):
+    """Fallback when no reference tree is on the box (oracle/_ref is staged by build() where /root/reference exists): the
+    line-by-line port of the same functions, oracle/ref_port.py (`kind: "port"`)."""
+    from oracle import ref_port as rp
+    why = "no reference tree on this box: oracle/ref_port.py, the line-by-line port"
+    if cfg["kind"] == "yolo":
+        nimg = min(batch, 8)
+        levels, _ = yolo_inputs(cfg, nimg, seed)
+        kw = dict(conf_thres=cfg["conf_thres"], compat=False) if "conf_thres" in cfg else {}
+        return (lambda i: rp.yolo_nms([t[i % nimg:i % nimg + 1] for t in levels], num_anchors=cfg["anchors"], **kw)), 1, "port", \
+            f"1 image per step; {why}"
+    if cfg["kind"] == "prior":
+        pri, loc, cls = prior_inputs(cfg, batch, seed)
+        return (lambda i: rp.ssd_nms(loc, cls, pri)), batch, "port", f"the full batch of {batch} images per step; {why}"
+    from objectdetectionpl_b200 import synth
+    heads, tg = targets_inputs(cfg, batch, seed)
+    stride = torch.tensor([8., 16., 32.])
+    anchors = torch.tensor(synth.YOLOV5_ANCHORS).float().view(3, -1, 2) / stride.view(-1, 1, 1)
+
+    def step(i):
+        p = [h.detach().requires_grad_(True) for h in heads]
+        tcls, tbox, idx, anch = rp.build_targets_v5([t.shape for t in p], tg, anchors, 3, 3)
+        l = 0
+        for k in range(3):
+            giou, _ = rp.v5_match_level(p[k], tbox[k], idx[k], anch[k])
+            l = l + (1.0 - giou).mean()
+        l.backward()
+    return step, batch, "port", f"the full batch of {batch} images per step (build_targets_v5 + matched-row GIoU fwd+bwd only); {why}"
 
 
 def run_cpu(cfg, batch, seed, steps, warmup, budget_s):
