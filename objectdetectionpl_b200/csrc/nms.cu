@@ -104,6 +104,22 @@ __device__ __forceinline__ bool removes(const float4 a, const float4 b, const fl
     return !(ratio <= thr);
 }
 
+// The same decision for VARIANT 0 with nms_thres >= 0 and the two +1-areas precomputed (identical fp32 values: box_area_plus1
+// of the same boxes), for the pair loops of the FAST path: inter == 0 can never exceed a non-negative threshold.
+__device__ __forceinline__ bool removes_v0_areas(const float4 a, const float aa, const float4 b, const float ab, const float thr) {
+    const float iw = fmaxf(__fadd_rn(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 1.0f), 0.0f);
+    const float ih = fmaxf(__fadd_rn(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 1.0f), 0.0f);
+    const float inter = __fmul_rn(iw, ih);
+    if (inter == 0.0f) return false;                                    // quotient +-0 or NaN: never > thr >= 0
+    const float den = __fadd_rn(__fsub_rn(__fadd_rn(aa, ab), inter), 1e-16f);   // accuracy.py:66
+    if (den > 0.0f && thr > 0.0f) {
+        const float q = __fmul_rn(thr, den);
+        if (inter > __fmul_rn(q, 1.000001f)) return true;
+        if (inter < __fmul_rn(q, 0.999999f)) return false;
+    }
+    return __fdiv_rn(inter, den) > thr;
+}
+
 // Conservative half2 summary of a corner box for the pair pre-filter (one 8-byte shared-memory word per row):
 //   lo = (x1, y1) rounded DOWN,  u = (x2 + 1, y2 + 1) - thr' * (w + 1, h + 1) rounded UP,  thr' = thr * (1 - 2^-7).
 // A pair can only reach IoU_+1 > thr if  min(u_a, u_b) > max(lo_a, lo_b)  in BOTH axes, because
@@ -249,6 +265,9 @@ nms_segment_kernel(const NmsParams p) {
     // 196 KB carve-out is 32.6 KB per CTA)
     __shared__ int16_t s_last[CT];
     __shared__ int s_mpre[CT / 32 + 1];  // exclusive prefix of the member bitmap's popcounts
+    // +1-areas of the chunk's rows for the exact pair tests of phase B (FAST): dead before the merge phase builds s_mlist
+    float* const s_area = reinterpret_cast<float*>(s_mlist);
+    __shared__ uint16_t s_task[NW * (NW + 1) + 2];       // phase-B task -> mask word << 8 | row group inside the word's range
     // TAB pre-filter (see box_bounds_f32): bound tables, per-row levels, per-warp candidate queues, chunk range
     __shared__ __align__(16) unsigned long long s_tab[TAB ? 4 : 1][TAB ? kNmsLevels : 1][TAB ? NW : 1];
     __shared__ uchar4 s_lvl[TAB ? CT : 1];           // level(u_x), level(lo_x), level(u_y), level(lo_y) of the row
@@ -317,6 +336,7 @@ nms_segment_kernel(const NmsParams p) {
                 s_box[j] = bx;
                 s_conf[j] = h ? f1 : f0;
                 if (FAST) s_q[j] = box_bounds_h2(bx, thr);
+                if (FAST && VARIANT == 0) s_area[j] = box_area_plus1(bx);
                 s_pre[j] = -1;
                 s_first[j] = -1;
                 s_nzw[j] = 0u;
@@ -341,6 +361,17 @@ nms_segment_kernel(const NmsParams p) {
             }
         }
         if (tid < NW) s_member[tid] = 0ull;      // 32-row groups past nc are never written by the ballots below
+        if (FAST && !TAB) {
+            // phase-B task table: task t -> (mask word w, row group 2w + rem); one thread per task resolves its own index once
+            const int ngr = (nc + 31) >> 5;
+            int nt = 0;
+            for (int w = 0; w < Wc; ++w) nt += ngr - 2 * w;
+            if (tid < nt) {
+                int w = 0, rem = tid;
+                while (rem >= ngr - 2 * w) { rem -= ngr - 2 * w; ++w; }
+                s_task[tid] = (uint16_t)((w << 8) | rem);
+            }
+        }
         __syncthreads();
 
         // ---- phase A: against keepers of earlier chunks ----------------------------------------
@@ -522,7 +553,12 @@ nms_segment_kernel(const NmsParams p) {
         }
         for (int t = tid >> 5; !TAB && t < n_tasks; t += NT / 32) {
             int w = 0, rem = t;
-            while (rem >= ngroups_b - 2 * w) { rem -= ngroups_b - 2 * w; ++w; }
+            if (FAST) {
+                const unsigned tk = s_task[t];
+                w = (int)(tk >> 8); rem = (int)(tk & 255u);
+            } else {
+                while (rem >= ngroups_b - 2 * w) { rem -= ngroups_b - 2 * w; ++w; }
+            }
             const int i0 = w << 6;
             {
                 const int j = ((2 * w + rem) << 5) + lane;
@@ -542,10 +578,19 @@ nms_segment_kernel(const NmsParams p) {
                         if (ni < 32) c_lo &= (1u << ni) - 1u;
                         else if (ni < 64) c_hi &= (1u << (ni - 32)) - 1u;
                         unsigned long long cand = ((unsigned long long)c_hi << 32) | c_lo;
-                        while (cand) {
-                            const int k = __ffsll((long long)cand) - 1;
-                            cand &= cand - 1ull;
-                            if (removes<VARIANT>(s_box[i0 + k], bj, thr)) bits |= 1ull << k;
+                        if (VARIANT == 0) {
+                            const float aj = s_area[j];
+                            while (cand) {
+                                const int k = __ffsll((long long)cand) - 1;
+                                cand &= cand - 1ull;
+                                if (removes_v0_areas(s_box[i0 + k], s_area[i0 + k], bj, aj, thr)) bits |= 1ull << k;
+                            }
+                        } else {
+                            while (cand) {
+                                const int k = __ffsll((long long)cand) - 1;
+                                cand &= cand - 1ull;
+                                if (removes<VARIANT>(s_box[i0 + k], bj, thr)) bits |= 1ull << k;
+                            }
                         }
                     } else {
                         for (int k = 0; k < ni; ++k) {
