@@ -298,6 +298,13 @@ int b200det_v5_loss_bwd(const float* pi, int32_t batch, int32_t na, int32_t ny, 
                         const float* tbox, const float* anch, int32_t m, float cp, float cn, float gamma, float alpha,
                         int32_t with_cls, const float* tobj, const float* g3, float inv_nbox, float inv_cells,
                         float inv_ncls, float* gpi, void* stream);
+/* Same as b200det_v5_loss_bwd, but gpi need NOT be initialised: the call defines every element (zeros outside the objectness
+ * column and the matched rows), written as one linear stream instead of a zero-fill pass followed by strided updates. */
+int b200det_v5_loss_bwd_full(const float* pi, int32_t batch, int32_t na, int32_t ny, int32_t nx, int32_t fields,
+                             const int32_t* b, const int32_t* a, const int32_t* gj, const int32_t* gi, const int32_t* tcls,
+                             const float* tbox, const float* anch, int32_t m, float cp, float cn, float gamma, float alpha,
+                             int32_t with_cls, const float* tobj, const float* g3, float inv_nbox, float inv_cells,
+                             float inv_ncls, float* gpi, void* stream);
 /* The tail of the same forward (losses.py:139-152): means[nl][3] (fp64, what b200det_v5_loss_fwd left per level) are added
  * in level order in fp32, scaled by the three gains and summed: out4 = (loss, Localization, Classification, Conf_obj).
  * _bwd: g3[3] for b200det_v5_loss_bwd (the same for every level) from the upstream gradients of those four outputs

@@ -52,7 +52,7 @@ int v5_loss_fwd_launch(const float*, int, int, int, int, int, const int32_t*, co
                        double*, cudaStream_t);
 int v5_loss_bwd_launch(const float*, int, int, int, int, int, const int32_t*, const int32_t*, const int32_t*, const int32_t*,
                        const int32_t*, const float*, const float*, int, float, float, float, float, int, const float*,
-                       const float*, float, float, float, float*, cudaStream_t);
+                       const float*, float, float, float, float*, int, cudaStream_t);
 int v5_loss_combine_launch(const double*, int, float, float, float, float*, cudaStream_t);
 int v5_loss_combine_bwd_launch(const float*, const float*, const float*, const float*, float, float, float, float*, cudaStream_t);
 size_t build_targets_ws_bytes(int, int, int, int);
@@ -307,7 +307,18 @@ int b200det_v5_loss_bwd(const float* pi, int32_t B, int32_t na, int32_t ny, int3
     B2_CHECK_ARG(pi && tobj && gpi && g3 && (m == 0 || (b && a && gj && gi && tcls && tbox && anch)), "null argument");
     B2_CHECK_ARG(((uintptr_t)tbox & 15) == 0, "tbox must be 16-byte aligned");
     return v5_loss_bwd_launch(pi, B, na, ny, nx, F, b, a, gj, gi, tcls, tbox, anch, m, cp, cn, gamma, alpha, with_cls, tobj,
-                              g3, inv_nbox, inv_cells, inv_ncls, gpi, (cudaStream_t)st);
+                              g3, inv_nbox, inv_cells, inv_ncls, gpi, 0, (cudaStream_t)st);
+}
+int b200det_v5_loss_bwd_full(const float* pi, int32_t B, int32_t na, int32_t ny, int32_t nx, int32_t F, const int32_t* b,
+                             const int32_t* a, const int32_t* gj, const int32_t* gi, const int32_t* tcls, const float* tbox,
+                             const float* anch, int32_t m, float cp, float cn, float gamma, float alpha, int32_t with_cls,
+                             const float* tobj, const float* g3, float inv_nbox, float inv_cells, float inv_ncls, float* gpi,
+                             void* st) {
+    B2_CHECK_ARG(B > 0 && na > 0 && ny > 0 && nx > 0 && m >= 0 && F >= 5, "bad sizes");
+    B2_CHECK_ARG(pi && tobj && gpi && g3 && (m == 0 || (b && a && gj && gi && tcls && tbox && anch)), "null argument");
+    B2_CHECK_ARG(((uintptr_t)tbox & 15) == 0, "tbox must be 16-byte aligned");
+    return v5_loss_bwd_launch(pi, B, na, ny, nx, F, b, a, gj, gi, tcls, tbox, anch, m, cp, cn, gamma, alpha, with_cls, tobj,
+                              g3, inv_nbox, inv_cells, inv_ncls, gpi, 1, (cudaStream_t)st);
 }
 
 int b200det_v5_loss_combine(const double* means, int32_t nl, float wbox, float wobj, float wcls, float* out4, void* st) {

@@ -7,6 +7,9 @@
 #include "common.cuh"
 #include "boxmath.cuh"
 
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
 namespace b200det {
 
 // ================================================================================================
@@ -55,20 +58,29 @@ struct Tv5Multi {
     Tv5Params lvl[B200DET_MAX_LEVELS];
 };
 
-__device__ __forceinline__ void build_targets_v5_body(const Tv5Params& p) {
+// One level.  CL = 1: one CTA walks all na * nt (anchor, target) pairs.  CL > 1: a thread-block cluster per level, CTA `crank`
+// owns the pair range [crank * per, (crank + 1) * per); the five flag totals of every CTA are exchanged over distributed
+// shared memory, so a CTA knows where its rows of each of the five concatenated groups start (accuracy.py:503: the groups are
+// concatenated, each in (anchor, target) order) without a second launch.  (One 1024-thread CTA per level took 59 us at
+// BASELINE config 4: ten rounds of IEEE divisions, fmodf and five block scans on one SM.)
+template <int CL>
+__device__ __forceinline__ void build_targets_v5_body(const Tv5Params& p, const int crank) {
     __shared__ int s_wtot[5][32];
     __shared__ int s_woff[5][32];
     __shared__ int s_carry[5];
     __shared__ int s_base[5];
+    __shared__ int s_tot[5];
     const int E = p.na * p.nt;
+    const int per = CL == 1 ? E : ((E + CL - 1) / CL + 1023) / 1024 * 1024;
+    const int e_lo = min(E, crank * per), e_hi = min(E, e_lo + per);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 5) s_carry[tid] = 0;
     __syncthreads();
 
-    // phase 0: block totals of the five flags (per-thread counts, one reduction); phase 1: ordered ranks + writes
+    // phase 0: totals of the five flags over the CTA's range (per-thread counts, one reduction)
     {
         int cnt[5] = {0, 0, 0, 0, 0};
-        for (int e = tid; e < E; e += 1024) {
+        for (int e = e_lo + tid; e < e_hi; e += 1024) {
             float gx, gy, gw, gh, tb, tc;
             const unsigned f = tv5_flags(p, e, gx, gy, gw, gh, tb, tc);
 #pragma unroll
@@ -82,71 +94,95 @@ __device__ __forceinline__ void build_targets_v5_body(const Tv5Params& p) {
             if (lane == 0) s_wtot[k][warp] = v;
         }
         __syncthreads();
-        if (tid == 0) {
-            int run = 0;
-            for (int k = 0; k < 5; ++k) {
-                int tot = 0;
-                for (int w = 0; w < 32; ++w) tot += s_wtot[k][w];
-                s_base[k] = run; run += tot;
+        if (tid < 5) {
+            int tot = 0;
+            for (int w = 0; w < 32; ++w) tot += s_wtot[tid][w];
+            s_tot[tid] = tot;
+        }
+        if (CL == 1) {
+            __syncthreads();
+            if (tid == 0) {
+                int run = 0;
+                for (int k = 0; k < 5; ++k) { s_base[k] = run; run += s_tot[k]; }
+                p.ocount[0] = run;
             }
-            p.ocount[0] = run;
+        } else {
+            cg::cluster_group cluster = cg::this_cluster();
+            cluster.sync();                                   // every CTA's s_tot is written
+            if (tid == 0) {
+                int run = 0;
+                for (int k = 0; k < 5; ++k) {
+                    int before = 0, all = 0;
+                    for (int c = 0; c < CL; ++c) {
+                        const int v = *cluster.map_shared_rank(&s_tot[k], c);
+                        all += v;
+                        if (c < crank) before += v;
+                    }
+                    s_base[k] = run + before;
+                    run += all;
+                }
+                if (crank == 0) p.ocount[0] = run;
+            }
+            cluster.sync();                                   // nobody leaves (or overwrites s_tot) while a peer still reads it
         }
         __syncthreads();
     }
-    for (int phase = 1; phase < 2; ++phase) {
-        for (int e0 = 0; e0 < E; e0 += 1024) {
-            const int e = e0 + tid;
-            float gx = 0, gy = 0, gw = 0, gh = 0, tb = 0, tc = 0;
-            const unsigned f = e < E ? tv5_flags(p, e, gx, gy, gw, gh, tb, tc) : 0u;
-            unsigned bal[5];
+    // phase 1: ordered ranks + writes
+    for (int e0 = e_lo; e0 < e_hi; e0 += 1024) {
+        const int e = e0 + tid;
+        float gx = 0, gy = 0, gw = 0, gh = 0, tb = 0, tc = 0;
+        const unsigned f = e < e_hi ? tv5_flags(p, e, gx, gy, gw, gh, tb, tc) : 0u;
+        unsigned bal[5];
 #pragma unroll
-            for (int k = 0; k < 5; ++k) bal[k] = __ballot_sync(0xFFFFFFFFu, (f >> k) & 1u);
-            if (lane == 0) {
+        for (int k = 0; k < 5; ++k) bal[k] = __ballot_sync(0xFFFFFFFFu, (f >> k) & 1u);
+        if (lane == 0) {
 #pragma unroll
-                for (int k = 0; k < 5; ++k) s_wtot[k][warp] = __popc(bal[k]);
-            }
-            __syncthreads();
-            if (warp < 5) {
-                const int v = s_wtot[warp][lane];
-                int inc = v;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int u = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-                    if (lane >= o) inc += u;
-                }
-                s_woff[warp][lane] = s_carry[warp] + inc - v;
-                __syncwarp();
-                if (lane == 31) s_carry[warp] += inc;
-            }
-            __syncthreads();
-            if (phase == 1 && f) {
-                const int a = e / p.nt;
-                const int ib = (int)tb, ic = (int)tc;                       // .long() truncation, accuracy.py:509
-#pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    if ((f >> k) & 1u) {
-                        const int row = s_base[k] + s_woff[k][warp] + __popc(bal[k] & lanemask_lt());
-                        const float ox = k == 1 ? 0.5f : (k == 3 ? -0.5f : 0.0f);   // off * g, accuracy.py:506
-                        const float oy = k == 2 ? 0.5f : (k == 4 ? -0.5f : 0.0f);
-                        const int gi = (int)__fsub_rn(gx, ox), gj = (int)__fsub_rn(gy, oy);   // accuracy.py:512
-                        p.ob[row] = ib; p.oa[row] = a; p.ogj[row] = gj; p.ogi[row] = gi; p.ocls[row] = ic;
-                        float* tbx = p.otbox + (size_t)row * 4;
-                        tbx[0] = __fsub_rn(gx, (float)gi); tbx[1] = __fsub_rn(gy, (float)gj);   // accuracy.py:517
-                        tbx[2] = gw; tbx[3] = gh;
-                        p.oanch[(size_t)row * 2] = p.anc[a][0];
-                        p.oanch[(size_t)row * 2 + 1] = p.anc[a][1];
-                    }
-                }
-            }
-            __syncthreads();
+            for (int k = 0; k < 5; ++k) s_wtot[k][warp] = __popc(bal[k]);
         }
+        __syncthreads();
+        if (warp < 5) {
+            const int v = s_wtot[warp][lane];
+            int inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= o) inc += u;
+            }
+            s_woff[warp][lane] = s_carry[warp] + inc - v;
+            __syncwarp();
+            if (lane == 31) s_carry[warp] += inc;
+        }
+        __syncthreads();
+        if (f) {
+            const int a = e / p.nt;
+            const int ib = (int)tb, ic = (int)tc;                       // .long() truncation, accuracy.py:509
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                if ((f >> k) & 1u) {
+                    const int row = s_base[k] + s_woff[k][warp] + __popc(bal[k] & lanemask_lt());
+                    const float ox = k == 1 ? 0.5f : (k == 3 ? -0.5f : 0.0f);   // off * g, accuracy.py:506
+                    const float oy = k == 2 ? 0.5f : (k == 4 ? -0.5f : 0.0f);
+                    const int gi = (int)__fsub_rn(gx, ox), gj = (int)__fsub_rn(gy, oy);   // accuracy.py:512
+                    p.ob[row] = ib; p.oa[row] = a; p.ogj[row] = gj; p.ogi[row] = gi; p.ocls[row] = ic;
+                    float* tbx = p.otbox + (size_t)row * 4;
+                    tbx[0] = __fsub_rn(gx, (float)gi); tbx[1] = __fsub_rn(gy, (float)gj);   // accuracy.py:517
+                    tbx[2] = gw; tbx[3] = gh;
+                    p.oanch[(size_t)row * 2] = p.anc[a][0];
+                    p.oanch[(size_t)row * 2 + 1] = p.anc[a][1];
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 
-__global__ void __launch_bounds__(1024) build_targets_v5_kernel(const Tv5Params p) { build_targets_v5_body(p); }
+__global__ void __launch_bounds__(1024) build_targets_v5_kernel(const Tv5Params p) { build_targets_v5_body<1>(p, 0); }
 
 // all levels in one launch: one CTA per level (the levels are independent, accuracy.py:482)
-__global__ void __launch_bounds__(1024) build_targets_v5_multi_kernel(const Tv5Multi m) { build_targets_v5_body(m.lvl[blockIdx.x]); }
+constexpr int kTv5Cluster = 8;
+__global__ void __launch_bounds__(1024) build_targets_v5_multi_kernel(const Tv5Multi m) {
+    build_targets_v5_body<kTv5Cluster>(m.lvl[blockIdx.y], (int)blockIdx.x);       // grid (cluster, levels), cluster dims (8, 1, 1)
+}
 
 // ================================================================================================
 // T4 — matched rows of one level: ps = pi[b,a,gj,gi] ; pxy = sigmoid*2-0.5 ; pwh = (sigmoid*2)^2*anch ;
@@ -563,8 +599,18 @@ int build_targets_v5_multi_launch(const float* targets, int nt, int nl, const fl
         p.ob = ob[l]; p.oa = oa[l]; p.ogj = ogj[l]; p.ogi = ogi[l]; p.ocls = ocls[l]; p.otbox = otbox[l]; p.oanch = oanch[l];
         p.ocount = ocount + l;
     }
-    build_targets_v5_multi_kernel<<<nl, 1024, 0, st>>>(m);
-    B2_LAUNCH_CHECK("build_targets_v5_multi_kernel");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kTv5Cluster, nl, 1);
+    cfg.blockDim = dim3(1024, 1, 1);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kTv5Cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B2_CUDA(cudaLaunchKernelEx(&cfg, build_targets_v5_multi_kernel, m));
     return 0;
 }
 
@@ -673,6 +719,44 @@ __global__ void __launch_bounds__(256) v5_loss_obj_bwd_kernel(const float* __res
         gpi[c * F + 4] = g_obj * focal_bce_grad(pi[c * F + 4], tobj[c], gamma, alpha);   // the only writer of column 4
 }
 
+// The same objectness gradient, but the kernel writes the WHOLE gradient tensor of its cells — zeros everywhere except
+// column 4 — as one linear stream (256 cells x F floats per CTA = one contiguous, 16-byte aligned block), so the caller needs
+// no zero-fill of the 548 MB gradient before it (a separate memset pass plus the read-modify-write of one 4-byte field per
+// 340-byte row afterwards).  The matched-row kernel then adds its terms on top, as before.
+__global__ void __launch_bounds__(256) v5_loss_obj_bwd_full_kernel(const float* __restrict__ pi, int F, long long cells,
+                                                                   const float* __restrict__ tobj, float gamma, float alpha,
+                                                                   const float* __restrict__ g3, float inv_cells,
+                                                                   float* __restrict__ gpi) {
+    __shared__ float s_g[256];
+    const float g_obj = g3[1] * inv_cells;
+    const int tid = threadIdx.x;
+    for (long long c0 = (long long)blockIdx.x * 256; c0 < cells; c0 += (long long)gridDim.x * 256) {
+        const long long c = c0 + tid;
+        __syncthreads();                                                        // previous block's s_g fully read
+        s_g[tid] = c < cells ? g_obj * focal_bce_grad(pi[c * F + 4], tobj[c], gamma, alpha) : 0.0f;
+        __syncthreads();
+        const int ncell = (int)min((long long)256, cells - c0);
+        const int n = ncell * F;                                                // floats of this block
+        float* out = gpi + c0 * F;                                              // 256 * F * 4 bytes per block: 16-byte aligned
+        const int n4 = n >> 2;
+        for (int v = tid; v < n4; v += 256) {
+            int idx = v << 2;
+            int cell = idx / F, f = idx - cell * F;
+            float r[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                r[k] = f == 4 ? s_g[cell] : 0.0f;
+                if (++f == F) { f = 0; ++cell; }
+            }
+            reinterpret_cast<float4*>(out)[v] = make_float4(r[0], r[1], r[2], r[3]);
+        }
+        for (int idx = (n4 << 2) + tid; idx < n; idx += 256) {                  // tail of the last block
+            const int cell = idx / F, f = idx - cell * F;
+            out[idx] = f == 4 ? s_g[cell] : 0.0f;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) v5_loss_rows_bwd_kernel(const MatchParams p, const int32_t* __restrict__ tcls, float cp,
                                                                float cn, float gamma, float alpha, int with_cls,
                                                                const float* __restrict__ g3, float inv_nbox, float inv_ncls,
@@ -777,11 +861,17 @@ int v5_loss_combine_bwd_launch(const float* g_loss, const float* g_box, const fl
 int v5_loss_bwd_launch(const float* pi, int B, int na, int ny, int nx, int F, const int32_t* b, const int32_t* a,
                        const int32_t* gj, const int32_t* gi, const int32_t* tcls, const float* tbox, const float* anch, int m,
                        float cp, float cn, float gamma, float alpha, int with_cls, const float* tobj, const float* g3,
-                       float inv_nbox, float inv_cells, float inv_ncls, float* gpi, cudaStream_t st) {
+                       float inv_nbox, float inv_cells, float inv_ncls, float* gpi, int fill, cudaStream_t st) {
     const long long cells = (long long)B * na * ny * nx;
     const int grid = (int)((cells + 255) / 256 < 148 * 8 ? (cells + 255) / 256 : 148 * 8);
-    v5_loss_obj_bwd_kernel<<<grid, 256, 0, st>>>(pi, F, cells, tobj, gamma, alpha, g3, inv_cells, gpi);
-    B2_LAUNCH_CHECK("v5_loss_obj_bwd_kernel");
+    if (fill && (((uintptr_t)gpi) & 15) == 0) {
+        v5_loss_obj_bwd_full_kernel<<<grid, 256, 0, st>>>(pi, F, cells, tobj, gamma, alpha, g3, inv_cells, gpi);
+        B2_LAUNCH_CHECK("v5_loss_obj_bwd_full_kernel");
+    } else {
+        if (fill) B2_CUDA(cudaMemsetAsync(gpi, 0, (size_t)cells * F * sizeof(float), st));
+        v5_loss_obj_bwd_kernel<<<grid, 256, 0, st>>>(pi, F, cells, tobj, gamma, alpha, g3, inv_cells, gpi);
+        B2_LAUNCH_CHECK("v5_loss_obj_bwd_kernel");
+    }
     if (m > 0) {
         MatchParams p{pi, B, na, ny, nx, F, b, a, gj, gi, tbox, anch, m};
         v5_loss_rows_bwd_kernel<<<ceil_div(m, 8), 256, 0, st>>>(p, tcls, cp, cn, gamma, alpha, with_cls, g3, inv_nbox, inv_ncls,

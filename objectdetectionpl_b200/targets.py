@@ -200,10 +200,10 @@ class _V5LossLevel(torch.autograd.Function):
         pid, idx, tb, ac, tobj = ctx.saved_tensors
         cp, cn, gamma, alpha, with_cls, m, cells, n_box, n_cls = ctx.cfg
         B, na, ny, nx, F = pid.shape
-        gpi = torch.zeros_like(pid)
+        gpi = torch.empty_like(pid)                                       # fully written by the call (no zero-fill pass)
         g3 = torch.stack((g_box, g_obj, g_cls)).float().contiguous()      # stays on the device: no sync in backward
         with torch.cuda.device(pid.device):
-            L.check(lib.b200det_v5_loss_bwd(pid.data_ptr(), B, na, ny, nx, F, idx[0].data_ptr(), idx[1].data_ptr(),
+            L.check(lib.b200det_v5_loss_bwd_full(pid.data_ptr(), B, na, ny, nx, F, idx[0].data_ptr(), idx[1].data_ptr(),
                                             idx[2].data_ptr(), idx[3].data_ptr(), idx[4].data_ptr(), tb.data_ptr(), ac.data_ptr(),
                                             m, cp, cn, gamma, alpha, with_cls, tobj.data_ptr(), g3.data_ptr(), 1.0 / n_box,
                                             1.0 / cells, 1.0 / n_cls, gpi.data_ptr(), L.stream_ptr(pid.device)), "v5_loss_bwd")
@@ -280,8 +280,8 @@ class _V5LossAll(torch.autograd.Function):
             for i, (pid, (ib, tb, ac)) in enumerate(zip(pids, ctx.levels)):
                 B, na, ny, nx, F = pid.shape
                 m, cells = ctx.ms[i], ctx.cells[i]
-                gpi = torch.zeros_like(pid)
-                L.check(lib.b200det_v5_loss_bwd(pid.data_ptr(), B, na, ny, nx, F, ib[0].data_ptr(), ib[1].data_ptr(),
+                gpi = torch.empty_like(pid)                               # fully written by the call (no zero-fill pass)
+                L.check(lib.b200det_v5_loss_bwd_full(pid.data_ptr(), B, na, ny, nx, F, ib[0].data_ptr(), ib[1].data_ptr(),
                                                 ib[2].data_ptr(), ib[3].data_ptr(), ib[4].data_ptr(), tb.data_ptr(), ac.data_ptr(),
                                                 m, cp, cn, gamma, alpha, int(with_cls), tobj.data_ptr() + 4 * t_off, g3.data_ptr(),
                                                 1.0 / max(m, 1), 1.0 / cells, 1.0 / max(m * (F - 5), 1), gpi.data_ptr(), st),
