@@ -194,8 +194,10 @@ struct MatchParams {
     const int32_t *b, *a, *gj, *gi;
     const float* tbox;
     const float* anch;
-    int m;
+    int m;                      // matched rows; with m_dev set: the CAPACITY of the row arrays (sizes the grids)
+    const int32_t* m_dev;       // optional: the row count lives on the device (no host sync between build_targets_v5 and the loss)
 };
+__device__ __forceinline__ int match_rows(const MatchParams& p) { return p.m_dev ? min(p.m, (int)*p.m_dev) : p.m; }
 
 __device__ __forceinline__ long long match_cell(const MatchParams& p, int i) {
     return (((long long)p.b[i] * p.na + p.a[i]) * p.ny + p.gj[i]) * p.nx + p.gi[i];
@@ -203,7 +205,7 @@ __device__ __forceinline__ long long match_cell(const MatchParams& p, int i) {
 
 __global__ void v5_match_fwd_kernel(const MatchParams p, float* __restrict__ giou, int* __restrict__ tobj_as_int) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.m) return;
+    if (i >= match_rows(p)) return;
     const long long cell = match_cell(p, i);
     const float* ps = p.pi + cell * p.F;
     const float sx = sigmoidf_acc(ps[0]), sy = sigmoidf_acc(ps[1]);
@@ -221,14 +223,14 @@ __global__ void v5_match_fwd_kernel(const MatchParams p, float* __restrict__ gio
 
 __global__ void v5_match_tobj_kernel(const MatchParams p, const float* __restrict__ giou, float* __restrict__ tobj) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.m) return;
+    if (i >= match_rows(p)) return;
     const long long cell = match_cell(p, i);
     if (reinterpret_cast<const int*>(tobj)[cell] == i + 1) tobj[cell] = fmaxf(giou[i], 0.0f);   // losses.py:123
 }
 
 __global__ void v5_match_bwd_kernel(const MatchParams p, const float* __restrict__ ggiou, float* __restrict__ gpi) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.m) return;
+    if (i >= match_rows(p)) return;
     const long long cell = match_cell(p, i);
     const float* ps = p.pi + cell * p.F;
     const float aw = p.anch[(size_t)i * 2], ah = p.anch[(size_t)i * 2 + 1];
@@ -618,7 +620,8 @@ int v5_match_fwd_launch(const float* pi, int B, int na, int ny, int nx, int F, c
                         const int32_t* gj, const int32_t* gi, const float* tbox, const float* anch, int m, float* giou,
                         float* tobj, cudaStream_t st) {
     if (m == 0) return 0;
-    MatchParams p{pi, B, na, ny, nx, F, b, a, gj, gi, tbox, anch, m};
+    const int32_t* m_dev = nullptr;
+    MatchParams p{pi, B, na, ny, nx, F, b, a, gj, gi, tbox, anch, m, m_dev};
     const int blocks = ceil_div(m, 256);
     v5_match_fwd_kernel<<<blocks, 256, 0, st>>>(p, giou, reinterpret_cast<int*>(tobj));
     B2_LAUNCH_CHECK("v5_match_fwd_kernel");
@@ -631,7 +634,8 @@ int v5_match_bwd_launch(const float* pi, int B, int na, int ny, int nx, int F, c
                         const int32_t* gj, const int32_t* gi, const float* tbox, const float* anch, int m,
                         const float* ggiou, float* gpi, cudaStream_t st) {
     if (m == 0) return 0;
-    MatchParams p{pi, B, na, ny, nx, F, b, a, gj, gi, tbox, anch, m};
+    const int32_t* m_dev = nullptr;
+    MatchParams p{pi, B, na, ny, nx, F, b, a, gj, gi, tbox, anch, m, m_dev};
     v5_match_bwd_kernel<<<ceil_div(m, 256), 256, 0, st>>>(p, ggiou, gpi);
     B2_LAUNCH_CHECK("v5_match_bwd_kernel");
     return 0;
@@ -689,7 +693,7 @@ __global__ void __launch_bounds__(256) v5_loss_rows_fwd_kernel(const MatchParams
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
     double box = 0.0, cls = 0.0;
-    if (i < p.m) {
+    if (i < match_rows(p)) {
         if (lane == 0) box = (double)(1.0f - giou[i]);
         if (with_cls) {
             const float* ps = p.pi + match_cell(p, i) * p.F + 5;
@@ -730,6 +734,7 @@ __global__ void __launch_bounds__(256) v5_loss_obj_bwd_full_kernel(const float* 
     __shared__ float s_g[256];
     const float g_obj = g3[1] * inv_cells;
     const int tid = threadIdx.x;
+    const int step_q = 1024 / F, step_r = 1024 - step_q * F;                    // 256 threads x 4 floats per step
     for (long long c0 = (long long)blockIdx.x * 256; c0 < cells; c0 += (long long)gridDim.x * 256) {
         const long long c = c0 + tid;
         __syncthreads();                                                        // previous block's s_g fully read
@@ -739,9 +744,10 @@ __global__ void __launch_bounds__(256) v5_loss_obj_bwd_full_kernel(const float* 
         const int n = ncell * F;                                                // floats of this block
         float* out = gpi + c0 * F;                                              // 256 * F * 4 bytes per block: 16-byte aligned
         const int n4 = n >> 2;
+        // (cell, field) of the thread's first float, then advanced by 1024 floats per step without dividing again
+        int cell0 = (tid << 2) / F, f0 = (tid << 2) - cell0 * F;
         for (int v = tid; v < n4; v += 256) {
-            int idx = v << 2;
-            int cell = idx / F, f = idx - cell * F;
+            int cell = cell0, f = f0;
             float r[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -749,6 +755,8 @@ __global__ void __launch_bounds__(256) v5_loss_obj_bwd_full_kernel(const float* 
                 if (++f == F) { f = 0; ++cell; }
             }
             reinterpret_cast<float4*>(out)[v] = make_float4(r[0], r[1], r[2], r[3]);
+            cell0 += step_q; f0 += step_r;
+            if (f0 >= F) { f0 -= F; ++cell0; }
         }
         for (int idx = (n4 << 2) + tid; idx < n; idx += 256) {                  // tail of the last block
             const int cell = idx / F, f = idx - cell * F;
@@ -763,7 +771,12 @@ __global__ void __launch_bounds__(256) v5_loss_rows_bwd_kernel(const MatchParams
                                                                float* __restrict__ gpi) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (i >= p.m) return;
+    if (i >= match_rows(p)) return;
+    if (p.m_dev) {                                                  // the means' divisors from the device-side row count
+        const long long mm = max(match_rows(p), 1);
+        inv_nbox = (float)(1.0 / (double)mm);
+        inv_ncls = (float)(1.0 / (double)max(mm * (p.F - 5), 1ll));
+    }
     const float g_box = g3[0] * inv_nbox, g_cls = g3[2] * inv_ncls;
     const long long cell = match_cell(p, i);
     const float* ps = p.pi + cell * p.F;
@@ -789,18 +802,24 @@ __global__ void __launch_bounds__(256) v5_loss_rows_bwd_kernel(const MatchParams
     }
 }
 
-__global__ void v5_loss_means_kernel(double* __restrict__ sums, double n_box, double n_cells, double n_cls) {
+__global__ void v5_loss_means_kernel(double* __restrict__ sums, double n_box, double n_cells, double n_cls,
+                                     const int32_t* __restrict__ m_dev, int cap, int C) {
+    if (m_dev) {
+        const long long mm = min((long long)cap, (long long)*m_dev);
+        n_box = (double)max(mm, 1ll);
+        n_cls = (double)max(mm * C, 1ll);
+    }
     if (threadIdx.x < 3) sums[threadIdx.x] = sums[threadIdx.x] / (threadIdx.x == 0 ? n_box : threadIdx.x == 1 ? n_cells : n_cls);
 }
 
 int v5_loss_fwd_launch(const float* pi, int B, int na, int ny, int nx, int F, const int32_t* b, const int32_t* a,
                        const int32_t* gj, const int32_t* gi, const int32_t* tcls, const float* tbox, const float* anch, int m,
                        float cp, float cn, float gamma, float alpha, int with_cls, float* giou, float* tobj, double* sums,
-                       cudaStream_t st) {
+                       const int32_t* m_dev, cudaStream_t st) {
     const long long cells = (long long)B * na * ny * nx;
     B2_CUDA(cudaMemsetAsync(sums, 0, 3 * sizeof(double), st));
     B2_CUDA(cudaMemsetAsync(tobj, 0, (size_t)cells * 4, st));                      // torch.zeros_like(pi[..., 0])  (:107)
-    MatchParams p{pi, B, na, ny, nx, F, b, a, gj, gi, tbox, anch, m};
+    MatchParams p{pi, B, na, ny, nx, F, b, a, gj, gi, tbox, anch, m, m_dev};
     if (m > 0) {
         const int blocks = ceil_div(m, 256);
         v5_match_fwd_kernel<<<blocks, 256, 0, st>>>(p, giou, reinterpret_cast<int*>(tobj));
@@ -815,7 +834,7 @@ int v5_loss_fwd_launch(const float* pi, int B, int na, int ny, int nx, int F, co
     B2_LAUNCH_CHECK("v5_loss_obj_fwd_kernel");
     // sums -> means in place: box / max(m, 1), obj / cells, cls / max(m * C, 1)   (reduction 'mean', losses.py:119-137)
     v5_loss_means_kernel<<<1, 32, 0, st>>>(sums, (double)(m > 0 ? m : 1), (double)cells,
-                                           (double)((long long)m * (F - 5) > 0 ? (long long)m * (F - 5) : 1));
+                                           (double)((long long)m * (F - 5) > 0 ? (long long)m * (F - 5) : 1), m_dev, m, F - 5);
     B2_LAUNCH_CHECK("v5_loss_means_kernel");
     return 0;
 }
@@ -861,7 +880,8 @@ int v5_loss_combine_bwd_launch(const float* g_loss, const float* g_box, const fl
 int v5_loss_bwd_launch(const float* pi, int B, int na, int ny, int nx, int F, const int32_t* b, const int32_t* a,
                        const int32_t* gj, const int32_t* gi, const int32_t* tcls, const float* tbox, const float* anch, int m,
                        float cp, float cn, float gamma, float alpha, int with_cls, const float* tobj, const float* g3,
-                       float inv_nbox, float inv_cells, float inv_ncls, float* gpi, int fill, cudaStream_t st) {
+                       float inv_nbox, float inv_cells, float inv_ncls, float* gpi, int fill, const int32_t* m_dev,
+                       cudaStream_t st) {
     const long long cells = (long long)B * na * ny * nx;
     const int grid = (int)((cells + 255) / 256 < 148 * 8 ? (cells + 255) / 256 : 148 * 8);
     if (fill && (((uintptr_t)gpi) & 15) == 0) {
@@ -873,7 +893,7 @@ int v5_loss_bwd_launch(const float* pi, int B, int na, int ny, int nx, int F, co
         B2_LAUNCH_CHECK("v5_loss_obj_bwd_kernel");
     }
     if (m > 0) {
-        MatchParams p{pi, B, na, ny, nx, F, b, a, gj, gi, tbox, anch, m};
+        MatchParams p{pi, B, na, ny, nx, F, b, a, gj, gi, tbox, anch, m, m_dev};
         v5_loss_rows_bwd_kernel<<<ceil_div(m, 8), 256, 0, st>>>(p, tcls, cp, cn, gamma, alpha, with_cls, g3, inv_nbox, inv_ncls,
                                                                 gpi);
         B2_LAUNCH_CHECK("v5_loss_rows_bwd_kernel");

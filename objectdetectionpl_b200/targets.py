@@ -75,9 +75,10 @@ def _host_anchors(anchors, nl, na):
     return (ctypes.c_float * (2 * na * nl))(*vals)
 
 
-def _build_targets_v5_raw(p, targets, anchors, nl, na):
+def _build_targets_v5_raw(p, targets, anchors, nl, na, sync=True):
     """One launch for all levels, one host sync for the row counts.  Per level: `(ib int32 [5, m] = b, a, gj, gi, cls
-    (rows of a wider buffer), tbox [m, 4], anch [m, 2])`."""
+    (rows of a wider buffer), tbox [m, 4], anch [m, 2])`.  `sync=False`: no host sync — returns the full-capacity buffers
+    `[(ib [5, cap], tbox [cap, 4], anch [cap, 2])]` and the device tensor of the per-level row counts."""
     lib = L.load()
     tg = L.require_cuda(targets, "targets").contiguous()
     dev = tg.device
@@ -100,7 +101,9 @@ def _build_targets_v5_raw(p, targets, anchors, nl, na):
         bufs.append((ib, tb, ac))
     with torch.cuda.device(dev):
         L.check(lib.b200det_build_targets_v5(tg.data_ptr() if nt else None, nt, nl, arr, na, nxs, nys, *ptrs, counts.data_ptr(),
-                                             L.stream_ptr(dev)), "build_targets_v5")     # one launch, one CTA per level
+                                             L.stream_ptr(dev)), "build_targets_v5")     # one launch, a cluster of 8 CTAs per level
+    if not sync:
+        return bufs, counts
     ms = counts.cpu().tolist()                                            # one host sync for all levels
     return [(ib[:, :m], tb[:m], ac[:m]) for (ib, tb, ac), m in zip(bufs, ms)]
 
@@ -227,10 +230,12 @@ _V5_GAINS = (0.05, 1.0, 0.58)          # box, obj, cls  (losses.py:139-141)
 
 class _V5LossAll(torch.autograd.Function):
     """All levels and the combination of `MultiScaleRegionLoss_v5.forward` as ONE autograd node: the per-level Python and
-    the ~15 tiny autograd nodes of the level-by-level form were two thirds of its wall time."""
+    the ~15 tiny autograd nodes of the level-by-level form were two thirds of its wall time.  The matched-row counts stay on
+    the device (`b200det_v5_loss_fwd_dev` / `_bwd_full_dev`): nothing between `build_targets_v5` and the loss value waits for
+    the GPU."""
 
     @staticmethod
-    def forward(ctx, levels, cfg, *pis):
+    def forward(ctx, levels, counts, cfg, *pis):
         lib = L.load()
         cp, cn, gamma, alpha, with_cls = cfg
         nl = len(pis)
@@ -242,9 +247,9 @@ class _V5LossAll(torch.autograd.Function):
             pids.append(pid)
         dev = pids[0].device
         cells = [pid.numel() // pid.shape[-1] for pid in pids]
-        ms = [int(ib.shape[1]) for ib, _, _ in levels]
+        caps = [int(ib.shape[1]) for ib, _, _ in levels]
         tobj = torch.empty((sum(cells),), dtype=torch.float32, device=dev)            # all levels, back to back
-        giou = torch.empty((max(sum(ms), 1),), dtype=torch.float32, device=dev)
+        giou = torch.empty((sum(caps),), dtype=torch.float32, device=dev)
         means = torch.empty((nl, 3), dtype=torch.float64, device=dev)
         out = torch.empty((4,), dtype=torch.float32, device=dev)
         st = L.stream_ptr(dev)
@@ -252,21 +257,22 @@ class _V5LossAll(torch.autograd.Function):
             t_off = g_off = 0
             for i, (pid, (ib, tb, ac)) in enumerate(zip(pids, levels)):
                 B, na, ny, nx, F = pid.shape
-                L.check(lib.b200det_v5_loss_fwd(pid.data_ptr(), B, na, ny, nx, F, ib[0].data_ptr(), ib[1].data_ptr(),
-                                                ib[2].data_ptr(), ib[3].data_ptr(), ib[4].data_ptr(), tb.data_ptr(), ac.data_ptr(),
-                                                ms[i], cp, cn, gamma, alpha, int(with_cls), giou.data_ptr() + 4 * g_off,
-                                                tobj.data_ptr() + 4 * t_off, means.data_ptr() + 24 * i, st), "v5_loss_fwd")
+                L.check(lib.b200det_v5_loss_fwd_dev(pid.data_ptr(), B, na, ny, nx, F, ib[0].data_ptr(), ib[1].data_ptr(),
+                                                    ib[2].data_ptr(), ib[3].data_ptr(), ib[4].data_ptr(), tb.data_ptr(),
+                                                    ac.data_ptr(), caps[i], counts.data_ptr() + 4 * i, cp, cn, gamma, alpha,
+                                                    int(with_cls), giou.data_ptr() + 4 * g_off, tobj.data_ptr() + 4 * t_off,
+                                                    means.data_ptr() + 24 * i, st), "v5_loss_fwd_dev")
                 t_off += cells[i]
-                g_off += ms[i]
+                g_off += caps[i]
             L.check(lib.b200det_v5_loss_combine(means.data_ptr(), nl, *_V5_GAINS, out.data_ptr(), st), "v5_loss_combine")
-        ctx.save_for_backward(tobj, *pids)
-        ctx.levels, ctx.cfg, ctx.cells, ctx.ms = levels, cfg, cells, ms
+        ctx.save_for_backward(tobj, counts, *pids)
+        ctx.levels, ctx.cfg, ctx.cells, ctx.caps = levels, cfg, cells, caps
         return out[0:1], out[1:2], out[2:3], out[3:4]
 
     @staticmethod
     def backward(ctx, g_loss, g_box, g_cls, g_obj):
         lib = L.load()
-        tobj, *pids = ctx.saved_tensors
+        tobj, counts, *pids = ctx.saved_tensors
         cp, cn, gamma, alpha, with_cls = ctx.cfg
         dev = tobj.device
         gs = [None if g is None else g.contiguous().float() for g in (g_loss, g_box, g_cls, g_obj)]
@@ -279,27 +285,27 @@ class _V5LossAll(torch.autograd.Function):
             t_off = 0
             for i, (pid, (ib, tb, ac)) in enumerate(zip(pids, ctx.levels)):
                 B, na, ny, nx, F = pid.shape
-                m, cells = ctx.ms[i], ctx.cells[i]
+                cells = ctx.cells[i]
                 gpi = torch.empty_like(pid)                               # fully written by the call (no zero-fill pass)
-                L.check(lib.b200det_v5_loss_bwd_full(pid.data_ptr(), B, na, ny, nx, F, ib[0].data_ptr(), ib[1].data_ptr(),
-                                                ib[2].data_ptr(), ib[3].data_ptr(), ib[4].data_ptr(), tb.data_ptr(), ac.data_ptr(),
-                                                m, cp, cn, gamma, alpha, int(with_cls), tobj.data_ptr() + 4 * t_off, g3.data_ptr(),
-                                                1.0 / max(m, 1), 1.0 / cells, 1.0 / max(m * (F - 5), 1), gpi.data_ptr(), st),
-                        "v5_loss_bwd")
+                L.check(lib.b200det_v5_loss_bwd_full_dev(pid.data_ptr(), B, na, ny, nx, F, ib[0].data_ptr(), ib[1].data_ptr(),
+                                                         ib[2].data_ptr(), ib[3].data_ptr(), ib[4].data_ptr(), tb.data_ptr(),
+                                                         ac.data_ptr(), ctx.caps[i], counts.data_ptr() + 4 * i, cp, cn, gamma,
+                                                         alpha, int(with_cls), tobj.data_ptr() + 4 * t_off, g3.data_ptr(),
+                                                         1.0 / cells, gpi.data_ptr(), st), "v5_loss_bwd_full_dev")
                 grads.append(gpi)
                 t_off += cells
-        return (None, None, *grads)
+        return (None, None, None, *grads)
 
 
 def v5_loss(output, target, anchors, nl, na, nc, cp=1.0, cn=0.0, gamma=1.5, alpha=0.25):
     """`MultiScaleRegionLoss_v5.forward` (losses.py:98-152, reduction 'mean', label smoothing 0, focal gamma 1.5):
-    `build_targets_v5` (one launch, one host sync), the fused per-level loss kernels and the gain-weighted combination, as
-    one autograd node.  `anchors` are the criterion's scaled anchors `[nl, na, 2]` (:95-96).
-    Returns the reference's metrics dict of shape-[1] tensors: loss, Localization, Classification, Conf_obj."""
-    levels = _build_targets_v5_raw(output, target, anchors, nl, na)         # int32 index rows go straight to the kernels
-    levels = [(ib, tb.contiguous(), ac.contiguous()) for ib, tb, ac in levels]
+    `build_targets_v5` (one launch), the fused per-level loss kernels and the gain-weighted combination, as one autograd
+    node and without a host sync (the row counts stay on the device).  `anchors` are the criterion's scaled anchors
+    `[nl, na, 2]` (:95-96).  Returns the reference's metrics dict of shape-[1] tensors: loss, Localization, Classification,
+    Conf_obj."""
+    levels, counts = _build_targets_v5_raw(output, target, anchors, nl, na, sync=False)   # full-capacity rows + device counts
     cfg = (float(cp), float(cn), float(gamma), float(alpha), nc > 1)
-    loss, lbox, lcls, lobj = _V5LossAll.apply(levels, cfg, *output)
+    loss, lbox, lcls, lobj = _V5LossAll.apply(levels, counts, cfg, *output)
     return {"loss": loss, "Localization": lbox, "Classification": lcls, "Conf_obj": lobj}
 
 
