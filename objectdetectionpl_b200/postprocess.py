@@ -177,19 +177,20 @@ def _yolo_nms_planned(plan, predictions, d, B, n_pad, dev, return_index):
     with torch.cuda.device(dev):
         ws = L.workspace(plan.ws_bytes, dev)
         spare, plan.spare = plan.spare, None
-        if spare is not None and spare[0].device == dev:
-            rows, count = spare
+        stream = L.stream_ptr(dev)
+        if spare is not None and spare[0].device == dev and spare[2] == stream:     # allocated under this very stream
+            rows, count = spare[0], spare[1]
         else:
             rows = torch.empty((B, n_pad, 7), dtype=torch.float32, device=dev)
             count = torch.empty((B,), dtype=torch.int32, device=dev)
         index = torch.empty((B, n_pad), dtype=torch.int32, device=dev) if return_index else None
         L.check(plan.fn(plan.dref, ws.data_ptr(), ws.numel(), rows.data_ptr(), index.data_ptr() if return_index else None,
-                        count.data_ptr(), plan.host.data_ptr(), plan.event.cuda_event, L.stream_ptr(dev)), "yolo_nms_early")
+                        count.data_ptr(), plan.host.data_ptr(), plan.event.cuda_event, stream), "yolo_nms_early")
         # ---- the GPU is busy for the next few hundred microseconds: everything that does not need the counts happens now ----
         views = list(rows.unbind(0))                     # B views [n_pad, 7]; shrunk in place once the counts are known
         iviews = list(index.long().unbind(0)) if return_index else None
         plan.spare = (torch.empty((B, n_pad, 7), dtype=torch.float32, device=dev),       # the next call's result buffers
-                      torch.empty((B,), dtype=torch.int32, device=dev))
+                      torch.empty((B,), dtype=torch.int32, device=dev), stream)
         # the one host sync of the call: it waits for the NMS stage only (the counts are final there and were written straight
         # into pinned host memory).  The emit kernel may still be writing the rows when this function returns; whatever the
         # caller does with them next is stream-ordered behind it, as with any torch op.
@@ -398,6 +399,7 @@ def prior_nms_raw(loc: torch.Tensor, cls: torch.Tensor, priors: torch.Tensor, to
 
 
 _prior_count_bufs = {}      # (device, batch) -> (pinned [2, B] int32, event)
+_prior_lock = threading.Lock()
 
 
 def prior_non_max_suppression(self, predictions, topk=100, nms_thresh=0.5, class_thresh=0.45, mode="union", *,
@@ -419,13 +421,13 @@ def prior_non_max_suppression(self, predictions, topk=100, nms_thresh=0.5, class
             _prior_count_bufs.clear()
         slot = _prior_count_bufs[key] = (torch.empty((2, B), dtype=torch.int32).pin_memory(), torch.cuda.Event())
     host, ev = slot
-    with torch.cuda.device(dev):
+    with _prior_lock, torch.cuda.device(dev):            # the pinned count buffer is shared by the calls of one (device, batch)
         host.copy_(count, non_blocking=True)             # kept rows [0] and candidates above the score threshold [1]
         ev.record()
         views = list(rows.unbind(0))                     # built while the GPU works; shrunk in place after the one sync
         iviews = list(index.long().unbind(0)) if return_index else None
         ev.synchronize()
-    kept, cand = host.tolist()
+        kept, cand = host.tolist()
     if compat and 1 in cand:
         raise IndexError("too many indices for tensor of dimension 1")   # model/SSD.py:262,266 (0-dim index)
     out = [v.resize_(k, 7) for v, k in zip(views, kept)]
