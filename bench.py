@@ -453,13 +453,18 @@ class YoloWorkload:
             if prev is not None:
                 nrows = sum(x.shape[0] for x in prev.result() if x is not None)
             prev = h
-        return sum(x.shape[0] for x in prev.result() if x is not None)
+        self.e2e_rows = sum(x.shape[0] for x in prev.result() if x is not None)
+        return self.e2e_rows
 
     def e2e_bytes(self):
-        return sum(t.numel() * 4 for t in self.pinned), self.B * self.n_pad * 7 * 4 + self.B * 4
+        # device -> host: the kept rows (the emit kernel writes them, packed, straight into pinned host memory) + per 8-image
+        # chunk the count | offsets words
+        chunks = (self.B + 7) // 8
+        return sum(t.numel() * 4 for t in self.pinned), self.e2e_rows * 28 + chunks * (2 * 8 + 1) * 4
 
-    e2e_api = ("objectdetectionpl_b200.non_max_suppression_host_async (pinned host in/out, 8-image chunks on 3 streams, "
-               "batch i+1 submitted before batch i is collected)")
+    e2e_api = ("objectdetectionpl_b200.non_max_suppression_host_async (pinned host in, 8-image chunks, H2D on one stream and the "
+               "pipeline on another; the emit kernel writes the kept rows straight into pinned host memory — no D2H copy; batch "
+               "i+1 submitted before batch i is collected)")
 
 
 class PriorWorkload:

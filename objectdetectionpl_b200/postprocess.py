@@ -220,20 +220,25 @@ def non_max_suppression(self, predictions, conf_thres=0.5, nms_thres=0.4, *, com
 
 
 class _HostPipe:
-    """Buffers and streams of the host-input pipeline for one (device, head shapes, chunk) configuration."""
+    """Buffers and streams of the host-input pipeline for one (device, per-image head shapes, chunk) configuration."""
 
     def __init__(self, dev, shapes, chunk, n_pad):
-        self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.s_in, self.s_cmp = (torch.cuda.Stream(dev) for _ in range(2))
         self.dev_in = [[torch.empty((chunk,) + tuple(sh[1:]), dtype=torch.float32, device=dev) for sh in shapes]
                        for _ in range(2)]
         self.buf_free = [None, None]      # event: the pipeline has consumed what dev_in[i] last held
         self.chunk_seq = 0                # chunks submitted so far (across calls): dev_in alternates on it
         self.calls = 0                    # calls submitted so far: the two pinned result sets alternate on it
         B = shapes[0][0]
-        self.batch, self.chunk, self.last_done = B, chunk, None
-        self.host = [(torch.empty((B, n_pad, 7), dtype=torch.float32).pin_memory(),
-                      torch.empty((B, n_pad), dtype=torch.int32).pin_memory(),
-                      torch.empty((B,), dtype=torch.int32).pin_memory()) for _ in range(2)]
+        self.batch, self.chunk, self.n_pad, self.last_done = B, chunk, n_pad, None
+        nchunks = (B + chunk - 1) // chunk
+        # Two result sets in PINNED (mapped) host memory.  The emit kernel writes the kept rows of a chunk straight into them
+        # (packed, chunk c in the region starting at row c * chunk * n_pad) and the prefix kernel the chunk's count | offsets
+        # words: no device->host copy is enqueued at all, and only kept rows cross the link.
+        self.host = [(torch.empty((B * n_pad, 7), dtype=torch.float32).pin_memory(),
+                      torch.empty((B * n_pad,), dtype=torch.int32).pin_memory(),
+                      torch.zeros((nchunks, 2 * chunk + 1), dtype=torch.int32).pin_memory()) for _ in range(2)]
+        self.dev_meta = [torch.empty((2 * chunk + 1,), dtype=torch.int32, device=dev) for _ in range(2)]
 
     def in_flight(self):
         return self.last_done is not None and not self.last_done.query()
@@ -249,10 +254,10 @@ def clear_host_pipes():
 
 
 class HostNmsHandle:
-    """A submitted `non_max_suppression_host_async` call; `result()` waits for its last device->host copy."""
+    """A submitted `non_max_suppression_host_async` call; `result()` waits for the last chunk's pipeline."""
 
-    def __init__(self, done, host, return_index, keep, pipe, generation, batch):
-        self._done, self._host, self._return_index, self._keep = done, host, return_index, keep
+    def __init__(self, done, host, return_index, chunks, pipe, generation, batch):
+        self._done, self._host, self._return_index, self._chunks = done, host, return_index, chunks
         self._pipe, self._generation, self._batch = pipe, generation, batch
         self._out = None
 
@@ -264,11 +269,20 @@ class HostNmsHandle:
                 raise RuntimeError("non_max_suppression_host_async: this call's pinned result buffer was overwritten by a "
                                    "later submission (at most two calls may be in flight per configuration)")
             self._done.synchronize()
-            self._keep = None
-            rows, index, count = (t[:self._batch] for t in self._host)
-            counts = count.tolist()
-            out: List[Optional[torch.Tensor]] = [r[:k] if k else None for r, k in zip(rows.unbind(0), counts)]
-            self._out = (out, [index[b, :k].long() if k else None for b, k in enumerate(counts)]) if self._return_index else out
+            rows, index, meta = self._host
+            n_pad = self._pipe.n_pad
+            out: List[Optional[torch.Tensor]] = []
+            idx: List[Optional[torch.Tensor]] = []
+            for c, (lo, hi) in enumerate(self._chunks):
+                nb = hi - lo
+                m = meta[c].tolist()                       # count [nb] | offsets [nb + 1], written by the device
+                base = lo * n_pad
+                for i in range(nb):
+                    k, o = m[i], base + m[nb + i]
+                    out.append(rows[o:o + k] if k else None)
+                    if self._return_index:
+                        idx.append(index[o:o + k].long() if k else None)
+            self._out = (out, idx) if self._return_index else out
         return self._out
 
 
@@ -276,9 +290,9 @@ def non_max_suppression_host_async(self, predictions, conf_thres=0.5, nms_thres=
                                    device=None, chunk_images=8, decode=None, anchors=None, strides=None, return_index=False):
     """Submit `non_max_suppression_host` without waiting: returns a `HostNmsHandle` whose `result()` is that function's
     return value.  Submitting batch i+1 before collecting batch i keeps the host->device link busy across batches (the
-    tail of a batch — the pipeline and the device->host copy of its last chunk — otherwise leaves it idle).  Two calls
-    may be in flight per (device, shapes) configuration: the rows of a call live in one of two pinned buffers and stay
-    valid until the second submission after it.  `predictions` must not be modified before `result()` returns."""
+    tail of a batch — the pipeline of its last chunk — otherwise leaves it idle).  Two calls may be in flight per
+    (device, shapes) configuration: the rows of a call live in one of two pinned buffers and stay valid until the second
+    submission after it.  `predictions` must not be modified before `result()` returns."""
     if not isinstance(predictions, (list, tuple)):
         predictions = [predictions]
     for i, t in enumerate(predictions):
@@ -286,6 +300,7 @@ def non_max_suppression_host_async(self, predictions, conf_thres=0.5, nms_thres=
             raise TypeError(f"predictions[{i}] must be a contiguous fp32 HOST tensor (use non_max_suppression for CUDA tensors)")
     if not torch.cuda.is_available():
         raise RuntimeError("b200det has no CPU path: non_max_suppression_host needs a CUDA device to run on")
+    lib = L.load()
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     B = predictions[0].shape[0]
     chunk = max(1, min(int(chunk_images), B))
@@ -314,13 +329,17 @@ def non_max_suppression_host_async(self, predictions, conf_thres=0.5, nms_thres=
     host = pipe.host[pipe.calls & 1]
     pipe.calls += 1
     generation = pipe.calls
-    keep = []
+    n_pad = pipe.n_pad
+    rows_h, index_h, meta_h = host
+    chunks = []
     with torch.cuda.device(dev):
         for c in range(nchunks):
             lo, hi = c * chunk, min(B, (c + 1) * chunk)
+            nb = hi - lo
+            chunks.append((lo, hi))
             slot = pipe.chunk_seq & 1
             pipe.chunk_seq += 1
-            dst = [t[:hi - lo] for t in pipe.dev_in[slot]]
+            dst = [t[:nb] for t in pipe.dev_in[slot]]
             ev_in, ev_done = torch.cuda.Event(), torch.cuda.Event()
             with torch.cuda.stream(pipe.s_in):
                 if pipe.buf_free[slot] is not None:
@@ -330,23 +349,20 @@ def non_max_suppression_host_async(self, predictions, conf_thres=0.5, nms_thres=
                 ev_in.record(pipe.s_in)
             with torch.cuda.stream(pipe.s_cmp):
                 pipe.s_cmp.wait_event(ev_in)
-                rows, index, count = yolo_nms_raw(dst, num_anchors, thr, nms_thres, decode, anchors, strides, return_index)
+                d = _yolo_desc(dst, num_anchors, thr, nms_thres, decode, anchors, strides)
+                ws_bytes = lib.b200det_yolo_workspace_bytes(ctypes.byref(d))
+                ws = L.workspace(ws_bytes, dev)
+                dm = pipe.dev_meta[slot]
+                L.check(lib.b200det_yolo_nms_packed(ctypes.byref(d), ws.data_ptr(), ws.numel(),
+                                                    rows_h.data_ptr() + lo * n_pad * 28,
+                                                    index_h.data_ptr() + lo * n_pad * 4 if return_index else None,
+                                                    dm.data_ptr(), dm.data_ptr() + 4 * nb, meta_h[c].data_ptr(), None,
+                                                    L.stream_ptr(dev)), "yolo_nms_packed")
                 ev_done.record(pipe.s_cmp)
             pipe.buf_free[slot] = ev_done
-            with torch.cuda.stream(pipe.s_out):
-                pipe.s_out.wait_event(ev_done)
-                host[0][lo:hi].copy_(rows, non_blocking=True)
-                host[2][lo:hi].copy_(count, non_blocking=True)
-                if return_index:
-                    host[1][lo:hi].copy_(index, non_blocking=True)
-            for t in (rows, index, count):
-                if t is not None:
-                    t.record_stream(pipe.s_out)
-            keep.append((rows, index, count))                        # alive until the copies have run
-        done = torch.cuda.Event()
-        done.record(pipe.s_out)
+        done = ev_done
     pipe.last_done = done
-    return HostNmsHandle(done, host, return_index, keep, pipe, generation, B)
+    return HostNmsHandle(done, host, return_index, chunks, pipe, generation, B)
 
 
 def non_max_suppression_host(self, predictions, conf_thres=0.5, nms_thres=0.4, *, compat=True, num_anchors=3,
@@ -354,8 +370,10 @@ def non_max_suppression_host(self, predictions, conf_thres=0.5, nms_thres=0.4, *
     """`non_max_suppression` for predictions that live in HOST memory (pinned memory for full PCIe speed).
 
     Same arguments and the same rows as `non_max_suppression` (model/YOLOV5.py:157); the batch is cut into chunks of
-    `chunk_images` images and the three legs run on separate streams, so the host->device copy of chunk k+1 overlaps
+    `chunk_images` images and the legs run on separate streams, so the host->device copy of chunk k+1 overlaps
     the CUDA pipeline of chunk k and the device->host copy of chunk k-1 (every image is independent).
+    The detections are not copied back: the emit kernel writes the kept rows, packed, straight into pinned (mapped) host
+    memory, so only kept rows cross the link and no device->host copy is enqueued.
     Returns a list of `None` / fp32 `[K,7]` HOST tensors: views into one of two pinned buffers that alternate between
     calls with the same shapes (clone them to keep them beyond the next call but one)."""
     return non_max_suppression_host_async(self, predictions, conf_thres, nms_thres, compat=compat, num_anchors=num_anchors,
