@@ -154,27 +154,35 @@ __device__ __forceinline__ bool may_remove(const uint2 qa, const uint2 qb) {
 // bit-inserted (HSET2 + ISETP + SEL + IADD3 on the ALU pipe) but accumulated on the FMA pipe: HSET2.BF yields 1.0 / 0.0
 // per axis, `acc = verdict * 2^k + acc` (HFMA2) collects 8 pairs per half in the mantissa of 1024 + v (exact, v < 256),
 // and three byte permutes + one AND per 32 pairs combine the two axes.  Per pair: 2 HMNMX2 + HSET2 (ALU), HFMA2 (FMA).
+// The ALU pipe (half rate: HMNMX2, HSET2, integer / logic) is what this kernel saturates, so the test is written without the two
+// min / max:  min(u_a, u_b) > max(lo_a, lo_b)  <=>  u_a > lo_b  and  u_b > lo_a  (and the two self-conditions u > lo of a box
+// with itself, which hold for every box with w + 1 > 0 — a box with w + 1 <= 0 has an empty +1-intersection with everything
+// and is rejected by the exact test).  Two HSET2.BF per pair (ALU) instead of two HMNMX2 + HSET2, and the two verdict streams
+// are accumulated separately on the FMA pipe (two HFMA2) and ANDed as bit masks at the end.
 __device__ __forceinline__ unsigned may_remove_mask32(const uint2* __restrict__ q, const uint2 qj) {
     const __half2 lo_j = *reinterpret_cast<const __half2*>(&qj.x);
     const __half2 u_j = *reinterpret_cast<const __half2*>(&qj.y);
-    unsigned u[4];
+    unsigned u1[4], u2[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-        __half2 acc = __floats2half2_rn(1024.0f, 1024.0f);
+        __half2 acc1 = __floats2half2_rn(1024.0f, 1024.0f), acc2 = acc1;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const uint2 qa = q[g * 8 + k];
-            const __half2 lo = __hmax2(*reinterpret_cast<const __half2*>(&qa.x), lo_j);
-            const __half2 up = __hmin2(*reinterpret_cast<const __half2*>(&qa.y), u_j);
-            const __half2 verdict = __hgt2(up, lo);                              // 1.0 where the axis passes
+            const __half2 v1 = __hgt2(*reinterpret_cast<const __half2*>(&qa.y), lo_j);       // u_a > lo_j, per axis: 1.0 / 0.0
+            const __half2 v2 = __hgt2(u_j, *reinterpret_cast<const __half2*>(&qa.x));        // u_j > lo_a
             const float w = (float)(1 << k);
-            acc = __hfma2(verdict, __floats2half2_rn(w, w), acc);
+            const __half2 w2 = __floats2half2_rn(w, w);
+            acc1 = __hfma2(v1, w2, acc1);
+            acc2 = __hfma2(v2, w2, acc2);
         }
-        u[g] = *reinterpret_cast<const unsigned*>(&acc);
+        u1[g] = *reinterpret_cast<const unsigned*>(&acc1);
+        u2[g] = *reinterpret_cast<const unsigned*>(&acc2);
     }
     // byte 0 / byte 2 of u[g] = the 8 verdicts of the x / y axis
-    const unsigned ra = __byte_perm(u[0], u[1], 0x6240);     // x bits 0..15 | y bits 0..15 << 16
-    const unsigned rb = __byte_perm(u[2], u[3], 0x6240);     // x bits 16..31 | y bits 16..31 << 16
+    const unsigned ra1 = __byte_perm(u1[0], u1[1], 0x6240), rb1 = __byte_perm(u1[2], u1[3], 0x6240);
+    const unsigned ra2 = __byte_perm(u2[0], u2[1], 0x6240), rb2 = __byte_perm(u2[2], u2[3], 0x6240);
+    const unsigned ra = ra1 & ra2, rb = rb1 & rb2;           // x bits 0..15 | y bits 0..15 << 16 ; x 16..31 | y 16..31 << 16
     return __byte_perm(ra, rb, 0x5410) & __byte_perm(ra, rb, 0x7632);
 }
 
