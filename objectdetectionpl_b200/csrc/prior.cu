@@ -352,7 +352,7 @@ int prior_stage_select_nms(const b200det_prior_desc* d, void* ws, size_t ws_byte
                               out_rows, out_index, out_count, d->batch, d->mode_min, st);
     if (rc) return rc;
     if (cand_count)
-        B2_CUDA(cudaMemcpyAsync(cand_count, w.count, (size_t)d->batch * 4, cudaMemcpyDeviceToDevice, st));
+        B2_CUDA(cudaMemcpyAsync(cand_count, w.count, (size_t)d->batch * 4, cudaMemcpyDefault, st));   // cand_count may be mapped host memory
     return 0;
 }
 

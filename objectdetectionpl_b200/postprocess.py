@@ -388,7 +388,10 @@ def non_max_suppression_v2(self, predictions, conf_thres=0.5, nms_thres=0.4, *, 
 
 
 def prior_nms_raw(loc: torch.Tensor, cls: torch.Tensor, priors: torch.Tensor, topk=100, nms_thresh=0.5,
-                  class_thresh=0.45, mode="union", compat=True, want_index=False):
+                  class_thresh=0.45, mode="union", compat=True, want_index=False, count_out: Optional[torch.Tensor] = None):
+    """Enqueue the prior pipeline; returns device tensors `(rows [B, topk, 7], index [B, topk] | None, count [2, B])` without
+    synchronising.  `count_out`: an int32 `[2, B]` buffer to receive the counts instead of a fresh device tensor — it may be
+    pinned (mapped) HOST memory, which the kernels then write directly."""
     if mode not in ("union", "min"):
         raise TypeError("Unknown nms mode: %s." % mode)  # model/SSD.py:298-299
     lib = L.load()
@@ -409,7 +412,7 @@ def prior_nms_raw(loc: torch.Tensor, cls: torch.Tensor, priors: torch.Tensor, to
         ws = L.workspace(ws_bytes, dev)
         rows = torch.empty((d.batch, d.topk, 7), dtype=torch.float32, device=dev)
         index = torch.empty((d.batch, d.topk), dtype=torch.int32, device=dev) if want_index else None
-        count = torch.empty((2, d.batch), dtype=torch.int32, device=dev)
+        count = count_out if count_out is not None else torch.empty((2, d.batch), dtype=torch.int32, device=dev)
         L.check(lib.b200det_prior_nms(ctypes.byref(d), ws.data_ptr(), ws.numel(), rows.data_ptr(),
                                       index.data_ptr() if want_index else None, count[0].data_ptr(), count[1].data_ptr(),
                                       L.stream_ptr(dev)), "prior_nms")
@@ -430,8 +433,8 @@ def prior_non_max_suppression(self, predictions, topk=100, nms_thresh=0.5, class
     if mode not in ("union", "min"):
         raise TypeError("Unknown nms mode: %s." % mode)  # model/SSD.py:298-299
     loc, cls = predictions
-    rows, index, count = prior_nms_raw(loc, cls, self.iou_boxes, topk, nms_thresh, class_thresh, mode, compat, return_index)
-    dev, B = rows.device, rows.shape[0]
+    L.require_cuda(loc, "loc_preds")
+    dev, B = loc.device, loc.shape[0]
     key = (dev.index, B)
     slot = _prior_count_bufs.get(key)
     if slot is None:
@@ -440,7 +443,9 @@ def prior_non_max_suppression(self, predictions, topk=100, nms_thresh=0.5, class
         slot = _prior_count_bufs[key] = (torch.empty((2, B), dtype=torch.int32).pin_memory(), torch.cuda.Event())
     host, ev = slot
     with _prior_lock, torch.cuda.device(dev):            # the pinned count buffer is shared by the calls of one (device, batch)
-        host.copy_(count, non_blocking=True)             # kept rows [0] and candidates above the score threshold [1]
+        # kept rows [0] and candidates above the score threshold [1] are written by the device straight into pinned host memory
+        rows, index, _ = prior_nms_raw(loc, cls, self.iou_boxes, topk, nms_thresh, class_thresh, mode, compat, return_index,
+                                       count_out=host)
         ev.record()
         views = list(rows.unbind(0))                     # built while the GPU works; shrunk in place after the one sync
         iviews = list(index.long().unbind(0)) if return_index else None

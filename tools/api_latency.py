@@ -15,9 +15,12 @@ for B, C, mode, thr in CASES:
         od.non_max_suppression(None, lv, **kw)
     torch.cuda.synchronize()
     n = 50
+    per = []
     t0 = time.perf_counter()
     for _ in range(n):
+        t1 = time.perf_counter()
         out = od.non_max_suppression(None, lv, **kw)
+        per.append((time.perf_counter() - t1) * 1e6)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / n
     t0 = time.perf_counter()
@@ -26,4 +29,5 @@ for B, C, mode, thr in CASES:
     torch.cuda.synchronize()
     dr = (time.perf_counter() - t0) / n
     print(f"B={B} C={C} {mode}: non_max_suppression {dt * 1e6:.0f} us/call, yolo_nms_raw (no sync, no list) {dr * 1e6:.0f} us/call, "
-          f"kept {sum(o.shape[0] for o in out if o is not None)}")
+          f"kept {sum(o.shape[0] for o in out if o is not None)}; per-call median {sorted(per)[n // 2]:.0f} us, max {max(per):.0f} us, "
+          f"calls above 2x the median: {sum(p > 2 * sorted(per)[n // 2] for p in per)}")
