@@ -117,6 +117,24 @@ def load():
     return _lib
 
 
+_glue = None
+
+
+def hostglue():
+    """The host-glue module (csrc/hostglue.cpp, built next to libb200det.so): the tail of the Python wrappers that runs
+    between the counts event and the return.  Host-only; like the library itself it has no stand-in."""
+    global _glue
+    if _glue is None:
+        try:
+            from . import _hostglue
+        except ImportError as e:
+            raise RuntimeError("objectdetectionpl_b200/_hostglue*.so not found or not loadable: build it with "
+                               "`python -c 'import __graft_entry__ as g; g.build()'` "
+                               f"(or `make -C objectdetectionpl_b200/csrc`) — {e}") from e
+        _glue = _hostglue
+    return _glue
+
+
 def check(rc: int, what: str = ""):
     if rc != 0:
         msg = load().b200det_last_error().decode("utf-8", "replace")
@@ -142,10 +160,11 @@ def stream_ptr(device) -> int:
 _ws_cache = {}
 
 
-def workspace(nbytes: int, device) -> torch.Tensor:
-    """Stream-keyed scratch buffer (uint8), grown on demand and reused between calls on the same stream."""
-    dev = torch.device(device)
-    key = (dev.index if dev.index is not None else torch.cuda.current_device(), stream_ptr(dev))
+def workspace(nbytes: int, device, stream: int = None) -> torch.Tensor:
+    """Stream-keyed scratch buffer (uint8), grown on demand and reused between calls on the same stream
+    (`stream`: the current stream's handle if the caller already has it)."""
+    dev = device if isinstance(device, torch.device) else torch.device(device)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), stream_ptr(dev) if stream is None else stream)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)

@@ -15,6 +15,7 @@ from __future__ import annotations
 import collections
 import ctypes
 import threading
+import time
 from typing import List, Optional, Sequence
 
 import torch
@@ -126,6 +127,9 @@ class _YoloPlan:
         self.host = torch.empty((2 * self.B + 1,), dtype=torch.int32).pin_memory()
         self.event = torch.cuda.Event()
         self.event.record()                               # creates the underlying cudaEvent_t
+        self.host_ptr = self.host.data_ptr()
+        self.event_ptr = self.event.cuda_event
+        self.finish = L.hostglue().finish_views
         self.fn = lib.b200det_yolo_nms_early
         self.lock = threading.Lock()                     # the descriptor and the pinned counts are per plan, not per call
         self.spare = None                                # result buffers allocated ahead for the next call (while the GPU was busy)
@@ -142,7 +146,7 @@ def _plan_key(levels, num_anchors, thr, nms_thres, decode, anchors, strides, lay
         return tuple(tuple(float(v) for v in torch.as_tensor(a, dtype=torch.float32).reshape(-1).tolist()) if not isinstance(a, (int, float))
                      else float(a) for a in x)
     t0 = levels[0]
-    return (t0.device.index, tuple(tuple(t.shape) for t in levels), num_anchors, float(thr), float(nms_thres), decode,
+    return (t0.device.index, tuple(t.shape for t in levels), num_anchors, float(thr), float(nms_thres), decode,
             freeze(anchors), freeze(strides), layout, float(scale_x_y))
 
 
@@ -158,7 +162,8 @@ def _yolo_nms(predictions, num_anchors, conf_thres, nms_thres, compat, decode, a
     key = _plan_key(predictions, num_anchors, thr, nms_thres, decode, anchors, strides, layout, scale_x_y)
     plan = _yolo_plans.get(key)
     if plan is None:
-        plan = _yolo_plans[key] = _YoloPlan(predictions, num_anchors, thr, nms_thres, decode, anchors, strides, layout, scale_x_y)
+        with torch.cuda.device(predictions[0].device):   # the plan's event belongs to the device of the heads
+            plan = _yolo_plans[key] = _YoloPlan(predictions, num_anchors, thr, nms_thres, decode, anchors, strides, layout, scale_x_y)
         while len(_yolo_plans) > _YOLO_PLANS_MAX:
             _yolo_plans.popitem(last=False)
     d, B, n_pad = plan.d, plan.B, plan.n_pad
@@ -167,38 +172,56 @@ def _yolo_nms(predictions, num_anchors, conf_thres, nms_thres, compat, decode, a
         return _yolo_nms_planned(plan, predictions, d, B, n_pad, dev, return_index)
 
 
+_trace = None        # tools/api_profile.py installs a list here: perf_counter stamps at the phase boundaries of the call
+
+
 def _yolo_nms_planned(plan, predictions, d, B, n_pad, dev, return_index):
+    tr = _trace
+    if tr is not None:
+        tr.append(time.perf_counter())
     for i, t in enumerate(predictions):                  # same shapes as the planned call (part of the key): only pointers move
         if t.device != dev:
             raise ValueError("all prediction levels must live on one device")
         if not t.is_contiguous():
             raise ValueError(f"predictions[{i}] must be contiguous (the reference .view()s it, model/YOLOV3.py:296)")
         d.head[i] = t.data_ptr()
-    with torch.cuda.device(dev):
-        ws = L.workspace(plan.ws_bytes, dev)
-        spare, plan.spare = plan.spare, None
-        stream = L.stream_ptr(dev)
-        if spare is not None and spare[0].device == dev and spare[2] == stream:     # allocated under this very stream
-            rows, count = spare[0], spare[1]
-        else:
-            rows = torch.empty((B, n_pad, 7), dtype=torch.float32, device=dev)
-            count = torch.empty((B,), dtype=torch.int32, device=dev)
-        index = torch.empty((B, n_pad), dtype=torch.int32, device=dev) if return_index else None
-        L.check(plan.fn(plan.dref, ws.data_ptr(), ws.numel(), rows.data_ptr(), index.data_ptr() if return_index else None,
-                        count.data_ptr(), plan.host.data_ptr(), plan.event.cuda_event, stream), "yolo_nms_early")
-        # ---- the GPU is busy for the next few hundred microseconds: everything that does not need the counts happens now ----
-        views = list(rows.unbind(0))                     # B views [n_pad, 7]; shrunk in place once the counts are known
-        iviews = list(index.long().unbind(0)) if return_index else None
-        plan.spare = (torch.empty((B, n_pad, 7), dtype=torch.float32, device=dev),       # the next call's result buffers
-                      torch.empty((B,), dtype=torch.int32, device=dev), stream)
-        # the one host sync of the call: it waits for the NMS stage only (the counts are final there and were written straight
-        # into pinned host memory).  The emit kernel may still be writing the rows when this function returns; whatever the
-        # caller does with them next is stream-ordered behind it, as with any torch op.
-        plan.event.synchronize()
-    counts = plan.host.tolist()[:B]
-    out: List[Optional[torch.Tensor]] = [v.resize_(k, 7) if k else None for v, k in zip(views, counts)]   # YOLOV3.py:306,333
+    if torch.cuda.current_device() != dev.index:        # allocations below go to the current device: switch only when needed
+        with torch.cuda.device(dev):
+            return _yolo_nms_planned(plan, predictions, d, B, n_pad, dev, return_index)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    ws = L.workspace(plan.ws_bytes, dev, stream)
+    spare, plan.spare = plan.spare, None
+    if spare is not None and spare[2] == stream:         # allocated under this very stream (and, by the plan key, this device)
+        rows, count = spare[0], spare[1]
+    else:
+        rows = torch.empty((B, n_pad, 7), dtype=torch.float32, device=dev)
+        count = torch.empty((B,), dtype=torch.int32, device=dev)
+    index = torch.empty((B, n_pad), dtype=torch.int32, device=dev) if return_index else None
+    if tr is not None:
+        tr.append(time.perf_counter())
+    L.check(plan.fn(plan.dref, ws.data_ptr(), ws.numel(), rows.data_ptr(), index.data_ptr() if return_index else None,
+                    count.data_ptr(), plan.host_ptr, plan.event_ptr, stream), "yolo_nms_early")
+    if tr is not None:
+        tr.append(time.perf_counter())
+    # ---- the GPU is busy for the next few hundred microseconds: everything that does not need the counts happens now ----
+    views = list(rows.unbind(0))                         # B views [n_pad, 7]; shrunk in place once the counts are known
+    iviews = list(index.long().unbind(0)) if return_index else None
+    plan.spare = (torch.empty((B, n_pad, 7), dtype=torch.float32, device=dev),           # the next call's result buffers
+                  torch.empty((B,), dtype=torch.int32, device=dev), stream)
+    if tr is not None:
+        tr.append(time.perf_counter())
+    # the one host sync of the call: it waits for the NMS stage only (the counts are final there and were written straight
+    # into pinned host memory).  The emit kernel may still be writing the rows when this function returns; whatever the
+    # caller does with them next is stream-ordered behind it, as with any torch op.
+    plan.event.synchronize()
+    if tr is not None:
+        tr.append(time.perf_counter())
+    # B shrinks in one call (csrc/hostglue.cpp): images without detections become None (YOLOV3.py:306,333)
+    out: List[Optional[torch.Tensor]] = plan.finish(views, plan.host_ptr, 7)
+    if tr is not None:
+        tr.append(time.perf_counter())
     if return_index:
-        return out, [v.resize_(k) if k else None for v, k in zip(iviews, counts)]
+        return out, plan.finish(iviews, plan.host_ptr, 0)
     return out
 
 

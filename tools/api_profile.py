@@ -29,39 +29,22 @@ print("drop result   : %.0f us/call" % wall(lambda: od.non_max_suppression(None,
 print("keep result   : %.0f us/call" % wall(keepit))
 print("raw (no sync) : %.0f us/call" % wall(lambda: od.yolo_nms_raw(lv, 3)))
 
-# phase breakdown (drop pattern)
-orig = P._yolo_nms_planned
-marks = []
-def timed(plan, predictions, d, B, n_pad, dev_, return_index):
-    t0 = time.perf_counter()
-    for i, t in enumerate(predictions):
-        d.head[i] = t.data_ptr()
-    with torch.cuda.device(dev_):
-        ws = L.workspace(plan.ws_bytes, dev_)
-        rows = torch.empty((B * n_pad, 7), dtype=torch.float32, device=dev_)
-        meta = torch.empty((2 * B + 1,), dtype=torch.int32, device=dev_)
-        mp = meta.data_ptr()
-        t1 = time.perf_counter()
-        L.check(plan.fn(plan.dref, ws.data_ptr(), ws.numel(), rows.data_ptr(), None, mp, mp + 4 * B, plan.host.data_ptr(),
-                        plan.event.cuda_event, L.stream_ptr(dev_)), "x")
-        t2 = time.perf_counter()
-        plan.event.synchronize()
-        t3 = time.perf_counter()
-    meta_h = plan.host.tolist()
-    counts, total = meta_h[:B], meta_h[2 * B]
-    t4 = time.perf_counter()
-    parts = torch.ops.aten.unsafe_split_with_sizes.default(rows[:total], counts)
-    t5 = time.perf_counter()
-    out = [p if k else None for p, k in zip(parts, counts)]
-    t6 = time.perf_counter()
-    marks.append((t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t6 - t5))
-    return out
-P._yolo_nms_planned = timed
+# phase breakdown: perf_counter stamps postprocess._yolo_nms_planned takes at its phase boundaries when P._trace is a list
 for pattern, fn in (("drop", lambda: od.non_max_suppression(None, lv)), ("keep", keepit)):
-    marks.clear()
+    P._trace = tr = []
     torch.cuda.synchronize()
-    for _ in range(100):
+    for _ in range(200):
         fn()
     torch.cuda.synchronize()
-    m = [statistics.median(x[i] for x in marks[10:]) * 1e6 for i in range(6)]
-    print(pattern, "alloc %.1f | launch %.1f | wait %.1f | tolist %.1f | split %.1f | list %.1f  (us, medians)" % tuple(m))
+    P._trace = None
+    calls = [tr[i:i + 6] for i in range(0, len(tr), 6)][10:]
+    m = [statistics.median(c[i + 1] - c[i] for c in calls) * 1e6 for i in range(5)]
+    gap = statistics.median(calls[i + 1][0] - calls[i][5] for i in range(len(calls) - 1)) * 1e6
+    print(pattern, "prologue %.1f | launch (one ctypes call) %.1f | views + next buffers %.1f | wait for the counts event %.1f | "
+          "finish_views %.1f | between calls (return, drop, plan lookup, entry) %.1f  (us, medians)" % (tuple(m) + (gap,)))
+ev0 = torch.cuda.Event()
+torch.cuda.synchronize()
+lat = []
+for _ in range(200):
+    ev0.record(); t0 = time.perf_counter(); ev0.synchronize(); lat.append(time.perf_counter() - t0)
+print("event synchronize right after its record on an idle stream: %.1f us median" % (statistics.median(lat) * 1e6))
