@@ -6,13 +6,14 @@
 // finish_views(views, counts_ptr, cols): `views` are B views [n_pad, cols] (cols == 0: [n_pad]) of the padded result the
 // emit kernel is writing, made while the GPU was busy; `counts_ptr` is the address of the pinned host buffer the NMS stage wrote
 // the B int32 counts into.  Every view is shrunk in place to its count (same storage, same offset: no allocation, no copy);
-// images without detections become None, as the reference returns them (model/YOLOV3.py:306,333).
+// images without detections become None, as the YOLO reference returns them (model/YOLOV3.py:306,333), or stay as empty
+// [0, cols] tensors with keep_empty (the SSD / RetinaNet reference stacks an empty result, model/SSD.py:304-310).
 #include <torch/extension.h>
 
 #include <cstdint>
 #include <vector>
 
-static py::object finish_views(const py::list& views, const int64_t counts_ptr, const int64_t cols) {
+static py::object finish_views(const py::list& views, const int64_t counts_ptr, const int64_t cols, const bool keep_empty) {
     const int32_t* counts = reinterpret_cast<const int32_t*>(static_cast<intptr_t>(counts_ptr));
     const Py_ssize_t n = PyList_GET_SIZE(views.ptr());
     PyObject* out = PyList_New(n);
@@ -20,7 +21,7 @@ static py::object finish_views(const py::list& views, const int64_t counts_ptr, 
     for (Py_ssize_t b = 0; b < n; ++b) {
         const int64_t k = counts[b];
         PyObject* o = Py_None;
-        if (k > 0) {
+        if (k > 0 || (keep_empty && k == 0)) {
             o = PyList_GET_ITEM(views.ptr(), b);                       // borrowed; the result list shares the very same objects
             if (!THPVariable_Check(o)) {
                 Py_DECREF(out);
@@ -42,5 +43,6 @@ static py::object finish_views(const py::list& views, const int64_t counts_ptr, 
 }
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
-    m.def("finish_views", &finish_views, "shrink the per-image views of a padded NMS result to their counts");
+    m.def("finish_views", &finish_views, "shrink the per-image views of a padded NMS result to their counts", py::arg("views"),
+          py::arg("counts_ptr"), py::arg("cols"), py::arg("keep_empty") = false);
 }

@@ -442,8 +442,28 @@ def prior_nms_raw(loc: torch.Tensor, cls: torch.Tensor, priors: torch.Tensor, to
     return rows, index, count
 
 
-_prior_count_bufs = {}      # (device, batch) -> (pinned [2, B] int32, event)
-_prior_lock = threading.Lock()
+class _PriorPlan:
+    """What a `prior_non_max_suppression` call needs beyond the three pointers, per (device, shapes, options): the descriptor,
+    the workspace size, a pinned host buffer the kernels write the two count rows into, the event behind them."""
+
+    def __init__(self, loc, cls, topk, nms_thresh, class_thresh, mode, compat):
+        lib = L.load()
+        d = self.d = L.PriorDesc()
+        d.batch, d.num_priors, d.num_classes = loc.shape[0], loc.shape[1], cls.shape[2]
+        d.topk, d.nms_thresh, d.class_thresh = int(topk), float(nms_thresh), float(class_thresh)
+        d.mode_min, d.compat = int(mode == "min"), int(bool(compat))
+        self.dref = ctypes.byref(d)
+        self.ws_bytes = lib.b200det_prior_workspace_bytes(self.dref)
+        self.B, self.topk = d.batch, d.topk
+        self.host = torch.empty((2, self.B), dtype=torch.int32).pin_memory()      # kept rows [0] | candidates above the threshold [1]
+        self.host_ptr = self.host.data_ptr()
+        self.event = torch.cuda.Event()
+        self.fn = lib.b200det_prior_nms
+        self.finish = L.hostglue().finish_views
+        self.lock = threading.Lock()
+
+
+_prior_plans = collections.OrderedDict()
 
 
 def prior_non_max_suppression(self, predictions, topk=100, nms_thresh=0.5, class_thresh=0.45, mode="union", *,
@@ -456,29 +476,44 @@ def prior_non_max_suppression(self, predictions, topk=100, nms_thresh=0.5, class
     if mode not in ("union", "min"):
         raise TypeError("Unknown nms mode: %s." % mode)  # model/SSD.py:298-299
     loc, cls = predictions
-    L.require_cuda(loc, "loc_preds")
-    dev, B = loc.device, loc.shape[0]
-    key = (dev.index, B)
-    slot = _prior_count_bufs.get(key)
-    if slot is None:
-        if len(_prior_count_bufs) >= 16:
-            _prior_count_bufs.clear()
-        slot = _prior_count_bufs[key] = (torch.empty((2, B), dtype=torch.int32).pin_memory(), torch.cuda.Event())
-    host, ev = slot
-    with _prior_lock, torch.cuda.device(dev):            # the pinned count buffer is shared by the calls of one (device, batch)
+    priors = self.iou_boxes
+    L.require_cuda(loc, "loc_preds"); L.require_cuda(cls, "cls_preds"); L.require_cuda(priors, "iou_boxes")
+    if loc.dim() != 3 or loc.shape[2] != 4 or cls.dim() != 3 or cls.shape[:2] != loc.shape[:2] or \
+            tuple(priors.shape) != (loc.shape[1], 4):
+        raise ValueError(f"expected loc [B,P,4], cls [B,P,C], priors [P,4]; got {tuple(loc.shape)}, {tuple(cls.shape)}, "
+                         f"{tuple(priors.shape)}")
+    dev = loc.device
+    key = (dev.index, loc.shape, cls.shape, int(topk), float(nms_thresh), float(class_thresh), mode, bool(compat))
+    plan = _prior_plans.get(key)
+    if plan is None:
+        with torch.cuda.device(dev):
+            plan = _prior_plans[key] = _PriorPlan(loc, cls, topk, nms_thresh, class_thresh, mode, compat)
+        while len(_prior_plans) > _YOLO_PLANS_MAX:
+            _prior_plans.popitem(last=False)
+    if torch.cuda.current_device() != dev.index:
+        with torch.cuda.device(dev):
+            return prior_non_max_suppression(self, predictions, topk, nms_thresh, class_thresh, mode, compat=compat,
+                                             return_index=return_index)
+    loc, cls, priors = loc.contiguous(), cls.contiguous(), priors.contiguous()
+    B, d = plan.B, plan.d
+    with plan.lock:                                      # the descriptor and the pinned counts are per plan, not per call
+        d.loc, d.cls, d.priors = loc.data_ptr(), cls.data_ptr(), priors.data_ptr()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws = L.workspace(plan.ws_bytes, dev, stream)
+        rows = torch.empty((B, plan.topk, 7), dtype=torch.float32, device=dev)
+        index = torch.empty((B, plan.topk), dtype=torch.int32, device=dev) if return_index else None
         # kept rows [0] and candidates above the score threshold [1] are written by the device straight into pinned host memory
-        rows, index, _ = prior_nms_raw(loc, cls, self.iou_boxes, topk, nms_thresh, class_thresh, mode, compat, return_index,
-                                       count_out=host)
-        ev.record()
+        L.check(plan.fn(plan.dref, ws.data_ptr(), ws.numel(), rows.data_ptr(), index.data_ptr() if return_index else None,
+                        plan.host_ptr, plan.host_ptr + 4 * B, stream), "prior_nms")
+        plan.event.record()
         views = list(rows.unbind(0))                     # built while the GPU works; shrunk in place after the one sync
         iviews = list(index.long().unbind(0)) if return_index else None
-        ev.synchronize()
-        kept, cand = host.tolist()
-    if compat and 1 in cand:
-        raise IndexError("too many indices for tensor of dimension 1")   # model/SSD.py:262,266 (0-dim index)
-    out = [v.resize_(k, 7) for v, k in zip(views, kept)]
-    if return_index:
-        return out, [v.resize_(k) for v, k in zip(iviews, kept)]
+        plan.event.synchronize()
+        if compat and 1 in plan.host[1].tolist():
+            raise IndexError("too many indices for tensor of dimension 1")   # model/SSD.py:262,266 (0-dim index)
+        out = plan.finish(views, plan.host_ptr, 7, True)
+        if return_index:
+            return out, plan.finish(iviews, plan.host_ptr, 0, True)
     return out
 
 

@@ -21,6 +21,8 @@ def test_finish_views_shrinks_in_place_and_maps_empty_images_to_none():
         assert out[b] is views[b]                                  # the very same tensor objects, shrunk
         assert out[b].shape == (k, 7) and out[b].is_contiguous() and out[b].data_ptr() == rows[b].data_ptr()
         assert torch.equal(out[b], rows[b, :k])
+    kept = H.finish_views(list(rows.unbind(0)), counts.data_ptr(), 7, True)   # keep_empty: [0, 7] tensors instead of None
+    assert kept[1].shape == (0, 7) and kept[4].shape == (0, 7) and torch.equal(kept[3], rows[3, :1])
     idx = torch.arange(B * n_pad, dtype=torch.int64).view(B, n_pad)
     out = H.finish_views(list(idx.unbind(0)), counts.data_ptr(), 0)
     assert out[1] is None and out[4] is None and torch.equal(out[5], idx[5, :17]) and out[2].shape == (40,)
