@@ -158,3 +158,18 @@ def test_slot_count_formula_of_the_host_pipeline_matches_the_library(lib):
         assert lib.b200det_yolo_num_candidates(ctypes.byref(d), ctypes.byref(n), ctypes.byref(n_pad)) == 0
         assert n.value == sum(A * g * g for g in grids)
         assert n_pad.value == sum((A * g * g + L.TILE - 1) // L.TILE * L.TILE for g in grids)
+
+
+def test_makefile_builds_every_source_the_library_and_the_host_glue_from_scratch():
+    """`make -n -B` (dry run, everything out of date): one sm_100a nvcc line per .cu under csrc/, the -shared link of
+    libb200det.so and the host-glue build — a fresh checkout must be buildable by `__graft_entry__.build()`."""
+    import glob
+    import subprocess
+    csrc = os.path.join(ROOT, "objectdetectionpl_b200", "csrc")
+    out = subprocess.run(["make", "-C", csrc, "-n", "-B"], capture_output=True, text=True, check=True).stdout
+    lines = out.splitlines()
+    for cu in sorted(glob.glob(os.path.join(csrc, "*.cu"))):
+        name = os.path.basename(cu)
+        assert any(f"-c {name} " in ln and "arch=compute_100a,code=sm_100a" in ln and "-lineinfo" in ln for ln in lines), name
+    assert any("-shared" in ln and "libb200det.so" in ln for ln in lines)
+    assert any("build_hostglue.py" in ln and "_hostglue" in ln for ln in lines)
