@@ -241,7 +241,7 @@ __device__ __forceinline__ void nms_stamp(unsigned long long* tr, int point) {
 // short (YOLOv3-416: 133 rows): a CTA then needs 14 KB instead of 32 KB of shared memory, 12 of them fit an SM and twice as
 // many segments hide each other's fixed latencies (loads, barriers, global stores).
 template <int VARIANT, bool FAST, int NT, int CT, bool TAB = false>
-__global__ void __launch_bounds__(NT, TAB ? (NT == 128 ? 10 : (NT == 256 ? 5 : 2)) : (NT == 128 ? 12 : (NT == 256 ? 6 : 3)))
+__global__ void __launch_bounds__(NT, NT == 1024 ? 1 : (TAB ? (NT == 128 ? 10 : (NT == 256 ? 5 : 2)) : (NT == 128 ? 12 : (NT == 256 ? 6 : 3))))
 nms_segment_kernel(const NmsParams p) {
     static_assert(!TAB || (VARIANT == 0 && FAST), "the table pre-filter is built for the YOLO class-aware NMS with nms_thres >= 0");
     constexpr int NW = CT / 64;                       // mask words per full row
@@ -1144,7 +1144,11 @@ int yolo_stage_nms(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, cudaSt
         else if (avg <= 160) nms_segment_kernel<0, true, 128, 192, true><<<grid, 128, 0, st>>>(p);
         else nms_segment_kernel<0, true, kNmsThreads, kNmsT, true><<<grid, kNmsThreads, 0, st>>>(p);
     } else if (d->nms_thres >= 0.0f) {
-        if (avg > kNmsT) nms_segment_kernel<0, true, 512, kNmsT><<<grid, 512, 0, st>>>(p);
+        // wide variant (segments longer than a chunk: few classes, dense crowds, single images): 512-row chunks; 1024 threads
+        // when there are not even enough segments for one CTA per SM.  Measured (profiles/README.md, round 2): crowd shard
+        // 313 us (512 threads x 384 rows) -> 299 us (512 x 512), 360 us (1024 x 512); one 20-class image 99 -> 90 -> 80 us.
+        if (avg > kNmsT && (long long)d->num_classes * d->batch <= 148) nms_segment_kernel<0, true, 1024, 512><<<grid, 1024, 0, st>>>(p);
+        else if (avg > kNmsT) nms_segment_kernel<0, true, 512, 512><<<grid, 512, 0, st>>>(p);
         else if (avg <= 160) nms_segment_kernel<0, true, 128, 192><<<grid, 128, 0, st>>>(p);
         else nms_segment_kernel<0, true, kNmsThreads, kNmsT><<<grid, kNmsThreads, 0, st>>>(p);
     } else {
