@@ -86,26 +86,45 @@ def _build_targets_v5_raw(p, targets, anchors, nl, na, sync=True):
     arr = _host_anchors(anchors, nl, na)
     cap = max(5 * na * nt, 1)
     counts = torch.empty((nl,), dtype=torch.int32, device=dev)
-    bufs = []
     nxs, nys = (ctypes.c_int32 * nl)(), (ctypes.c_int32 * nl)()
     ptrs = [(ctypes.c_void_p * nl)() for _ in range(7)]                  # b, a, gj, gi, cls, tbox, anch per level
+    # one buffer per kind for all levels (three allocations per call, addresses by arithmetic: no per-level tensor ops)
+    ib_all = torch.empty((nl, 5, cap), dtype=torch.int32, device=dev)    # b, a, gj, gi, cls
+    tb_all = torch.empty((nl, cap, 4), dtype=torch.float32, device=dev)
+    ac_all = torch.empty((nl, cap, 2), dtype=torch.float32, device=dev)
+    ib0, tb0, ac0 = ib_all.data_ptr(), tb_all.data_ptr(), ac_all.data_ptr()
     for i in range(nl):
         shape = p[i].shape if isinstance(p[i], torch.Tensor) else tuple(p[i])
         nys[i], nxs[i] = int(shape[2]), int(shape[3])
-        ib = torch.empty((5, cap), dtype=torch.int32, device=dev)        # b, a, gj, gi, cls
-        tb = torch.empty((cap, 4), dtype=torch.float32, device=dev)
-        ac = torch.empty((cap, 2), dtype=torch.float32, device=dev)
         for k in range(5):
-            ptrs[k][i] = ib[k].data_ptr()
-        ptrs[5][i], ptrs[6][i] = tb.data_ptr(), ac.data_ptr()
-        bufs.append((ib, tb, ac))
-    with torch.cuda.device(dev):
+            ptrs[k][i] = ib0 + 4 * cap * (5 * i + k)
+        ptrs[5][i], ptrs[6][i] = tb0 + 16 * cap * i, ac0 + 8 * cap * i
+    if torch.cuda.current_device() != dev.index:
+        with torch.cuda.device(dev):
+            L.check(lib.b200det_build_targets_v5(tg.data_ptr() if nt else None, nt, nl, arr, na, nxs, nys, *ptrs,
+                                                 counts.data_ptr(), L.stream_ptr(dev)), "build_targets_v5")
+    else:
         L.check(lib.b200det_build_targets_v5(tg.data_ptr() if nt else None, nt, nl, arr, na, nxs, nys, *ptrs, counts.data_ptr(),
                                              L.stream_ptr(dev)), "build_targets_v5")     # one launch, a cluster of 8 CTAs per level
     if not sync:
-        return bufs, counts
+        return _V5Rows(ib_all, tb_all, ac_all, cap, nl), counts
     ms = counts.cpu().tolist()                                            # one host sync for all levels
-    return [(ib[:, :m], tb[:m], ac[:m]) for (ib, tb, ac), m in zip(bufs, ms)]
+    return [(ib_all[i, :, :m], tb_all[i, :m], ac_all[i, :m]) for i, m in enumerate(ms)]
+
+
+class _V5Rows:
+    """The full-capacity target rows of all levels (`sync=False` form of `_build_targets_v5_raw`): three buffers and the
+    addresses of every level's arrays in them.  `ptrs(i)` = (b, a, gj, gi, cls, tbox, anch) of level i."""
+    __slots__ = ("ib", "tb", "ac", "cap", "nl", "_ptrs")
+
+    def __init__(self, ib, tb, ac, cap, nl):
+        self.ib, self.tb, self.ac, self.cap, self.nl = ib, tb, ac, cap, nl
+        ib0, tb0, ac0 = ib.data_ptr(), tb.data_ptr(), ac.data_ptr()
+        self._ptrs = [tuple(ib0 + 4 * cap * (5 * i + k) for k in range(5)) + (tb0 + 16 * cap * i, ac0 + 8 * cap * i)
+                      for i in range(nl)]
+
+    def ptrs(self, i):
+        return self._ptrs[i]
 
 
 def build_targets_v5(p, targets, anchors, nl, na):
@@ -246,27 +265,27 @@ class _V5LossAll(torch.autograd.Function):
                 raise ValueError("pi must be contiguous [B,na,ny,nx,5+C]")
             pids.append(pid)
         dev = pids[0].device
+        if torch.cuda.current_device() != dev.index:
+            with torch.cuda.device(dev):
+                return _V5LossAll.forward(ctx, levels, counts, cfg, *pis)
+        ctx.set_materialize_grads(False)            # the three metric outputs usually get no gradient: None, not a zero tensor each
         cells = [pid.numel() // pid.shape[-1] for pid in pids]
-        caps = [int(ib.shape[1]) for ib, _, _ in levels]
+        cap = levels.cap
         tobj = torch.empty((sum(cells),), dtype=torch.float32, device=dev)            # all levels, back to back
-        giou = torch.empty((sum(caps),), dtype=torch.float32, device=dev)
+        giou = torch.empty((nl * cap,), dtype=torch.float32, device=dev)
         means = torch.empty((nl, 3), dtype=torch.float64, device=dev)
         out = torch.empty((4,), dtype=torch.float32, device=dev)
         st = L.stream_ptr(dev)
-        with torch.cuda.device(dev):
-            t_off = g_off = 0
-            for i, (pid, (ib, tb, ac)) in enumerate(zip(pids, levels)):
-                B, na, ny, nx, F = pid.shape
-                L.check(lib.b200det_v5_loss_fwd_dev(pid.data_ptr(), B, na, ny, nx, F, ib[0].data_ptr(), ib[1].data_ptr(),
-                                                    ib[2].data_ptr(), ib[3].data_ptr(), ib[4].data_ptr(), tb.data_ptr(),
-                                                    ac.data_ptr(), caps[i], counts.data_ptr() + 4 * i, cp, cn, gamma, alpha,
-                                                    int(with_cls), giou.data_ptr() + 4 * g_off, tobj.data_ptr() + 4 * t_off,
-                                                    means.data_ptr() + 24 * i, st), "v5_loss_fwd_dev")
-                t_off += cells[i]
-                g_off += caps[i]
-            L.check(lib.b200det_v5_loss_combine(means.data_ptr(), nl, *_V5_GAINS, out.data_ptr(), st), "v5_loss_combine")
+        t_ptr, g_ptr, m_ptr, c_ptr = tobj.data_ptr(), giou.data_ptr(), means.data_ptr(), counts.data_ptr()
+        for i, pid in enumerate(pids):
+            B, na, ny, nx, F = pid.shape
+            L.check(lib.b200det_v5_loss_fwd_dev(pid.data_ptr(), B, na, ny, nx, F, *levels.ptrs(i), cap, c_ptr + 4 * i, cp, cn,
+                                                gamma, alpha, int(with_cls), g_ptr + 4 * cap * i, t_ptr, m_ptr + 24 * i, st),
+                    "v5_loss_fwd_dev")
+            t_ptr += 4 * cells[i]
+        L.check(lib.b200det_v5_loss_combine(m_ptr, nl, *_V5_GAINS, out.data_ptr(), st), "v5_loss_combine")
         ctx.save_for_backward(tobj, counts, *pids)
-        ctx.levels, ctx.cfg, ctx.cells, ctx.caps = levels, cfg, cells, caps
+        ctx.levels, ctx.cfg, ctx.cells = levels, cfg, cells
         return out[0:1], out[1:2], out[2:3], out[3:4]
 
     @staticmethod
@@ -275,25 +294,26 @@ class _V5LossAll(torch.autograd.Function):
         tobj, counts, *pids = ctx.saved_tensors
         cp, cn, gamma, alpha, with_cls = ctx.cfg
         dev = tobj.device
+        if torch.cuda.current_device() != dev.index:
+            with torch.cuda.device(dev):
+                return _V5LossAll.backward(ctx, g_loss, g_box, g_cls, g_obj)
         gs = [None if g is None else g.contiguous().float() for g in (g_loss, g_box, g_cls, g_obj)]
         g3 = torch.empty((3,), dtype=torch.float32, device=dev)
         st = L.stream_ptr(dev)
+        levels, cap = ctx.levels, ctx.levels.cap
         grads = []
-        with torch.cuda.device(dev):
-            L.check(lib.b200det_v5_loss_combine_bwd(*(None if g is None else g.data_ptr() for g in gs), *_V5_GAINS, g3.data_ptr(),
-                                                    st), "v5_loss_combine_bwd")
-            t_off = 0
-            for i, (pid, (ib, tb, ac)) in enumerate(zip(pids, ctx.levels)):
-                B, na, ny, nx, F = pid.shape
-                cells = ctx.cells[i]
-                gpi = torch.empty_like(pid)                               # fully written by the call (no zero-fill pass)
-                L.check(lib.b200det_v5_loss_bwd_full_dev(pid.data_ptr(), B, na, ny, nx, F, ib[0].data_ptr(), ib[1].data_ptr(),
-                                                         ib[2].data_ptr(), ib[3].data_ptr(), ib[4].data_ptr(), tb.data_ptr(),
-                                                         ac.data_ptr(), ctx.caps[i], counts.data_ptr() + 4 * i, cp, cn, gamma,
-                                                         alpha, int(with_cls), tobj.data_ptr() + 4 * t_off, g3.data_ptr(),
-                                                         1.0 / cells, gpi.data_ptr(), st), "v5_loss_bwd_full_dev")
-                grads.append(gpi)
-                t_off += cells
+        L.check(lib.b200det_v5_loss_combine_bwd(*(None if g is None else g.data_ptr() for g in gs), *_V5_GAINS, g3.data_ptr(),
+                                                st), "v5_loss_combine_bwd")
+        t_ptr, c_ptr, g3_ptr = tobj.data_ptr(), counts.data_ptr(), g3.data_ptr()
+        for i, pid in enumerate(pids):
+            B, na, ny, nx, F = pid.shape
+            cells = ctx.cells[i]
+            gpi = torch.empty_like(pid)                               # fully written by the call (no zero-fill pass)
+            L.check(lib.b200det_v5_loss_bwd_full_dev(pid.data_ptr(), B, na, ny, nx, F, *levels.ptrs(i), cap, c_ptr + 4 * i, cp, cn,
+                                                     gamma, alpha, int(with_cls), t_ptr, g3_ptr, 1.0 / cells, gpi.data_ptr(), st),
+                    "v5_loss_bwd_full_dev")
+            grads.append(gpi)
+            t_ptr += 4 * cells
         return (None, None, None, *grads)
 
 
