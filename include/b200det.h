@@ -308,16 +308,20 @@ int b200det_v5_loss_bwd_full(const float* pi, int32_t batch, int32_t na, int32_t
 /* Sync-free forms: the row count m stays on the DEVICE (m_dev = the count_out word b200det_build_targets_v5 wrote for this
  * level), the row arrays are passed at their capacity `cap` (5 * na * nt) and every kernel bounds itself by min(cap, *m_dev), so
  * the host never waits between target assignment and loss.  The means' divisors (max(m, 1), max(m * C, 1)) are formed on the
- * device from the same word.  Results are identical to the host-count forms. */
+ * device from the same word.  Results are identical to the host-count forms.
+ * obj_grad [cells] (may be NULL): the forward also leaves d FL / d logit of every cell's objectness term there, and a backward
+ * that is given it reads those 4 contiguous bytes per cell instead of re-reading column 4 of pi with a (5+C)-float stride while
+ * it streams the gradient out (tobj may then be NULL in the backward). */
 int b200det_v5_loss_fwd_dev(const float* pi, int32_t batch, int32_t na, int32_t ny, int32_t nx, int32_t fields,
                             const int32_t* b, const int32_t* a, const int32_t* gj, const int32_t* gi, const int32_t* tcls,
                             const float* tbox, const float* anch, int32_t cap, const int32_t* m_dev, float cp, float cn,
-                            float gamma, float alpha, int32_t with_cls, float* giou, float* tobj, double* sums, void* stream);
+                            float gamma, float alpha, int32_t with_cls, float* giou, float* tobj, float* obj_grad,
+                            double* sums, void* stream);
 int b200det_v5_loss_bwd_full_dev(const float* pi, int32_t batch, int32_t na, int32_t ny, int32_t nx, int32_t fields,
                                  const int32_t* b, const int32_t* a, const int32_t* gj, const int32_t* gi, const int32_t* tcls,
                                  const float* tbox, const float* anch, int32_t cap, const int32_t* m_dev, float cp, float cn,
-                                 float gamma, float alpha, int32_t with_cls, const float* tobj, const float* g3, float inv_cells,
-                                 float* gpi, void* stream);
+                                 float gamma, float alpha, int32_t with_cls, const float* tobj, const float* obj_grad,
+                                 const float* g3, float inv_cells, float* gpi, void* stream);
 /* The tail of the same forward (losses.py:139-152): means[nl][3] (fp64, what b200det_v5_loss_fwd left per level) are added
  * in level order in fp32, scaled by the three gains and summed: out4 = (loss, Localization, Classification, Conf_obj).
  * _bwd: g3[3] for b200det_v5_loss_bwd (the same for every level) from the upstream gradients of those four outputs

@@ -77,9 +77,9 @@ SIGNATURES = {
     "b200det_v5_loss_bwd_full": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f, _f, _f, _f,
                                         _i32, _vp, _vp, _f, _f, _f, _vp, _vp]),
     "b200det_v5_loss_fwd_dev": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _f, _f, _f, _f,
-                                       _i32, _vp, _vp, _vp, _vp]),
+                                       _i32, _vp, _vp, _vp, _vp, _vp]),
     "b200det_v5_loss_bwd_full_dev": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _f, _f,
-                                            _f, _f, _i32, _vp, _vp, _f, _vp, _vp]),
+                                            _f, _f, _i32, _vp, _vp, _vp, _f, _vp, _vp]),
     "b200det_build_targets_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "b200det_build_targets": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f, _vp, _sz] + [_vp] * 10 + [_vp]),
     "b200det_ssd_match_workspace_bytes": (_sz, [_i32, _i32]),

@@ -49,10 +49,10 @@ int v5_match_bwd_launch(const float*, int, int, int, int, int, const int32_t*, c
                         const int32_t*, const float*, const float*, int, const float*, float*, cudaStream_t);
 int v5_loss_fwd_launch(const float*, int, int, int, int, int, const int32_t*, const int32_t*, const int32_t*, const int32_t*,
                        const int32_t*, const float*, const float*, int, float, float, float, float, int, float*, float*,
-                       double*, const int32_t*, cudaStream_t);
+                       double*, const int32_t*, float*, cudaStream_t);
 int v5_loss_bwd_launch(const float*, int, int, int, int, int, const int32_t*, const int32_t*, const int32_t*, const int32_t*,
                        const int32_t*, const float*, const float*, int, float, float, float, float, int, const float*,
-                       const float*, float, float, float, float*, int, const int32_t*, cudaStream_t);
+                       const float*, float, float, float, float*, int, const int32_t*, const float*, cudaStream_t);
 int v5_loss_combine_launch(const double*, int, float, float, float, float*, cudaStream_t);
 int v5_loss_combine_bwd_launch(const float*, const float*, const float*, const float*, float, float, float, float*, cudaStream_t);
 size_t build_targets_ws_bytes(int, int, int, int);
@@ -296,17 +296,17 @@ int b200det_v5_loss_fwd(const float* pi, int32_t B, int32_t na, int32_t ny, int3
     B2_CHECK_ARG(pi && tobj && sums && (m == 0 || (b && a && gj && gi && tcls && tbox && anch && giou)), "null argument");
     B2_CHECK_ARG(((uintptr_t)tbox & 15) == 0 && ((uintptr_t)sums & 7) == 0, "tbox must be 16-byte, sums 8-byte aligned");
     return v5_loss_fwd_launch(pi, B, na, ny, nx, F, b, a, gj, gi, tcls, tbox, anch, m, cp, cn, gamma, alpha, with_cls, giou,
-                              tobj, sums, nullptr, (cudaStream_t)st);
+                              tobj, sums, nullptr, nullptr, (cudaStream_t)st);
 }
 int b200det_v5_loss_fwd_dev(const float* pi, int32_t B, int32_t na, int32_t ny, int32_t nx, int32_t F, const int32_t* b,
                             const int32_t* a, const int32_t* gj, const int32_t* gi, const int32_t* tcls, const float* tbox,
                             const float* anch, int32_t cap, const int32_t* m_dev, float cp, float cn, float gamma, float alpha,
-                            int32_t with_cls, float* giou, float* tobj, double* sums, void* st) {
+                            int32_t with_cls, float* giou, float* tobj, float* obj_grad, double* sums, void* st) {
     B2_CHECK_ARG(B > 0 && na > 0 && ny > 0 && nx > 0 && cap > 0 && F >= 5, "bad sizes");
     B2_CHECK_ARG(pi && tobj && sums && m_dev && b && a && gj && gi && tcls && tbox && anch && giou, "null argument");
     B2_CHECK_ARG(((uintptr_t)tbox & 15) == 0 && ((uintptr_t)sums & 7) == 0, "tbox must be 16-byte, sums 8-byte aligned");
     return v5_loss_fwd_launch(pi, B, na, ny, nx, F, b, a, gj, gi, tcls, tbox, anch, cap, cp, cn, gamma, alpha, with_cls, giou,
-                              tobj, sums, m_dev, (cudaStream_t)st);
+                              tobj, sums, m_dev, obj_grad, (cudaStream_t)st);
 }
 int b200det_v5_loss_bwd(const float* pi, int32_t B, int32_t na, int32_t ny, int32_t nx, int32_t F, const int32_t* b,
                         const int32_t* a, const int32_t* gj, const int32_t* gi, const int32_t* tcls, const float* tbox,
@@ -317,7 +317,7 @@ int b200det_v5_loss_bwd(const float* pi, int32_t B, int32_t na, int32_t ny, int3
     B2_CHECK_ARG(pi && tobj && gpi && g3 && (m == 0 || (b && a && gj && gi && tcls && tbox && anch)), "null argument");
     B2_CHECK_ARG(((uintptr_t)tbox & 15) == 0, "tbox must be 16-byte aligned");
     return v5_loss_bwd_launch(pi, B, na, ny, nx, F, b, a, gj, gi, tcls, tbox, anch, m, cp, cn, gamma, alpha, with_cls, tobj,
-                              g3, inv_nbox, inv_cells, inv_ncls, gpi, 0, nullptr, (cudaStream_t)st);
+                              g3, inv_nbox, inv_cells, inv_ncls, gpi, 0, nullptr, nullptr, (cudaStream_t)st);
 }
 int b200det_v5_loss_bwd_full(const float* pi, int32_t B, int32_t na, int32_t ny, int32_t nx, int32_t F, const int32_t* b,
                              const int32_t* a, const int32_t* gj, const int32_t* gi, const int32_t* tcls, const float* tbox,
@@ -328,18 +328,18 @@ int b200det_v5_loss_bwd_full(const float* pi, int32_t B, int32_t na, int32_t ny,
     B2_CHECK_ARG(pi && tobj && gpi && g3 && (m == 0 || (b && a && gj && gi && tcls && tbox && anch)), "null argument");
     B2_CHECK_ARG(((uintptr_t)tbox & 15) == 0, "tbox must be 16-byte aligned");
     return v5_loss_bwd_launch(pi, B, na, ny, nx, F, b, a, gj, gi, tcls, tbox, anch, m, cp, cn, gamma, alpha, with_cls, tobj,
-                              g3, inv_nbox, inv_cells, inv_ncls, gpi, 1, nullptr, (cudaStream_t)st);
+                              g3, inv_nbox, inv_cells, inv_ncls, gpi, 1, nullptr, nullptr, (cudaStream_t)st);
 }
 int b200det_v5_loss_bwd_full_dev(const float* pi, int32_t B, int32_t na, int32_t ny, int32_t nx, int32_t F, const int32_t* b,
                                  const int32_t* a, const int32_t* gj, const int32_t* gi, const int32_t* tcls, const float* tbox,
                                  const float* anch, int32_t cap, const int32_t* m_dev, float cp, float cn, float gamma,
-                                 float alpha, int32_t with_cls, const float* tobj, const float* g3, float inv_cells, float* gpi,
-                                 void* st) {
+                                 float alpha, int32_t with_cls, const float* tobj, const float* obj_grad, const float* g3,
+                                 float inv_cells, float* gpi, void* st) {
     B2_CHECK_ARG(B > 0 && na > 0 && ny > 0 && nx > 0 && cap > 0 && F >= 5, "bad sizes");
-    B2_CHECK_ARG(pi && tobj && gpi && g3 && m_dev && b && a && gj && gi && tcls && tbox && anch, "null argument");
+    B2_CHECK_ARG(pi && (tobj || obj_grad) && gpi && g3 && m_dev && b && a && gj && gi && tcls && tbox && anch, "null argument");
     B2_CHECK_ARG(((uintptr_t)tbox & 15) == 0, "tbox must be 16-byte aligned");
     return v5_loss_bwd_launch(pi, B, na, ny, nx, F, b, a, gj, gi, tcls, tbox, anch, cap, cp, cn, gamma, alpha, with_cls, tobj,
-                              g3, 0.0f, inv_cells, 0.0f, gpi, 1, m_dev, (cudaStream_t)st);
+                              g3, 0.0f, inv_cells, 0.0f, gpi, 1, m_dev, obj_grad, (cudaStream_t)st);
 }
 
 int b200det_v5_loss_combine(const double* means, int32_t nl, float wbox, float wobj, float wcls, float* out4, void* st) {

@@ -649,24 +649,38 @@ int v5_match_bwd_launch(const float* pi, int B, int na, int ny, int nx, int F, c
 // Forward leaves sums[3] (fp64): sum(1 - giou), sum FL_obj over all cells, sum FL_cls over the m x C matched logits;
 // backward takes the three upstream scalars already divided by the element counts.
 // ================================================================================================
+// The focal terms are evaluated 1.6 M (objectness) + m x C (classes) times per level and direction, and the kernels that do it
+// were bound by this arithmetic, not by memory (two expf, log1pf, a division and the generic powf: ~400 instructions per logit).
+// One expf(-|x|) now serves the log-sigmoid and the sigmoid, and (1 - p_t)^gamma is q * sqrt(q) for the criterion's gamma = 1.5
+// (any other gamma takes powf).  Same formulas as losses.py:37-64 up to the last-ulp rounding of the elementary functions
+// (parity tolerance: 1e-5 relative on the loss terms, tests/test_gpu_targets.py).
+__device__ __forceinline__ void bce_and_sigmoid(const float x, const float t, float& bce, float& pr) {
+    const float e = expf(-fabsf(x));                                               // (0, 1]
+    const float ls = fminf(x, 0.0f) - log1pf(e);                                   // log_sigmoid(x)
+    bce = (1.0f - t) * x - ls;                                                     // BCEWithLogits, pos_weight = 1
+    const float r = 1.0f / (1.0f + e);
+    pr = x >= 0.0f ? r : e * r;                                                    // sigmoid(x)
+}
 __device__ __forceinline__ float focal_bce(const float x, const float t, const float gamma, const float alpha) {
-    const float ls = fminf(x, 0.0f) - log1pf(expf(-fabsf(x)));                    // log_sigmoid(x)
-    const float bce = (1.0f - t) * x - ls;                                         // BCEWithLogits, pos_weight = 1
-    const float pr = sigmoidf_acc(x);
+    float bce, pr;
+    bce_and_sigmoid(x, t, bce, pr);
     const float p_t = t * pr + (1.0f - t) * (1.0f - pr);                           // losses.py:54
     const float af = t * alpha + (1.0f - t) * (1.0f - alpha);                      // :55
-    return bce * (af * powf(1.0f - p_t, gamma));                                   // :56-57
+    const float q = 1.0f - p_t;
+    const float mf = gamma == 1.5f ? q * sqrtf(q) : powf(q, gamma);
+    return bce * (af * mf);                                                        // :56-57
 }
 __device__ __forceinline__ float focal_bce_grad(const float x, const float t, const float gamma, const float alpha) {
-    const float ls = fminf(x, 0.0f) - log1pf(expf(-fabsf(x)));
-    const float bce = (1.0f - t) * x - ls;
-    const float pr = sigmoidf_acc(x);
+    float bce, pr;
+    bce_and_sigmoid(x, t, bce, pr);
     const float p_t = t * pr + (1.0f - t) * (1.0f - pr);
     const float af = t * alpha + (1.0f - t) * (1.0f - alpha);
     const float q = 1.0f - p_t;
-    const float mf = powf(q, gamma);
+    float mf, pw1;                                                                 // q^gamma, q^(gamma - 1)
+    if (gamma == 1.5f) { pw1 = sqrtf(q); mf = q * pw1; }
+    else { mf = powf(q, gamma); pw1 = powf(q, gamma - 1.0f); }
     const float dpt = (2.0f * t - 1.0f) * pr * (1.0f - pr);
-    const float dmf = q > 0.0f ? -gamma * powf(q, gamma - 1.0f) * dpt : 0.0f;
+    const float dmf = q > 0.0f ? -gamma * pw1 * dpt : 0.0f;
     return af * ((pr - t) * mf + bce * dmf);
 }
 
@@ -705,12 +719,19 @@ __global__ void __launch_bounds__(256) v5_loss_rows_fwd_kernel(const MatchParams
     block_add_double(cls, sums + 2);
 }
 
+// obj_grad (may be null): d FL / d logit of every cell, for the backward pass.  The backward would otherwise re-read column 4
+// of pi with a 340-byte stride WHILE it streams the gradient tensor out, and those reads are what it then waits for (level 0 of
+// the headline: 418 MB written; fill alone 62-69 us, with the strided reads 96-109 us — tools/ubench/gradfill.cu); here the
+// logit is in a register anyway, and the backward reads 4 contiguous bytes per cell instead.
 __global__ void __launch_bounds__(256) v5_loss_obj_fwd_kernel(const float* __restrict__ pi, int F, long long cells,
                                                               const float* __restrict__ tobj, float gamma, float alpha,
-                                                              double* __restrict__ sums) {
+                                                              double* __restrict__ sums, float* __restrict__ obj_grad) {
     double acc = 0.0;
-    for (long long c = (long long)blockIdx.x * 256 + threadIdx.x; c < cells; c += (long long)gridDim.x * 256)
-        acc += (double)focal_bce(pi[c * F + 4], tobj[c], gamma, alpha);
+    for (long long c = (long long)blockIdx.x * 256 + threadIdx.x; c < cells; c += (long long)gridDim.x * 256) {
+        const float x = pi[c * F + 4], t = tobj[c];
+        acc += (double)focal_bce(x, t, gamma, alpha);
+        if (obj_grad) obj_grad[c] = focal_bce_grad(x, t, gamma, alpha);
+    }
     block_add_double(acc, sums + 1);
 }
 
@@ -724,43 +745,45 @@ __global__ void __launch_bounds__(256) v5_loss_obj_bwd_kernel(const float* __res
 }
 
 // The same objectness gradient, but the kernel writes the WHOLE gradient tensor of its cells — zeros everywhere except
-// column 4 — as one linear stream (256 cells x F floats per CTA = one contiguous, 16-byte aligned block), so the caller needs
-// no zero-fill of the 548 MB gradient before it (a separate memset pass plus the read-modify-write of one 4-byte field per
-// 340-byte row afterwards).  The matched-row kernel then adds its terms on top, as before.
+// column 4 — so the caller needs no zero-fill of the 548 MB gradient before it (a separate memset pass plus the
+// read-modify-write of one 4-byte field per 340-byte row afterwards).  A CTA takes 256 cells per step, 64 at a time: the
+// 64 x F floats (contiguous, 16-byte aligned) are zero-filled with plain float4 stores and, after a CTA barrier (which orders
+// the two stores to the same words), the 64 owners store their cell's column 4 into lines that are still in L2 — 26 MB are
+// in flight over the whole GPU.  The per-cell factor d FL / d logit comes from the forward pass (obj_grad, 4 contiguous bytes
+// per cell) and the NEXT step's value is loaded before the fill.  History (level 0 = 418 MB; plain memset of it: 58-60 us):
+// an index walk composing every float4 inside the store loop 105 us; fill + patch with the logit re-read from pi 102-104 us —
+// tools/ubench/gradfill.cu shows that it is those 340-byte-strided reads next to the write stream that cost the 35-40 us, not
+// the composition or the patch (DRAM reads 163 MB for 39 MB of sectors asked for).
+// The matched-row kernel then adds its terms on top, as before.
 __global__ void __launch_bounds__(256) v5_loss_obj_bwd_full_kernel(const float* __restrict__ pi, int F, long long cells,
-                                                                   const float* __restrict__ tobj, float gamma, float alpha,
+                                                                   const float* __restrict__ tobj,
+                                                                   const float* __restrict__ obj_grad, float gamma, float alpha,
                                                                    const float* __restrict__ g3, float inv_cells,
                                                                    float* __restrict__ gpi) {
-    __shared__ float s_g[256];
     const float g_obj = g3[1] * inv_cells;
     const int tid = threadIdx.x;
-    const int step_q = 1024 / F, step_r = 1024 - step_q * F;                    // 256 threads x 4 floats per step
-    for (long long c0 = (long long)blockIdx.x * 256; c0 < cells; c0 += (long long)gridDim.x * 256) {
-        const long long c = c0 + tid;
-        __syncthreads();                                                        // previous block's s_g fully read
-        s_g[tid] = c < cells ? g_obj * focal_bce_grad(pi[c * F + 4], tobj[c], gamma, alpha) : 0.0f;
-        __syncthreads();
+    const long long stride = (long long)gridDim.x * 256;
+    long long c0 = (long long)blockIdx.x * 256;
+    // d FL / d logit of this thread's cell: from the forward pass (obj_grad), else recomputed from the strided logit
+    auto cell_grad = [&](const long long c) -> float {
+        if (c >= cells) return 0.0f;
+        return obj_grad ? obj_grad[c] : focal_bce_grad(pi[c * F + 4], tobj[c], gamma, alpha);
+    };
+    float h = cell_grad(c0 + tid);
+    const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    for (; c0 < cells; c0 += stride) {
+        const float g = g_obj * h;
+        h = cell_grad(c0 + stride + tid);                                       // next step's cell of this thread
         const int ncell = (int)min((long long)256, cells - c0);
-        const int n = ncell * F;                                                // floats of this block
-        float* out = gpi + c0 * F;                                              // 256 * F * 4 bytes per block: 16-byte aligned
-        const int n4 = n >> 2;
-        // (cell, field) of the thread's first float, then advanced by 1024 floats per step without dividing again
-        int cell0 = (tid << 2) / F, f0 = (tid << 2) - cell0 * F;
-        for (int v = tid; v < n4; v += 256) {
-            int cell = cell0, f = f0;
-            float r[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                r[k] = f == 4 ? s_g[cell] : 0.0f;
-                if (++f == F) { f = 0; ++cell; }
-            }
-            reinterpret_cast<float4*>(out)[v] = make_float4(r[0], r[1], r[2], r[3]);
-            cell0 += step_q; f0 += step_r;
-            if (f0 >= F) { f0 -= F; ++cell0; }
-        }
-        for (int idx = (n4 << 2) + tid; idx < n; idx += 256) {                  // tail of the last block
-            const int cell = idx / F, f = idx - cell * F;
-            out[idx] = f == 4 ? s_g[cell] : 0.0f;
+        float* out = gpi + c0 * F;
+        for (int cb = 0; cb < ncell; cb += 64) {
+            const int nsub = min(64, ncell - cb);
+            float* o = out + cb * F;                                            // 64 * F * 4 bytes per sub-block: 16-byte aligned
+            const int n = nsub * F, n4 = n >> 2;
+            for (int v = tid; v < n4; v += 256) reinterpret_cast<float4*>(o)[v] = z;
+            for (int idx = (n4 << 2) + tid; idx < n; idx += 256) o[idx] = 0.0f; // tail of the tensor's last sub-block
+            __syncthreads();
+            if (tid >= cb && tid < cb + nsub) out[tid * F + 4] = g;
         }
     }
 }
@@ -815,7 +838,7 @@ __global__ void v5_loss_means_kernel(double* __restrict__ sums, double n_box, do
 int v5_loss_fwd_launch(const float* pi, int B, int na, int ny, int nx, int F, const int32_t* b, const int32_t* a,
                        const int32_t* gj, const int32_t* gi, const int32_t* tcls, const float* tbox, const float* anch, int m,
                        float cp, float cn, float gamma, float alpha, int with_cls, float* giou, float* tobj, double* sums,
-                       const int32_t* m_dev, cudaStream_t st) {
+                       const int32_t* m_dev, float* obj_grad, cudaStream_t st) {
     const long long cells = (long long)B * na * ny * nx;
     B2_CUDA(cudaMemsetAsync(sums, 0, 3 * sizeof(double), st));
     B2_CUDA(cudaMemsetAsync(tobj, 0, (size_t)cells * 4, st));                      // torch.zeros_like(pi[..., 0])  (:107)
@@ -830,7 +853,7 @@ int v5_loss_fwd_launch(const float* pi, int B, int na, int ny, int nx, int F, co
         B2_LAUNCH_CHECK("v5_loss_rows_fwd_kernel");
     }
     const int grid = (int)((cells + 255) / 256 < 148 * 8 ? (cells + 255) / 256 : 148 * 8);
-    v5_loss_obj_fwd_kernel<<<grid, 256, 0, st>>>(pi, F, cells, tobj, gamma, alpha, sums);
+    v5_loss_obj_fwd_kernel<<<grid, 256, 0, st>>>(pi, F, cells, tobj, gamma, alpha, sums, obj_grad);
     B2_LAUNCH_CHECK("v5_loss_obj_fwd_kernel");
     // sums -> means in place: box / max(m, 1), obj / cells, cls / max(m * C, 1)   (reduction 'mean', losses.py:119-137)
     v5_loss_means_kernel<<<1, 32, 0, st>>>(sums, (double)(m > 0 ? m : 1), (double)cells,
@@ -881,11 +904,11 @@ int v5_loss_bwd_launch(const float* pi, int B, int na, int ny, int nx, int F, co
                        const int32_t* gj, const int32_t* gi, const int32_t* tcls, const float* tbox, const float* anch, int m,
                        float cp, float cn, float gamma, float alpha, int with_cls, const float* tobj, const float* g3,
                        float inv_nbox, float inv_cells, float inv_ncls, float* gpi, int fill, const int32_t* m_dev,
-                       cudaStream_t st) {
+                       const float* obj_grad, cudaStream_t st) {
     const long long cells = (long long)B * na * ny * nx;
     const int grid = (int)((cells + 255) / 256 < 148 * 8 ? (cells + 255) / 256 : 148 * 8);
     if (fill && (((uintptr_t)gpi) & 15) == 0) {
-        v5_loss_obj_bwd_full_kernel<<<grid, 256, 0, st>>>(pi, F, cells, tobj, gamma, alpha, g3, inv_cells, gpi);
+        v5_loss_obj_bwd_full_kernel<<<grid, 256, 0, st>>>(pi, F, cells, tobj, obj_grad, gamma, alpha, g3, inv_cells, gpi);
         B2_LAUNCH_CHECK("v5_loss_obj_bwd_full_kernel");
     } else {
         if (fill) B2_CUDA(cudaMemsetAsync(gpi, 0, (size_t)cells * F * sizeof(float), st));

@@ -272,28 +272,30 @@ class _V5LossAll(torch.autograd.Function):
         cells = [pid.numel() // pid.shape[-1] for pid in pids]
         cap = levels.cap
         tobj = torch.empty((sum(cells),), dtype=torch.float32, device=dev)            # all levels, back to back
+        gobj = torch.empty((sum(cells),), dtype=torch.float32, device=dev)            # d FL_obj / d logit per cell, for the backward
         giou = torch.empty((nl * cap,), dtype=torch.float32, device=dev)
         means = torch.empty((nl, 3), dtype=torch.float64, device=dev)
         out = torch.empty((4,), dtype=torch.float32, device=dev)
         st = L.stream_ptr(dev)
-        t_ptr, g_ptr, m_ptr, c_ptr = tobj.data_ptr(), giou.data_ptr(), means.data_ptr(), counts.data_ptr()
+        t_ptr, g_ptr, m_ptr, c_ptr, h_ptr = tobj.data_ptr(), giou.data_ptr(), means.data_ptr(), counts.data_ptr(), gobj.data_ptr()
         for i, pid in enumerate(pids):
             B, na, ny, nx, F = pid.shape
             L.check(lib.b200det_v5_loss_fwd_dev(pid.data_ptr(), B, na, ny, nx, F, *levels.ptrs(i), cap, c_ptr + 4 * i, cp, cn,
-                                                gamma, alpha, int(with_cls), g_ptr + 4 * cap * i, t_ptr, m_ptr + 24 * i, st),
+                                                gamma, alpha, int(with_cls), g_ptr + 4 * cap * i, t_ptr, h_ptr, m_ptr + 24 * i, st),
                     "v5_loss_fwd_dev")
             t_ptr += 4 * cells[i]
+            h_ptr += 4 * cells[i]
         L.check(lib.b200det_v5_loss_combine(m_ptr, nl, *_V5_GAINS, out.data_ptr(), st), "v5_loss_combine")
-        ctx.save_for_backward(tobj, counts, *pids)
+        ctx.save_for_backward(gobj, counts, *pids)         # tobj is not needed again: the backward gets its effect through gobj
         ctx.levels, ctx.cfg, ctx.cells = levels, cfg, cells
         return out[0:1], out[1:2], out[2:3], out[3:4]
 
     @staticmethod
     def backward(ctx, g_loss, g_box, g_cls, g_obj):
         lib = L.load()
-        tobj, counts, *pids = ctx.saved_tensors
+        gobj, counts, *pids = ctx.saved_tensors
         cp, cn, gamma, alpha, with_cls = ctx.cfg
-        dev = tobj.device
+        dev = gobj.device
         if torch.cuda.current_device() != dev.index:
             with torch.cuda.device(dev):
                 return _V5LossAll.backward(ctx, g_loss, g_box, g_cls, g_obj)
@@ -304,16 +306,16 @@ class _V5LossAll(torch.autograd.Function):
         grads = []
         L.check(lib.b200det_v5_loss_combine_bwd(*(None if g is None else g.data_ptr() for g in gs), *_V5_GAINS, g3.data_ptr(),
                                                 st), "v5_loss_combine_bwd")
-        t_ptr, c_ptr, g3_ptr = tobj.data_ptr(), counts.data_ptr(), g3.data_ptr()
+        h_ptr, c_ptr, g3_ptr = gobj.data_ptr(), counts.data_ptr(), g3.data_ptr()
         for i, pid in enumerate(pids):
             B, na, ny, nx, F = pid.shape
             cells = ctx.cells[i]
             gpi = torch.empty_like(pid)                               # fully written by the call (no zero-fill pass)
             L.check(lib.b200det_v5_loss_bwd_full_dev(pid.data_ptr(), B, na, ny, nx, F, *levels.ptrs(i), cap, c_ptr + 4 * i, cp, cn,
-                                                     gamma, alpha, int(with_cls), t_ptr, g3_ptr, 1.0 / cells, gpi.data_ptr(), st),
-                    "v5_loss_bwd_full_dev")
+                                                     gamma, alpha, int(with_cls), None, h_ptr, g3_ptr, 1.0 / cells, gpi.data_ptr(),
+                                                     st), "v5_loss_bwd_full_dev")
             grads.append(gpi)
-            t_ptr += 4 * cells
+            h_ptr += 4 * cells
         return (None, None, None, *grads)
 
 
