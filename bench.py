@@ -556,12 +556,12 @@ class TargetsWorkload:
         # nt*24 in + sum m_i (4*8 + 16 + 8 + 8) out + gathered sum m_i (5+C)*4; plus what the fused loss tail must touch:
         # the objectness logit of every cell (read, and its gradient written) and the gradient rows of the matched cells
         self.alg_bytes = self.nt * 24 + M * (32 + 16 + 8 + 8) + 2 * M * F * 4 + 2 * cells * 4
-        self.kernel = ("whole step: build_targets_v5_kernel + v5_loss_rows/obj fwd + bwd kernels (latency-bound; the objectness column "
-                       "is one 4-byte field per 340-byte row)")
+        self.kernel = ("whole step: build_targets_v5 + the fused v5 loss forward / backward, one launch per stage for all levels "
+                       "(9 launches; the 548 MB gradient stream of the objectness backward is its largest kernel)")
         self.stage_names = []
-        # build_targets_v5 (1); forward per level: rows + objectness kernels (2 x 3) and the combine (1); backward: combine (1) and
-        # per level rows + objectness kernels (2 x 3).  (torch's own zero-fill kernels of tobj / the gradient buffers are not ours.)
-        self.launches_pipe = self.launches_api = 1 + 6 + 1 + 1 + 6
+        # build_targets_v5 (1); forward, all levels per launch: match, tobj scatter, matched-row terms, objectness terms,
+        # means + combination (5); backward: combination (1), objectness gradient stream, matched-row gradients (2)
+        self.launches_pipe = self.launches_api = 1 + 5 + 1 + 2
         self.l2 = f"heads {self.head_bytes / 1e6:.1f} MB per GPU > 126 MB L2 (no flush needed)"
 
     def api_step(self, i):

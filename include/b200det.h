@@ -305,23 +305,33 @@ int b200det_v5_loss_bwd_full(const float* pi, int32_t batch, int32_t na, int32_t
                              const float* tbox, const float* anch, int32_t m, float cp, float cn, float gamma, float alpha,
                              int32_t with_cls, const float* tobj, const float* g3, float inv_nbox, float inv_cells,
                              float inv_ncls, float* gpi, void* stream);
-/* Sync-free forms: the row count m stays on the DEVICE (m_dev = the count_out word b200det_build_targets_v5 wrote for this
- * level), the row arrays are passed at their capacity `cap` (5 * na * nt) and every kernel bounds itself by min(cap, *m_dev), so
- * the host never waits between target assignment and loss.  The means' divisors (max(m, 1), max(m * C, 1)) are formed on the
- * device from the same word.  Results are identical to the host-count forms.
- * obj_grad [cells] (may be NULL): the forward also leaves d FL / d logit of every cell's objectness term there, and a backward
- * that is given it reads those 4 contiguous bytes per cell instead of re-reading column 4 of pi with a (5+C)-float stride while
- * it streams the gradient out (tobj may then be NULL in the backward). */
-int b200det_v5_loss_fwd_dev(const float* pi, int32_t batch, int32_t na, int32_t ny, int32_t nx, int32_t fields,
-                            const int32_t* b, const int32_t* a, const int32_t* gj, const int32_t* gi, const int32_t* tcls,
-                            const float* tbox, const float* anch, int32_t cap, const int32_t* m_dev, float cp, float cn,
-                            float gamma, float alpha, int32_t with_cls, float* giou, float* tobj, float* obj_grad,
-                            double* sums, void* stream);
-int b200det_v5_loss_bwd_full_dev(const float* pi, int32_t batch, int32_t na, int32_t ny, int32_t nx, int32_t fields,
-                                 const int32_t* b, const int32_t* a, const int32_t* gj, const int32_t* gi, const int32_t* tcls,
-                                 const float* tbox, const float* anch, int32_t cap, const int32_t* m_dev, float cp, float cn,
-                                 float gamma, float alpha, int32_t with_cls, const float* tobj, const float* obj_grad,
-                                 const float* g3, float inv_cells, float* gpi, void* stream);
+/* All levels of the criterion per call, sync-free (what `v5_loss` of the Python layer uses): one launch per STAGE for all levels
+ * (the per-level kernels are 5-45 us each; ~30 launches per step level by level, 11 this way), the matched-row count of every
+ * level stays on the DEVICE (m_dev = the count_out word b200det_build_targets_v5 wrote for it; the row arrays are passed at their
+ * capacity `cap` = 5 * na * nt and every kernel bounds itself by min(cap, *m_dev), the means' divisors max(m, 1), max(m * C, 1)
+ * are formed on the device from the same word), and the gain-weighted combination (losses.py:139-152) is part of the call:
+ * out4 = (loss, Localization, Classification, Conf_obj).  Results are identical to the per-level host-count forms + combine.
+ *   giou [nl, cap], tobj [sum of cells] (levels back to back; scratch), sums [nl, 3] fp64 (scratch; holds the three means of
+ *   every level afterwards), obj_grad [sum of cells]: d FL / d logit of every cell's objectness term, which the backward reads
+ *   (4 contiguous bytes per cell) instead of re-reading column 4 of pi with a (5+C)-float stride next to its write stream.
+ * _bwd_all: every level's gpi (same shape as pi, 16-byte aligned) is DEFINED by the call (zeros outside column 4 and the
+ *   matched rows; no zero-fill needed); g_loss / g_box / g_cls / g_obj are the upstream gradients of out4 (device scalars, NULL =
+ *   none), g3 [3] is scratch. */
+typedef struct {
+    const float* pi;                                       /* [batch, na, ny, nx, fields] fp32                         */
+    int32_t batch, na, ny, nx, fields;
+    const int32_t *b, *a, *gj, *gi, *tcls;                 /* [cap] rows of b200det_build_targets_v5 for this level     */
+    const float* tbox;                                     /* [cap, 4], 16-byte aligned                                */
+    const float* anch;                                     /* [cap, 2]                                                 */
+    const int32_t* m_dev;                                  /* device word: rows in use                                  */
+    float* gpi;                                            /* backward only                                            */
+} b200det_v5_level;
+int b200det_v5_loss_fwd_all(const b200det_v5_level* levels, int32_t nl, int32_t cap, float cp, float cn, float gamma, float alpha,
+                            int32_t with_cls, float wbox, float wobj, float wcls, float* giou, float* tobj, float* obj_grad,
+                            double* sums, float* out4, void* stream);
+int b200det_v5_loss_bwd_all(const b200det_v5_level* levels, int32_t nl, int32_t cap, float cp, float cn, float gamma, float alpha,
+                            int32_t with_cls, float wbox, float wobj, float wcls, const float* obj_grad, const float* g_loss,
+                            const float* g_box, const float* g_cls, const float* g_obj, float* g3, void* stream);
 /* The tail of the same forward (losses.py:139-152): means[nl][3] (fp64, what b200det_v5_loss_fwd left per level) are added
  * in level order in fp32, scaled by the three gains and summed: out4 = (loss, Localization, Classification, Conf_obj).
  * _bwd: g3[3] for b200det_v5_loss_bwd (the same for every level) from the upstream gradients of those four outputs

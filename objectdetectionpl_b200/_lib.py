@@ -31,6 +31,12 @@ class PriorDesc(Structure):
                 ("class_thresh", c_float), ("mode_min", c_int32), ("compat", c_int32)]
 
 
+class V5Level(Structure):
+    _fields_ = [("pi", c_void_p), ("batch", c_int32), ("na", c_int32), ("ny", c_int32), ("nx", c_int32), ("fields", c_int32),
+                ("b", c_void_p), ("a", c_void_p), ("gj", c_void_p), ("gi", c_void_p), ("tcls", c_void_p), ("tbox", c_void_p),
+                ("anch", c_void_p), ("m_dev", c_void_p), ("gpi", c_void_p)]
+
+
 _vp, _i32, _i64, _f, _sz = c_void_p, c_int32, c_int64, c_float, c_size_t
 _PY, _PP = POINTER(YoloDesc), POINTER(PriorDesc)
 
@@ -76,10 +82,8 @@ SIGNATURES = {
                                    _i32, _vp, _vp, _f, _f, _f, _vp, _vp]),
     "b200det_v5_loss_bwd_full": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f, _f, _f, _f,
                                         _i32, _vp, _vp, _f, _f, _f, _vp, _vp]),
-    "b200det_v5_loss_fwd_dev": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _f, _f, _f, _f,
-                                       _i32, _vp, _vp, _vp, _vp, _vp]),
-    "b200det_v5_loss_bwd_full_dev": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _f, _f,
-                                            _f, _f, _i32, _vp, _vp, _vp, _f, _vp, _vp]),
+    "b200det_v5_loss_fwd_all": (_i32, [_vp, _i32, _i32, _f, _f, _f, _f, _i32, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200det_v5_loss_bwd_all": (_i32, [_vp, _i32, _i32, _f, _f, _f, _f, _i32, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200det_build_targets_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "b200det_build_targets": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f, _vp, _sz] + [_vp] * 10 + [_vp]),
     "b200det_ssd_match_workspace_bytes": (_sz, [_i32, _i32]),

@@ -1,5 +1,6 @@
 // C ABI of libb200det.so (include/b200det.h): argument checks + dispatch to the stage launchers.
 #include "yolo_ws.cuh"
+#include "targets.cuh"
 
 namespace b200det {
 
@@ -298,16 +299,6 @@ int b200det_v5_loss_fwd(const float* pi, int32_t B, int32_t na, int32_t ny, int3
     return v5_loss_fwd_launch(pi, B, na, ny, nx, F, b, a, gj, gi, tcls, tbox, anch, m, cp, cn, gamma, alpha, with_cls, giou,
                               tobj, sums, nullptr, nullptr, (cudaStream_t)st);
 }
-int b200det_v5_loss_fwd_dev(const float* pi, int32_t B, int32_t na, int32_t ny, int32_t nx, int32_t F, const int32_t* b,
-                            const int32_t* a, const int32_t* gj, const int32_t* gi, const int32_t* tcls, const float* tbox,
-                            const float* anch, int32_t cap, const int32_t* m_dev, float cp, float cn, float gamma, float alpha,
-                            int32_t with_cls, float* giou, float* tobj, float* obj_grad, double* sums, void* st) {
-    B2_CHECK_ARG(B > 0 && na > 0 && ny > 0 && nx > 0 && cap > 0 && F >= 5, "bad sizes");
-    B2_CHECK_ARG(pi && tobj && sums && m_dev && b && a && gj && gi && tcls && tbox && anch && giou, "null argument");
-    B2_CHECK_ARG(((uintptr_t)tbox & 15) == 0 && ((uintptr_t)sums & 7) == 0, "tbox must be 16-byte, sums 8-byte aligned");
-    return v5_loss_fwd_launch(pi, B, na, ny, nx, F, b, a, gj, gi, tcls, tbox, anch, cap, cp, cn, gamma, alpha, with_cls, giou,
-                              tobj, sums, m_dev, obj_grad, (cudaStream_t)st);
-}
 int b200det_v5_loss_bwd(const float* pi, int32_t B, int32_t na, int32_t ny, int32_t nx, int32_t F, const int32_t* b,
                         const int32_t* a, const int32_t* gj, const int32_t* gi, const int32_t* tcls, const float* tbox,
                         const float* anch, int32_t m, float cp, float cn, float gamma, float alpha, int32_t with_cls,
@@ -330,16 +321,48 @@ int b200det_v5_loss_bwd_full(const float* pi, int32_t B, int32_t na, int32_t ny,
     return v5_loss_bwd_launch(pi, B, na, ny, nx, F, b, a, gj, gi, tcls, tbox, anch, m, cp, cn, gamma, alpha, with_cls, tobj,
                               g3, inv_nbox, inv_cells, inv_ncls, gpi, 1, nullptr, nullptr, (cudaStream_t)st);
 }
-int b200det_v5_loss_bwd_full_dev(const float* pi, int32_t B, int32_t na, int32_t ny, int32_t nx, int32_t F, const int32_t* b,
-                                 const int32_t* a, const int32_t* gj, const int32_t* gi, const int32_t* tcls, const float* tbox,
-                                 const float* anch, int32_t cap, const int32_t* m_dev, float cp, float cn, float gamma,
-                                 float alpha, int32_t with_cls, const float* tobj, const float* obj_grad, const float* g3,
-                                 float inv_cells, float* gpi, void* st) {
-    B2_CHECK_ARG(B > 0 && na > 0 && ny > 0 && nx > 0 && cap > 0 && F >= 5, "bad sizes");
-    B2_CHECK_ARG(pi && (tobj || obj_grad) && gpi && g3 && m_dev && b && a && gj && gi && tcls && tbox && anch, "null argument");
-    B2_CHECK_ARG(((uintptr_t)tbox & 15) == 0, "tbox must be 16-byte aligned");
-    return v5_loss_bwd_launch(pi, B, na, ny, nx, F, b, a, gj, gi, tcls, tbox, anch, cap, cp, cn, gamma, alpha, with_cls, tobj,
-                              g3, 0.0f, inv_cells, 0.0f, gpi, 1, m_dev, obj_grad, (cudaStream_t)st);
+// ---- all levels of the criterion per call (targets.cu: V5Multi) ----
+static int v5_fill_levels(V5Multi* mp, const b200det_v5_level* levels, int32_t nl, int32_t cap, bool backward) {
+    B2_CHECK_ARG(levels && nl > 0 && nl <= kV5MaxLevels, "need 1..5 levels");
+    B2_CHECK_ARG(cap > 0, "bad row capacity");
+    memset(mp, 0, sizeof(*mp));
+    mp->nl = nl;
+    for (int i = 0; i < nl; ++i) {
+        const b200det_v5_level& l = levels[i];
+        B2_CHECK_ARG(l.batch > 0 && l.na > 0 && l.ny > 0 && l.nx > 0 && l.fields >= 5, "bad level sizes");
+        B2_CHECK_ARG(l.pi && l.b && l.a && l.gj && l.gi && l.tcls && l.tbox && l.anch && l.m_dev, "null level argument");
+        B2_CHECK_ARG(((uintptr_t)l.tbox & 15) == 0, "tbox must be 16-byte aligned");
+        B2_CHECK_ARG(!backward || (l.gpi && ((uintptr_t)l.gpi & 15) == 0), "gpi must be non-null and 16-byte aligned");
+        V5Level& L = mp->lv[i];
+        L.p = MatchParams{l.pi, l.batch, l.na, l.ny, l.nx, l.fields, l.b, l.a, l.gj, l.gi, l.tbox, l.anch, cap, l.m_dev};
+        L.tcls = l.tcls;
+        L.gpi = l.gpi;
+        L.cells = (long long)l.batch * l.na * l.ny * l.nx;
+    }
+    return 0;
+}
+int b200det_v5_loss_fwd_all(const b200det_v5_level* levels, int32_t nl, int32_t cap, float cp, float cn, float gamma, float alpha,
+                            int32_t with_cls, float wbox, float wobj, float wcls, float* giou, float* tobj, float* obj_grad,
+                            double* sums, float* out4, void* st) {
+    V5Multi mp;
+    int rc = v5_fill_levels(&mp, levels, nl, cap, false);
+    if (rc) return rc;
+    B2_CHECK_ARG(giou && tobj && sums && out4, "null argument");
+    B2_CHECK_ARG(((uintptr_t)sums & 7) == 0, "sums must be 8-byte aligned");
+    mp.cp = cp; mp.cn = cn; mp.gamma = gamma; mp.alpha = alpha; mp.with_cls = with_cls;
+    mp.wbox = wbox; mp.wobj = wobj; mp.wcls = wcls;
+    return v5_loss_fwd_all_launch(mp, cap, giou, tobj, obj_grad, sums, out4, (cudaStream_t)st);
+}
+int b200det_v5_loss_bwd_all(const b200det_v5_level* levels, int32_t nl, int32_t cap, float cp, float cn, float gamma, float alpha,
+                            int32_t with_cls, float wbox, float wobj, float wcls, const float* obj_grad, const float* g_loss,
+                            const float* g_box, const float* g_cls, const float* g_obj, float* g3, void* st) {
+    V5Multi mp;
+    int rc = v5_fill_levels(&mp, levels, nl, cap, true);
+    if (rc) return rc;
+    B2_CHECK_ARG(obj_grad && g3, "null argument");
+    mp.cp = cp; mp.cn = cn; mp.gamma = gamma; mp.alpha = alpha; mp.with_cls = with_cls;
+    mp.wbox = wbox; mp.wobj = wobj; mp.wcls = wcls;
+    return v5_loss_bwd_all_launch(mp, cap, obj_grad, g_loss, g_box, g_cls, g_obj, g3, (cudaStream_t)st);
 }
 
 int b200det_v5_loss_combine(const double* means, int32_t nl, float wbox, float wobj, float wcls, float* out4, void* st) {

@@ -10,6 +10,8 @@
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
+#include "targets.cuh"
+
 namespace b200det {
 
 // ================================================================================================
@@ -188,23 +190,15 @@ __global__ void __launch_bounds__(1024) build_targets_v5_multi_kernel(const Tv5M
 // T4 — matched rows of one level: ps = pi[b,a,gj,gi] ; pxy = sigmoid*2-0.5 ; pwh = (sigmoid*2)^2*anch ;
 // giou = bbox_iou_v5(pbox, tbox, xywh, GIoU) ; tobj[cell] = clamp(giou, 0), last row wins.
 // ================================================================================================
-struct MatchParams {
-    const float* pi;
-    int B, na, ny, nx, F;
-    const int32_t *b, *a, *gj, *gi;
-    const float* tbox;
-    const float* anch;
-    int m;                      // matched rows; with m_dev set: the CAPACITY of the row arrays (sizes the grids)
-    const int32_t* m_dev;       // optional: the row count lives on the device (no host sync between build_targets_v5 and the loss)
-};
 __device__ __forceinline__ int match_rows(const MatchParams& p) { return p.m_dev ? min(p.m, (int)*p.m_dev) : p.m; }
 
 __device__ __forceinline__ long long match_cell(const MatchParams& p, int i) {
     return (((long long)p.b[i] * p.na + p.a[i]) * p.ny + p.gj[i]) * p.nx + p.gi[i];
 }
 
-__global__ void v5_match_fwd_kernel(const MatchParams p, float* __restrict__ giou, int* __restrict__ tobj_as_int) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void v5_match_fwd_body(const MatchParams& p, float* __restrict__ giou, int* __restrict__ tobj_as_int,
+                                                  const int bid) {
+    const int i = bid * blockDim.x + threadIdx.x;
     if (i >= match_rows(p)) return;
     const long long cell = match_cell(p, i);
     const float* ps = p.pi + cell * p.F;
@@ -220,12 +214,19 @@ __global__ void v5_match_fwd_kernel(const MatchParams p, float* __restrict__ gio
     giou[i] = iou_v5_forward(pb, tb, false, B200DET_GIOU);                          // losses.py:118
     atomicMax(&tobj_as_int[cell], i + 1);                                           // winner = highest row
 }
+__global__ void v5_match_fwd_kernel(const MatchParams p, float* __restrict__ giou, int* __restrict__ tobj_as_int) {
+    v5_match_fwd_body(p, giou, tobj_as_int, (int)blockIdx.x);
+}
 
-__global__ void v5_match_tobj_kernel(const MatchParams p, const float* __restrict__ giou, float* __restrict__ tobj) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void v5_match_tobj_body(const MatchParams& p, const float* __restrict__ giou, float* __restrict__ tobj,
+                                                   const int bid) {
+    const int i = bid * blockDim.x + threadIdx.x;
     if (i >= match_rows(p)) return;
     const long long cell = match_cell(p, i);
     if (reinterpret_cast<const int*>(tobj)[cell] == i + 1) tobj[cell] = fmaxf(giou[i], 0.0f);   // losses.py:123
+}
+__global__ void v5_match_tobj_kernel(const MatchParams p, const float* __restrict__ giou, float* __restrict__ tobj) {
+    v5_match_tobj_body(p, giou, tobj, (int)blockIdx.x);
 }
 
 __global__ void v5_match_bwd_kernel(const MatchParams p, const float* __restrict__ ggiou, float* __restrict__ gpi) {
@@ -701,11 +702,11 @@ __device__ __forceinline__ void block_add_double(double v, double* target) {
 // One WARP per matched row: the 5+C fields of a row are contiguous, so the lanes read (and, backward, update) them
 // coalesced; one thread per row walks 340-byte rows with a 32-way scattered access pattern (measured 182 / 214 us for the
 // three levels of config 4 forward / backward).
-__global__ void __launch_bounds__(256) v5_loss_rows_fwd_kernel(const MatchParams p, const int32_t* __restrict__ tcls,
-                                                               const float* __restrict__ giou, float cp, float cn,
-                                                               float gamma, float alpha, int with_cls, double* __restrict__ sums) {
+__device__ __forceinline__ void v5_loss_rows_fwd_body(const MatchParams& p, const int32_t* __restrict__ tcls,
+                                                      const float* __restrict__ giou, float cp, float cn, float gamma,
+                                                      float alpha, int with_cls, double* __restrict__ sums, const int bid) {
     const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int i = bid * 8 + (threadIdx.x >> 5);
     double box = 0.0, cls = 0.0;
     if (i < match_rows(p)) {
         if (lane == 0) box = (double)(1.0f - giou[i]);
@@ -718,21 +719,46 @@ __global__ void __launch_bounds__(256) v5_loss_rows_fwd_kernel(const MatchParams
     block_add_double(box, sums + 0);
     block_add_double(cls, sums + 2);
 }
+__global__ void __launch_bounds__(256) v5_loss_rows_fwd_kernel(const MatchParams p, const int32_t* __restrict__ tcls,
+                                                               const float* __restrict__ giou, float cp, float cn,
+                                                               float gamma, float alpha, int with_cls, double* __restrict__ sums) {
+    v5_loss_rows_fwd_body(p, tcls, giou, cp, cn, gamma, alpha, with_cls, sums, (int)blockIdx.x);
+}
 
 // obj_grad (may be null): d FL / d logit of every cell, for the backward pass.  The backward would otherwise re-read column 4
 // of pi with a 340-byte stride WHILE it streams the gradient tensor out, and those reads are what it then waits for (level 0 of
 // the headline: 418 MB written; fill alone 62-69 us, with the strided reads 96-109 us — tools/ubench/gradfill.cu); here the
 // logit is in a register anyway, and the backward reads 4 contiguous bytes per cell instead.
+__device__ __forceinline__ void v5_loss_obj_fwd_body(const float* __restrict__ pi, int F, long long cells,
+                                                     const float* __restrict__ tobj, float gamma, float alpha,
+                                                     double* __restrict__ sums, float* __restrict__ obj_grad, const int bid,
+                                                     const int nblk) {
+    double acc = 0.0;
+    const long long stride = (long long)nblk * 256;
+    // four cells of the thread in flight at once: the 340-byte-strided logit reads are one L2 / DRAM round trip each
+    for (long long c = (long long)bid * 256 + threadIdx.x; c < cells; c += 4 * stride) {
+        float x[4], t[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long ck = c + k * stride;
+            x[k] = ck < cells ? pi[ck * F + 4] : 0.0f;
+            t[k] = ck < cells ? tobj[ck] : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long ck = c + k * stride;
+            if (ck < cells) {
+                acc += (double)focal_bce(x[k], t[k], gamma, alpha);
+                if (obj_grad) obj_grad[ck] = focal_bce_grad(x[k], t[k], gamma, alpha);
+            }
+        }
+    }
+    block_add_double(acc, sums + 1);
+}
 __global__ void __launch_bounds__(256) v5_loss_obj_fwd_kernel(const float* __restrict__ pi, int F, long long cells,
                                                               const float* __restrict__ tobj, float gamma, float alpha,
                                                               double* __restrict__ sums, float* __restrict__ obj_grad) {
-    double acc = 0.0;
-    for (long long c = (long long)blockIdx.x * 256 + threadIdx.x; c < cells; c += (long long)gridDim.x * 256) {
-        const float x = pi[c * F + 4], t = tobj[c];
-        acc += (double)focal_bce(x, t, gamma, alpha);
-        if (obj_grad) obj_grad[c] = focal_bce_grad(x, t, gamma, alpha);
-    }
-    block_add_double(acc, sums + 1);
+    v5_loss_obj_fwd_body(pi, F, cells, tobj, gamma, alpha, sums, obj_grad, (int)blockIdx.x, (int)gridDim.x);
 }
 
 __global__ void __launch_bounds__(256) v5_loss_obj_bwd_kernel(const float* __restrict__ pi, int F, long long cells,
@@ -755,15 +781,15 @@ __global__ void __launch_bounds__(256) v5_loss_obj_bwd_kernel(const float* __res
 // tools/ubench/gradfill.cu shows that it is those 340-byte-strided reads next to the write stream that cost the 35-40 us, not
 // the composition or the patch (DRAM reads 163 MB for 39 MB of sectors asked for).
 // The matched-row kernel then adds its terms on top, as before.
-__global__ void __launch_bounds__(256) v5_loss_obj_bwd_full_kernel(const float* __restrict__ pi, int F, long long cells,
-                                                                   const float* __restrict__ tobj,
-                                                                   const float* __restrict__ obj_grad, float gamma, float alpha,
-                                                                   const float* __restrict__ g3, float inv_cells,
-                                                                   float* __restrict__ gpi) {
+__device__ __forceinline__ void v5_loss_obj_bwd_full_body(const float* __restrict__ pi, int F, long long cells,
+                                                          const float* __restrict__ tobj, const float* __restrict__ obj_grad,
+                                                          float gamma, float alpha, const float* __restrict__ g3,
+                                                          float inv_cells, float* __restrict__ gpi, const int bid,
+                                                          const int nblk) {
     const float g_obj = g3[1] * inv_cells;
     const int tid = threadIdx.x;
-    const long long stride = (long long)gridDim.x * 256;
-    long long c0 = (long long)blockIdx.x * 256;
+    const long long stride = (long long)nblk * 256;
+    long long c0 = (long long)bid * 256;
     // d FL / d logit of this thread's cell: from the forward pass (obj_grad), else recomputed from the strided logit
     auto cell_grad = [&](const long long c) -> float {
         if (c >= cells) return 0.0f;
@@ -787,13 +813,19 @@ __global__ void __launch_bounds__(256) v5_loss_obj_bwd_full_kernel(const float* 
         }
     }
 }
+__global__ void __launch_bounds__(256) v5_loss_obj_bwd_full_kernel(const float* __restrict__ pi, int F, long long cells,
+                                                                   const float* __restrict__ tobj,
+                                                                   const float* __restrict__ obj_grad, float gamma, float alpha,
+                                                                   const float* __restrict__ g3, float inv_cells,
+                                                                   float* __restrict__ gpi) {
+    v5_loss_obj_bwd_full_body(pi, F, cells, tobj, obj_grad, gamma, alpha, g3, inv_cells, gpi, (int)blockIdx.x, (int)gridDim.x);
+}
 
-__global__ void __launch_bounds__(256) v5_loss_rows_bwd_kernel(const MatchParams p, const int32_t* __restrict__ tcls, float cp,
-                                                               float cn, float gamma, float alpha, int with_cls,
-                                                               const float* __restrict__ g3, float inv_nbox, float inv_ncls,
-                                                               float* __restrict__ gpi) {
+__device__ __forceinline__ void v5_loss_rows_bwd_body(const MatchParams& p, const int32_t* __restrict__ tcls, float cp, float cn,
+                                                      float gamma, float alpha, int with_cls, const float* __restrict__ g3,
+                                                      float inv_nbox, float inv_ncls, float* __restrict__ gpi, const int bid) {
     const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int i = bid * 8 + (threadIdx.x >> 5);
     if (i >= match_rows(p)) return;
     if (p.m_dev) {                                                  // the means' divisors from the device-side row count
         const long long mm = max(match_rows(p), 1);
@@ -823,6 +855,12 @@ __global__ void __launch_bounds__(256) v5_loss_rows_bwd_kernel(const MatchParams
         for (int c = lane; c < p.F - 5; c += 32)
             atomicAdd(gp + 5 + c, g_cls * focal_bce_grad(ps[5 + c], c == lab ? cp : cn, gamma, alpha));
     }
+}
+__global__ void __launch_bounds__(256) v5_loss_rows_bwd_kernel(const MatchParams p, const int32_t* __restrict__ tcls, float cp,
+                                                               float cn, float gamma, float alpha, int with_cls,
+                                                               const float* __restrict__ g3, float inv_nbox, float inv_ncls,
+                                                               float* __restrict__ gpi) {
+    v5_loss_rows_bwd_body(p, tcls, cp, cn, gamma, alpha, with_cls, g3, inv_nbox, inv_ncls, gpi, (int)blockIdx.x);
 }
 
 __global__ void v5_loss_means_kernel(double* __restrict__ sums, double n_box, double n_cells, double n_cls,
@@ -921,6 +959,119 @@ int v5_loss_bwd_launch(const float* pi, int B, int na, int ny, int nx, int F, co
                                                                 gpi);
         B2_LAUNCH_CHECK("v5_loss_rows_bwd_kernel");
     }
+    return 0;
+}
+
+// ================================================================================================
+// All levels of the criterion in one launch per stage (blockIdx.y = level): the per-level kernels above are 5-45 us each and a
+// level-by-level step is ~30 launches whose ramps and tails — the stride-32 level has 300 CTAs of work — add up to a quarter of
+// it.  Same bodies, same arithmetic, same results.
+// ================================================================================================
+__global__ void v5_match_fwd_multi_kernel(const __grid_constant__ V5Multi mp) {
+    const V5Level& L = mp.lv[blockIdx.y];
+    if ((int)blockIdx.x * 256 >= L.p.m) return;
+    v5_match_fwd_body(L.p, L.giou, reinterpret_cast<int*>(L.tobj), (int)blockIdx.x);
+}
+__global__ void v5_match_tobj_multi_kernel(const __grid_constant__ V5Multi mp) {
+    const V5Level& L = mp.lv[blockIdx.y];
+    if ((int)blockIdx.x * 256 >= L.p.m) return;
+    v5_match_tobj_body(L.p, L.giou, L.tobj, (int)blockIdx.x);
+}
+__global__ void __launch_bounds__(256) v5_loss_rows_fwd_multi_kernel(const __grid_constant__ V5Multi mp) {
+    const V5Level& L = mp.lv[blockIdx.y];
+    if ((int)blockIdx.x * 8 >= match_rows(L.p)) return;                         // CTA-uniform: nothing to add to the sums
+    v5_loss_rows_fwd_body(L.p, L.tcls, L.giou, mp.cp, mp.cn, mp.gamma, mp.alpha, mp.with_cls, L.sums, (int)blockIdx.x);
+}
+__global__ void __launch_bounds__(256) v5_loss_obj_fwd_multi_kernel(const __grid_constant__ V5Multi mp) {
+    const V5Level& L = mp.lv[blockIdx.y];
+    if ((int)blockIdx.x >= L.obj_blocks) return;
+    v5_loss_obj_fwd_body(L.p.pi, L.p.F, L.cells, L.tobj, mp.gamma, mp.alpha, L.sums, L.obj_grad, (int)blockIdx.x, L.obj_blocks);
+}
+__global__ void __launch_bounds__(256) v5_loss_obj_bwd_full_multi_kernel(const __grid_constant__ V5Multi mp) {
+    const V5Level& L = mp.lv[blockIdx.y];
+    if ((int)blockIdx.x >= L.obj_blocks) return;
+    v5_loss_obj_bwd_full_body(L.p.pi, L.p.F, L.cells, L.tobj, L.obj_grad, mp.gamma, mp.alpha, mp.g3, L.inv_cells, L.gpi,
+                              (int)blockIdx.x, L.obj_blocks);
+}
+__global__ void __launch_bounds__(256) v5_loss_rows_bwd_multi_kernel(const __grid_constant__ V5Multi mp) {
+    const V5Level& L = mp.lv[blockIdx.y];
+    if ((int)blockIdx.x * 8 >= match_rows(L.p)) return;
+    v5_loss_rows_bwd_body(L.p, L.tcls, mp.cp, mp.cn, mp.gamma, mp.alpha, mp.with_cls, mp.g3, 0.0f, 0.0f, L.gpi, (int)blockIdx.x);
+}
+// sums -> means per level (reduction 'mean', losses.py:119-137: box / max(m, 1), obj / cells, cls / max(m * C, 1)), then the
+// gain-weighted combination of losses.py:139-152 in level order — v5_loss_means_kernel x nl + v5_loss_combine_kernel in one thread
+__global__ void v5_loss_means_combine_multi_kernel(const __grid_constant__ V5Multi mp, float* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float lbox = 0.f, lobj = 0.f, lcls = 0.f;
+    for (int i = 0; i < mp.nl; ++i) {
+        const V5Level& L = mp.lv[i];
+        const long long mm = match_rows(L.p);
+        const double n_box = (double)max(mm, 1ll), n_cls = (double)max(mm * (L.p.F - 5), 1ll);
+        const double m0 = L.sums[0] / n_box, m1 = L.sums[1] / (double)L.cells, m2 = L.sums[2] / n_cls;
+        L.sums[0] = m0; L.sums[1] = m1; L.sums[2] = m2;
+        lbox = __fadd_rn(lbox, (float)m0);
+        lobj = __fadd_rn(lobj, (float)m1);
+        lcls = __fadd_rn(lcls, (float)m2);
+    }
+    lbox = __fmul_rn(lbox, mp.wbox); lobj = __fmul_rn(lobj, mp.wobj); lcls = __fmul_rn(lcls, mp.wcls);
+    out[0] = __fadd_rn(__fadd_rn(lbox, lobj), lcls);
+    out[1] = lbox; out[2] = lcls; out[3] = lobj;
+}
+
+static int v5_obj_blocks(long long cells) { return (int)((cells + 255) / 256 < 148 * 8 ? (cells + 255) / 256 : 148 * 8); }
+
+// tobj / obj_grad: the levels back to back ([sum of cells]); giou: [nl][cap]; sums: [nl][3]
+int v5_loss_fwd_all_launch(V5Multi& mp, int cap, float* giou, float* tobj, float* obj_grad, double* sums, float* out4,
+                           cudaStream_t st) {
+    long long total = 0;
+    int max_obj = 0;
+    for (int i = 0; i < mp.nl; ++i) {
+        V5Level& L = mp.lv[i];
+        L.giou = giou + (size_t)i * cap;
+        L.tobj = tobj + total;
+        L.obj_grad = obj_grad ? obj_grad + total : nullptr;
+        L.sums = sums + 3 * i;
+        L.obj_blocks = v5_obj_blocks(L.cells);
+        max_obj = max(max_obj, L.obj_blocks);
+        total += L.cells;
+    }
+    B2_CUDA(cudaMemsetAsync(sums, 0, (size_t)mp.nl * 3 * sizeof(double), st));
+    B2_CUDA(cudaMemsetAsync(tobj, 0, (size_t)total * 4, st));                      // torch.zeros_like(pi[..., 0])  (:107)
+    const dim3 grows(ceil_div(cap, 256), mp.nl);
+    v5_match_fwd_multi_kernel<<<grows, 256, 0, st>>>(mp);
+    B2_LAUNCH_CHECK("v5_match_fwd_multi_kernel");
+    v5_match_tobj_multi_kernel<<<grows, 256, 0, st>>>(mp);
+    B2_LAUNCH_CHECK("v5_match_tobj_multi_kernel");
+    v5_loss_rows_fwd_multi_kernel<<<dim3(ceil_div(cap, 8), mp.nl), 256, 0, st>>>(mp);
+    B2_LAUNCH_CHECK("v5_loss_rows_fwd_multi_kernel");
+    v5_loss_obj_fwd_multi_kernel<<<dim3(max_obj, mp.nl), 256, 0, st>>>(mp);
+    B2_LAUNCH_CHECK("v5_loss_obj_fwd_multi_kernel");
+    v5_loss_means_combine_multi_kernel<<<1, 32, 0, st>>>(mp, out4);
+    B2_LAUNCH_CHECK("v5_loss_means_combine_multi_kernel");
+    return 0;
+}
+
+// g3 (device, [3]) is scratch: the upstream gradients of the four outputs -> d/d mean_box, d/d mean_obj, d/d mean_cls
+int v5_loss_bwd_all_launch(V5Multi& mp, int cap, const float* obj_grad, const float* g_loss, const float* g_box,
+                           const float* g_cls, const float* g_obj, float* g3, cudaStream_t st) {
+    long long total = 0;
+    int max_obj = 0;
+    for (int i = 0; i < mp.nl; ++i) {
+        V5Level& L = mp.lv[i];
+        L.obj_grad = const_cast<float*>(obj_grad) + total;
+        L.tobj = nullptr;
+        L.obj_blocks = v5_obj_blocks(L.cells);
+        L.inv_cells = (float)(1.0 / (double)L.cells);
+        max_obj = max(max_obj, L.obj_blocks);
+        total += L.cells;
+    }
+    mp.g3 = g3;
+    v5_loss_combine_bwd_kernel<<<1, 32, 0, st>>>(g_loss, g_box, g_cls, g_obj, mp.wbox, mp.wobj, mp.wcls, g3);
+    B2_LAUNCH_CHECK("v5_loss_combine_bwd_kernel");
+    v5_loss_obj_bwd_full_multi_kernel<<<dim3(max_obj, mp.nl), 256, 0, st>>>(mp);
+    B2_LAUNCH_CHECK("v5_loss_obj_bwd_full_multi_kernel");
+    v5_loss_rows_bwd_multi_kernel<<<dim3(ceil_div(cap, 8), mp.nl), 256, 0, st>>>(mp);
+    B2_LAUNCH_CHECK("v5_loss_rows_bwd_multi_kernel");
     return 0;
 }
 

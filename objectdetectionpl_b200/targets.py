@@ -271,23 +271,23 @@ class _V5LossAll(torch.autograd.Function):
         ctx.set_materialize_grads(False)            # the three metric outputs usually get no gradient: None, not a zero tensor each
         cells = [pid.numel() // pid.shape[-1] for pid in pids]
         cap = levels.cap
-        tobj = torch.empty((sum(cells),), dtype=torch.float32, device=dev)            # all levels, back to back
+        lv = (L.V5Level * nl)()
+        for i, pid in enumerate(pids):
+            l = lv[i]
+            l.pi = pid.data_ptr()
+            l.batch, l.na, l.ny, l.nx, l.fields = pid.shape
+            l.b, l.a, l.gj, l.gi, l.tcls, l.tbox, l.anch = levels.ptrs(i)
+            l.m_dev = counts.data_ptr() + 4 * i
+        tobj = torch.empty((sum(cells),), dtype=torch.float32, device=dev)            # all levels, back to back (scratch)
         gobj = torch.empty((sum(cells),), dtype=torch.float32, device=dev)            # d FL_obj / d logit per cell, for the backward
         giou = torch.empty((nl * cap,), dtype=torch.float32, device=dev)
         means = torch.empty((nl, 3), dtype=torch.float64, device=dev)
         out = torch.empty((4,), dtype=torch.float32, device=dev)
-        st = L.stream_ptr(dev)
-        t_ptr, g_ptr, m_ptr, c_ptr, h_ptr = tobj.data_ptr(), giou.data_ptr(), means.data_ptr(), counts.data_ptr(), gobj.data_ptr()
-        for i, pid in enumerate(pids):
-            B, na, ny, nx, F = pid.shape
-            L.check(lib.b200det_v5_loss_fwd_dev(pid.data_ptr(), B, na, ny, nx, F, *levels.ptrs(i), cap, c_ptr + 4 * i, cp, cn,
-                                                gamma, alpha, int(with_cls), g_ptr + 4 * cap * i, t_ptr, h_ptr, m_ptr + 24 * i, st),
-                    "v5_loss_fwd_dev")
-            t_ptr += 4 * cells[i]
-            h_ptr += 4 * cells[i]
-        L.check(lib.b200det_v5_loss_combine(m_ptr, nl, *_V5_GAINS, out.data_ptr(), st), "v5_loss_combine")
+        L.check(lib.b200det_v5_loss_fwd_all(lv, nl, cap, cp, cn, gamma, alpha, int(with_cls), *_V5_GAINS, giou.data_ptr(),
+                                            tobj.data_ptr(), gobj.data_ptr(), means.data_ptr(), out.data_ptr(), L.stream_ptr(dev)),
+                "v5_loss_fwd_all")                 # 2 memsets + 5 launches for all levels, the combination included
         ctx.save_for_backward(gobj, counts, *pids)         # tobj is not needed again: the backward gets its effect through gobj
-        ctx.levels, ctx.cfg, ctx.cells = levels, cfg, cells
+        ctx.levels, ctx.cfg, ctx.lv = levels, cfg, lv
         return out[0:1], out[1:2], out[2:3], out[3:4]
 
     @staticmethod
@@ -301,21 +301,13 @@ class _V5LossAll(torch.autograd.Function):
                 return _V5LossAll.backward(ctx, g_loss, g_box, g_cls, g_obj)
         gs = [None if g is None else g.contiguous().float() for g in (g_loss, g_box, g_cls, g_obj)]
         g3 = torch.empty((3,), dtype=torch.float32, device=dev)
-        st = L.stream_ptr(dev)
-        levels, cap = ctx.levels, ctx.levels.cap
-        grads = []
-        L.check(lib.b200det_v5_loss_combine_bwd(*(None if g is None else g.data_ptr() for g in gs), *_V5_GAINS, g3.data_ptr(),
-                                                st), "v5_loss_combine_bwd")
-        h_ptr, c_ptr, g3_ptr = gobj.data_ptr(), counts.data_ptr(), g3.data_ptr()
-        for i, pid in enumerate(pids):
-            B, na, ny, nx, F = pid.shape
-            cells = ctx.cells[i]
-            gpi = torch.empty_like(pid)                               # fully written by the call (no zero-fill pass)
-            L.check(lib.b200det_v5_loss_bwd_full_dev(pid.data_ptr(), B, na, ny, nx, F, *levels.ptrs(i), cap, c_ptr + 4 * i, cp, cn,
-                                                     gamma, alpha, int(with_cls), None, h_ptr, g3_ptr, 1.0 / cells, gpi.data_ptr(),
-                                                     st), "v5_loss_bwd_full_dev")
-            grads.append(gpi)
-            h_ptr += 4 * cells
+        lv, nl = ctx.lv, len(pids)
+        grads = [torch.empty_like(pid) for pid in pids]               # fully written by the call (no zero-fill pass)
+        for i, gpi in enumerate(grads):
+            lv[i].gpi = gpi.data_ptr()
+        L.check(lib.b200det_v5_loss_bwd_all(lv, nl, ctx.levels.cap, cp, cn, gamma, alpha, int(with_cls), *_V5_GAINS, gobj.data_ptr(),
+                                            *(None if g is None else g.data_ptr() for g in gs), g3.data_ptr(), L.stream_ptr(dev)),
+                "v5_loss_bwd_all")                 # 3 launches for all levels
         return (None, None, None, *grads)
 
 

@@ -62,6 +62,9 @@ int main(void) {
   printf("%zu %zu %zu %zu %zu %zu\n", sizeof(b200det_prior_desc), offsetof(b200det_prior_desc, loc),
          offsetof(b200det_prior_desc, priors), offsetof(b200det_prior_desc, topk), offsetof(b200det_prior_desc, mode_min),
          offsetof(b200det_prior_desc, compat));
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(b200det_v5_level), offsetof(b200det_v5_level, batch),
+         offsetof(b200det_v5_level, fields), offsetof(b200det_v5_level, b), offsetof(b200det_v5_level, tbox),
+         offsetof(b200det_v5_level, m_dev), offsetof(b200det_v5_level, gpi));
   return 0;
 }''')
     exe = tmp_path / "layout"
@@ -85,6 +88,9 @@ int main(void) {
     p = [int(v) for v in out[1].split()]
     P = L.PriorDesc
     assert p == [ctypes.sizeof(P), P.loc.offset, P.priors.offset, P.topk.offset, P.mode_min.offset, P.compat.offset]
+    v = [int(x) for x in out[2].split()]
+    V = L.V5Level
+    assert v == [ctypes.sizeof(V), V.batch.offset, V.fields.offset, V.b.offset, V.tbox.offset, V.m_dev.offset, V.gpi.offset]
 
 
 def _desc(B=64, A=3, C=80, grids=(80, 40, 20)):
