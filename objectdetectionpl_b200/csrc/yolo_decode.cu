@@ -49,8 +49,13 @@ yolo_decode_filter_kernel(const K1Params p) {
     __shared__ int s_scan[33];
     __shared__ K1Stage s_stage;
 
-    const int b = blockIdx.y;
-    const int tile = blockIdx.x;
+    // Launch order.  Default: x = tile, y = image.  A head with an odd plane (13 x 13 ...) has a few scalar-load tiles that
+    // each take several times as long as a vector tile; with the default order image b's scalar tile only starts after the
+    // b * n_tiles CTAs before it, and the last ones are the launch's tail.  slow_first: x = image, y = tile rotated so that
+    // the first scalar level's tiles are y = 0 — all of them start at once and the vector tiles fill in around them.
+    const int b = p.slow_first ? blockIdx.x : blockIdx.y;
+    int tile = p.slow_first ? (int)blockIdx.y + p.slow_first - 1 : (int)blockIdx.x;
+    if (p.slow_first && tile >= p.n_tiles) tile -= p.n_tiles;
     const int tid = threadIdx.x;
     int lvl = 0;
 #pragma unroll
@@ -237,8 +242,14 @@ int yolo_validate(const b200det_yolo_desc* d, const void* ws, size_t ws_bytes) {
     return 0;
 }
 
-static int launch_k1(const b200det_yolo_desc* d, const K1Params& p, cudaStream_t st) {
+static int launch_k1(const b200det_yolo_desc* d, const K1Params& p_in, cudaStream_t st) {
+    K1Params p = p_in;
     dim3 grid(p.n_tiles, d->batch);
+    p.slow_first = 0;
+    for (int l = 0; l < p.nlevels && !p.slow_first; ++l)
+        if ((p.GG[l] & 3) != 0 || (((uintptr_t)p.head[l]) & 15) != 0) p.slow_first = p.tile_off[l] + 1;   // first scalar-tile level
+    if (p.slow_first && p.n_tiles <= 65535) grid = dim3(d->batch, p.n_tiles);
+    else p.slow_first = 0;
     const size_t smem = (size_t)d->num_classes * sizeof(int);
     constexpr int VEC = 4;
     // U = 8 loads in flight per thread, <= 80 registers (6 CTAs/SM): best of the measured (U, occupancy, cache-hint,

@@ -13,6 +13,7 @@ struct K1Params {
     float stride[B200DET_MAX_LEVELS];
     float anc[B200DET_MAX_LEVELS][B200DET_MAX_ANCHORS][2];
     int nlevels, A, C, N, n_pad, n_tiles;
+    int slow_first;                         // > 0: grid is (batch, tiles) and CTA row y takes tile (y + slow_first - 1) % n_tiles
     float conf_thres;
     float sxy, soff;                        // DECODE_YOLOV4_NORM: scale_x_y and 0.5 * (scale_x_y - 1)
     // outputs
