@@ -126,4 +126,48 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* 
     return res;
 }
 
+// SSD / RetinaNet prior decode of one prior (model/SSD.py:253-258): loc = (dx, dy, dw, dh), prior = (cx, cy, w, h) -> corners.
+// One definition for the decode+filter kernel (prior.cu) and the NMS epilogue (nms.cu), which re-derives the box and label of
+// the few output rows that the reference gathers with score-filtered indices from its unfiltered arrays (SSD.py:303-307).
+__device__ __forceinline__ float4 prior_decode_box(const float4 l, const float4 pr) {
+    const float cx = __fadd_rn(__fmul_rn(l.x, pr.z), pr.x);          // SSD.py:256
+    const float cy = __fadd_rn(__fmul_rn(l.y, pr.w), pr.y);
+    const float w = __fmul_rn(expf(l.z), pr.z);                      // SSD.py:257
+    const float h = __fmul_rn(expf(l.w), pr.w);
+    const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
+    return make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+}
+// torch.max(dim) over one row of class logits: first maximal index, the first NaN wins over everything (aten TensorCompareKernel).
+// The row is cold (it was last read by the decode kernel, a gigabyte ago): eight 128-bit loads are in flight at a time.
+__device__ __forceinline__ int prior_row_argmax(const float* __restrict__ row, const int C) {
+    float best = row[0];
+    int besti = 0;
+    int c = 1;
+    if ((C & 3) == 0 && (((uintptr_t)row) & 15) == 0) {
+        const float4* r4 = reinterpret_cast<const float4*>(row);
+        const int n4 = C >> 2;
+        for (int c4 = 0; c4 < n4; c4 += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = c4 + u < n4 ? __ldg(r4 + c4 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (c4 + u >= n4) break;
+                const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int cc = ((c4 + u) << 2) + k;
+                    if (cc > 0 && !(e[k] <= best) && (best == best)) { best = e[k]; besti = cc; }
+                }
+            }
+        }
+        return besti;
+    }
+    for (; c < C; ++c) {
+        const float v = row[c];
+        if (!(v <= best) && (best == best)) { best = v; besti = c; }
+    }
+    return besti;
+}
+
 }  // namespace b200det

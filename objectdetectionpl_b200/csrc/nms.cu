@@ -54,8 +54,9 @@ struct NmsParams {
     const uint32_t* tile_prefix;   // [B][n_tiles] exclusive scan of tile_count (filtered index of a slot)
     int n_tiles;
     const uint32_t* orig;          // [B][n_pad] prior index of a slot
-    const float4* dense_box;       // [B][P] decoded boxes of ALL priors (quirk ii)
-    const int32_t* dense_label;    // [B][P]
+    const float* loc;              // [B][P][4]  the call's inputs: box and label of ANY prior are re-derived from them for
+    const float* pcls;             // [B][P][C]  the few output rows that need it (quirk ii)
+    const float* priors;           // [P][4]
     int P;
     float* out_rows;               // [B][topk][7]
     int32_t* out_index;            // [B][topk] or null
@@ -968,9 +969,12 @@ nms_segment_kernel(const NmsParams p) {
             if (p.compat) {
                 // quirk (ii): `keep` indexes the score-filtered set, but boxes/labels are gathered from the
                 // UNFILTERED arrays with it (SSD.py:303-307)
+                // ... i.e. row k of the output carries prior number f = (filtered index of the kept candidate): decode that
+                // prior here (<= topk rows per image) instead of keeping dense box / label arrays of all B x P priors around
                 const int f = (int)(tp[slot >> kTileShift] + (slot & (kTile - 1)));
-                bx = p.dense_box[(size_t)b * p.P + f];
-                label = p.dense_label[(size_t)b * p.P + f];
+                bx = prior_decode_box(*reinterpret_cast<const float4*>(p.loc + ((size_t)b * p.P + f) * 4),
+                                      *reinterpret_cast<const float4*>(p.priors + (size_t)f * 4));
+                label = prior_row_argmax(p.pcls + ((size_t)b * p.P + f) * p.C, p.C);
                 src = f;
             }
             float* o = p.out_rows + ((size_t)b * p.topk + kidx) * 7;
@@ -1183,14 +1187,14 @@ int yolo_stage_emit(const b200det_yolo_desc* d, void* ws, size_t ws_bytes, float
 
 int prior_nms_launch_raw(const uint32_t* count, const uint32_t* spay, const float4* box4, const float2* cc2,
                          float4* kbox, uint32_t* kpos, int n_pad, float thr, int topk, int compat,
-                         const uint32_t* tile_prefix, int n_tiles, const uint32_t* orig, const float4* dense_box,
-                         const int32_t* dense_label, int P, float* out_rows, int32_t* out_index, int32_t* out_count,
+                         const uint32_t* tile_prefix, int n_tiles, const uint32_t* orig, const float* loc,
+                         const float* cls, const float* priors, int P, int C, float* out_rows, int32_t* out_index, int32_t* out_count,
                          int batch, int mode_min, cudaStream_t st) {
     NmsParams p;
     memset(&p, 0, sizeof(p));
     p.count = count; p.spay = spay; p.box4 = box4; p.cc2 = cc2; p.kbox = kbox; p.kpos = kpos;
     p.n_pad = n_pad; p.thr = thr; p.topk = topk; p.compat = compat; p.tile_prefix = tile_prefix; p.n_tiles = n_tiles;
-    p.orig = orig; p.dense_box = dense_box; p.dense_label = dense_label; p.P = P;
+    p.orig = orig; p.loc = loc; p.pcls = cls; p.priors = priors; p.P = P; p.C = C;
     p.out_rows = out_rows; p.out_index = out_index; p.out_count = out_count;
     dim3 grid(1, batch);
     if (mode_min) nms_segment_kernel<2, false, kNmsThreads, kNmsT><<<grid, kNmsThreads, 0, st>>>(p);

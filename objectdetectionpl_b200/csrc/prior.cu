@@ -34,8 +34,6 @@ struct PriorWs {
     uint32_t* pay[2];
     float4* kbox;           // [B][n_pad]
     uint32_t* kpos;         // [B][n_pad]
-    float4* dense_box;      // [B][P]
-    int32_t* dense_label;   // [B][P]
     size_t total_bytes;
     int n_pad, n_tiles;
 };
@@ -62,8 +60,6 @@ static void prior_ws_layout(const b200det_prior_desc* d, void* base, PriorWs* w)
     for (int i = 0; i < 2; ++i) w->pay[i] = (uint32_t*)take(B * P * 4);
     w->kbox = (float4*)take(B * P * 16);
     w->kpos = (uint32_t*)take(B * P * 4);
-    w->dense_box = (float4*)take(B * (size_t)d->num_priors * 16);
-    w->dense_label = (int32_t*)take(B * (size_t)d->num_priors * 4);
     w->total_bytes = off;
 }
 
@@ -73,7 +69,6 @@ struct K1pParams {
     const float* priors;
     int P, C, n_pad, n_tiles;
     float class_thresh;
-    int write_dense;
     float4* box4;
     float2* cc2;
     uint32_t* orig;
@@ -81,8 +76,6 @@ struct K1pParams {
     uint32_t* pay;
     uint32_t* tile_count;
     uint32_t* count;
-    float4* dense_box;
-    int32_t* dense_label;
 };
 
 // argmax step for a rotated scan order: first maximal index wins, first NaN wins over everything
@@ -191,18 +184,9 @@ __global__ void __launch_bounds__(kPriRows) prior_decode_filter_kernel(const K1p
         if (tid < nrows) {
             const float4 l = *reinterpret_cast<const float4*>(p.loc + ((size_t)b * p.P + pi) * 4);
             const float4 pr = *reinterpret_cast<const float4*>(p.priors + (size_t)pi * 4);
-            const float cx = __fadd_rn(__fmul_rn(l.x, pr.z), pr.x);          // SSD.py:256
-            const float cy = __fadd_rn(__fmul_rn(l.y, pr.w), pr.y);
-            const float w = __fmul_rn(expf(l.z), pr.z);                      // SSD.py:257
-            const float h = __fmul_rn(expf(l.w), pr.w);
-            const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
-            bx = make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+            bx = prior_decode_box(l, pr);
             score = sigmoidf_acc(best);                                       // SSD.py:260
             keep = score > p.class_thresh;                                    // SSD.py:261
-            if (p.write_dense) {
-                p.dense_box[(size_t)b * p.P + pi] = bx;
-                p.dense_label[(size_t)b * p.P + pi] = besti;
-            }
         }
         int total;
         const int ex = block_exclusive_scan(keep ? 1 : 0, s_scan, &total);
@@ -250,8 +234,8 @@ int score_sort_launch(const uint32_t* tile_count, const uint32_t* count, uint32_
 struct NmsParams;
 int prior_nms_launch_raw(const uint32_t* count, const uint32_t* spay, const float4* box4, const float2* cc2,
                          float4* kbox, uint32_t* kpos, int n_pad, float thr, int topk, int compat,
-                         const uint32_t* tile_prefix, int n_tiles, const uint32_t* orig, const float4* dense_box,
-                         const int32_t* dense_label, int P, float* out_rows, int32_t* out_index, int32_t* out_count,
+                         const uint32_t* tile_prefix, int n_tiles, const uint32_t* orig, const float* loc,
+                         const float* cls, const float* priors, int P, int C, float* out_rows, int32_t* out_index, int32_t* out_count,
                          int batch, int mode_min, cudaStream_t st);
 
 static int prior_validate(const b200det_prior_desc* d) {
@@ -304,9 +288,9 @@ int prior_stage_decode(const b200det_prior_desc* d, void* ws, size_t ws_bytes, c
     memset(&p, 0, sizeof(p));
     p.loc = d->loc; p.cls = d->cls; p.priors = d->priors;
     p.P = d->num_priors; p.C = d->num_classes; p.n_pad = w.n_pad; p.n_tiles = w.n_tiles;
-    p.class_thresh = d->class_thresh; p.write_dense = d->compat ? 1 : 0;
+    p.class_thresh = d->class_thresh;
     p.box4 = w.box4; p.cc2 = w.cc2; p.orig = w.orig; p.key = w.key[0]; p.pay = w.pay[0];
-    p.tile_count = w.tile_count; p.count = use_select ? nullptr : w.count; p.dense_box = w.dense_box; p.dense_label = w.dense_label;
+    p.tile_count = w.tile_count; p.count = use_select ? nullptr : w.count;
     const int cc = d->num_classes < kPriMaxCC ? d->num_classes : kPriMaxCC;
     const size_t smem = (size_t)kPriRows * cc * sizeof(float);
     dim3 grid(w.n_tiles, d->batch);
@@ -348,7 +332,7 @@ int prior_stage_select_nms(const b200det_prior_desc* d, void* ws, size_t ws_byte
         rc = score_sort_launch(w.tile_count, w.count, w.digit_hist, w.ticket, w.status, w.key, w.pay, w.n_pad, w.n_tiles, d->batch, st);
     if (rc) return rc;
     rc = prior_nms_launch_raw(w.count, w.pay[0], w.box4, w.cc2, w.kbox, w.kpos, w.n_pad, d->nms_thresh, d->topk,
-                              d->compat, w.tile_prefix, w.n_tiles, w.orig, w.dense_box, w.dense_label, d->num_priors,
+                              d->compat, w.tile_prefix, w.n_tiles, w.orig, d->loc, d->cls, d->priors, d->num_priors, d->num_classes,
                               out_rows, out_index, out_count, d->batch, d->mode_min, st);
     if (rc) return rc;
     if (cand_count)
