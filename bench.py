@@ -35,6 +35,7 @@ from __future__ import annotations
 
 import argparse
 import ctypes
+import gc
 import json
 import os
 import statistics
@@ -130,7 +131,7 @@ class ClockSampler:
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.01)          # ~100 samples per second: enough for the median, and the timed host loop keeps the GIL
 
     def __enter__(self):
         if self.ok:
@@ -645,17 +646,22 @@ def main():
     b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k1_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
     barrier()
-    with ClockSampler(local) as clk:
-        a0.record()
-        for i in range(K):
-            wl.api_step(i)
-        a1.record()
-        barrier()
-        b0.record()
-        for i in range(K):
-            wl.pipe_step(i, k1_ev[i])
-        b1.record()
-        barrier()
+    gc.collect()
+    gc.disable()            # as `timeit` does: no collector pauses inside the timed host loops
+    try:
+        with ClockSampler(local) as clk:
+            a0.record()
+            for i in range(K):
+                wl.api_step(i)
+            a1.record()
+            barrier()
+            b0.record()
+            for i in range(K):
+                wl.pipe_step(i, k1_ev[i])
+            b1.record()
+            barrier()
+    finally:
+        gc.enable()
     api_ms = max_over_ranks(a0.elapsed_time(a1))
     pipe_ms = max_over_ranks(b0.elapsed_time(b1))
     value = world * B * K / (api_ms * 1e-3)
